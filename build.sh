@@ -1,0 +1,24 @@
+#!/usr/bin/env bash
+# Builds libdinomc.so (all CUDA kernels + the C ABI) for sm_100a, in-tree.
+set -euo pipefail
+ROOT="$(cd "$(dirname "$0")" && pwd)"
+PKG="$ROOT/self-supervised-learning-for-aerial-image-segmentation_b200"
+SRC="$PKG/csrc"
+OUT="$PKG/libdinomc.so"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
+       -I"$ROOT/include" -I"$SRC" --expt-relaxed-constexpr)
+mkdir -p "$PKG/build"
+objs=()
+pids=()
+for f in api gemm_sm100 gemm_simt rowops teacher ce ema; do
+  o="$PKG/build/$f.o"
+  objs+=("$o")
+  if [[ ! -f "$o" || "$SRC/$f.cu" -nt "$o" || "$SRC/dmc_common.cuh" -nt "$o" || "$SRC/dmc_ptx.cuh" -nt "$o" || "$ROOT/include/dinomc.h" -nt "$o" ]]; then
+    "$NVCC" "${FLAGS[@]}" ${DMC_PTXAS_V:+-Xptxas -v} -c "$SRC/$f.cu" -o "$o" &
+    pids+=($!)
+  fi
+done
+for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
+"$NVCC" -shared -o "$OUT" "${objs[@]}" -gencode arch=compute_100a,code=sm_100a -cudart static
+echo "built $OUT"

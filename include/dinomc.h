@@ -1,0 +1,177 @@
+/*
+ * dinomc.h -- C ABI of libdinomc.so: the B200 (sm_100a) kernels behind the DINO-MC
+ * head + loss + center + EMA step.
+ *
+ * The reference (HaykSahakyan11/Self-Supervised-Learning-for-Aerial-Image-Segmentation) has no
+ * native layer: its hot path is eager PyTorch.  Each entry point below therefore cites the
+ * reference *Python* lines whose arithmetic it replaces (paths relative to the reference root).
+ * The Python drop-in modules (DINOHead / DINOLoss / ema_update_) bind these with ctypes; see
+ * INTEGRATION.md for the stub a maintainer of the reference would add.
+ *
+ * Conventions (every entry point):
+ *   - plain C types only; all tensor arguments are raw DEVICE pointers owned by the caller
+ *     (the library never frees or retains them) unless the name ends in `_host`;
+ *   - matrices are row-major with an explicit leading dimension in ELEMENTS;
+ *   - `stream` is a cudaStream_t passed as void*; work is only enqueued, the library never
+ *     synchronises the device and never allocates: scratch comes from a caller-supplied
+ *     workspace whose size is returned by the matching *_workspace_bytes() query;
+ *   - return value: 0 = ok, < 0 = invalid argument (see dmc_last_error_string()),
+ *     > 0 = a cudaError_t raised while enqueuing;
+ *   - re-entrant and stream-safe: no global mutable state except the thread-local error string.
+ */
+#ifndef DINOMC_H_
+#define DINOMC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMC_VERSION 100 /* major*100 + minor */
+
+/* element types of tensor arguments */
+enum { DMC_F32 = 0, DMC_BF16 = 1 };
+
+/* GEMM epilogue activation */
+enum {
+  DMC_ACT_NONE = 0,
+  DMC_ACT_GELU = 1,     /* D = gelu(z); if aux != NULL also aux = z (pre-activation, saved for backward) */
+  DMC_ACT_GELU_BWD = 2  /* D = z * gelu'(aux)   (aux = the saved pre-activation)                        */
+};
+
+int dmc_version(void);
+/* Message for the last non-zero return on the calling thread ("" if none). */
+const char* dmc_last_error_string(void);
+/* 0 if device `device` is an sm_100 part this library can run on, else an error. */
+int dmc_device_check(int device);
+
+/* ---------------------------------------------------------------------------------------------
+ * GEMM:  D[M,N] = epilogue( sum_k A(m,k) * B(n,k) ),  fp32 accumulation.
+ *
+ * Replaces the nn.Linear calls of DINOHead.forward (utils/vision_transformer.py:291,293: the MLP
+ * and the weight-normed last layer x @ W^T) and their autograd backward (dgrad / wgrad), reached
+ * from main_dino_mc.py:386/393.
+ *
+ * Operand layout is described per operand:  *_mn_major == 0 : the contraction index k is the
+ * contiguous one (A stored [M,K], B stored [N,K]);  == 1 : the M (resp. N) index is contiguous
+ * (A stored [K,M], B stored [K,N]).  ld* is the row stride of the stored matrix, in elements.
+ *   forward  x @ W^T ............ A=x [M,K] k-major,      B=W [N,K] k-major
+ *   dgrad    dY @ W .............. A=dY [M,K] k-major,     B=W stored [K,N] -> b_mn_major=1
+ *   wgrad    dY^T @ X ............ A=dY stored [K,M] -> a_mn_major=1, B=X stored [K,N] -> b_mn_major=1
+ *
+ * in_dtype == DMC_BF16 : one bf16 tcgen05 pass (kind::f16).
+ * in_dtype == DMC_F32  : operands are fp32 read as TF32 (kind::tf32).  If A_lo and B_lo are given,
+ *                        A = A + A_lo, B = B + B_lo (hi/lo split made by dmc_split_tf32) and three
+ *                        passes hi*hi + hi*lo + lo*hi are accumulated ("3xTF32", ~fp32 accuracy).
+ * Epilogue, in this order:  z = acc * col_scale[n] * alpha * (*alpha_dev) + bias[n];  activation;
+ * store as out_dtype.  Every pointer in the epilogue may be NULL (= skipped).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct dmc_gemm_args {
+  int64_t M, N, K;
+  const void* A;    int64_t lda; int32_t a_mn_major;
+  const void* B;    int64_t ldb; int32_t b_mn_major;
+  const void* A_lo; /* fp32 residuals for 3xTF32, or NULL */
+  const void* B_lo;
+  int32_t in_dtype;   /* DMC_BF16 | DMC_F32 */
+  void* D;          int64_t ldd; int32_t out_dtype;
+  const float* col_scale;  /* [N] or NULL : the weight-norm factor g_k/||v_k|| when folded in here */
+  const float* bias;       /* [N] or NULL */
+  const float* alpha_dev;  /* device scalar or NULL (upstream grad / loss scale) */
+  float alpha;             /* host scalar, 1.0f for none */
+  int32_t act;             /* DMC_ACT_* */
+  void* aux;        int64_t ldaux; int32_t aux_dtype;
+  int32_t split_k;         /* 0 = let the library choose, >= 1 = forced */
+  void* workspace;  size_t workspace_bytes; /* needed when split_k != 1, see query */
+} dmc_gemm_args;
+
+/* Upper bound of the split-K workspace dmc_gemm may need for this problem. */
+size_t dmc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int32_t in_dtype);
+/* tcgen05 / TMEM / TMA tile kernel (sm_100a). */
+int dmc_gemm(const dmc_gemm_args* args, void* stream);
+/* Same contract on the fp32 FMA pipes (no tensor cores, A_lo/B_lo ignored, in_dtype must be F32):
+ * the exact-fp32 arm used to cross-check the tensor-core kernel on the device. */
+int dmc_gemm_simt(const dmc_gemm_args* args, void* stream);
+
+/* Split fp32 `x` into hi = tf32-rounded x (low 13 mantissa bits zero) and lo = x - hi. */
+int dmc_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
+/* fp32 -> bf16 (round to nearest even). */
+int dmc_cast_f32_to_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
+/* out[n] = sum_m X[m,n]   (bias gradients of the MLP Linears).  X is F32 or BF16. */
+size_t dmc_colsum_workspace_bytes(int64_t M, int64_t N);
+int dmc_colsum(const void* X, int32_t dtype, int64_t M, int64_t N, int64_t ld, float* out,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row kernels of the head.
+ * ------------------------------------------------------------------------------------------- */
+/* F.normalize(x, dim=-1, p=2) (utils/vision_transformer.py:292): zhat = z / max(||z||_2, eps).
+ * Writes any of zhat_f32 / zhat_bf16 / zhat_lo (tf32 residual of zhat_f32) that is non-NULL and
+ * inv_den[N] = 1/max(||z||,eps) (saved for backward).  z is F32 or BF16 [N,dim], row stride ld. */
+int dmc_normalize_rows_fwd(const void* z, int32_t z_dtype, int64_t n_rows, int64_t dim, int64_t ld, float eps,
+                           float* zhat_f32, void* zhat_bf16, float* zhat_lo, float* inv_den, void* stream);
+/* Backward of the above: dz = (dzhat - (dzhat . zhat) zhat) * inv_den (rows whose norm was clamped to
+ * eps get dz = dzhat * inv_den).  dz is F32 or BF16. */
+int dmc_normalize_rows_bwd(const float* dzhat, const float* zhat, const float* inv_den, int64_t n_rows,
+                           int64_t dim, float eps, void* dz, int32_t dz_dtype, void* stream);
+/* nn.utils.weight_norm pre-hook (utils/vision_transformer.py:279): w_k = g_k * v_k / ||v_k||_2 for every
+ * output row k of v [K,dim].  Writes any non-NULL of w_f32 (tf32-rounded when w_lo is given) / w_lo /
+ * w_bf16, and scale[K] = g_k/||v_k||, inv_vnorm[K] = 1/||v_k|| (saved for backward). */
+int dmc_weightnorm_fwd(const float* v, const float* g, int64_t K, int64_t dim,
+                       float* w_f32, float* w_lo, void* w_bf16, float* scale, float* inv_vnorm, void* stream);
+/* Backward: dv = scale * (dw - (dw . vhat) vhat), dg = dw . vhat (dg may be NULL: frozen gain,
+ * utils/vision_transformer.py:281-282). */
+int dmc_weightnorm_bwd(const float* dw, const float* v, const float* scale, const float* inv_vnorm,
+                       int64_t K, int64_t dim, float* dv, float* dg, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * DINOLoss (main_dino_mc.py:419-473).  Rows are crop-major: row v*B + b = crop v of sample b
+ * (the layout MultiCropWrapper guarantees, utils/utils.py:627-646).  Logits are F32 or BF16.
+ * ------------------------------------------------------------------------------------------- */
+/* One pass over the teacher logits t [Nt,K] (main_dino_mc.py:446 and :468): per-row statistics of
+ * softmax((t - center) * inv_temp) as row_stats[Nt][2] = {row max, 1/sum exp} and the per-GPU batch
+ * column sum colsum[K] = sum_rows t (input of the center all-reduce). */
+size_t dmc_teacher_workspace_bytes(int64_t Nt, int64_t K);
+int dmc_teacher_stats_colsum(const void* t, int32_t dtype, int64_t Nt, int64_t K, int64_t ld,
+                             const float* center, float inv_temp, float* row_stats, float* colsum,
+                             void* workspace, size_t workspace_bytes, void* stream);
+/* center_out = center_in * momentum + (colsum / count) * one_minus_momentum  (main_dino_mc.py:470-473)
+ * with the reference's fp32 roundings: true division by count (= Nt * world_size), separate multiplies and
+ * add (no FMA).  center_out may alias center_in.  `momentum` and `one_minus_momentum` are passed
+ * separately because the reference forms (1 - momentum) in float64 before the cast to fp32. */
+int dmc_center_update(const float* center_in, float* center_out, const float* colsum, int64_t K, float count,
+                      float momentum, float one_minus_momentum, void* stream);
+
+/* Crop-pair cross-entropy forward (main_dino_mc.py:441-459) in closed form: every student and every
+ * teacher logit is read once.  Outputs s_lse[C*B] (log-sum-exp of s/tau_s per student row, saved for
+ * backward) and loss[1]. */
+size_t dmc_ce_workspace_bytes(int64_t B, int32_t C, int32_t G, int64_t K);
+int dmc_ce_fwd(const void* s, int32_t s_dtype, int64_t lds, const void* t, int32_t t_dtype, int64_t ldt,
+               const float* center, const float* t_row_stats, int64_t B, int32_t C, int32_t G, int64_t K,
+               float inv_student_temp, float inv_teacher_temp, float* s_lse, float* loss,
+               void* workspace, size_t workspace_bytes, void* stream);
+/* Backward: ds[v*B+b,k] = grad_out * (n_v p_v - sum_{i != v} q_i) / (n B tau_s), written once as
+ * ds_dtype.  grad_out is a DEVICE scalar (the upstream gradient of the 0-dim loss). */
+int dmc_ce_bwd(const void* s, int32_t s_dtype, int64_t lds, const void* t, int32_t t_dtype, int64_t ldt,
+               const float* center, const float* t_row_stats, const float* s_lse, const float* grad_out,
+               int64_t B, int32_t C, int32_t G, int64_t K, float inv_student_temp, float inv_teacher_temp,
+               void* ds, int32_t ds_dtype, int64_t ldds, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * EMA teacher update (main_dino_mc.py:403-406):  p_k = fp32(p_k * m) + fp32((1-m) * p_q) for every
+ * (student, teacher) parameter pair, as ONE launch over a chunk table ("plan").
+ * The plan is built once on the host from the parameter pointer lists, copied to the device by the
+ * caller, and reused every step while the parameter storages do not move.
+ * ------------------------------------------------------------------------------------------- */
+size_t dmc_ema_plan_bytes(const int64_t* numels_host, int64_t n_tensors);
+/* Fills plan_host (capacity from dmc_ema_plan_bytes) and *n_chunks_out.  Host-only; no CUDA calls. */
+int dmc_ema_build_plan(const void* const* teacher_ptrs_host, const void* const* student_ptrs_host,
+                       const int64_t* numels_host, int64_t n_tensors, void* plan_host, size_t plan_bytes,
+                       int64_t* n_chunks_out);
+int dmc_ema_multi_tensor(const void* plan_dev, int64_t n_chunks, float m, float one_minus_m, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DINOMC_H_ */

@@ -1,0 +1,23 @@
+"""dinomc_b200 -- B200-native (sm_100a) implementation of DINO-MC's per-step hot path:
+DINOHead -> DINOLoss -> teacher-center update -> EMA teacher update.
+
+Import it as `dinomc_b200` (the alias package at the repo root; this directory's name is not a valid
+Python identifier).  Public surface mirrors the reference:
+
+    DINOHead(in_dim, out_dim, use_bn=False, norm_last_layer=True, nlayers=3, hidden_dim=2048, bottleneck_dim=256)
+    DINOLoss(out_dim, ncrops, warmup_teacher_temp, teacher_temp, warmup_teacher_temp_epochs, nepochs,
+             teacher_crops_number=2, student_temp=0.1, center_momentum=0.9)
+    ema_update_(teacher_params, student_params, m)
+    dropin.install()   # patch the reference's modules in place
+
+All compute goes through libdinomc.so (hand-written CUDA behind the C ABI in include/dinomc.h).
+There is no CPU fallback and no alternative backend: if the library is missing, importing the
+kernels raises.
+"""
+from . import _lib, functional, ops  # noqa: F401
+from .ema import ema_update_  # noqa: F401
+from .head import DINOHead, get_default_precision, set_default_precision  # noqa: F401
+from .loss import DINOLoss  # noqa: F401
+
+__all__ = ["DINOHead", "DINOLoss", "ema_update_", "set_default_precision", "get_default_precision",
+           "ops", "functional"]

@@ -1,0 +1,39 @@
+// api.cu -- version, error reporting and device check of libdinomc.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "dmc_common.cuh"
+
+namespace dmc {
+namespace {
+thread_local char g_err[512] = "";
+}
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_status(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+  return static_cast<int>(e);
+}
+}  // namespace dmc
+
+extern "C" int dmc_version(void) { return DMC_VERSION; }
+
+extern "C" const char* dmc_last_error_string(void) { return dmc::g_err; }
+
+extern "C" int dmc_device_check(int device) {
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return dmc::cuda_status(e, "cudaGetDeviceProperties");
+  if (prop.major != 10) {
+    dmc::set_error("libdinomc is built for sm_100a (B200); device %d is sm_%d%d", device, prop.major, prop.minor);
+    return -1;
+  }
+  return 0;
+}

@@ -1,0 +1,356 @@
+// ce.cu -- the crop-pair cross-entropy of DINOLoss (main_dino_mc.py:441-459) and its backward.
+//
+// The reference evaluates G*C - min(G,C) (teacher view, student view) pairs, each with its own
+// log_softmax over [B,K] (14 logit-sized passes forward, the same again in autograd, 14 saved [B,K]
+// log-prob tensors).  Here the closed form is used:
+//
+//   L = 1/(n B) sum_b [ sum_v n_v lse_v[b]  -  sum_k ( Q[b,k] S[b,k] - sum_{i<min(G,C)} q_i[b,k] x_i[b,k] ) ]
+//   dL/ds_v[b,k] = (n_v p_v[b,k] - Q[b,k] + [v<G] q_v[b,k]) / (n B tau_s)
+//
+// with x_v = s_v/tau_s, lse_v = logsumexp_k x_v, p_v = softmax(x_v), q_i = softmax((t_i - c)/tau_t),
+// Q = sum_i q_i, S = sum_v x_v, n_v = G - [v<G].  A CTA owns (sample b, column chunk): it loads the C
+// student and G teacher vectors of that chunk once, so every logit is read exactly once per pass and
+// the gradient is written exactly once.  HBM-bound streaming kernels: 128-bit loads, per-thread online
+// softmax statistics, warp-shuffle + shared-memory block reductions, deterministic partials (no atomics).
+#include <math.h>
+
+#include "dmc_common.cuh"
+
+namespace dmc {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kIters = 4;          // vectors per thread per row per CTA
+
+struct CeArgs {
+  const void* s; long long lds;
+  const void* t; long long ldt;
+  const float* center; const float2* t_stats;
+  long long B, K;
+  int C, G;
+  float inv_ts, inv_tt;
+  int nchunks; bool vec_ok;
+  // forward
+  float2* ws_s; float* ws_x;
+  // backward
+  const float* s_lse; const float* gout; float coef;
+  void* ds; long long ldds;
+};
+
+template <typename T>
+__device__ __forceinline__ void load_guard(const T* rowp, long long col, long long K, bool fast, float (&v)[Vec<T>::N]) {
+  if (fast) {
+    Vec<T>::load(rowp + col, v);
+  } else {
+#pragma unroll
+    for (int j = 0; j < Vec<T>::N; ++j) v[j] = (col + j < K) ? Vec<T>::load1(rowp + col + j) : 0.f;
+  }
+}
+
+// CT / GT: compile-time crop counts (0 = runtime, bounded by 16 / 4).
+template <typename T, int CT, int GT>
+__global__ void __launch_bounds__(kThreads)
+ce_fwd_kernel(const CeArgs a) {
+  constexpr int VEC = Vec<T>::N;
+  constexpr int MAXC = CT ? CT : 16, MAXG = GT ? GT : 4;
+  const int C = CT ? CT : a.C, G = GT ? GT : a.G;
+  const long long b = blockIdx.y;
+  const int chunk = blockIdx.x;
+  const long long col_begin = static_cast<long long>(chunk) * (kThreads * VEC * kIters);
+  const long long col_end = min(a.K, col_begin + kThreads * VEC * kIters);
+  const T* s = static_cast<const T*>(a.s);
+  const T* t = static_cast<const T*>(a.t);
+
+  float tm[MAXG], tinv[MAXG];
+#pragma unroll
+  for (int i = 0; i < MAXG; ++i)
+    if (i < G) { const float2 st = a.t_stats[i * a.B + b]; tm[i] = st.x; tinv[i] = st.y; }
+  float m[MAXC], l[MAXC];
+#pragma unroll
+  for (int v = 0; v < MAXC; ++v) { m[v] = -INFINITY; l[v] = 0.f; }
+  float cross = 0.f;
+
+  for (long long col = col_begin + threadIdx.x * VEC; col < col_end; col += kThreads * VEC) {
+    const bool fast = a.vec_ok && (col + VEC <= a.K);
+    float tv[MAXG][VEC], xv[MAXC][VEC];
+    // ---- load phase: all independent 128-bit loads first ----
+#pragma unroll
+    for (int i = 0; i < MAXG; ++i)
+      if (i < G) load_guard<T>(t + (i * a.B + b) * a.ldt, col, a.K, fast, tv[i]);
+#pragma unroll
+    for (int v = 0; v < MAXC; ++v)
+      if (v < C) load_guard<T>(s + (v * a.B + b) * a.lds, col, a.K, fast, xv[v]);
+    float cen[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) cen[e] = (col + e < a.K) ? __ldg(a.center + col + e) : 0.f;
+    // ---- teacher probabilities ----
+    float Q[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) Q[e] = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXG; ++i)
+      if (i < G) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          float q = __expf((tv[i][e] - cen[e]) * a.inv_tt - tm[i]) * tinv[i];
+          if (!fast && col + e >= a.K) q = 0.f;
+          tv[i][e] = q;
+          Q[e] += q;
+        }
+      }
+    // ---- student rows ----
+    float S[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) S[e] = 0.f;
+#pragma unroll
+    for (int v = 0; v < MAXC; ++v)
+      if (v < C) {
+        float vm = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const float x = xv[v][e] * a.inv_ts;
+          xv[v][e] = x;
+          S[e] += x;                                     // invalid columns: x = 0 and Q = 0 there
+          if (fast || col + e < a.K) vm = fmaxf(vm, x);
+        }
+        if (vm > m[v]) { l[v] *= __expf(m[v] - vm); m[v] = vm; }
+        if (vm > -INFINITY) {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e)
+            if (fast || col + e < a.K) l[v] += __expf(xv[v][e] - m[v]);
+        }
+        if (v < MAXG && v < G) {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) cross = fmaf(-tv[v < MAXG ? v : 0][e], xv[v][e], cross);
+        }
+      }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) cross = fmaf(Q[e], S[e], cross);
+  }
+
+  // ---- block reduction: (m,l) per student row by online merge, cross by sum ----
+  __shared__ float red[kThreads / 32][2 * MAXC + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int v = 0; v < MAXC; ++v)
+    if (v < C) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m[v], o);
+        const float l2 = __shfl_xor_sync(0xffffffffu, l[v], o);
+        online_merge(m[v], l[v], m2, l2);
+      }
+      if (lane == 0) { red[warp][2 * v] = m[v]; red[warp][2 * v + 1] = l[v]; }
+    }
+  cross = warp_sum(cross);
+  if (lane == 0) red[warp][2 * MAXC] = cross;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    const int v = threadIdx.x;
+    float mm = -INFINITY, ll = 0.f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) online_merge(mm, ll, red[w][2 * v], red[w][2 * v + 1]);
+    a.ws_s[(v * a.B + b) * a.nchunks + chunk] = make_float2(mm, ll);
+  }
+  if (threadIdx.x == 32) {
+    float c = 0.f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) c += red[w][2 * MAXC];
+    a.ws_x[b * a.nchunks + chunk] = c;
+  }
+}
+
+// Single CTA: merges the per-chunk partials into s_lse[C*B] and the scalar loss (fixed order).
+__global__ void __launch_bounds__(1024)
+ce_finalize_kernel(const float2* __restrict__ ws_s, const float* __restrict__ ws_x, long long B, int C, int G, int nchunks,
+                   float* __restrict__ s_lse, float* __restrict__ loss) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  const long long rows = static_cast<long long>(C) * B;
+  for (long long r = threadIdx.x; r < rows; r += blockDim.x) {
+    float m = -INFINITY, l = 0.f;
+    for (int c = 0; c < nchunks; ++c) { const float2 p = ws_s[r * nchunks + c]; online_merge(m, l, p.x, p.y); }
+    const float lse = m + logf(l);
+    s_lse[r] = lse;
+    const int v = static_cast<int>(r / B);
+    acc += static_cast<double>((v < G) ? (G - 1) : G) * static_cast<double>(lse);
+  }
+  for (long long i = threadIdx.x; i < B * nchunks; i += blockDim.x) acc -= static_cast<double>(ws_x[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+    const int n_terms = G * C - (G < C ? G : C);
+    loss[0] = static_cast<float>(tot / (static_cast<double>(n_terms) * static_cast<double>(B)));
+  }
+}
+
+template <typename T, int CT, int GT>
+__global__ void __launch_bounds__(kThreads)
+ce_bwd_kernel(const CeArgs a) {
+  constexpr int VEC = Vec<T>::N;
+  constexpr int MAXC = CT ? CT : 16, MAXG = GT ? GT : 4;
+  const int C = CT ? CT : a.C, G = GT ? GT : a.G;
+  const long long b = blockIdx.y;
+  const long long col_begin = static_cast<long long>(blockIdx.x) * (kThreads * VEC * kIters);
+  const long long col_end = min(a.K, col_begin + kThreads * VEC * kIters);
+  const T* s = static_cast<const T*>(a.s);
+  const T* t = static_cast<const T*>(a.t);
+  T* ds = static_cast<T*>(a.ds);
+  const float scale = a.coef * __ldg(a.gout);
+
+  float tm[MAXG], tinv[MAXG], lse[MAXC];
+#pragma unroll
+  for (int i = 0; i < MAXG; ++i)
+    if (i < G) { const float2 st = a.t_stats[i * a.B + b]; tm[i] = st.x; tinv[i] = st.y; }
+#pragma unroll
+  for (int v = 0; v < MAXC; ++v)
+    if (v < C) lse[v] = a.s_lse[v * a.B + b];
+
+  for (long long col = col_begin + threadIdx.x * VEC; col < col_end; col += kThreads * VEC) {
+    const bool fast = a.vec_ok && (col + VEC <= a.K);
+    float tv[MAXG][VEC], xv[MAXC][VEC];
+#pragma unroll
+    for (int i = 0; i < MAXG; ++i)
+      if (i < G) load_guard<T>(t + (i * a.B + b) * a.ldt, col, a.K, fast, tv[i]);
+#pragma unroll
+    for (int v = 0; v < MAXC; ++v)
+      if (v < C) load_guard<T>(s + (v * a.B + b) * a.lds, col, a.K, fast, xv[v]);
+    float cen[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) cen[e] = (col + e < a.K) ? __ldg(a.center + col + e) : 0.f;
+    float Q[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) Q[e] = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXG; ++i)
+      if (i < G) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const float q = __expf((tv[i][e] - cen[e]) * a.inv_tt - tm[i]) * tinv[i];
+          tv[i][e] = q;
+          Q[e] += q;
+        }
+      }
+#pragma unroll
+    for (int v = 0; v < MAXC; ++v)
+      if (v < C) {
+        const float nv = static_cast<float>((v < G) ? (G - 1) : G);
+        float d[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const float p = __expf(fmaf(xv[v][e], a.inv_ts, -lse[v]));
+          float qs = Q[e];
+          if (v < MAXG && v < G) qs -= tv[v < MAXG ? v : 0][e];
+          d[e] = scale * fmaf(nv, p, -qs);
+        }
+        T* dst = ds + (v * a.B + b) * a.ldds + col;
+        if (fast) {
+          Vec<T>::store(dst, d);
+        } else {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e)
+            if (col + e < a.K) Vec<T>::store1(dst + e, d[e]);
+        }
+      }
+  }
+}
+
+template <typename T>
+int launch_fwd(const CeArgs& a, dim3 grid, cudaStream_t st) {
+  if (a.C == 8 && a.G == 2) ce_fwd_kernel<T, 8, 2><<<grid, kThreads, 0, st>>>(a);
+  else if (a.C == 9 && a.G == 3) ce_fwd_kernel<T, 9, 3><<<grid, kThreads, 0, st>>>(a);
+  else ce_fwd_kernel<T, 0, 0><<<grid, kThreads, 0, st>>>(a);
+  DMC_LAUNCH_CHECK("ce_fwd_kernel launch");
+  return 0;
+}
+template <typename T>
+int launch_bwd(const CeArgs& a, dim3 grid, cudaStream_t st) {
+  if (a.C == 8 && a.G == 2) ce_bwd_kernel<T, 8, 2><<<grid, kThreads, 0, st>>>(a);
+  else if (a.C == 9 && a.G == 3) ce_bwd_kernel<T, 9, 3><<<grid, kThreads, 0, st>>>(a);
+  else ce_bwd_kernel<T, 0, 0><<<grid, kThreads, 0, st>>>(a);
+  DMC_LAUNCH_CHECK("ce_bwd_kernel launch");
+  return 0;
+}
+
+int chunk_cols(int dtype) { return kThreads * (dtype == DMC_BF16 ? 8 : 4) * kIters; }
+
+int check_common(const char* who, const void* s, int s_dtype, int64_t lds, const void* t, int t_dtype, int64_t ldt,
+                 const float* center, const float* t_row_stats, int64_t B, int C, int G, int64_t K) {
+  DMC_REQUIRE(s && t && center && t_row_stats, "%s: null pointer", who);
+  DMC_REQUIRE(s_dtype == t_dtype && (s_dtype == DMC_F32 || s_dtype == DMC_BF16), "%s: student/teacher logits must share one dtype (F32 or BF16)", who);
+  DMC_REQUIRE(B > 0 && K > 0 && lds >= K && ldt >= K, "%s: bad shape B=%lld K=%lld", who, (long long)B, (long long)K);
+  DMC_REQUIRE(C >= 1 && C <= 16 && G >= 1 && G <= 4, "%s: ncrops must be in [1,16] and teacher crops in [1,4] (got %d, %d)", who, C, G);
+  DMC_REQUIRE(G * C - (G < C ? G : C) > 0, "%s: no (teacher, student) pair left: ncrops=%d teacher_crops=%d", who, C, G);
+  DMC_REQUIRE(B <= 65535, "%s: batch per GPU too large for the launch grid (%lld)", who, (long long)B);
+  return 0;
+}
+
+}  // namespace
+}  // namespace dmc
+
+using namespace dmc;
+
+extern "C" size_t dmc_ce_workspace_bytes(int64_t B, int32_t C, int32_t G, int64_t K) {
+  if (B <= 0 || C <= 0 || K <= 0) return 0;
+  (void)G;
+  const int64_t nchunks = ceil_div(K, chunk_cols(DMC_F32));   // fp32 has the most chunks
+  const size_t a = (static_cast<size_t>(C) * B * nchunks * sizeof(float2) + 255) & ~static_cast<size_t>(255);
+  return a + static_cast<size_t>(B) * nchunks * sizeof(float);
+}
+
+extern "C" int dmc_ce_fwd(const void* s, int32_t s_dtype, int64_t lds, const void* t, int32_t t_dtype, int64_t ldt,
+                          const float* center, const float* t_row_stats, int64_t B, int32_t C, int32_t G, int64_t K,
+                          float inv_student_temp, float inv_teacher_temp, float* s_lse, float* loss, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  int rc = check_common("dmc_ce_fwd", s, s_dtype, lds, t, t_dtype, ldt, center, t_row_stats, B, C, G, K);
+  if (rc) return rc;
+  DMC_REQUIRE(s_lse && loss && workspace, "dmc_ce_fwd: null output");
+  DMC_REQUIRE(workspace_bytes >= dmc_ce_workspace_bytes(B, C, G, K), "dmc_ce_fwd: workspace too small");
+  DMC_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "dmc_ce_fwd: workspace must be 16-byte aligned");
+  const int esz = s_dtype == DMC_BF16 ? 2 : 4;
+  CeArgs a{};
+  a.s = s; a.lds = lds; a.t = t; a.ldt = ldt; a.center = center; a.t_stats = reinterpret_cast<const float2*>(t_row_stats);
+  a.B = B; a.K = K; a.C = C; a.G = G; a.inv_ts = inv_student_temp; a.inv_tt = inv_teacher_temp;
+  a.nchunks = static_cast<int>(ceil_div(K, chunk_cols(s_dtype)));
+  a.vec_ok = ((reinterpret_cast<uintptr_t>(s) & 15) == 0) && ((reinterpret_cast<uintptr_t>(t) & 15) == 0) &&
+             ((lds * esz) % 16 == 0) && ((ldt * esz) % 16 == 0);
+  const size_t s_bytes = (static_cast<size_t>(C) * B * a.nchunks * sizeof(float2) + 255) & ~static_cast<size_t>(255);
+  a.ws_s = static_cast<float2*>(workspace);
+  a.ws_x = reinterpret_cast<float*>(static_cast<char*>(workspace) + s_bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid((unsigned)a.nchunks, (unsigned)B);
+  rc = (s_dtype == DMC_BF16) ? launch_fwd<__nv_bfloat16>(a, grid, st) : launch_fwd<float>(a, grid, st);
+  if (rc) return rc;
+  ce_finalize_kernel<<<1, 1024, 0, st>>>(a.ws_s, a.ws_x, B, C, G, a.nchunks, s_lse, loss);
+  DMC_LAUNCH_CHECK("ce_finalize_kernel launch");
+  return 0;
+}
+
+extern "C" int dmc_ce_bwd(const void* s, int32_t s_dtype, int64_t lds, const void* t, int32_t t_dtype, int64_t ldt,
+                          const float* center, const float* t_row_stats, const float* s_lse, const float* grad_out, int64_t B,
+                          int32_t C, int32_t G, int64_t K, float inv_student_temp, float inv_teacher_temp, void* ds,
+                          int32_t ds_dtype, int64_t ldds, void* stream) {
+  int rc = check_common("dmc_ce_bwd", s, s_dtype, lds, t, t_dtype, ldt, center, t_row_stats, B, C, G, K);
+  if (rc) return rc;
+  DMC_REQUIRE(s_lse && grad_out && ds, "dmc_ce_bwd: null pointer");
+  DMC_REQUIRE(ds_dtype == s_dtype && ldds >= K, "dmc_ce_bwd: gradient must have the logits' dtype and ld >= K");
+  const int esz = s_dtype == DMC_BF16 ? 2 : 4;
+  CeArgs a{};
+  a.s = s; a.lds = lds; a.t = t; a.ldt = ldt; a.center = center; a.t_stats = reinterpret_cast<const float2*>(t_row_stats);
+  a.B = B; a.K = K; a.C = C; a.G = G; a.inv_ts = inv_student_temp; a.inv_tt = inv_teacher_temp;
+  a.nchunks = static_cast<int>(ceil_div(K, chunk_cols(s_dtype)));
+  a.vec_ok = ((reinterpret_cast<uintptr_t>(s) & 15) == 0) && ((reinterpret_cast<uintptr_t>(t) & 15) == 0) &&
+             ((reinterpret_cast<uintptr_t>(ds) & 15) == 0) && ((lds * esz) % 16 == 0) && ((ldt * esz) % 16 == 0) &&
+             ((ldds * esz) % 16 == 0);
+  a.s_lse = s_lse; a.gout = grad_out;
+  const int n_terms = G * C - (G < C ? G : C);
+  a.coef = static_cast<float>(static_cast<double>(inv_student_temp) / (static_cast<double>(n_terms) * static_cast<double>(B)));
+  a.ds = ds; a.ldds = ldds;
+  dim3 grid((unsigned)a.nchunks, (unsigned)B);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return (s_dtype == DMC_BF16) ? launch_bwd<__nv_bfloat16>(a, grid, st) : launch_bwd<float>(a, grid, st);
+}

@@ -1,0 +1,114 @@
+// dmc_common.cuh -- shared host/device helpers for libdinomc (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dinomc.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libdinomc is written for sm_100a (B200) only"
+#endif
+
+namespace dmc {
+
+// ---- host side: error reporting -------------------------------------------------------------
+void set_error(const char* fmt, ...);                 // api.cu
+int cuda_status(cudaError_t e, const char* what);     // api.cu : 0 if ok else (int)e, message recorded
+
+#define DMC_REQUIRE(cond, ...)            \
+  do {                                    \
+    if (!(cond)) {                        \
+      ::dmc::set_error(__VA_ARGS__);      \
+      return -1;                          \
+    }                                     \
+  } while (0)
+
+#define DMC_LAUNCH_CHECK(what)                                         \
+  do {                                                                 \
+    cudaError_t e__ = cudaGetLastError();                              \
+    if (e__ != cudaSuccess) return ::dmc::cuda_status(e__, what);      \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- device side ----------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// exact (erf) GELU of nn.GELU() and its derivative
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * __expf(-0.5f * x * x) * 0.39894228040143268f;
+}
+
+// Streaming 128-bit global accesses (data touched once: do not allocate in L1).
+__device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_u4(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {  // a -> low half, b -> high half (RNE)
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// A "vector" of logits is what one 128-bit load brings: 4 fp32 or 8 bf16.
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  __device__ static __forceinline__ void load(const float* p, float (&v)[4]) {
+    uint4 r = ld_stream_u4(p);
+    v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+  }
+  __device__ static __forceinline__ void store(float* p, const float (&v)[4]) {
+    st_stream_u4(p, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
+  }
+  __device__ static __forceinline__ float load1(const float* p) { return *p; }
+  __device__ static __forceinline__ void store1(float* p, float v) { *p = v; }
+};
+template <> struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 r = ld_stream_u4(p);
+    v[0] = bf16_lo(r.x); v[1] = bf16_hi(r.x); v[2] = bf16_lo(r.y); v[3] = bf16_hi(r.y);
+    v[4] = bf16_lo(r.z); v[5] = bf16_hi(r.z); v[6] = bf16_lo(r.w); v[7] = bf16_hi(r.w);
+  }
+  __device__ static __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    st_stream_u4(p, make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7])));
+  }
+  __device__ static __forceinline__ float load1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  __device__ static __forceinline__ void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+// online softmax statistic merge: (m, l) <- (m, l) (+) (m2, l2), l = sum exp(x - m)
+__device__ __forceinline__ void online_merge(float& m, float& l, float m2, float l2) {
+  float mn = fmaxf(m, m2);
+  float a = (m == -INFINITY) ? 0.f : __expf(m - mn);
+  float b = (m2 == -INFINITY) ? 0.f : __expf(m2 - mn);
+  l = l * a + l2 * b;
+  m = mn;
+}
+
+#endif  // __CUDACC__
+}  // namespace dmc

@@ -1,0 +1,522 @@
+// gemm_sm100.cu -- the tensor-core path of libdinomc: a persistent, warp-specialised
+// tcgen05 / TMEM / TMA GEMM for sm_100a.
+//
+//   D[M,N] = epilogue( sum_k A(m,k) B(n,k) )            (contract in include/dinomc.h: dmc_gemm)
+//
+// It serves the weight-normed last layer of DINOHead (utils/vision_transformer.py:293: M = crops*batch,
+// N = out_dim = 65536, K = bottleneck = 256), its dgrad (contraction over out_dim, split-K) and wgrad
+// (MN-major operands straight from the row-major gradient), and the MLP Linears (:291).
+//
+// Structure (one CTA per SM, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor tiles into a ring of 128B-swizzled smem stages
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=block_n, K=32 bytes/row)
+//               into one of two TMEM accumulators (2 x 256 fp32 columns = all 512 TMEM columns)
+//   warps 2..5  epilogue: tcgen05.ld the finished accumulator, apply scale/bias/activation, store;
+//               overlaps the MMAs of the next tile thanks to the double-buffered accumulator.
+// Three mbarrier pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue).
+//
+// Operands may be K-major or MN-major (tcgen05 reads both through the smem matrix descriptor), in
+// bf16 (kind::f16) or fp32-as-TF32 (kind::tf32) with an optional 3-pass hi/lo split ("3xTF32").
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "dmc_common.cuh"
+#include "dmc_ptx.cuh"
+
+namespace dmc {
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kRowBytes = 128;          // one swizzle row: 64 bf16 or 32 tf32 along the contiguous dim
+constexpr int kMaxStages = 8;
+constexpr int kMmaPerKBlock = 4;        // 128 B / 32 B: four tcgen05.mma per k-block
+constexpr int kTmemCols = 512;
+constexpr int kAccCols = 256;
+constexpr int kThreads = 192;
+constexpr uint32_t kABytes = kBlockM * kRowBytes;  // 16 KiB per stage for A
+
+struct GemmDev {
+  int M, N;
+  int block_n;
+  int m_tiles, n_tiles;
+  int kb_total;       // k-blocks per pass
+  int vk_total;       // passes * kb_total "virtual" k-blocks
+  int splits, vk_per_split;
+  int stages;
+  uint32_t b_bytes;   // block_n * 128
+  // epilogue
+  void* D; long long ldd; int out_dtype;
+  float* partial;     // split-K partial sums [splits][M][N] (raw accumulators) or nullptr
+  const float* col_scale; const float* bias; const float* alpha_dev; float alpha;
+  int act; void* aux; long long ldaux; int aux_dtype;
+};
+
+struct Epilogue {
+  const float* col_scale; const float* bias; float alpha; int act;
+  void* aux; long long ldaux; int aux_dtype;
+  void* D; long long ldd; int out_dtype;
+};
+
+__device__ __forceinline__ float load_elem(const void* p, long long idx, int dtype) {
+  return dtype == DMC_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[idx])
+                           : reinterpret_cast<const float*>(p)[idx];
+}
+__device__ __forceinline__ void store_elem(void* p, long long idx, int dtype, float v) {
+  if (dtype == DMC_BF16) reinterpret_cast<__nv_bfloat16*>(p)[idx] = __float2bfloat16_rn(v);
+  else reinterpret_cast<float*>(p)[idx] = v;
+}
+
+// Apply the epilogue to `n` (<= 32) consecutive columns [col0, col0+n) of one row and store them.
+// `acc` holds raw fp32 accumulators.  vec_ok: all pointers/strides allow 16-byte accesses.
+__device__ __forceinline__ void epilogue_store_row(const Epilogue& e, float (&acc)[32], long long row, int col0, int n,
+                                                   bool vec_ok) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (j < n) {
+      float v = acc[j];
+      if (e.col_scale) v *= __ldg(e.col_scale + col0 + j);
+      v *= e.alpha;
+      if (e.bias) v += __ldg(e.bias + col0 + j);
+      acc[j] = v;
+    }
+  }
+  if (e.act == DMC_ACT_GELU) {
+    if (e.aux) {
+      if (vec_ok && n == 32) {
+        if (e.aux_dtype == DMC_BF16) {
+          uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.aux) + row * e.ldaux + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            p[j] = make_uint4(pack_bf16(acc[8 * j], acc[8 * j + 1]), pack_bf16(acc[8 * j + 2], acc[8 * j + 3]),
+                              pack_bf16(acc[8 * j + 4], acc[8 * j + 5]), pack_bf16(acc[8 * j + 6], acc[8 * j + 7]));
+        } else {
+          float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.aux) + row * e.ldaux + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) p[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        }
+      } else {
+        for (int j = 0; j < n; ++j) store_elem(e.aux, row * e.ldaux + col0 + j, e.aux_dtype, acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = gelu_f(acc[j]);
+  } else if (e.act == DMC_ACT_GELU_BWD) {
+    if (vec_ok && n == 32 && e.aux_dtype == DMC_BF16) {
+      const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.aux) + row * e.ldaux + col0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 w = p[j];
+        acc[8 * j + 0] *= gelu_grad_f(bf16_lo(w.x)); acc[8 * j + 1] *= gelu_grad_f(bf16_hi(w.x));
+        acc[8 * j + 2] *= gelu_grad_f(bf16_lo(w.y)); acc[8 * j + 3] *= gelu_grad_f(bf16_hi(w.y));
+        acc[8 * j + 4] *= gelu_grad_f(bf16_lo(w.z)); acc[8 * j + 5] *= gelu_grad_f(bf16_hi(w.z));
+        acc[8 * j + 6] *= gelu_grad_f(bf16_lo(w.w)); acc[8 * j + 7] *= gelu_grad_f(bf16_hi(w.w));
+      }
+    } else {
+      for (int j = 0; j < n; ++j) acc[j] *= gelu_grad_f(load_elem(e.aux, row * e.ldaux + col0 + j, e.aux_dtype));
+    }
+  }
+  if (vec_ok && n == 32) {
+    if (e.out_dtype == DMC_BF16) {
+      uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.D) + row * e.ldd + col0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        p[j] = make_uint4(pack_bf16(acc[8 * j], acc[8 * j + 1]), pack_bf16(acc[8 * j + 2], acc[8 * j + 3]),
+                          pack_bf16(acc[8 * j + 4], acc[8 * j + 5]), pack_bf16(acc[8 * j + 6], acc[8 * j + 7]));
+    } else {
+      float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.D) + row * e.ldd + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) p[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+    }
+  } else {
+    for (int j = 0; j < n; ++j) store_elem(e.D, row * e.ldd + col0 + j, e.out_dtype, acc[j]);
+  }
+}
+
+template <int ESZ, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+               const GemmDev p) {
+  constexpr int BLOCK_K = kRowBytes / ESZ;       // elements per k-block (64 bf16 / 32 tf32)
+  constexpr int UMMA_K = 32 / ESZ;               // elements per tcgen05.mma (16 / 8)
+  constexpr int BOX_MN = kRowBytes / ESZ;        // MN-major box width in elements (64 / 32)
+  constexpr uint32_t kBoxBytes = BLOCK_K * kRowBytes;   // one MN-major box: BLOCK_K k-rows x 128 B
+  constexpr bool kTf32 = (ESZ == 4);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);   // 1024-B aligned (SWIZZLE_128B atoms)
+
+  const uint32_t stage_bytes = kABytes + p.b_bytes;
+  uint8_t* tiles = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full = empty_bar + kMaxStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmA0); ptx::prefetch_tensormap(&tmB0);
+    ptx::prefetch_tensormap(&tmA1); ptx::prefetch_tensormap(&tmB1);
+    for (int i = 0; i < p.stages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], 4); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {               // this warp owns the TMEM allocation (alloc + dealloc)
+    ptx::tmem_alloc(tmem_ptr, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int num_work = p.m_tiles * p.n_tiles * p.splits;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int mt = w % p.m_tiles;
+        const int rest = w / p.m_tiles;
+        const int nt = rest % p.n_tiles;
+        const int sp = rest / p.n_tiles;
+        const int m0 = mt * kBlockM, n0 = nt * p.block_n;
+        const int vk0 = sp * p.vk_per_split;
+        const int vk1 = min(vk0 + p.vk_per_split, p.vk_total);
+        for (int vk = vk0; vk < vk1; ++vk) {
+          const int pass = vk / p.kb_total;
+          const int k0 = (vk - pass * p.kb_total) * BLOCK_K;
+          const CUtensorMap* ta = (pass == 2) ? &tmA1 : &tmA0;   // passes: hi*hi, hi*lo, lo*hi
+          const CUtensorMap* tb = (pass == 1) ? &tmB1 : &tmB0;
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+          uint8_t* sA = tiles + static_cast<size_t>(stage) * stage_bytes;
+          uint8_t* sB = sA + kABytes;
+          if constexpr (!A_MN) {
+            ptx::tma_load_2d(sA, ta, &full_bar[stage], k0, m0);                 // box {BLOCK_K, 128}
+          } else {
+#pragma unroll
+            for (int j = 0; j < kBlockM / BOX_MN; ++j)                            // boxes {BOX_MN, BLOCK_K}
+              ptx::tma_load_2d(sA + j * kBoxBytes, ta, &full_bar[stage], m0 + j * BOX_MN, k0);
+          }
+          if constexpr (!B_MN) {
+            ptx::tma_load_2d(sB, tb, &full_bar[stage], k0, n0);                 // box {BLOCK_K, block_n}
+          } else {
+            for (int j = 0; j < p.block_n / BOX_MN; ++j)
+              ptx::tma_load_2d(sB + j * kBoxBytes, tb, &full_bar[stage], n0 + j * BOX_MN, k0);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_instr_desc(kTf32 ? 2u : 1u, A_MN, B_MN, kBlockM, static_cast<uint32_t>(p.block_n));
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+        const int sp = (w / p.m_tiles) / p.n_tiles;
+        const int vk0 = sp * p.vk_per_split;
+        const int vk1 = min(vk0 + p.vk_per_split, p.vk_total);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);      // epilogue has drained this accumulator
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccCols);
+        for (int vk = vk0; vk < vk1; ++vk) {
+          ptx::mbar_wait(&full_bar[stage], phase);              // TMA bytes have landed
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(tiles + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int k = 0; k < kMmaPerKBlock; ++k) {
+            // K-major: rows of 128 B, 8-row groups 1024 B apart (SBO); advance 32 B per MMA inside the swizzle row.
+            // MN-major: boxes of BLOCK_K k-rows x 128 B; LBO = box stride along MN, SBO = 1024 B (8 k-rows);
+            //           advance UMMA_K k-rows = UMMA_K * 128 B per MMA.
+            const uint64_t da = A_MN ? ptx::make_smem_desc_sw128(a_addr + k * (UMMA_K * kRowBytes), kBoxBytes, 1024)
+                                     : ptx::make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? ptx::make_smem_desc_sw128(b_addr + k * (UMMA_K * kRowBytes), kBoxBytes, 1024)
+                                     : ptx::make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            ptx::umma<kTf32>(d_tmem, da, db, idesc, (vk > vk0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[stage]);                  // frees the smem stage when these MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        ptx::umma_commit(&tmem_full[acc]);                      // accumulator complete -> epilogue
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                                     // TMEM lane quadrant this warp may access
+    Epilogue e{p.col_scale, p.bias, p.alpha, p.act, p.aux, p.ldaux, p.aux_dtype, p.D, p.ldd, p.out_dtype};
+    if (p.alpha_dev) e.alpha *= __ldg(p.alpha_dev);
+    const int out_esz = (p.out_dtype == DMC_BF16) ? 2 : 4;
+    bool vec_ok = ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) && ((p.ldd * out_esz) % 16 == 0);
+    if (p.aux) {
+      const int aux_esz = (p.aux_dtype == DMC_BF16) ? 2 : 4;
+      vec_ok = vec_ok && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) && ((p.ldaux * aux_esz) % 16 == 0);
+    }
+    int it = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+      const int mt = w % p.m_tiles;
+      const int rest = w / p.m_tiles;
+      const int nt = rest % p.n_tiles;
+      const int sp = rest / p.n_tiles;
+      const int n0 = nt * p.block_n;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      const long long row = static_cast<long long>(mt) * kBlockM + q * 32 + lane;
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc * kAccCols) + (static_cast<uint32_t>(q * 32) << 16);
+      const int ncols = min(p.block_n, p.N - n0);
+      for (int c = 0; c < p.block_n; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(t_addr + c, r);
+        ptx::tmem_ld_wait();
+        if (c + 32 >= p.block_n) {                              // last read of this accumulator: hand it back
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+        }
+        const int n = min(32, ncols - c);
+        if (row < p.M && n > 0) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.partial) {                                      // split-K: raw partial sums, epilogue runs in the reducer
+            float* dst = p.partial + (static_cast<long long>(sp) * p.M + row) * p.N + n0 + c;
+            if (n == 32 && (p.N % 4 == 0)) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+              for (int j = 0; j < n; ++j) dst[j] = v[j];
+            }
+          } else {
+            epilogue_store_row(e, v, row, n0 + c, n, vec_ok);
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// Sums the split-K partials and applies the epilogue.  One thread per 4 consecutive columns.
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long M, int N, Epilogue e, const float* alpha_dev) {
+  const long long groups_per_row = (N + 3) / 4;
+  const long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (g >= M * groups_per_row) return;
+  const long long row = g / groups_per_row;
+  const int col0 = static_cast<int>(g % groups_per_row) * 4;
+  const int n = min(4, N - col0);
+  if (alpha_dev) e.alpha *= __ldg(alpha_dev);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int s = 0; s < splits; ++s) {
+    const float* src = partial + (static_cast<long long>(s) * M + row) * N + col0;
+    if (n == 4 && (N % 4 == 0)) {
+      float4 t = *reinterpret_cast<const float4*>(src);
+      acc[0] += t.x; acc[1] += t.y; acc[2] += t.z; acc[3] += t.w;
+    } else {
+      for (int j = 0; j < n; ++j) acc[j] += src[j];
+    }
+  }
+  for (int j = 0; j < n; ++j) {
+    float v = acc[j];
+    const int col = col0 + j;
+    if (e.col_scale) v *= __ldg(e.col_scale + col);
+    v *= e.alpha;
+    if (e.bias) v += __ldg(e.bias + col);
+    if (e.act == DMC_ACT_GELU) {
+      if (e.aux) store_elem(e.aux, row * e.ldaux + col, e.aux_dtype, v);
+      v = gelu_f(v);
+    } else if (e.act == DMC_ACT_GELU_BWD) {
+      v *= gelu_grad_f(load_elem(e.aux, row * e.ldaux + col, e.aux_dtype));
+    }
+    store_elem(e.D, row * e.ldd + col, e.out_dtype, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;      // benign race: every thread computes the same pointer
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// Tensor map over a row-major matrix with `rows` rows of `cols` contiguous elements (row stride ld),
+// box = {box_cols (inner, 128 bytes), box_rows}, 128B swizzle, out-of-bounds elements read as zero.
+int make_tmap(CUtensorMap* tm, const void* base, int esz, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  DMC_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  DMC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "dmc_gemm: operand base pointer must be 16-byte aligned");
+  DMC_REQUIRE((ld * esz) % 16 == 0, "dmc_gemm: operand row stride must be a multiple of 16 bytes (ld=%lld)", (long long)ld);
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * esz};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DMC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+struct Plan {
+  int block_n, m_tiles, n_tiles, kb_total, passes, vk_total, splits, vk_per_split, stages;
+  size_t smem_bytes, workspace_bytes;
+};
+
+Plan make_plan(int64_t M, int64_t N, int64_t K, int in_dtype, bool three_pass, int forced_split) {
+  Plan pl{};
+  const int esz = (in_dtype == DMC_BF16) ? 2 : 4;
+  const int block_k = kRowBytes / esz;
+  pl.block_n = N >= 256 ? 256 : (N > 64 ? 128 : 64);
+  if (N > 128 && N < 256) pl.block_n = 256;
+  pl.m_tiles = static_cast<int>(ceil_div(M, kBlockM));
+  pl.n_tiles = static_cast<int>(ceil_div(N, pl.block_n));
+  pl.kb_total = static_cast<int>(ceil_div(K, block_k));
+  pl.passes = three_pass ? 3 : 1;
+  pl.vk_total = pl.kb_total * pl.passes;
+  const int tiles = pl.m_tiles * pl.n_tiles;
+  int splits = 1;
+  if (forced_split >= 1) {
+    splits = forced_split;
+  } else if (tiles * 2 <= kNumSMs) {                       // under half a wave: split the contraction
+    splits = kNumSMs / tiles;
+    const int max_by_k = pl.vk_total / 4 > 0 ? pl.vk_total / 4 : 1;   // keep >= 4 k-blocks per split
+    if (splits > max_by_k) splits = max_by_k;
+  }
+  if (splits > pl.vk_total) splits = pl.vk_total;
+  if (splits < 1) splits = 1;
+  pl.vk_per_split = static_cast<int>(ceil_div(pl.vk_total, splits));
+  pl.splits = static_cast<int>(ceil_div(pl.vk_total, pl.vk_per_split));   // every split owns >= 1 k-block
+  const size_t stage_bytes = kABytes + static_cast<size_t>(pl.block_n) * kRowBytes;
+  const size_t budget = 227 * 1024 - 1024 /*alignment slack*/ - 256 /*barriers*/;
+  int stages = static_cast<int>(budget / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  pl.stages = stages;
+  pl.smem_bytes = static_cast<size_t>(stages) * stage_bytes + 256 + 1024;
+  pl.workspace_bytes = pl.splits > 1 ? static_cast<size_t>(pl.splits) * M * N * sizeof(float) : 0;
+  return pl;
+}
+
+template <int ESZ, bool A_MN, bool B_MN>
+int launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
+              const GemmDev& dev, size_t smem_bytes, int grid, cudaStream_t st) {
+  auto kern = gemm_tc_kernel<ESZ, A_MN, B_MN>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
+  if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(gemm_tc_kernel)");
+  kern<<<grid, kThreads, smem_bytes, st>>>(a0, a1, b0, b1, dev);
+  DMC_LAUNCH_CHECK("gemm_tc_kernel launch");
+  return 0;
+}
+
+}  // namespace
+}  // namespace dmc
+
+using namespace dmc;
+
+extern "C" size_t dmc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int32_t in_dtype) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  Plan a = make_plan(M, N, K, in_dtype, false, 0);
+  Plan b = make_plan(M, N, K, in_dtype, in_dtype == DMC_F32, 0);
+  return a.workspace_bytes > b.workspace_bytes ? a.workspace_bytes : b.workspace_bytes;
+}
+
+extern "C" int dmc_gemm(const dmc_gemm_args* a, void* stream) {
+  DMC_REQUIRE(a != nullptr, "dmc_gemm: null args");
+  DMC_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "dmc_gemm: empty problem M=%lld N=%lld K=%lld", (long long)a->M, (long long)a->N, (long long)a->K);
+  DMC_REQUIRE(a->M < (1ll << 31) && a->N < (1ll << 31) && a->K < (1ll << 31), "dmc_gemm: dimension too large");
+  DMC_REQUIRE(a->A && a->B && a->D, "dmc_gemm: null operand");
+  DMC_REQUIRE(a->in_dtype == DMC_BF16 || a->in_dtype == DMC_F32, "dmc_gemm: bad in_dtype %d", a->in_dtype);
+  DMC_REQUIRE(a->out_dtype == DMC_BF16 || a->out_dtype == DMC_F32, "dmc_gemm: bad out_dtype %d", a->out_dtype);
+  DMC_REQUIRE(a->act >= DMC_ACT_NONE && a->act <= DMC_ACT_GELU_BWD, "dmc_gemm: bad act %d", a->act);
+  DMC_REQUIRE(a->act != DMC_ACT_GELU_BWD || a->aux != nullptr, "dmc_gemm: DMC_ACT_GELU_BWD needs aux");
+  DMC_REQUIRE((a->A_lo == nullptr) == (a->B_lo == nullptr), "dmc_gemm: A_lo and B_lo must be given together");
+  const bool three = (a->A_lo != nullptr);
+  DMC_REQUIRE(!three || a->in_dtype == DMC_F32, "dmc_gemm: hi/lo split operands require in_dtype F32");
+  const int esz = (a->in_dtype == DMC_BF16) ? 2 : 4;
+  const int block_k = kRowBytes / esz, box_mn = kRowBytes / esz;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  Plan pl = make_plan(a->M, a->N, a->K, a->in_dtype, three, a->split_k);
+  if (pl.splits > 1) {
+    DMC_REQUIRE(a->workspace != nullptr && a->workspace_bytes >= pl.workspace_bytes,
+                "dmc_gemm: split-K needs a workspace of %zu bytes (got %zu)", pl.workspace_bytes, a->workspace_bytes);
+    DMC_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace) & 15) == 0, "dmc_gemm: workspace must be 16-byte aligned");
+  }
+
+  CUtensorMap tA0, tA1, tB0, tB1;
+  int rc;
+  auto mapA = [&](CUtensorMap* tm, const void* base) {
+    return a->a_mn_major ? make_tmap(tm, base, esz, a->K, a->M, a->lda, box_mn, block_k)      // stored [K,M]
+                         : make_tmap(tm, base, esz, a->M, a->K, a->lda, block_k, kBlockM);    // stored [M,K]
+  };
+  auto mapB = [&](CUtensorMap* tm, const void* base) {
+    return a->b_mn_major ? make_tmap(tm, base, esz, a->K, a->N, a->ldb, box_mn, block_k)      // stored [K,N]
+                         : make_tmap(tm, base, esz, a->N, a->K, a->ldb, block_k, pl.block_n); // stored [N,K]
+  };
+  if ((rc = mapA(&tA0, a->A))) return rc;
+  if ((rc = mapB(&tB0, a->B))) return rc;
+  if ((rc = mapA(&tA1, three ? a->A_lo : a->A))) return rc;
+  if ((rc = mapB(&tB1, three ? a->B_lo : a->B))) return rc;
+
+  GemmDev d{};
+  d.M = static_cast<int>(a->M); d.N = static_cast<int>(a->N);
+  d.block_n = pl.block_n; d.m_tiles = pl.m_tiles; d.n_tiles = pl.n_tiles;
+  d.kb_total = pl.kb_total; d.vk_total = pl.vk_total; d.splits = pl.splits; d.vk_per_split = pl.vk_per_split;
+  d.stages = pl.stages; d.b_bytes = static_cast<uint32_t>(pl.block_n) * kRowBytes;
+  d.D = a->D; d.ldd = a->ldd; d.out_dtype = a->out_dtype;
+  d.partial = pl.splits > 1 ? static_cast<float*>(a->workspace) : nullptr;
+  d.col_scale = a->col_scale; d.bias = a->bias; d.alpha_dev = a->alpha_dev; d.alpha = a->alpha;
+  d.act = a->act; d.aux = a->aux; d.ldaux = a->ldaux; d.aux_dtype = a->aux_dtype;
+
+  const int num_work = pl.m_tiles * pl.n_tiles * pl.splits;
+  const int grid = num_work < kNumSMs ? num_work : kNumSMs;
+  const bool amn = a->a_mn_major != 0, bmn = a->b_mn_major != 0;
+#define DMC_DISPATCH(ESZ_)                                                                                   \
+  (amn ? (bmn ? launch_tc<ESZ_, true, true>(tA0, tA1, tB0, tB1, d, pl.smem_bytes, grid, st)                  \
+              : launch_tc<ESZ_, true, false>(tA0, tA1, tB0, tB1, d, pl.smem_bytes, grid, st))                \
+       : (bmn ? launch_tc<ESZ_, false, true>(tA0, tA1, tB0, tB1, d, pl.smem_bytes, grid, st)                 \
+              : launch_tc<ESZ_, false, false>(tA0, tA1, tB0, tB1, d, pl.smem_bytes, grid, st)))
+  rc = (esz == 2) ? DMC_DISPATCH(2) : DMC_DISPATCH(4);
+#undef DMC_DISPATCH
+  if (rc) return rc;
+
+  if (pl.splits > 1) {
+    Epilogue e{a->col_scale, a->bias, a->alpha, a->act, a->aux, a->ldaux, a->aux_dtype, a->D, a->ldd, a->out_dtype};
+    const long long groups = a->M * ((a->N + 3) / 4);
+    const int blocks = static_cast<int>(ceil_div(groups, 256));
+    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(static_cast<const float*>(a->workspace), pl.splits, a->M,
+                                                 static_cast<int>(a->N), e, a->alpha_dev);
+    DMC_LAUNCH_CHECK("splitk_reduce_kernel launch");
+  }
+  return 0;
+}

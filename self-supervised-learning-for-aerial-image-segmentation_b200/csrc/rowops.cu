@@ -1,0 +1,264 @@
+// rowops.cu -- the small row-wise kernels of DINOHead around the last-layer GEMM:
+// F.normalize (utils/vision_transformer.py:292) forward/backward, the weight_norm re-parameterisation
+// (utils/vision_transformer.py:279) forward/backward, dtype casts / TF32 splits and a column sum
+// (bias gradients).  All are HBM-bound streaming kernels: one warp per row, coalesced accesses,
+// warp-shuffle reductions, no shared memory.
+#include "dmc_common.cuh"
+
+namespace dmc {
+namespace {
+
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ float ld_in(const void* p, long long i, int dt) {
+  return dt == DMC_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]) : reinterpret_cast<const float*>(p)[i];
+}
+
+constexpr int kWarpsPerBlock = 8;
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+normalize_fwd_kernel(const void* __restrict__ z, int z_dtype, long long n_rows, int dim, long long ld, float eps,
+                     float* __restrict__ zhat_f32, __nv_bfloat16* __restrict__ zhat_bf16, float* __restrict__ zhat_lo,
+                     float* __restrict__ inv_den) {
+  const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  float ss = 0.f;
+  for (int c = lane; c < dim; c += 32) { float v = ld_in(z, row * ld + c, z_dtype); ss = fmaf(v, v, ss); }
+  ss = warp_sum(ss);
+  const float den = fmaxf(sqrtf(ss), eps);
+  const float inv = 1.0f / den;
+  if (lane == 0) inv_den[row] = inv;
+  for (int c = lane; c < dim; c += 32) {
+    const float v = ld_in(z, row * ld + c, z_dtype) / den;
+    const long long o = row * dim + c;
+    if (zhat_lo) {                 // 3xTF32 operand pair: hi is tf32-exact, lo the residual
+      const float hi = tf32_round(v);
+      if (zhat_f32) zhat_f32[o] = hi;
+      zhat_lo[o] = tf32_round(v - hi);
+    } else if (zhat_f32) {
+      zhat_f32[o] = v;
+    }
+    if (zhat_bf16) zhat_bf16[o] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+normalize_bwd_kernel(const float* __restrict__ dzhat, const float* __restrict__ zhat, const float* __restrict__ inv_den,
+                     long long n_rows, int dim, float eps, void* __restrict__ dz, int dz_dtype) {
+  const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  const float inv = inv_den[row];
+  const bool clamped = (inv * eps >= 1.0f);          // ||z|| < eps: zhat = z/eps, no projection term
+  float proj = 0.f;
+  if (!clamped)
+    for (int c = lane; c < dim; c += 32) proj = fmaf(dzhat[row * dim + c], zhat[row * dim + c], proj);
+  proj = warp_sum(proj);
+  for (int c = lane; c < dim; c += 32) {
+    const long long o = row * dim + c;
+    const float v = (dzhat[o] - proj * zhat[o]) * inv;
+    if (dz_dtype == DMC_BF16) reinterpret_cast<__nv_bfloat16*>(dz)[o] = __float2bfloat16_rn(v);
+    else reinterpret_cast<float*>(dz)[o] = v;
+  }
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+weightnorm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, long long K, int dim,
+                      float* __restrict__ w_f32, float* __restrict__ w_lo, __nv_bfloat16* __restrict__ w_bf16,
+                      float* __restrict__ scale, float* __restrict__ inv_vnorm) {
+  const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= K) return;
+  const int lane = threadIdx.x & 31;
+  const float* vr = v + row * dim;
+  float ss = 0.f;
+  for (int c = lane; c < dim; c += 32) { float x = vr[c]; ss = fmaf(x, x, ss); }
+  ss = warp_sum(ss);
+  const float nrm = sqrtf(ss);
+  const float sc = g[row] / nrm;                      // torch _weight_norm: v * (g / ||v||)
+  if (lane == 0) { scale[row] = sc; inv_vnorm[row] = 1.0f / nrm; }
+  for (int c = lane; c < dim; c += 32) {
+    const float w = vr[c] * sc;
+    const long long o = row * dim + c;
+    if (w_lo) {
+      const float hi = tf32_round(w);
+      if (w_f32) w_f32[o] = hi;
+      w_lo[o] = tf32_round(w - hi);
+    } else if (w_f32) {
+      w_f32[o] = w;
+    }
+    if (w_bf16) w_bf16[o] = __float2bfloat16_rn(w);
+  }
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+weightnorm_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v, const float* __restrict__ scale,
+                      const float* __restrict__ inv_vnorm, long long K, int dim, float* __restrict__ dv, float* __restrict__ dg) {
+  const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= K) return;
+  const int lane = threadIdx.x & 31;
+  const float iv = inv_vnorm[row], sc = scale[row];
+  float dot = 0.f;
+  for (int c = lane; c < dim; c += 32) dot = fmaf(dw[row * dim + c], v[row * dim + c] * iv, dot);
+  dot = warp_sum(dot);                                 // dW . v_hat
+  if (dg && lane == 0) dg[row] = dot;
+  for (int c = lane; c < dim; c += 32) {
+    const long long o = row * dim + c;
+    dv[o] = sc * (dw[o] - dot * (v[o] * iv));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = x[i];
+    const float h = tf32_round(v);
+    hi[i] = h;
+    lo[i] = tf32_round(v - h);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long n4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0) ? n / 4 : 0;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    reinterpret_cast<uint2*>(y)[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+  for (long long i = n4 * 4 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    y[i] = __float2bfloat16_rn(x[i]);
+}
+
+// Column sum in two deterministic steps: [row_splits][N] partials, then a fixed-order reduction.
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const void* __restrict__ X, int dtype, long long M, int N, long long ld, int rows_per_split,
+                      float* __restrict__ partial) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_split;
+  const long long r1 = min(r0 + rows_per_split, M);
+  float s = 0.f;
+  if (col < N)
+    for (long long r = r0 + ry; r < r1; r += 8) s += ld_in(X, r * ld + col, dtype);
+  red[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && col < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][cx];
+    partial[static_cast<long long>(blockIdx.y) * N + col] = t;
+  }
+}
+__global__ void __launch_bounds__(256)
+colsum_final_kernel(const float* __restrict__ partial, int splits, int N, float* __restrict__ out) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= N) return;
+  float t = 0.f;
+  for (int s = 0; s < splits; ++s) t += partial[static_cast<long long>(s) * N + col];
+  out[col] = t;
+}
+
+int colsum_splits(int64_t M, int64_t N) {
+  const int64_t col_blocks = ceil_div(N, 32);
+  int64_t s = ceil_div(2 * kNumSMs, col_blocks);
+  if (s > ceil_div(M, 8)) s = ceil_div(M, 8);
+  if (s < 1) s = 1;
+  if (s > 1024) s = 1024;
+  return static_cast<int>(s);
+}
+
+int grid_1d(long long n, int per_block) {
+  long long b = ceil_div(n, per_block);
+  const long long cap = static_cast<long long>(kNumSMs) * 16;
+  return static_cast<int>(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace
+}  // namespace dmc
+
+using namespace dmc;
+
+extern "C" int dmc_normalize_rows_fwd(const void* z, int32_t z_dtype, int64_t n_rows, int64_t dim, int64_t ld, float eps,
+                                      float* zhat_f32, void* zhat_bf16, float* zhat_lo, float* inv_den, void* stream) {
+  DMC_REQUIRE(z && inv_den, "dmc_normalize_rows_fwd: null pointer");
+  DMC_REQUIRE(n_rows > 0 && dim > 0 && dim < (1 << 30) && ld >= dim, "dmc_normalize_rows_fwd: bad shape n_rows=%lld dim=%lld ld=%lld", (long long)n_rows, (long long)dim, (long long)ld);
+  DMC_REQUIRE(z_dtype == DMC_F32 || z_dtype == DMC_BF16, "dmc_normalize_rows_fwd: bad dtype");
+  DMC_REQUIRE(zhat_f32 || zhat_bf16, "dmc_normalize_rows_fwd: no output requested");
+  normalize_fwd_kernel<<<(unsigned)ceil_div(n_rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      z, z_dtype, n_rows, (int)dim, ld, eps, zhat_f32, static_cast<__nv_bfloat16*>(zhat_bf16), zhat_lo, inv_den);
+  DMC_LAUNCH_CHECK("normalize_fwd_kernel launch");
+  return 0;
+}
+
+extern "C" int dmc_normalize_rows_bwd(const float* dzhat, const float* zhat, const float* inv_den, int64_t n_rows,
+                                      int64_t dim, float eps, void* dz, int32_t dz_dtype, void* stream) {
+  DMC_REQUIRE(dzhat && zhat && inv_den && dz, "dmc_normalize_rows_bwd: null pointer");
+  DMC_REQUIRE(n_rows > 0 && dim > 0 && dim < (1 << 30), "dmc_normalize_rows_bwd: bad shape");
+  DMC_REQUIRE(dz_dtype == DMC_F32 || dz_dtype == DMC_BF16, "dmc_normalize_rows_bwd: bad dtype");
+  normalize_bwd_kernel<<<(unsigned)ceil_div(n_rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      dzhat, zhat, inv_den, n_rows, (int)dim, eps, dz, dz_dtype);
+  DMC_LAUNCH_CHECK("normalize_bwd_kernel launch");
+  return 0;
+}
+
+extern "C" int dmc_weightnorm_fwd(const float* v, const float* g, int64_t K, int64_t dim, float* w_f32, float* w_lo,
+                                  void* w_bf16, float* scale, float* inv_vnorm, void* stream) {
+  DMC_REQUIRE(v && g && scale && inv_vnorm, "dmc_weightnorm_fwd: null pointer");
+  DMC_REQUIRE(K > 0 && dim > 0 && dim < (1 << 30), "dmc_weightnorm_fwd: bad shape");
+  weightnorm_fwd_kernel<<<(unsigned)ceil_div(K, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      v, g, K, (int)dim, w_f32, w_lo, static_cast<__nv_bfloat16*>(w_bf16), scale, inv_vnorm);
+  DMC_LAUNCH_CHECK("weightnorm_fwd_kernel launch");
+  return 0;
+}
+
+extern "C" int dmc_weightnorm_bwd(const float* dw, const float* v, const float* scale, const float* inv_vnorm,
+                                  int64_t K, int64_t dim, float* dv, float* dg, void* stream) {
+  DMC_REQUIRE(dw && v && scale && inv_vnorm && dv, "dmc_weightnorm_bwd: null pointer");
+  DMC_REQUIRE(K > 0 && dim > 0 && dim < (1 << 30), "dmc_weightnorm_bwd: bad shape");
+  weightnorm_bwd_kernel<<<(unsigned)ceil_div(K, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      dw, v, scale, inv_vnorm, K, (int)dim, dv, dg);
+  DMC_LAUNCH_CHECK("weightnorm_bwd_kernel launch");
+  return 0;
+}
+
+extern "C" int dmc_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
+  DMC_REQUIRE(x && hi && lo && n > 0, "dmc_split_tf32: bad arguments");
+  split_tf32_kernel<<<grid_1d(n, 256), 256, 0, (cudaStream_t)stream>>>(x, hi, lo, n);
+  DMC_LAUNCH_CHECK("split_tf32_kernel launch");
+  return 0;
+}
+
+extern "C" int dmc_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream) {
+  DMC_REQUIRE(x && y && n > 0, "dmc_cast_f32_to_bf16: bad arguments");
+  cast_bf16_kernel<<<grid_1d(n, 1024), 256, 0, (cudaStream_t)stream>>>(x, static_cast<__nv_bfloat16*>(y), n);
+  DMC_LAUNCH_CHECK("cast_bf16_kernel launch");
+  return 0;
+}
+
+extern "C" size_t dmc_colsum_workspace_bytes(int64_t M, int64_t N) {
+  if (M <= 0 || N <= 0) return 0;
+  return static_cast<size_t>(colsum_splits(M, N)) * N * sizeof(float);
+}
+
+extern "C" int dmc_colsum(const void* X, int32_t dtype, int64_t M, int64_t N, int64_t ld, float* out, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  DMC_REQUIRE(X && out && workspace, "dmc_colsum: null pointer");
+  DMC_REQUIRE(M > 0 && N > 0 && N < (1ll << 31) && ld >= N, "dmc_colsum: bad shape");
+  DMC_REQUIRE(dtype == DMC_F32 || dtype == DMC_BF16, "dmc_colsum: bad dtype");
+  const int splits = colsum_splits(M, N);
+  DMC_REQUIRE(workspace_bytes >= static_cast<size_t>(splits) * N * sizeof(float), "dmc_colsum: workspace too small");
+  const int rows_per_split = static_cast<int>(ceil_div(M, splits));
+  dim3 grid((unsigned)ceil_div(N, 32), (unsigned)splits);
+  colsum_partial_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, dtype, M, (int)N, ld, rows_per_split, static_cast<float*>(workspace));
+  DMC_LAUNCH_CHECK("colsum_partial_kernel launch");
+  colsum_final_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, (cudaStream_t)stream>>>(static_cast<const float*>(workspace), splits, (int)N, out);
+  DMC_LAUNCH_CHECK("colsum_final_kernel launch");
+  return 0;
+}

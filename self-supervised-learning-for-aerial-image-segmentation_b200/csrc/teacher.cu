@@ -1,0 +1,212 @@
+// teacher.cu -- fused teacher kernels of DINOLoss.
+//
+//   main_dino_mc.py:446   softmax((teacher_output - center) / temp)     -> per-row (max, 1/sum exp)
+//   main_dino_mc.py:468   torch.sum(teacher_output, dim=0)              -> per-GPU batch column sum
+//   main_dino_mc.py:470-473  center EMA                                  -> dmc_center_update
+//
+// teacher_pass_kernel reads every teacher logit exactly once and produces BOTH reductions: each warp
+// walks rows of a 1024-column chunk, a lane keeps its 32 columns' running sums in registers (column
+// direction) and reduces max / sum-exp across the warp with shuffles (row direction).  Partials go to a
+// small workspace and are merged in a fixed order (deterministic, no atomics).
+// HBM-bound: algorithmic bytes = Nt*K*sizeof(logit) read; everything else is O(Nt + K).
+#include <math.h>
+
+#include "dmc_common.cuh"
+
+namespace dmc {
+namespace {
+
+constexpr int kChunk = 1024;     // columns per CTA
+constexpr int kWarps = 8;
+
+template <typename T>
+__device__ __forceinline__ void load_guard(const T* rowp, long long col, long long K, bool vec_ok, float* v) {
+  constexpr int N = Vec<T>::N;
+  if (vec_ok && col + N <= K) {
+    float tmp[N];
+    Vec<T>::load(rowp + col, tmp);
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] = tmp[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] = (col + j < K) ? Vec<T>::load1(rowp + col + j) : 0.f;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kWarps * 32)
+teacher_pass_kernel(const T* __restrict__ t, long long Nt, long long K, long long ld, const float* __restrict__ center,
+                    float inv_temp, float2* __restrict__ ws_stats, float* __restrict__ ws_colsum, int rows_per_block,
+                    int nchunks, bool vec_ok) {
+  constexpr int VEC = Vec<T>::N;
+  constexpr int NV = 32 / VEC;                        // vectors per lane per row
+  __shared__ __align__(16) float sm[kWarps][kChunk];  // 32 KiB: per-warp column sums
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x;
+  const long long col0 = static_cast<long long>(chunk) * kChunk;
+  const bool full = (col0 + kChunk <= K);
+
+  float cen[32], cs[32];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const long long c = col0 + (i * 32 + lane) * VEC;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      cen[i * VEC + e] = (c + e < K) ? __ldg(center + c + e) : 0.f;
+      cs[i * VEC + e] = 0.f;
+    }
+  }
+  const long long r_begin = static_cast<long long>(blockIdx.y) * rows_per_block;
+  const long long r_end = min(r_begin + rows_per_block, Nt);
+  for (long long r = r_begin + warp; r < r_end; r += kWarps) {
+    float x[32];
+    const T* rowp = t + r * ld;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) load_guard<T>(rowp, col0 + (i * 32 + lane) * VEC, K, vec_ok, &x[i * VEC]);
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const int j = i * VEC + e;
+        cs[j] += x[j];
+        float y = (x[j] - cen[j]) * inv_temp;
+        if (!full && (col0 + (i * 32 + lane) * VEC + e >= K)) y = -INFINITY;
+        x[j] = y;
+        m = fmaxf(m, y);
+      }
+    m = warp_max(m);
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) l += __expf(x[j] - m);
+    l = warp_sum(l);
+    if (lane == 0) ws_stats[r * nchunks + chunk] = make_float2(m, l);
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) sm[warp][(i * 32 + lane) * VEC + e] = cs[i * VEC + e];
+  __syncthreads();
+  {
+    const int c = threadIdx.x * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      const float4 v = *reinterpret_cast<const float4*>(&sm[w][c]);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float* dst = ws_colsum + static_cast<long long>(blockIdx.y) * K + col0 + c;
+    if (col0 + c + 0 < K) dst[0] = acc.x;
+    if (col0 + c + 1 < K) dst[1] = acc.y;
+    if (col0 + c + 2 < K) dst[2] = acc.z;
+    if (col0 + c + 3 < K) dst[3] = acc.w;
+  }
+}
+
+// blocks [0, row_blocks): one warp per teacher row merges the per-chunk (max, sum) partials;
+// blocks [row_blocks, ...): one thread per column adds the per-row-block column sums in fixed order.
+__global__ void __launch_bounds__(256)
+teacher_finalize_kernel(const float2* __restrict__ ws_stats, const float* __restrict__ ws_colsum, long long Nt, long long K,
+                        int nchunks, int nrb, int row_blocks, float2* __restrict__ row_stats, float* __restrict__ colsum) {
+  if (static_cast<int>(blockIdx.x) < row_blocks) {
+    const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (r >= Nt) return;
+    const int lane = threadIdx.x & 31;
+    float m = -INFINITY, l = 0.f;
+    for (int c = lane; c < nchunks; c += 32) {
+      const float2 p = ws_stats[r * nchunks + c];
+      online_merge(m, l, p.x, p.y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+      const float l2 = __shfl_xor_sync(0xffffffffu, l, o);
+      online_merge(m, l, m2, l2);
+    }
+    if (lane == 0) row_stats[r] = make_float2(m, 1.0f / l);
+  } else {
+    const long long k = static_cast<long long>(blockIdx.x - row_blocks) * 256 + threadIdx.x;
+    if (k >= K) return;
+    float s = 0.f;
+    for (int b = 0; b < nrb; ++b) s += ws_colsum[static_cast<long long>(b) * K + k];
+    colsum[k] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+center_update_kernel(const float* center_in, float* center_out, const float* __restrict__ colsum, long long K, float count, float mom, float omm) {
+  const long long k = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (k >= K) return;
+  const float bc = __fdiv_rn(colsum[k], count);                        // batch_center / (len * world)
+  center_out[k] = __fadd_rn(__fmul_rn(center_in[k], mom), __fmul_rn(bc, omm));  // center * m + bc * (1 - m), no FMA
+}
+
+struct TeacherPlan { int nchunks, nrb, rows_per_block; size_t stats_bytes, colsum_bytes; };
+
+TeacherPlan teacher_plan(int64_t Nt, int64_t K) {
+  TeacherPlan p{};
+  p.nchunks = static_cast<int>(ceil_div(K, kChunk));
+  int64_t nrb = ceil_div(4 * kNumSMs, p.nchunks);
+  const int64_t max_rb = ceil_div(Nt, kWarps);
+  if (nrb > max_rb) nrb = max_rb;
+  if (nrb < 1) nrb = 1;
+  int64_t rpb = ceil_div(Nt, nrb);
+  rpb = ceil_div(rpb, kWarps) * kWarps;
+  p.rows_per_block = static_cast<int>(rpb);
+  p.nrb = static_cast<int>(ceil_div(Nt, rpb));
+  p.stats_bytes = (static_cast<size_t>(Nt) * p.nchunks * sizeof(float2) + 255) & ~static_cast<size_t>(255);
+  p.colsum_bytes = static_cast<size_t>(p.nrb) * K * sizeof(float);
+  return p;
+}
+
+}  // namespace
+}  // namespace dmc
+
+using namespace dmc;
+
+extern "C" size_t dmc_teacher_workspace_bytes(int64_t Nt, int64_t K) {
+  if (Nt <= 0 || K <= 0) return 0;
+  TeacherPlan p = teacher_plan(Nt, K);
+  return p.stats_bytes + p.colsum_bytes;
+}
+
+extern "C" int dmc_teacher_stats_colsum(const void* t, int32_t dtype, int64_t Nt, int64_t K, int64_t ld, const float* center,
+                                        float inv_temp, float* row_stats, float* colsum, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  DMC_REQUIRE(t && center && row_stats && colsum && workspace, "dmc_teacher_stats_colsum: null pointer");
+  DMC_REQUIRE(Nt > 0 && K > 0 && ld >= K, "dmc_teacher_stats_colsum: bad shape Nt=%lld K=%lld ld=%lld", (long long)Nt, (long long)K, (long long)ld);
+  DMC_REQUIRE(dtype == DMC_F32 || dtype == DMC_BF16, "dmc_teacher_stats_colsum: bad dtype %d", dtype);
+  TeacherPlan p = teacher_plan(Nt, K);
+  DMC_REQUIRE(workspace_bytes >= p.stats_bytes + p.colsum_bytes, "dmc_teacher_stats_colsum: workspace too small (%zu < %zu)",
+              workspace_bytes, p.stats_bytes + p.colsum_bytes);
+  DMC_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "dmc_teacher_stats_colsum: workspace must be 16-byte aligned");
+  DMC_REQUIRE(p.nrb <= 65535, "dmc_teacher_stats_colsum: too many row blocks");
+  float2* ws_stats = static_cast<float2*>(workspace);
+  float* ws_colsum = reinterpret_cast<float*>(static_cast<char*>(workspace) + p.stats_bytes);
+  const int esz = dtype == DMC_BF16 ? 2 : 4;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(t) & 15) == 0) && ((ld * esz) % 16 == 0);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid((unsigned)p.nchunks, (unsigned)p.nrb);
+  if (dtype == DMC_BF16)
+    teacher_pass_kernel<__nv_bfloat16><<<grid, kWarps * 32, 0, st>>>(static_cast<const __nv_bfloat16*>(t), Nt, K, ld, center, inv_temp,
+                                                                     ws_stats, ws_colsum, p.rows_per_block, p.nchunks, vec_ok);
+  else
+    teacher_pass_kernel<float><<<grid, kWarps * 32, 0, st>>>(static_cast<const float*>(t), Nt, K, ld, center, inv_temp, ws_stats,
+                                                             ws_colsum, p.rows_per_block, p.nchunks, vec_ok);
+  DMC_LAUNCH_CHECK("teacher_pass_kernel launch");
+  const int row_blocks = static_cast<int>(ceil_div(Nt, 8));
+  const int col_blocks = static_cast<int>(ceil_div(K, 256));
+  teacher_finalize_kernel<<<row_blocks + col_blocks, 256, 0, st>>>(ws_stats, ws_colsum, Nt, K, p.nchunks, p.nrb, row_blocks,
+                                                                   reinterpret_cast<float2*>(row_stats), colsum);
+  DMC_LAUNCH_CHECK("teacher_finalize_kernel launch");
+  return 0;
+}
+
+extern "C" int dmc_center_update(const float* center_in, float* center_out, const float* colsum, int64_t K, float count,
+                                 float momentum, float one_minus_momentum, void* stream) {
+  DMC_REQUIRE(center_in && center_out && colsum && K > 0 && count > 0.f, "dmc_center_update: bad arguments");
+  center_update_kernel<<<(unsigned)ceil_div(K, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(center_in, center_out, colsum, K, count,
+                                                                                                 momentum, one_minus_momentum);
+  DMC_LAUNCH_CHECK("center_update_kernel launch");
+  return 0;
+}

@@ -1,0 +1,192 @@
+"""autograd.Functions that stitch the libdinomc kernels into the DINOHead / DINOLoss graph.
+
+Precision modes (how the GEMMs run; everything around them is fp32):
+  "bf16"      bf16 operands on tcgen05 (kind::f16), fp32 accumulate in TMEM; logits and their gradient are
+              stored as bf16.  The analogue of the reference's default fp16 autocast (main_dino_mc.py:89,372).
+  "fp32"      fp32 operands split hi/lo and run as three TF32 tcgen05 passes (3xTF32, ~fp32 accuracy);
+              logits stored fp32.  Parity mode: 1e-5 against the reference.
+  "fp32_simt" fp32 FFMA kernel, no tensor cores (cross-check arm).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+MODES = ("bf16", "fp32", "fp32_simt")
+
+
+class Operand:
+    """A GEMM operand in the representation a mode needs: bf16 tensor, (hi, lo) TF32 pair, or plain fp32."""
+    __slots__ = ("main", "lo")
+
+    def __init__(self, main, lo=None):
+        self.main, self.lo = main, lo
+
+
+def prep(t: torch.Tensor, mode: str) -> Operand:
+    if mode == "bf16":
+        return Operand(ops.cast_bf16(t))
+    t = t if t.dtype == torch.float32 else t.float()
+    t = ops._rows2d(t)
+    if mode == "fp32":
+        hi, lo = ops.split_tf32(t)
+        return Operand(hi, lo)
+    return Operand(t)
+
+
+def store_dtype(mode: str) -> torch.dtype:
+    return torch.bfloat16 if mode == "bf16" else torch.float32
+
+
+def resolve_mode(mode: str, *dims) -> str:
+    """The tensor-core kernel reads operands through TMA descriptors, which need every stored row to be a
+    multiple of 16 bytes.  Shapes that cannot satisfy this run on the (still on-device, hand-written) FFMA
+    kernel instead -- never on the CPU or through torch."""
+    if mode not in MODES:
+        raise ValueError(f"unknown precision mode {mode!r}; expected one of {MODES}")
+    if mode == "fp32_simt":
+        return mode
+    per16 = 8 if mode == "bf16" else 4
+    return mode if all(int(d) % per16 == 0 for d in dims) else "fp32_simt"
+
+
+def mm(mode, a: Operand, b: Operand, M, N, K, *, a_mn=False, b_mn=False, **kw):
+    """Mode-aware GEMM (mode already resolved by resolve_mode)."""
+    if mode == "fp32_simt":
+        return ops.gemm(a.main, b.main, M, N, K, a_mn=a_mn, b_mn=b_mn, simt=True, **kw)
+    return ops.gemm(a.main, b.main, M, N, K, a_mn=a_mn, b_mn=b_mn, A_lo=a.lo, B_lo=b.lo, **kw)
+
+
+class MlpFn(torch.autograd.Function):
+    """The Linear/GELU chain of DINOHead.mlp (utils/vision_transformer.py:264-277, use_bn=False).
+    forward(mode, x, W0, b0, W1, b1, ...) -> z_last (fp32).  Bias + GELU are fused into the GEMM epilogue
+    (which also saves the pre-activation); backward fuses gelu' into the dgrad epilogue."""
+
+    @staticmethod
+    def forward(ctx, mode, x, *wb):
+        n = len(wb) // 2
+        rows = x.shape[0]
+        mode = resolve_mode(mode, x.shape[1], *[d for li in range(n) for d in wb[2 * li].shape])
+        acts = [prep(x.detach(), mode)]
+        wops, zs = [], []
+        sd = store_dtype(mode)
+        out = None
+        for li in range(n):
+            W, b = wb[2 * li].detach(), wb[2 * li + 1]
+            wop = prep(W, mode)
+            wops.append(wop)
+            fo, fi = W.shape
+            bias = None if b is None else b.detach().float().contiguous()
+            if li < n - 1:
+                z = torch.empty((rows, fo), dtype=sd, device=x.device)
+                h = mm(mode, acts[li], wop, rows, fo, fi, out_dtype=sd, bias=bias, act=L.ACT_GELU, aux=z)
+                zs.append(z)
+                acts.append(prep(h, mode))
+            else:
+                out = mm(mode, acts[li], wop, rows, fo, fi, out_dtype=torch.float32, bias=bias)
+        ctx.mode, ctx.n, ctx.rows = mode, n, rows
+        ctx.acts, ctx.wops, ctx.zs = acts, wops, zs
+        ctx.shapes = [tuple(wb[2 * li].shape) for li in range(n)]
+        ctx.has_bias = [wb[2 * li + 1] is not None for li in range(n)]
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        mode, n, rows = ctx.mode, ctx.n, ctx.rows
+        sd = store_dtype(mode)
+        grads = [None] * (2 * n)
+        d_full = dy.contiguous()
+        d = prep(d_full, mode)
+        dx = None
+        for li in range(n - 1, -1, -1):
+            fo, fi = ctx.shapes[li]
+            # wgrad: dW[fo,fi] = d^T . act   (both operands MN-major straight from their row-major storage)
+            if ctx.needs_input_grad[2 + 2 * li]:
+                grads[2 * li] = mm(mode, d, ctx.acts[li], fo, fi, rows, a_mn=True, b_mn=True, out_dtype=torch.float32)
+            if ctx.has_bias[li] and ctx.needs_input_grad[3 + 2 * li]:
+                grads[2 * li + 1] = ops.colsum(d_full)
+            if li > 0:
+                # dgrad with gelu'(z_{li-1}) fused: d_prev = (d . W) * gelu'(z)
+                d_full = mm(mode, d, ctx.wops[li], rows, fi, fo, b_mn=True, out_dtype=sd, act=L.ACT_GELU_BWD,
+                            aux=ctx.zs[li - 1])
+                d = prep(d_full, mode)
+            elif ctx.needs_input_grad[1]:
+                dx = mm(mode, d, ctx.wops[0], rows, fi, fo, b_mn=True, out_dtype=torch.float32)
+        return (None, dx, *grads)
+
+
+class NormLastLayerFn(torch.autograd.Function):
+    """F.normalize -> weight_norm(Linear(bottleneck, out_dim, bias=False))
+    (utils/vision_transformer.py:292-293, :279).  forward(mode, z, weight_g, weight_v) -> logits."""
+
+    @staticmethod
+    def forward(ctx, mode, z, g, v):
+        rows, dim = z.shape
+        K = v.shape[0]
+        mode = resolve_mode(mode, dim, K)
+        zhat, zhat_bf16, inv_den = ops.normalize_rows_fwd(z.detach(), want_bf16=(mode == "bf16"))
+        if mode == "bf16":
+            zop = Operand(zhat_bf16)
+            w, _, scale, inv_vnorm = ops.weightnorm_fwd(v.detach(), g.detach().reshape(-1), "bf16")
+            wop = Operand(w)
+        elif mode == "fp32":
+            zop = prep(zhat, mode)
+            w_hi, w_lo, scale, inv_vnorm = ops.weightnorm_fwd(v.detach(), g.detach().reshape(-1), "tf32x3")
+            wop = Operand(w_hi, w_lo)
+        else:
+            zop = Operand(zhat)
+            w, _, scale, inv_vnorm = ops.weightnorm_fwd(v.detach(), g.detach().reshape(-1), "f32")
+            wop = Operand(w)
+        logits = mm(mode, zop, wop, rows, K, dim, out_dtype=store_dtype(mode))
+        ctx.mode = mode
+        ctx.zop, ctx.wop = zop, wop
+        ctx.save_for_backward(zhat, inv_den, v.detach(), scale, inv_vnorm)
+        ctx.dims = (rows, dim, K)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        mode = ctx.mode
+        zhat, inv_den, v, scale, inv_vnorm = ctx.saved_tensors
+        rows, dim, K = ctx.dims
+        if dlogits.dtype != store_dtype(mode):
+            dlogits = dlogits.to(store_dtype(mode))
+        d = prep(dlogits, mode) if mode != "bf16" else Operand(ops._rows2d(dlogits))
+        dz = dg = dv = None
+        if ctx.needs_input_grad[1]:
+            # dgrad: contraction over out_dim (split-K), W read MN-major from its [K,dim] storage
+            dzhat = mm(mode, d, ctx.wop, rows, dim, K, b_mn=True, out_dtype=torch.float32)
+            dz = ops.normalize_rows_bwd(dzhat, zhat, inv_den)
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            # wgrad: dW[K,dim] = dlogits^T . zhat, both MN-major
+            dw = mm(mode, d, ctx.zop, K, dim, rows, a_mn=True, b_mn=True, out_dtype=torch.float32)
+            dv, dg = ops.weightnorm_bwd(dw, v, scale, inv_vnorm, want_dg=ctx.needs_input_grad[2])
+            if not ctx.needs_input_grad[3]:
+                dv = None
+        return None, dz, dg, dv
+
+
+class DinoLossFn(torch.autograd.Function):
+    """DINOLoss.forward (main_dino_mc.py:437-459) on the OLD center.  forward(student, teacher, center,
+    inv_ts, inv_tt, B, C, G) -> (loss, colsum); colsum = per-GPU batch column sum of the teacher logits
+    (input of update_center), produced by the same pass that computes the teacher softmax statistics."""
+
+    @staticmethod
+    def forward(ctx, s, t, center, inv_ts, inv_tt, B, C, G):
+        s_d, t_d = s.detach(), t.detach()
+        center = center.detach().reshape(-1)
+        t_stats, colsum = ops.teacher_stats_colsum(t_d, center, inv_tt)
+        loss, s_lse = ops.ce_fwd(s_d, t_d, center, t_stats, B, C, G, inv_ts, inv_tt)
+        ctx.save_for_backward(s_d, t_d, center, t_stats, s_lse)
+        ctx.cfg = (B, C, G, inv_ts, inv_tt)
+        ctx.mark_non_differentiable(colsum)
+        return loss, colsum
+
+    @staticmethod
+    def backward(ctx, gloss, _gcolsum):
+        s, t, center, t_stats, s_lse = ctx.saved_tensors
+        B, C, G, inv_ts, inv_tt = ctx.cfg
+        ds = ops.ce_bwd(s, t, center, t_stats, s_lse, gloss, B, C, G, inv_ts, inv_tt)
+        return ds, None, None, None, None, None, None, None

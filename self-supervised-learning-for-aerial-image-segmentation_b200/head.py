@@ -1,0 +1,123 @@
+"""DINOHead -- drop-in for the reference's `utils.vision_transformer.DINOHead`
+(utils/vision_transformer.py:260-294): same constructor signature, same sub-module / parameter names,
+registration order, shapes, init and state_dict keys, so `main_dino_mc.py:236-246` can construct it
+unchanged and checkpoints move both ways.  The forward/backward run on the libdinomc kernels.
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import torch
+import torch.nn as nn
+
+from . import functional as Fn
+
+_default_precision = os.environ.get("DINOMC_PRECISION", "auto")
+
+
+def set_default_precision(mode: str):
+    """'auto' (bf16 under torch autocast, fp32 otherwise), 'bf16', 'fp32' or 'fp32_simt'."""
+    global _default_precision
+    if mode != "auto" and mode not in Fn.MODES:
+        raise ValueError(f"unknown precision {mode!r}")
+    _default_precision = mode
+
+
+def get_default_precision() -> str:
+    return _default_precision
+
+
+def _trunc_normal_(tensor, mean=0., std=1., a=-2., b=2.):
+    """Same sampling procedure as utils/utils.py:529-567 (inverse-CDF of a truncated uniform), so that a
+    given torch RNG state yields the same weights as the reference's trunc_normal_."""
+    def norm_cdf(x):
+        return (1. + math.erf(x / math.sqrt(2.))) / 2.
+    with torch.no_grad():
+        lo = norm_cdf((a - mean) / std)
+        up = norm_cdf((b - mean) / std)
+        tensor.uniform_(2 * lo - 1, 2 * up - 1)
+        tensor.erfinv_()
+        tensor.mul_(std * math.sqrt(2.))
+        tensor.add_(mean)
+        tensor.clamp_(min=a, max=b)
+    return tensor
+
+
+class _WeightNormLinear(nn.Module):
+    """Parameter container equal to `nn.utils.weight_norm(nn.Linear(in, out, bias=False))`:
+    parameters `weight_g` [out,1] then `weight_v` [out,in] (that registration order), no bias."""
+
+    def __init__(self, in_features, out_features):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        lin = nn.Linear(in_features, out_features, bias=False)       # default nn.Linear init, as the reference
+        w = lin.weight.detach()
+        self.weight_g = nn.Parameter(w.norm(dim=1, keepdim=True))
+        self.weight_v = nn.Parameter(w.clone())
+
+    @property
+    def weight(self):
+        """The effective weight g * v / ||v|| (what the reference's pre-hook materialises); for inspection."""
+        v = self.weight_v
+        return v * (self.weight_g / v.norm(dim=1, keepdim=True))
+
+    def extra_repr(self):
+        return f"in_features={self.in_features}, out_features={self.out_features}, bias=False, weight_norm"
+
+
+class DINOHead(nn.Module):
+    def __init__(self, in_dim, out_dim, use_bn=False, norm_last_layer=True, nlayers=3, hidden_dim=2048,
+                 bottleneck_dim=256):
+        super().__init__()
+        nlayers = max(nlayers, 1)
+        if nlayers == 1:
+            self.mlp = nn.Linear(in_dim, bottleneck_dim)
+        else:
+            layers = [nn.Linear(in_dim, hidden_dim)]
+            if use_bn:
+                layers.append(nn.BatchNorm1d(hidden_dim))
+            layers.append(nn.GELU())
+            for _ in range(nlayers - 2):
+                layers.append(nn.Linear(hidden_dim, hidden_dim))
+                if use_bn:
+                    layers.append(nn.BatchNorm1d(hidden_dim))
+                layers.append(nn.GELU())
+            layers.append(nn.Linear(hidden_dim, bottleneck_dim))
+            self.mlp = nn.Sequential(*layers)
+        self.apply(self._init_weights)          # before last_layer exists, exactly like the reference (:278)
+        self.last_layer = _WeightNormLinear(bottleneck_dim, out_dim)
+        self.last_layer.weight_g.data.fill_(1)
+        if norm_last_layer:
+            self.last_layer.weight_g.requires_grad = False
+        self.use_bn = use_bn
+        self.precision = None                   # None -> module default (set_default_precision / autocast)
+
+    def _init_weights(self, m):
+        if isinstance(m, nn.Linear):
+            _trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+
+    def _mode(self):
+        mode = self.precision or _default_precision
+        if mode == "auto":
+            mode = "bf16" if torch.is_autocast_enabled() else "fp32"
+        return mode
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("dinomc_b200.DINOHead runs on CUDA (sm_100a) only; there is no CPU fallback")
+        mode = self._mode()
+        with torch.autocast("cuda", enabled=False):
+            if self.use_bn:
+                # BatchNorm1d / SyncBatchNorm stay torch modules (reference option, off by default);
+                # the weight-normed last layer below is still ours.
+                z = self.mlp(x.float())
+            else:
+                linears = [self.mlp] if isinstance(self.mlp, nn.Linear) else [m for m in self.mlp if isinstance(m, nn.Linear)]
+                wb = []
+                for lin in linears:
+                    wb += [lin.weight, lin.bias]
+                z = Fn.MlpFn.apply(mode, x, *wb)
+            return Fn.NormLastLayerFn.apply(mode, z, self.last_layer.weight_g, self.last_layer.weight_v)

@@ -1,0 +1,70 @@
+"""DINOLoss -- drop-in for the reference's `main_dino_mc.DINOLoss` (main_dino_mc.py:419-473): same
+constructor, attributes, `center` buffer / state_dict, forward(student_output, teacher_output, epoch)
+returning a 0-dim loss with autograd to student_output, and the center update (with its cross-rank
+all-reduce) as a side effect AFTER the loss, on the libdinomc kernels.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import functional as Fn
+from . import ops
+
+
+class DINOLoss(nn.Module):
+    def __init__(self, out_dim, ncrops, warmup_teacher_temp, teacher_temp, warmup_teacher_temp_epochs, nepochs,
+                 teacher_crops_number=2, student_temp=0.1, center_momentum=0.9):
+        super().__init__()
+        self.student_temp = student_temp
+        self.center_momentum = center_momentum
+        self.ncrops = ncrops
+        self.teacher_crops_number = teacher_crops_number
+        self.register_buffer("center", torch.zeros(1, out_dim))
+        # same schedule construction as main_dino_mc.py:431-435
+        self.teacher_temp_schedule = np.concatenate((
+            np.linspace(warmup_teacher_temp, teacher_temp, warmup_teacher_temp_epochs),
+            np.ones(nepochs - warmup_teacher_temp_epochs) * teacher_temp,
+        ))
+
+    @staticmethod
+    def _common(student_output, teacher_output):
+        """Bring both logit tensors to one kernel dtype (fp32 or bf16) without touching values needlessly."""
+        if student_output.dtype == torch.bfloat16 and teacher_output.dtype == torch.bfloat16:
+            return student_output, teacher_output
+        return student_output.float(), teacher_output.float()
+
+    def forward(self, student_output, teacher_output, epoch):
+        if not student_output.is_cuda:
+            raise RuntimeError("dinomc_b200.DINOLoss runs on CUDA (sm_100a) only; there is no CPU fallback")
+        C, G = self.ncrops, self.teacher_crops_number
+        if student_output.shape[0] % C or teacher_output.shape[0] % G:
+            raise ValueError("student/teacher rows must be ncrops*B / teacher_crops_number*B (crop-major)")
+        B = student_output.shape[0] // C
+        if teacher_output.shape[0] // G != B:
+            raise ValueError("student and teacher batches differ")
+        temp = float(self.teacher_temp_schedule[epoch])
+        s, t = self._common(student_output, teacher_output.detach())
+        loss, colsum = Fn.DinoLossFn.apply(s, t, self.center, 1.0 / self.student_temp, 1.0 / temp, B, C, G)
+        self._update_center_from_colsum(colsum, teacher_output.shape[0])
+        return loss
+
+    @torch.no_grad()
+    def _update_center_from_colsum(self, colsum, n_rows):
+        world = 1
+        if dist.is_available() and dist.is_initialized():
+            world = dist.get_world_size()
+            if world > 1:
+                dist.all_reduce(colsum)                 # main_dino_mc.py:469 (65536 fp32 = 256 KiB over NCCL)
+        # rebinding the buffer (like the reference, :473) keeps the old tensor alive for backward
+        self.center = ops.center_update(self.center, colsum, n_rows * world, self.center_momentum)
+
+    @torch.no_grad()
+    def update_center(self, teacher_output):
+        """Public API of the reference (main_dino_mc.py:463-473) for callers that use it directly."""
+        t = teacher_output.detach()
+        t = t if t.dtype == torch.bfloat16 else t.float()
+        _, colsum = ops.teacher_stats_colsum(t, self.center.reshape(-1), 1.0)
+        self._update_center_from_colsum(colsum, teacher_output.shape[0])

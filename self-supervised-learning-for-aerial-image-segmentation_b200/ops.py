@@ -1,0 +1,338 @@
+"""Tensor-level wrappers over the C ABI (include/dinomc.h).
+
+PyTorch is used here only as plumbing: device memory (tensors), the current CUDA stream and dtype
+bookkeeping.  Every arithmetic operation is a libdinomc kernel; nothing falls back to torch ops or
+to the CPU -- non-CUDA tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+# kernel launches issued through this module (bench.py reports it as `gpu_launches`)
+launch_count = 0
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return L.DMC_F32
+    if t.dtype == torch.bfloat16:
+        return L.DMC_BF16
+    raise TypeError(f"dinomc_b200 kernels take float32 or bfloat16 tensors, got {t.dtype}")
+
+
+def _dtype_code(dtype: torch.dtype) -> int:
+    return L.DMC_BF16 if dtype == torch.bfloat16 else L.DMC_F32
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("dinomc_b200 has no CPU path: all tensors must be CUDA tensors "
+                               f"(got a tensor on {t.device})")
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _rows2d(t: torch.Tensor) -> torch.Tensor:
+    """2-D tensor whose rows are contiguous (stride(1) == 1); copies only if it must."""
+    if t.dim() != 2:
+        raise ValueError(f"expected a 2-D tensor, got shape {tuple(t.shape)}")
+    if t.stride(1) != 1 or t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    return t
+
+
+# ---------------------------------------------------------------------------------------------
+# workspace: one growing byte buffer per (device, stream); kernels on a stream use it in order
+# ---------------------------------------------------------------------------------------------
+_workspaces = {}
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    key = (torch.device(device).index, _stream())
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+# ---------------------------------------------------------------------------------------------
+# GEMM
+# ---------------------------------------------------------------------------------------------
+def tma_ok(t: torch.Tensor) -> bool:
+    """Can the tensor-core kernel's TMA descriptor express this stored matrix?"""
+    return t.data_ptr() % 16 == 0 and (t.stride(0) * t.element_size()) % 16 == 0
+
+
+def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, A_lo=None, B_lo=None, out=None, out_dtype=torch.float32,
+         col_scale=None, bias=None, alpha=1.0, alpha_dev=None, act=L.ACT_NONE, aux=None, simt=False, split_k=0):
+    """D[M,N] = epilogue(sum_k A(m,k) B(n,k)).  A is stored [M,K] (a_mn=False) or [K,M] (a_mn=True);
+    B is stored [N,K] (b_mn=False) or [K,N] (b_mn=True).  See dmc_gemm in include/dinomc.h."""
+    lib = L.load()
+    A, B = _rows2d(A), _rows2d(B)
+    _need_cuda(A, B, out, aux, col_scale, bias, alpha_dev, A_lo, B_lo)
+    exp_a = (K, M) if a_mn else (M, K)
+    exp_b = (K, N) if b_mn else (N, K)
+    if tuple(A.shape) != exp_a or tuple(B.shape) != exp_b:
+        raise ValueError(f"gemm: operand shapes {tuple(A.shape)}, {tuple(B.shape)} do not match "
+                         f"M={M} N={N} K={K} a_mn={a_mn} b_mn={b_mn}")
+    if A.dtype != B.dtype:
+        raise TypeError("gemm: A and B must share a dtype")
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=A.device)
+    g = L.GemmArgs()
+    g.M, g.N, g.K = M, N, K
+    g.A, g.lda, g.a_mn_major = A.data_ptr(), A.stride(0), int(a_mn)
+    g.B, g.ldb, g.b_mn_major = B.data_ptr(), B.stride(0), int(b_mn)
+    if A_lo is not None:
+        A_lo, B_lo = _rows2d(A_lo), _rows2d(B_lo)
+        assert A_lo.stride(0) == A.stride(0) and B_lo.stride(0) == B.stride(0)
+    g.A_lo, g.B_lo = _p(A_lo), _p(B_lo)
+    g.in_dtype = _dt(A)
+    g.D, g.ldd, g.out_dtype = out.data_ptr(), out.stride(0), _dt(out)
+    g.col_scale, g.bias, g.alpha_dev, g.alpha = _p(col_scale), _p(bias), _p(alpha_dev), float(alpha)
+    g.act = act
+    if aux is not None:
+        g.aux, g.ldaux, g.aux_dtype = aux.data_ptr(), aux.stride(0), _dt(aux)
+    g.split_k = split_k
+    if simt:
+        L.check(lib.dmc_gemm_simt(C.byref(g), _stream()), "dmc_gemm_simt")
+        _count()
+        return out
+    nbytes = lib.dmc_gemm_workspace_bytes(M, N, K, g.in_dtype) if split_k == 0 else split_k * M * N * 4
+    if nbytes:
+        ws = workspace(nbytes, A.device)
+        g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel()
+    L.check(lib.dmc_gemm(C.byref(g), _stream()), "dmc_gemm")
+    _count(2 if nbytes else 1)
+    return out
+
+
+def split_tf32(x: torch.Tensor):
+    lib = L.load()
+    _need_cuda(x)
+    x = x.contiguous()
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    L.check(lib.dmc_split_tf32(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), _stream()), "dmc_split_tf32")
+    _count()
+    return hi, lo
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    lib = L.load()
+    _need_cuda(x)
+    if x.dtype == torch.bfloat16:
+        return x
+    x = x.float().contiguous() if x.dtype != torch.float32 else x.contiguous()
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    L.check(lib.dmc_cast_f32_to_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "dmc_cast_f32_to_bf16")
+    _count()
+    return y
+
+
+def colsum(X: torch.Tensor) -> torch.Tensor:
+    lib = L.load()
+    X = _rows2d(X)
+    _need_cuda(X)
+    M, N = X.shape
+    out = torch.empty(N, dtype=torch.float32, device=X.device)
+    nbytes = lib.dmc_colsum_workspace_bytes(M, N)
+    ws = workspace(nbytes, X.device)
+    L.check(lib.dmc_colsum(X.data_ptr(), _dt(X), M, N, X.stride(0), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+            "dmc_colsum")
+    _count(2)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# head row kernels
+# ---------------------------------------------------------------------------------------------
+def normalize_rows_fwd(z: torch.Tensor, eps=1e-12, want_bf16=False):
+    """Returns (zhat_f32 [N,dim], zhat_bf16 or None, inv_den [N])."""
+    lib = L.load()
+    z = _rows2d(z)
+    _need_cuda(z)
+    n, dim = z.shape
+    zhat = torch.empty((n, dim), dtype=torch.float32, device=z.device)
+    zb = torch.empty((n, dim), dtype=torch.bfloat16, device=z.device) if want_bf16 else None
+    inv_den = torch.empty(n, dtype=torch.float32, device=z.device)
+    L.check(lib.dmc_normalize_rows_fwd(z.data_ptr(), _dt(z), n, dim, z.stride(0), eps, zhat.data_ptr(), _p(zb), None,
+                                       inv_den.data_ptr(), _stream()), "dmc_normalize_rows_fwd")
+    _count()
+    return zhat, zb, inv_den
+
+
+def normalize_rows_bwd(dzhat, zhat, inv_den, eps=1e-12, out_dtype=torch.float32):
+    lib = L.load()
+    _need_cuda(dzhat, zhat, inv_den)
+    dzhat, zhat = dzhat.contiguous(), zhat.contiguous()
+    assert dzhat.dtype == torch.float32 and zhat.dtype == torch.float32
+    n, dim = zhat.shape
+    dz = torch.empty((n, dim), dtype=out_dtype, device=zhat.device)
+    L.check(lib.dmc_normalize_rows_bwd(dzhat.data_ptr(), zhat.data_ptr(), inv_den.data_ptr(), n, dim, eps, dz.data_ptr(),
+                                       _dt(dz), _stream()), "dmc_normalize_rows_bwd")
+    _count()
+    return dz
+
+
+def weightnorm_fwd(v: torch.Tensor, g: torch.Tensor, mode: str):
+    """mode 'bf16' -> (w_bf16, None); 'tf32x3' -> (w_hi, w_lo); 'f32' -> (w_f32, None).
+    Also returns scale[K] = g/||v|| and inv_vnorm[K]."""
+    lib = L.load()
+    _need_cuda(v, g)
+    v = v.contiguous()
+    g = g.contiguous()
+    if v.dtype != torch.float32 or g.dtype != torch.float32:
+        raise TypeError("weight_norm parameters must be float32")
+    K, dim = v.shape
+    dev = v.device
+    scale = torch.empty(K, dtype=torch.float32, device=dev)
+    inv_vnorm = torch.empty(K, dtype=torch.float32, device=dev)
+    w_f32 = w_lo = w_bf16 = None
+    if mode == "bf16":
+        w_bf16 = torch.empty((K, dim), dtype=torch.bfloat16, device=dev)
+    else:
+        w_f32 = torch.empty((K, dim), dtype=torch.float32, device=dev)
+        if mode == "tf32x3":
+            w_lo = torch.empty((K, dim), dtype=torch.float32, device=dev)
+    L.check(lib.dmc_weightnorm_fwd(v.data_ptr(), g.data_ptr(), K, dim, _p(w_f32), _p(w_lo), _p(w_bf16), scale.data_ptr(),
+                                   inv_vnorm.data_ptr(), _stream()), "dmc_weightnorm_fwd")
+    _count()
+    return (w_bf16, None, scale, inv_vnorm) if mode == "bf16" else (w_f32, w_lo, scale, inv_vnorm)
+
+
+def weightnorm_bwd(dw, v, scale, inv_vnorm, want_dg: bool):
+    lib = L.load()
+    _need_cuda(dw, v)
+    dw, v = dw.contiguous(), v.contiguous()
+    assert dw.dtype == torch.float32
+    K, dim = v.shape
+    dv = torch.empty_like(v)
+    dg = torch.empty((K, 1), dtype=torch.float32, device=v.device) if want_dg else None
+    L.check(lib.dmc_weightnorm_bwd(dw.data_ptr(), v.data_ptr(), scale.data_ptr(), inv_vnorm.data_ptr(), K, dim, dv.data_ptr(),
+                                   _p(dg), _stream()), "dmc_weightnorm_bwd")
+    _count()
+    return dv, dg
+
+
+# ---------------------------------------------------------------------------------------------
+# loss kernels
+# ---------------------------------------------------------------------------------------------
+def teacher_stats_colsum(t: torch.Tensor, center: torch.Tensor, inv_temp: float):
+    """One pass over teacher logits: (row_stats [Nt,2] = (max, 1/sum), colsum [K])."""
+    lib = L.load()
+    t = _rows2d(t)
+    _need_cuda(t, center)
+    Nt, K = t.shape
+    center = center.reshape(-1)
+    assert center.dtype == torch.float32 and center.numel() == K and center.is_contiguous()
+    row_stats = torch.empty((Nt, 2), dtype=torch.float32, device=t.device)
+    colsum_ = torch.empty(K, dtype=torch.float32, device=t.device)
+    nbytes = lib.dmc_teacher_workspace_bytes(Nt, K)
+    ws = workspace(nbytes, t.device)
+    L.check(lib.dmc_teacher_stats_colsum(t.data_ptr(), _dt(t), Nt, K, t.stride(0), center.data_ptr(), inv_temp,
+                                         row_stats.data_ptr(), colsum_.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+            "dmc_teacher_stats_colsum")
+    _count(2)
+    return row_stats, colsum_
+
+
+def center_update(center: torch.Tensor, colsum_: torch.Tensor, count: float, momentum: float) -> torch.Tensor:
+    """Returns the NEW center tensor (same shape as `center`); `center` itself is left untouched."""
+    lib = L.load()
+    _need_cuda(center, colsum_)
+    out = torch.empty_like(center)
+    K = center.numel()
+    L.check(lib.dmc_center_update(center.data_ptr(), out.data_ptr(), colsum_.data_ptr(), K, float(count), float(momentum),
+                                  float(1 - momentum), _stream()), "dmc_center_update")
+    _count()
+    return out
+
+
+def ce_fwd(s, t, center, t_stats, B, C, G, inv_ts, inv_tt):
+    lib = L.load()
+    s, t = _rows2d(s), _rows2d(t)
+    _need_cuda(s, t, center, t_stats)
+    K = s.shape[1]
+    s_lse = torch.empty(C * B, dtype=torch.float32, device=s.device)
+    loss = torch.empty((), dtype=torch.float32, device=s.device)
+    nbytes = lib.dmc_ce_workspace_bytes(B, C, G, K)
+    ws = workspace(nbytes, s.device)
+    L.check(lib.dmc_ce_fwd(s.data_ptr(), _dt(s), s.stride(0), t.data_ptr(), _dt(t), t.stride(0), center.data_ptr(),
+                           t_stats.data_ptr(), B, C, G, K, inv_ts, inv_tt, s_lse.data_ptr(), loss.data_ptr(),
+                           ws.data_ptr(), ws.numel(), _stream()), "dmc_ce_fwd")
+    _count(2)
+    return loss, s_lse
+
+
+def ce_bwd(s, t, center, t_stats, s_lse, grad_out, B, C, G, inv_ts, inv_tt):
+    lib = L.load()
+    s, t = _rows2d(s), _rows2d(t)
+    _need_cuda(s, t, center, t_stats, s_lse, grad_out)
+    K = s.shape[1]
+    ds = torch.empty((s.shape[0], K), dtype=s.dtype, device=s.device)
+    grad_out = grad_out.to(torch.float32).contiguous()
+    L.check(lib.dmc_ce_bwd(s.data_ptr(), _dt(s), s.stride(0), t.data_ptr(), _dt(t), t.stride(0), center.data_ptr(),
+                           t_stats.data_ptr(), s_lse.data_ptr(), grad_out.data_ptr(), B, C, G, K, inv_ts, inv_tt,
+                           ds.data_ptr(), _dt(ds), ds.stride(0), _stream()), "dmc_ce_bwd")
+    _count()
+    return ds
+
+
+# ---------------------------------------------------------------------------------------------
+# EMA
+# ---------------------------------------------------------------------------------------------
+class EmaPlan:
+    """Device-resident chunk table for one (teacher, student) parameter-list pair."""
+
+    def __init__(self, teacher_params, student_params):
+        lib = L.load()
+        teacher_params, student_params = list(teacher_params), list(student_params)
+        n = min(len(teacher_params), len(student_params))      # zip() semantics of main_dino_mc.py:405
+        if n == 0:
+            raise ValueError("ema: empty parameter list")
+        tp, sp = teacher_params[:n], student_params[:n]
+        for pk, pq in zip(tp, sp):
+            _need_cuda(pk, pq)
+            if pk.dtype != torch.float32 or pq.dtype != torch.float32:
+                raise TypeError("ema: parameters must be float32")
+            if pk.shape != pq.shape:
+                raise ValueError(f"ema: shape mismatch {tuple(pk.shape)} vs {tuple(pq.shape)}")
+            if not pk.is_contiguous() or not pq.is_contiguous():
+                raise ValueError("ema: parameters must be contiguous")
+        self.key = tuple((pk.data_ptr(), pq.data_ptr(), pk.numel()) for pk, pq in zip(tp, sp))
+        numels = (L.i64 * n)(*[pk.numel() for pk in tp])
+        tptr = (L.vp * n)(*[pk.data_ptr() for pk in tp])
+        sptr = (L.vp * n)(*[pq.data_ptr() for pq in sp])
+        nbytes = lib.dmc_ema_plan_bytes(numels, n)
+        host = torch.empty(max(nbytes, 8), dtype=torch.uint8).pin_memory()
+        n_chunks = L.i64(0)
+        L.check(lib.dmc_ema_build_plan(tptr, sptr, numels, n, host.data_ptr(), host.numel(), C.byref(n_chunks)),
+                "dmc_ema_build_plan")
+        self.n_chunks = n_chunks.value
+        self.n_params = sum(pk.numel() for pk in tp)
+        self.device = tp[0].device
+        self.plan = host.to(self.device, non_blocking=False)
+
+    def run(self, m: float):
+        lib = L.load()
+        # m is float64 (momentum_schedule[it]); (1 - m) is formed in float64 like the reference, then both -> fp32
+        L.check(lib.dmc_ema_multi_tensor(self.plan.data_ptr(), self.n_chunks, float(m), float(1.0 - float(m)), _stream()),
+                "dmc_ema_multi_tensor")
+        _count()

@@ -1,0 +1,137 @@
+"""CPU: the C-ABI library loads and exports every symbol include/dinomc.h declares (no compute calls),
+argument validation that needs no device, and the host-only EMA plan builder."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "dinomc.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dmc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_is_built_and_exports_every_declared_symbol():
+    import dinomc_b200
+    lib = dinomc_b200._lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"libdinomc.so does not export {name}"
+    assert sorted(dinomc_b200._lib.SIGNATURES) == declared      # the ctypes table covers the whole header
+    assert lib.dmc_version() == 100
+    assert lib.dmc_last_error_string() == b""
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    import dinomc_b200
+    L = dinomc_b200._lib
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", "/nonexistent/libdinomc.so")
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        L.load()
+
+
+def test_workspace_queries_are_host_only():
+    import dinomc_b200
+    lib = dinomc_b200._lib.load()
+    # dgrad of the last layer (rows 2048, bottleneck 256, contraction 65536) is split-K: needs partials
+    assert lib.dmc_gemm_workspace_bytes(2048, 256, 65536, 1) >= 2 * 2048 * 256 * 4
+    # the forward is not split
+    assert lib.dmc_gemm_workspace_bytes(2048, 65536, 256, 1) == 0
+    assert lib.dmc_teacher_workspace_bytes(512, 65536) > 512 * 64 * 8
+    assert lib.dmc_ce_workspace_bytes(256, 8, 2, 65536) > 0
+    assert lib.dmc_colsum_workspace_bytes(2048, 2048) >= 2048 * 4
+
+
+def test_argument_validation_without_a_device():
+    import dinomc_b200
+    L = dinomc_b200._lib
+    lib = L.load()
+    g = L.GemmArgs()
+    assert lib.dmc_gemm(C.byref(g), None) < 0
+    assert b"empty problem" in lib.dmc_last_error_string()
+    assert lib.dmc_ce_fwd(None, 0, 0, None, 0, 0, None, None, 1, 1, 1, 1, 1.0, 1.0, None, None, None, 0, None) < 0
+    assert b"null pointer" in lib.dmc_last_error_string()
+    assert lib.dmc_ema_multi_tensor(None, 0, 0.9, 0.1, None) < 0
+    with pytest.raises(RuntimeError, match="libdinomc"):
+        L.check(-1, "unit test")
+
+
+def test_ema_plan_builder_chunks_on_host():
+    import dinomc_b200
+    L = dinomc_b200._lib
+    lib = L.load()
+    numels = [5, 16384, 16385, 0, 100000]
+    n = len(numels)
+    arr = (L.i64 * n)(*numels)
+    nbytes = lib.dmc_ema_plan_bytes(arr, n)
+    expect_chunks = sum((x + 16383) // 16384 for x in numels)
+    assert nbytes == expect_chunks * 24
+    tp = (L.vp * n)(*[0x1000 * (i + 1) for i in range(n)])
+    sp = (L.vp * n)(*[0x100000 * (i + 1) for i in range(n)])
+    buf = (C.c_uint8 * nbytes)()
+    out = L.i64(0)
+    assert lib.dmc_ema_build_plan(tp, sp, arr, n, buf, nbytes, C.byref(out)) == 0
+    assert out.value == expect_chunks
+    entries = [(int.from_bytes(bytes(buf[i * 24:i * 24 + 8]), "little"),
+                int.from_bytes(bytes(buf[i * 24 + 8:i * 24 + 16]), "little"),
+                int.from_bytes(bytes(buf[i * 24 + 16:i * 24 + 24]), "little")) for i in range(expect_chunks)]
+    assert entries[0] == (0x1000, 0x100000, 5)
+    assert entries[1] == (0x2000, 0x200000, 16384)
+    assert entries[2] == (0x3000, 0x300000, 16384) and entries[3] == (0x3000 + 16384 * 4, 0x300000 + 16384 * 4, 1)
+    assert sum(e[2] for e in entries) == sum(numels)
+    assert lib.dmc_ema_build_plan(tp, sp, arr, n, buf, 8, C.byref(out)) < 0      # buffer too small
+
+
+def test_module_surface_matches_reference_signature():
+    import inspect
+    import dinomc_b200 as D
+    assert list(inspect.signature(D.DINOHead.__init__).parameters)[1:] == [
+        "in_dim", "out_dim", "use_bn", "norm_last_layer", "nlayers", "hidden_dim", "bottleneck_dim"]
+    assert list(inspect.signature(D.DINOLoss.__init__).parameters)[1:] == [
+        "out_dim", "ncrops", "warmup_teacher_temp", "teacher_temp", "warmup_teacher_temp_epochs", "nepochs",
+        "teacher_crops_number", "student_temp", "center_momentum"]
+    assert list(inspect.signature(D.DINOLoss.forward).parameters)[1:] == ["student_output", "teacher_output", "epoch"]
+    h = D.DINOHead(384, 4096)
+    assert [n for n, _ in h.named_parameters()] == [
+        "mlp.0.weight", "mlp.0.bias", "mlp.2.weight", "mlp.2.bias", "mlp.4.weight", "mlp.4.bias",
+        "last_layer.weight_g", "last_layer.weight_v"]
+    assert h.last_layer.weight_g.shape == (4096, 1) and not h.last_layer.weight_g.requires_grad
+    assert torch.all(h.last_layer.weight_g == 1)
+    assert D.DINOHead(384, 64, norm_last_layer=False).last_layer.weight_g.requires_grad
+    one = D.DINOHead(32, 64, nlayers=1)
+    assert [n for n, _ in one.named_parameters()][:2] == ["mlp.weight", "mlp.bias"]
+    bn = D.DINOHead(32, 64, use_bn=True, hidden_dim=16)
+    assert any(isinstance(m, torch.nn.BatchNorm1d) for m in bn.mlp)
+    loss = D.DINOLoss(64, 8, 0.04, 0.07, 3, 10)
+    assert list(loss.state_dict().keys()) == ["center"] and loss.center.shape == (1, 64)
+    assert len(loss.teacher_temp_schedule) == 10 and loss.teacher_temp_schedule[-1] == 0.07
+
+
+@pytest.mark.reference
+def test_init_matches_reference_rng_stream():
+    """Same torch seed -> same initial weights as the reference's DINOHead (container only)."""
+    from oracle import reference_loader
+    if not reference_loader.available():
+        pytest.skip("reference not present")
+    import warnings
+    import dinomc_b200 as D
+    _, vits, _ = reference_loader.load()
+    torch.manual_seed(123)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = vits.DINOHead(48, 256, hidden_dim=64, bottleneck_dim=32)
+    torch.manual_seed(123)
+    ours = D.DINOHead(48, 256, hidden_dim=64, bottleneck_dim=32)
+    rsd, osd = ref.state_dict(), ours.state_dict()
+    assert list(rsd.keys()) == list(osd.keys())
+    for k in rsd:
+        assert torch.equal(rsd[k], osd[k]), k
+    ours.load_state_dict(rsd)                                   # and checkpoints move both ways
+    ref.load_state_dict(osd)

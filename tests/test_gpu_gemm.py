@@ -1,0 +1,155 @@
+"""GPU: the tcgen05 GEMM (dmc_gemm) and the FFMA GEMM (dmc_gemm_simt) through the C ABI, against a
+float64 numpy product of the same (already rounded) operands."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    import dinomc_b200
+    return dinomc_b200.ops, dinomc_b200._lib
+
+
+def _make(M, N, K, a_mn, b_mn, dtype, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(N, K, generator=g)
+    if dtype == torch.bfloat16:
+        A, B = A.bfloat16().float(), B.bfloat16().float()       # exactly representable operands
+    A_st = (A.t().contiguous() if a_mn else A).to(dtype).cuda()
+    B_st = (B.t().contiguous() if b_mn else B).to(dtype).cuda()
+    ref = A.double().numpy() @ B.double().numpy().T
+    return A_st, B_st, ref
+
+
+SHAPES = [(128, 256, 64), (128, 64, 128), (200, 320, 136), (512, 2048, 256), (384, 128, 1000)]
+LAYOUTS = [(False, False), (False, True), (True, False), (True, True)]
+
+
+@pytest.mark.parametrize("a_mn,b_mn", LAYOUTS)
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_bf16(M, N, K, a_mn, b_mn):
+    ops, _ = _ops()
+    A, B, ref = _make(M, N, K, a_mn, b_mn, torch.bfloat16)
+    D = ops.gemm(A, B, M, N, K, a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert rel_err(D.cpu().numpy(), ref) < 2e-5      # exact products, fp32 accumulation
+
+
+@pytest.mark.parametrize("a_mn,b_mn", LAYOUTS)
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_3xtf32(M, N, K, a_mn, b_mn):
+    ops, _ = _ops()
+    A, B, ref = _make(M, N, K, a_mn, b_mn, torch.float32, seed=1)
+    Ah, Al = ops.split_tf32(A)
+    Bh, Bl = ops.split_tf32(B)
+    D = ops.gemm(Ah, Bh, M, N, K, a_mn=a_mn, b_mn=b_mn, A_lo=Al, B_lo=Bl, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert rel_err(D.cpu().numpy(), ref) < 5e-6      # ~fp32 accuracy from three TF32 passes
+
+
+@pytest.mark.parametrize("a_mn,b_mn", LAYOUTS)
+def test_gemm_tf32_single_pass(a_mn, b_mn):
+    ops, _ = _ops()
+    M, N, K = 256, 256, 256
+    A, B, ref = _make(M, N, K, a_mn, b_mn, torch.float32, seed=2)
+    D = ops.gemm(A, B, M, N, K, a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert rel_err(D.cpu().numpy(), ref) < 5e-3      # plain TF32: 10-bit mantissa operands
+
+
+@pytest.mark.parametrize("a_mn,b_mn", LAYOUTS)
+@pytest.mark.parametrize("M,N,K", [(130, 70, 45), (64, 64, 16), (257, 129, 300)])
+def test_gemm_simt(M, N, K, a_mn, b_mn):
+    ops, _ = _ops()
+    A, B, ref = _make(M, N, K, a_mn, b_mn, torch.float32, seed=3)
+    D = ops.gemm(A, B, M, N, K, a_mn=a_mn, b_mn=b_mn, simt=True)
+    torch.cuda.synchronize()
+    assert rel_err(D.cpu().numpy(), ref) < 2e-6
+
+
+@pytest.mark.parametrize("split", [0, 1, 3, 8])
+def test_gemm_split_k(split):
+    """dgrad-shaped problem: tiny output, long contraction -> split-K partials + deterministic reduce."""
+    ops, _ = _ops()
+    M, N, K = 256, 256, 8192
+    A, B, ref = _make(M, N, K, False, True, torch.bfloat16, seed=4)
+    D = ops.gemm(A, B, M, N, K, b_mn=True, split_k=split)
+    D2 = ops.gemm(A, B, M, N, K, b_mn=True, split_k=split)
+    torch.cuda.synchronize()
+    assert rel_err(D.cpu().numpy(), ref) < 2e-5
+    assert torch.equal(D, D2)                          # deterministic (no atomics)
+
+
+def _gelu(x):
+    from oracle.np_oracle import gelu
+    return gelu(x)
+
+
+@pytest.mark.parametrize("simt", [False, True])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_gemm_epilogue(simt, out_dtype):
+    from oracle.np_oracle import gelu, gelu_grad
+    ops, L = _ops()
+    M, N, K = 192, 320, 128
+    dt = torch.float32 if simt else torch.bfloat16
+    A, B, ref = _make(M, N, K, False, False, dt if not simt else torch.bfloat16, seed=5)
+    if simt:
+        A, B = A.float(), B.float()
+    g = torch.Generator().manual_seed(9)
+    scale = (torch.rand(N, generator=g) + 0.5).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    alpha_dev = torch.tensor(0.75, device="cuda")
+    z_ref = ref * scale.cpu().double().numpy() * (0.5 * 0.75) + bias.cpu().double().numpy()
+    tol = 2e-5 if out_dtype == torch.float32 else 1e-2
+    # scale/alpha/bias + GELU forward with saved pre-activation
+    aux = torch.empty(M, N, dtype=out_dtype, device="cuda")
+    D = ops.gemm(A, B, M, N, K, out_dtype=out_dtype, col_scale=scale, bias=bias, alpha=0.5, alpha_dev=alpha_dev,
+                 act=L.ACT_GELU, aux=aux, simt=simt)
+    torch.cuda.synchronize()
+    assert rel_err(aux.float().cpu().numpy(), z_ref) < tol
+    assert rel_err(D.float().cpu().numpy(), gelu(z_ref)) < tol
+    # GELU backward: D = z * gelu'(aux)
+    pre = torch.randn(M, N, generator=g).to(out_dtype).cuda()
+    D = ops.gemm(A, B, M, N, K, out_dtype=out_dtype, act=L.ACT_GELU_BWD, aux=pre, simt=simt)
+    torch.cuda.synchronize()
+    assert rel_err(D.float().cpu().numpy(), ref * gelu_grad(pre.float().cpu().double().numpy())) < tol
+
+
+def test_gemm_headline_shape():
+    """The last-layer forward at its real size (rows 2048, out_dim 65536, bottleneck 256), checked on a
+    random sample of output entries and through linearity in A."""
+    ops, _ = _ops()
+    M, N, K = 2048, 65536, 256
+    g = torch.Generator().manual_seed(7)
+    A = torch.randn(M, K, generator=g).bfloat16().cuda()
+    B = (torch.randn(N, K, generator=g) * 0.06).bfloat16().cuda()
+    D = ops.gemm(A, B, M, N, K, out_dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    rows = torch.randint(0, M, (64,), generator=g)
+    cols = torch.randint(0, N, (64,), generator=g)
+    ref = A[rows].double().cpu().numpy() @ B[cols].double().cpu().numpy().T
+    got = D[rows][:, cols].float().cpu().numpy()
+    assert rel_err(got, ref) < 1e-2                     # bf16 output rounding
+    # linearity: (2A) B^T == 2 (A B^T) exactly in floating point (power-of-two scaling)
+    D2 = ops.gemm((A.float() * 2).bfloat16(), B, M, N, K, out_dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    assert torch.equal(D2[:256].float(), D[:256].float() * 2)
+
+
+def test_gemm_argument_errors():
+    ops, _ = _ops()
+    A = torch.zeros(128, 64, dtype=torch.bfloat16, device="cuda")
+    B = torch.zeros(128, 64, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(ValueError):
+        ops.gemm(A, B, 128, 128, 32)                   # K does not match the operands
+    with pytest.raises(RuntimeError):
+        ops.gemm(A.cpu(), B.cpu(), 128, 128, 64)       # no CPU path
+    A_odd = torch.zeros(128, 20, dtype=torch.bfloat16, device="cuda")[:, :12]   # 40-byte row stride
+    B_odd = torch.zeros(128, 20, dtype=torch.bfloat16, device="cuda")[:, :12]
+    with pytest.raises(RuntimeError, match="16 bytes"):
+        ops.gemm(A_odd, B_odd, 128, 128, 12)

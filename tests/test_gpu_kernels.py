@@ -1,0 +1,183 @@
+"""GPU: the row / loss / EMA kernels through the C ABI against oracle/np_oracle.py."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import np_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    import dinomc_b200
+    return dinomc_b200.ops
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+@pytest.mark.parametrize("n,dim", [(37, 256), (8, 32), (513, 64), (5, 16)])
+def test_normalize_rows(n, dim):
+    ops = _ops()
+    z = _rand(n, dim, seed=1)
+    z[0] = 0.0                                            # exercises the eps clamp (row of zeros)
+    zhat, zb, inv_den = ops.normalize_rows_fwd(z.cuda(), want_bf16=True)
+    zn = z.double().numpy()
+    den = np.maximum(np.sqrt((zn * zn).sum(-1, keepdims=True)), 1e-12)
+    assert rel_err(zhat.cpu().numpy(), zn / den) < 1e-6
+    assert rel_err(zb.float().cpu().numpy(), zn / den) < 5e-3
+    assert rel_err(inv_den.cpu().numpy()[1:], (1.0 / den[1:, 0])) < 1e-6
+    # backward against the oracle's hand-derived formula
+    dzh = _rand(n, dim, seed=2)
+    dz = ops.normalize_rows_bwd(dzh.cuda(), zhat, inv_den)
+    zh = zn / den
+    proj = (dzh.double().numpy() * zh).sum(-1, keepdims=True)
+    ref = (dzh.double().numpy() - proj * zh) / den
+    ref[0] = dzh.double().numpy()[0] / 1e-12
+    assert rel_err(dz.cpu().numpy()[1:], ref[1:]) < 2e-6
+    assert rel_err(dz.cpu().numpy()[0], ref[0]) < 2e-6
+
+
+@pytest.mark.parametrize("K,dim", [(512, 32), (1000, 256), (65, 64)])
+def test_weightnorm(K, dim):
+    ops = _ops()
+    v = _rand(K, dim, seed=3, scale=0.05)
+    g = torch.rand(K, generator=torch.Generator().manual_seed(4)) + 0.5
+    vn, gn = v.double().numpy(), g.double().numpy()[:, None]
+    nrm = np.sqrt((vn * vn).sum(-1, keepdims=True))
+    w_ref = vn * (gn / nrm)
+    w, _, scale, inv_vnorm = ops.weightnorm_fwd(v.cuda(), g.cuda(), "f32")
+    assert rel_err(w.cpu().numpy(), w_ref) < 1e-6
+    wb, _, _, _ = ops.weightnorm_fwd(v.cuda(), g.cuda(), "bf16")
+    assert rel_err(wb.float().cpu().numpy(), w_ref) < 5e-3
+    whi, wlo, _, _ = ops.weightnorm_fwd(v.cuda(), g.cuda(), "tf32x3")
+    assert rel_err((whi.double() + wlo.double()).cpu().numpy(), w_ref) < 1e-6
+    assert torch.all((whi.view(torch.int32) & 0x1FFF) == 0)          # hi part is TF32-exact
+    dw = _rand(K, dim, seed=5)
+    dv, dg = ops.weightnorm_bwd(dw.cuda(), v.cuda(), scale, inv_vnorm, want_dg=True)
+    vhat = vn / nrm
+    dot = (dw.double().numpy() * vhat).sum(-1, keepdims=True)
+    assert rel_err(dg.cpu().numpy(), dot) < 2e-6
+    assert rel_err(dv.cpu().numpy(), (gn / nrm) * (dw.double().numpy() - dot * vhat)) < 2e-6
+    dv2, dg2 = ops.weightnorm_bwd(dw.cuda(), v.cuda(), scale, inv_vnorm, want_dg=False)
+    assert dg2 is None and torch.equal(dv, dv2)
+
+
+@pytest.mark.parametrize("M,N", [(2048, 256), (100, 70), (7, 2048)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_colsum(M, N, dtype):
+    ops = _ops()
+    x = _rand(M, N, seed=6).to(dtype)
+    out = ops.colsum(x.cuda())
+    assert rel_err(out.cpu().numpy(), x.double().numpy().sum(0)) < 1e-5
+
+
+def test_split_and_cast():
+    ops = _ops()
+    x = _rand(1000, 33, seed=7)
+    hi, lo = ops.split_tf32(x.cuda())
+    assert torch.all((hi.view(torch.int32) & 0x1FFF) == 0)
+    assert rel_err((hi.double() + lo.double()).cpu().numpy(), x.double().numpy()) < 3e-7
+    y = ops.cast_bf16(x.cuda())
+    assert torch.equal(y.cpu(), x.bfloat16())                         # round-to-nearest-even, like torch
+
+
+@pytest.mark.parametrize("Nt,K", [(64, 512), (16, 384), (6, 1000), (512, 4096), (40, 65536)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_teacher_stats_colsum(Nt, K, dtype):
+    ops = _ops()
+    t = _rand(Nt, K, seed=8, scale=2.0).to(dtype)
+    c = _rand(K, seed=9, scale=0.3)
+    inv_temp = 1.0 / 0.04
+    stats, colsum = ops.teacher_stats_colsum(t.cuda(), c.cuda(), inv_temp)
+    y = (t.double().numpy() - c.double().numpy()) / 0.04
+    m = y.max(-1)
+    s = np.exp(y - m[:, None]).sum(-1)
+    assert rel_err(stats[:, 0].cpu().numpy(), m) < 1e-6
+    assert rel_err(stats[:, 1].cpu().numpy(), 1.0 / s) < 1e-5
+    assert rel_err(colsum.cpu().numpy(), t.double().numpy().sum(0)) < 1e-6
+
+
+def test_center_update_bit_exact():
+    ops = _ops()
+    K, Nt, W = 1000, 48, 8
+    c = _rand(1, K, seed=10, scale=0.3)
+    colsum = _rand(K, seed=11, scale=5.0)
+    new = ops.center_update(c.cuda(), colsum.cuda(), Nt * W, 0.9)
+    # the reference's fp32 arithmetic: bc / (len*world); center*0.9 + bc*(1-0.9)   (main_dino_mc.py:470-473)
+    bc = colsum.reshape(1, K) / (Nt * W)
+    ref = c * 0.9 + bc * (1 - 0.9)
+    assert new.shape == c.shape and torch.equal(new.cpu(), ref)
+
+
+CE_CASES = [(4, 8, 2, 512), (3, 9, 3, 384), (5, 2, 2, 256), (2, 10, 2, 1000), (3, 7, 3, 4096), (2, 1, 2, 264),
+            (2, 8, 2, 65536)]
+
+
+@pytest.mark.parametrize("B,C,G,K", CE_CASES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_ce_fwd_bwd(B, C, G, K, dtype):
+    ops = _ops()
+    s = _rand(C * B, K, seed=12, scale=1.5).to(dtype)
+    t = _rand(G * B, K, seed=13, scale=1.5).to(dtype)
+    c = _rand(K, seed=14, scale=0.3)
+    temp, ts = 0.05, 0.1
+    sd, td, cd = s.cuda(), t.cuda(), c.cuda()
+    stats, _ = ops.teacher_stats_colsum(td, cd, 1.0 / temp)
+    loss, lse = ops.ce_fwd(sd, td, cd, stats, B, C, G, 1.0 / ts, 1.0 / temp)
+    s64, t64 = s.double().numpy(), t.double().numpy()
+    ref = O.dino_loss_closed(s64, t64, c.double().numpy(), temp, C, G, ts)
+    ref_loop = O.dino_loss_loop(s64, t64, c.double().numpy(), temp, C, G, ts)
+    assert abs(ref - ref_loop) < 1e-9
+    assert abs(float(loss) - ref) / abs(ref) < 1e-5       # fp32 statistics; operands identical to the oracle's
+    gout = torch.tensor(3.0, device="cuda")
+    ds = ops.ce_bwd(sd, td, cd, stats, lse, gout, B, C, G, 1.0 / ts, 1.0 / temp)
+    gref = 3.0 * O.dino_loss_grad(s64, t64, c.double().numpy(), temp, C, G, ts)
+    assert ds.dtype == dtype
+    assert rel_err(ds.float().cpu().numpy(), gref) < (1e-5 if dtype == torch.float32 else 6e-3)
+    # every gradient row sums to zero (softmax minus a distribution): size-independent property
+    rs = ds.float().sum(-1).abs().max().item()
+    assert rs < (1e-6 if dtype == torch.float32 else 1e-2) * 3.0 / (B * ts)
+
+
+def test_ce_rejects_bad_config():
+    ops = _ops()
+    s = torch.zeros(2, 256, device="cuda")
+    t = torch.zeros(2, 256, device="cuda")
+    c = torch.zeros(256, device="cuda")
+    stats = torch.zeros(2, 2, device="cuda")
+    with pytest.raises(RuntimeError, match="no .*pair"):
+        ops.ce_fwd(s, t, c, stats, 2, 1, 1, 10.0, 25.0)   # one crop, one teacher view: n_loss_terms == 0
+
+
+@pytest.mark.parametrize("sizes", [[64], [5, 16384, 16385, 3, 100000], [1 << 20, 7, 1 << 14]])
+def test_ema_bit_exact(sizes):
+    import dinomc_b200
+    g = torch.Generator().manual_seed(15)
+    teacher = [torch.randn(n, generator=g).cuda() for n in sizes]
+    student = [torch.randn(n, generator=g).cuda() for n in sizes]
+    m = float(O.cosine_scheduler(0.996, 1, 10, 7)[5])
+    ref = O.ema_update_fp32([p.cpu().numpy() for p in teacher], [p.cpu().numpy() for p in student], m)
+    keep = [p.clone() for p in student]
+    dinomc_b200.ema_update_(teacher, student, m)
+    dinomc_b200.ema_update_(teacher, student, m)          # cached plan, second step
+    ref = O.ema_update_fp32(ref, [p.cpu().numpy() for p in student], m)
+    for p, r, s0, s1 in zip(teacher, ref, keep, student):
+        assert np.array_equal(p.cpu().numpy(), r)
+        assert torch.equal(s0, s1)                         # student untouched
+
+
+def test_ema_unaligned_views():
+    """Parameters that are 4-byte- but not 16-byte-aligned views take the scalar path; still exact."""
+    import dinomc_b200
+    g = torch.Generator().manual_seed(16)
+    base_t = torch.randn(40003, generator=g).cuda()
+    base_s = torch.randn(40003, generator=g).cuda()
+    teacher, student = [base_t[1:20001], base_t[20001:]], [base_s[3:20003], base_s[20001:]]
+    ref = O.ema_update_fp32([p.cpu().numpy() for p in teacher], [p.cpu().numpy() for p in student], 0.99)
+    dinomc_b200.ema_update_(teacher, student, 0.99)
+    for p, r in zip(teacher, ref):
+        assert np.array_equal(p.cpu().numpy(), r)

@@ -1,0 +1,218 @@
+"""GPU: the drop-in modules (DINOHead, DINOLoss, ema_update_) end to end against the golden vectors
+produced by the reference's own modules, plus size-independent properties at the headline size.
+
+Tolerances are the north star's: loss and gradients 1e-5 relative in fp32 mode, 2e-2 in bf16-GEMM mode;
+center and EMA parameters 1e-6 (EMA is in fact bit-exact).  "Relative" = max|a-b| / max|b| (conftest.rel_err).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+MODES = [("fp32", 1e-5), ("fp32_simt", 1e-5), ("bf16", 2e-2)]
+
+
+def _build(golden, mode):
+    import dinomc_b200 as D
+    c = golden.cfg
+    kw = dict(use_bn=False, norm_last_layer=c["norm_last_layer"], nlayers=c["nlayers"], hidden_dim=c["hidden_dim"],
+              bottleneck_dim=c["bottleneck_dim"])
+    student = D.DINOHead(c["in_dim"], c["out_dim"], **kw).cuda()
+    teacher = D.DINOHead(c["in_dim"], c["out_dim"], **kw).cuda()
+    student.load_state_dict({k: torch.from_numpy(v) for k, v in golden.sd("student").items()})
+    teacher.load_state_dict({k: torch.from_numpy(v) for k, v in golden.sd("teacher").items()})
+    student.precision = teacher.precision = mode
+    for p in teacher.parameters():
+        p.requires_grad = False
+    loss = D.DINOLoss(c["out_dim"], c["ncrops"], golden.cfg["warmup_tt"], golden.cfg["tt"], c["warmup_epochs"],
+                      c["nepochs"], teacher_crops_number=c["G"]).cuda()
+    loss.center.copy_(torch.from_numpy(golden.inputs["center0"]))
+    return D, student, teacher, loss
+
+
+@pytest.mark.parametrize("mode,tol", MODES)
+def test_golden_step(golden, mode, tol):
+    D, student, teacher, loss_mod = _build(golden, mode)
+    c = golden.cfg
+    ref = golden.ref64
+    xs = torch.from_numpy(golden.inputs["x_student"]).cuda().requires_grad_(True)
+    xt = torch.from_numpy(golden.inputs["x_teacher"]).cuda()
+    with torch.no_grad():
+        t_out = teacher(xt)
+    s_out = student(xs)
+    assert s_out.shape == (c["ncrops"] * c["B"], c["out_dim"])
+    assert rel_err(s_out.float().cpu().numpy(), ref["student_logits"]) < tol
+    assert rel_err(t_out.float().cpu().numpy(), ref["teacher_logits"]) < tol
+    loss = loss_mod(s_out, t_out, c["epoch"])
+    assert loss.dim() == 0 and loss.dtype == torch.float32
+    assert abs(float(loss) - float(ref["loss1"])) / abs(float(ref["loss1"])) < tol
+    loss.backward()
+    assert rel_err(xs.grad.cpu().numpy(), ref["grad.x"]) < tol
+    n_checked = 0
+    for name, p in student.named_parameters():
+        key = "grad." + name
+        if key in ref:
+            assert p.grad is not None, name
+            assert rel_err(p.grad.cpu().numpy().reshape(ref[key].shape), ref[key]) < tol, name
+            n_checked += 1
+        else:
+            assert p.grad is None, name                       # frozen weight_g gets no gradient
+    assert n_checked >= 3
+    # center: updated AFTER the loss, from the teacher logits (1e-6 in fp32 modes)
+    ctol = 1e-6 if mode != "bf16" else 2e-3
+    assert loss_mod.center.shape == (1, c["out_dim"])
+    assert rel_err(loss_mod.center.cpu().numpy(), ref["center1"]) < ctol
+    with torch.no_grad():
+        loss2 = loss_mod(s_out.detach(), t_out, c["epoch"])     # second call sees the NEW center
+    assert abs(float(loss2) - float(ref["loss2"])) / abs(float(ref["loss2"])) < tol
+    assert rel_err(loss_mod.center.cpu().numpy(), ref["center2"]) < ctol
+    assert list(loss_mod.state_dict().keys()) == ["center"]
+    # EMA over the head parameters, zip order = registration order (bit-exact in every mode)
+    D.ema_update_(list(teacher.parameters()), list(student.parameters()), float(golden.inputs["ema_m"]))
+    for name, p in teacher.named_parameters():
+        assert np.array_equal(p.detach().cpu().numpy(), golden.ref32["ema." + name]), name
+
+
+def test_auto_precision_follows_autocast(golden):
+    if golden.name != "mc_wide":
+        pytest.skip("one case is enough")
+    D, student, teacher, loss_mod = _build(golden, None)
+    xs = torch.from_numpy(golden.inputs["x_student"]).cuda()
+    assert student(xs).dtype == torch.float32
+    with torch.autocast("cuda", dtype=torch.float16):
+        out = student(xs)
+    assert out.dtype == torch.bfloat16
+
+
+def test_grad_scaler_and_amp(golden):
+    """The reference's default AMP path (main_dino_mc.py:372,393-400): autocast + GradScaler."""
+    if golden.name != "mc_small":
+        pytest.skip("one case is enough")
+    D, student, teacher, loss_mod = _build(golden, None)
+    c = golden.cfg
+    xs = torch.from_numpy(golden.inputs["x_student"]).cuda()
+    xt = torch.from_numpy(golden.inputs["x_teacher"]).cuda()
+    scaler = torch.amp.GradScaler("cuda", init_scale=1024.0)
+    opt = torch.optim.SGD([p for p in student.parameters() if p.requires_grad], lr=0.0)
+    with torch.autocast("cuda", dtype=torch.float16):
+        with torch.no_grad():
+            t_out = teacher(xt)
+        s_out = student(xs)
+        loss = loss_mod(s_out, t_out, c["epoch"])
+    scaler.scale(loss).backward()
+    scaler.unscale_(opt)
+    ref = golden.ref64
+    assert abs(float(loss) - float(ref["loss1"])) / abs(float(ref["loss1"])) < 2e-2
+    g = student.last_layer.weight_v.grad
+    assert torch.isfinite(g).all()
+    assert rel_err(g.cpu().numpy(), ref["grad.last_layer.weight_v"]) < 2e-2
+
+
+def test_state_dict_round_trip_and_names(golden):
+    D, student, teacher, loss_mod = _build(golden, "fp32")
+    names = [n for n, _ in student.named_parameters()]
+    assert names[-2:] == ["last_layer.weight_g", "last_layer.weight_v"]
+    assert student.last_layer.weight_g.shape == (golden.cfg["out_dim"], 1)
+    assert student.last_layer.weight_g.requires_grad == (not golden.cfg["norm_last_layer"])
+    assert any("last_layer" in n for n in names)              # cancel_gradients_last_layer keys on this substring
+    teacher.load_state_dict(student.state_dict())             # main_dino_mc.py:262
+    for a, b in zip(student.state_dict().values(), teacher.state_dict().values()):
+        assert torch.equal(a, b)
+
+
+def test_cpu_tensors_are_rejected():
+    import dinomc_b200 as D
+    head = D.DINOHead(32, 64, hidden_dim=32, bottleneck_dim=16)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        head(torch.zeros(4, 32))
+    loss = D.DINOLoss(64, 2, 0.04, 0.04, 0, 2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        loss(torch.zeros(4, 64), torch.zeros(4, 64), 0)
+
+
+def test_ddp_wrapping_single_rank(golden):
+    """DDP must see ordinary leaf parameters and get their gradients through the custom Functions."""
+    if golden.name != "mc_small":
+        pytest.skip("one case is enough")
+    import os
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    created = False
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29577")
+        dist.init_process_group("nccl", rank=0, world_size=1)
+        created = True
+    try:
+        D, student, teacher, loss_mod = _build(golden, "fp32")
+        c = golden.cfg
+        ddp = DDP(student, device_ids=[0])
+        xs = torch.from_numpy(golden.inputs["x_student"]).cuda()
+        xt = torch.from_numpy(golden.inputs["x_teacher"]).cuda()
+        with torch.no_grad():
+            t_out = teacher(xt)
+        loss = loss_mod(ddp(xs), t_out, c["epoch"])
+        loss.backward()
+        ref = golden.ref64
+        assert abs(float(loss) - float(ref["loss1"])) / abs(float(ref["loss1"])) < 1e-5
+        assert rel_err(student.last_layer.weight_v.grad.cpu().numpy(), ref["grad.last_layer.weight_v"]) < 1e-5
+        assert rel_err(loss_mod.center.cpu().numpy(), ref["center1"]) < 1e-6   # all_reduce over world 1
+    finally:
+        if created:
+            dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_headline_size_properties(mode):
+    """ViT-S/8 head at BASELINE cfg2 size (D=384, K=65536, B=256/4 to bound memory in fp32, 2+6 crops):
+    properties that need no oracle at this size."""
+    import dinomc_b200 as D
+    from oracle import np_oracle as O
+    torch.manual_seed(0)
+    B, C, G, K, Din = (256 if mode == "bf16" else 64), 8, 2, 65536, 384
+    student = D.DINOHead(Din, K).cuda()
+    teacher = D.DINOHead(Din, K).cuda()
+    teacher.load_state_dict(student.state_dict())
+    student.precision = teacher.precision = mode
+    loss_mod = D.DINOLoss(K, C, 0.04, 0.04, 0, 10, teacher_crops_number=G).cuda()
+    xs = torch.randn(C * B, Din, device="cuda", requires_grad=True)
+    xt = torch.randn(G * B, Din, device="cuda")
+    with torch.no_grad():
+        t_out = teacher(xt)
+    s_out = student(xs)
+    s_out.retain_grad()
+    center0 = loss_mod.center.clone()
+    loss = loss_mod(s_out, t_out, 0)
+    loss.backward()
+    # (1) rows of logits are bounded by ||zhat|| * ||w_k|| = 1 * g_k = 1
+    assert s_out.float().abs().max().item() <= 1.0 + 2e-2
+    # (2) loss equals the oracle's closed form evaluated on OUR logits for a few samples' worth of rows
+    sub = slice(0, 4)
+    idx_s = torch.cat([torch.arange(v * B, v * B + 4) for v in range(C)])
+    idx_t = torch.cat([torch.arange(i * B, i * B + 4) for i in range(G)])
+    ref_sub = O.dino_loss_closed(s_out.detach()[idx_s].double().cpu().numpy(), t_out[idx_t].double().cpu().numpy(),
+                                 center0.double().cpu().numpy(), 0.04, C, G)
+    full_ref_scale = abs(ref_sub)
+    assert abs(float(loss) - ref_sub) / full_ref_scale < 5e-2          # 4 samples estimate the batch mean
+    # (3) every dlogits row sums to ~0 and the whole gradient is finite
+    gl = s_out.grad.float()
+    assert torch.isfinite(gl).all()
+    assert gl.sum(-1).abs().max().item() < 1e-2 / B
+    # (4) center = 0.9*0 + 0.1*mean(teacher logits)
+    ref_c = 0.1 * t_out.float().mean(0, keepdim=True)
+    assert rel_err(loss_mod.center.cpu().numpy(), ref_c.double().cpu().numpy()) < (1e-5 if mode == "fp32" else 1e-3)
+    # (5) frozen gain: no grad; direction grads orthogonal to v (weight-norm property: dv . v = 0 per row)
+    assert student.last_layer.weight_g.grad is None
+    dv, v = student.last_layer.weight_v.grad, student.last_layer.weight_v.detach()
+    ortho = (dv * v).sum(-1).abs().max().item()
+    assert ortho < 1e-4 * dv.abs().max().item() + 1e-12
+    # (6) EMA with m=1 is the identity, with m=0 copies the student
+    tp, sp = list(teacher.parameters()), list(student.parameters())
+    before = [p.detach().clone() for p in tp]
+    D.ema_update_(tp, sp, 1.0)
+    assert all(torch.equal(a, b) for a, b in zip(before, tp))
+    D.ema_update_(tp, sp, 0.0)
+    assert all(torch.equal(a.detach(), b.detach()) for a, b in zip(tp, sp))
