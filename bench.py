@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- the DINO-MC head + loss + center + EMA step on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2] [--mode bf16|fp32]
+
+One "step"  = teacher-head forward (no grad) on [G*B, D] + student-head forward on [C*B, D]
++ DINOLoss.forward (teacher statistics, column sum, center all-reduce over ranks, center EMA) + backward to
+the head parameters AND the feature tensor (+ DDP/NCCL gradient all-reduce when N > 1) + EMA of the whole
+backbone+head parameter list.  Synthetic features, reference-shaped random-init weights.
+
+Prints ONE JSON line (rank 0).  `value` = samples/s with inputs resident in HBM; `e2e` = the same step
+through the public modules with HOST (pinned) feature buffers copied in and the loss read back each step;
+`roofline` = the dominant kernel, timed live with CUDA events; `cpu_baseline` = oracle/torch_port.py (the
+reference's eager-PyTorch path restated) timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+# ----------------------------------------------------------------------------------------------------
+# workloads (BASELINE.json configs; cfg2 is the headline the metric is quoted on)
+# ----------------------------------------------------------------------------------------------------
+WORKLOADS = {
+    "cfg1": dict(arch="vit_small_p8", D=384, K=65536, B=32, C=8, G=2, note="reference CPU-runnable case"),
+    "cfg2": dict(arch="vit_small_p8", D=384, K=65536, B=256, C=8, G=2, note="ViT-S/8 headline, per GPU"),
+    "cfg3": dict(arch="resnet50", D=2048, K=65536, B=512, C=8, G=2, note="ResNet-50 features"),
+    "cfg4": dict(arch="swin_t", D=768, K=65536, B=256, C=8, G=2, note="Swin-tiny features"),
+    "cfg5": dict(arch="wide_resnet50_2", D=2048, K=65536, B=256, C=8, G=2, note="WRN-50-2, out_dim sweep via --out-dim"),
+}
+H, BN = 2048, 256   # DINOHead hidden / bottleneck (utils/vision_transformer.py:261)
+
+
+def backbone_param_shapes(arch: str):
+    """Shapes of the backbone parameters the EMA runs over (no backbone forward is ever executed)."""
+    if arch == "vit_small_p8":   # utils/vision_transformer.py:134-256, vit_small(patch_size=8)
+        E, depth, patch, img = 384, 12, 8, 224
+        shapes = [(1, 1, E), (1, 1 + (img // patch) ** 2, E), (E, 3, patch, patch), (E,)]
+        for _ in range(depth):
+            shapes += [(E,), (E,), (3 * E, E), (3 * E,), (E, E), (E,), (E,), (E,), (4 * E, E), (4 * E,), (E, 4 * E), (E,)]
+        shapes += [(E,), (E,)]
+        return shapes
+    import torchvision
+    with torch.device("meta"):
+        m = getattr(torchvision.models, arch)()
+    for attr in ("fc", "head"):                # MultiCropWrapper replaces these by Identity (utils/utils.py:623)
+        if hasattr(m, attr):
+            setattr(m, attr, torch.nn.Identity())
+    return [tuple(p.shape) for p in m.parameters()]
+
+
+def roofline_model(w, P, logit_bytes):
+    """Algorithmic FLOPs and bytes per step per GPU (SURVEY.md 8d formulas)."""
+    D, K, B, C, G = w["D"], w["K"], w["B"], w["C"], w["G"]
+    Ns, Nt = C * B, G * B
+    f_mlp = lambda n: 2 * n * (D * H + H * H + H * BN)
+    f_last = lambda n: 2 * n * BN * K
+    flops = 3 * (f_mlp(Ns) + f_last(Ns)) + f_mlp(Nt) + f_last(Nt)
+    e = logit_bytes
+    nbytes = (e * K * (6 * Ns + 4 * Nt) + 7 * 4 * K * BN + 12 * P + 4 * (D + 2 * H + BN) * (3 * Ns + Nt)
+              + 16 * (D * H + H * H + H * BN) + 12 * K)
+    return flops, nbytes
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1400.0, source="fallback")
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks sampler (NVML), runs during the timed region
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._stop, self._t = [], set(), None, threading.Event(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        if self._t is not None:
+            self._stop.set()
+            self._t.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------
+class Step:
+    """Owns the modules/buffers of one rank and runs one whole step on the current stream."""
+
+    def __init__(self, w, mode, rank, world, device):
+        import dinomc_b200 as D
+        self.D, self.w, self.world, self.device = D, w, world, device
+        torch.manual_seed(0)                                          # identical weights on every rank
+        Din, K, B, C, G = w["D"], w["K"], w["B"], w["C"], w["G"]
+        self.student = D.DINOHead(Din, K).to(device)
+        self.teacher = D.DINOHead(Din, K).to(device)
+        self.teacher.load_state_dict(self.student.state_dict())      # main_dino_mc.py:262
+        for p in self.teacher.parameters():
+            p.requires_grad = False
+        self.student.precision = self.teacher.precision = mode
+        self.loss_mod = D.DINOLoss(K, C, 0.04, 0.04, 0, 100, teacher_crops_number=G).to(device)
+        g = torch.Generator(device="cpu").manual_seed(99)
+        shapes = backbone_param_shapes(w["arch"])
+        self.bb_student = [(torch.randn(s, generator=g) * 0.02).to(device) for s in shapes]
+        self.bb_teacher = [t.clone() for t in self.bb_student]
+        # zip order of main_dino_mc.py:405: MultiCropWrapper registers backbone first, then head
+        self.ema_student = self.bb_student + list(self.student.parameters())
+        self.ema_teacher = self.bb_teacher + list(self.teacher.parameters())
+        self.P = sum(t.numel() for t in self.ema_student)
+        self.n_tensors = len(self.ema_student)
+        self.model = self.student
+        if world > 1:
+            from torch.nn.parallel import DistributedDataParallel as DDP
+            self.model = DDP(self.student, device_ids=[device.index])  # main_dino_mc.py:260
+        gs = torch.Generator(device="cpu").manual_seed(1234 + rank)
+        gt = torch.Generator(device="cpu").manual_seed(4321 + rank)
+        self.x_student_host = torch.randn(C * B, Din, generator=gs).pin_memory()
+        self.x_teacher_host = torch.randn(G * B, Din, generator=gt).pin_memory()
+        self.x_student = self.x_student_host.to(device).requires_grad_(True)
+        self.x_teacher = self.x_teacher_host.to(device)
+        self.loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+        self.m = 0.996
+
+    def run(self, x_student=None, x_teacher=None):
+        xs = self.x_student if x_student is None else x_student
+        xt = self.x_teacher if x_teacher is None else x_teacher
+        for p in self.student.parameters():
+            p.grad = None
+        xs.grad = None
+        with torch.no_grad():
+            t_out = self.teacher(xt)
+        s_out = self.model(xs)
+        loss = self.loss_mod(s_out, t_out, 0)
+        loss.backward()
+        self.D.ema_update_(self.ema_teacher, self.ema_student, self.m)
+        return loss
+
+    def run_e2e(self):
+        """Public-API step from HOST buffers: H2D of this step's features, D2H of the loss."""
+        xs = self.x_student_host.to(self.device, non_blocking=True).requires_grad_(True)
+        xt = self.x_teacher_host.to(self.device, non_blocking=True)
+        loss = self.run(xs, xt)
+        self.loss_host.copy_(loss.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self.loss_host)
+
+
+def timed(fn, steps, world, device):
+    """barrier + sync, K steps between CUDA events on the current stream, sync + barrier; max over ranks."""
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    return ms
+
+
+def per_kernel_times(step, steps):
+    """Per-op device time, measured live with CUDA events around every libdinomc call (ops.profile)."""
+    ops = step.D.ops
+    ops.profile_begin()
+    for _ in range(steps):
+        step.run()
+    torch.cuda.synchronize()
+    return ops.profile_end()
+
+
+def cpu_baseline(w, sample_B, steps, warmup):
+    """oracle/torch_port.py (the reference's eager path restated) on the host cores, bounded sample."""
+    from oracle import torch_port as T
+    torch.set_num_threads(os.cpu_count() or 1)
+    Din, K, C, G = w["D"], w["K"], w["C"], w["G"]
+    sp = T.make_head_params(Din, K, seed=0)
+    tp = {k: v.detach().clone() for k, v in sp.items()}
+    g = torch.Generator().manual_seed(99)
+    shapes = backbone_param_shapes(w["arch"])
+    bb_s = [torch.randn(s, generator=g) * 0.02 for s in shapes]
+    bb_t = [t.clone() for t in bb_s]
+    st = T.LossState(K, C, 0.04, 0.04, 0, 100, teacher_crops_number=G)
+    xs = torch.randn(C * sample_B, Din, generator=g)
+    xt = torch.randn(G * sample_B, Din, generator=g)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        T.step(xs, xt, sp, tp, st, 0, 0.996, ema_extra=(bb_t, bb_s))
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    med = float(np.median(times))
+    return dict(value=sample_B / med, unit="samples/s", cores=torch.get_num_threads(), kind="port",
+                sample=f"B={sample_B} of {w['B']} samples per step (same D={Din}, K={K}, {C} crops, full "
+                       f"{sum(t.numel() for t in bb_s) / 1e6 + sum(v.numel() for v in sp.values()) / 1e6:.1f}M-param EMA), "
+                       f"{warmup} warm-up + {steps} steps, torch CPU fp32, median",
+                ms_per_step=med * 1e3)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32", "fp32_simt"])
+    ap.add_argument("--out-dim", type=int, default=None)
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--graph", type=int, default=1, help="replay the N=1 step from a CUDA graph (0 = eager launches)")
+    ap.add_argument("--cpu-sample-batch", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    w = dict(WORKLOADS[args.workload])
+    if args.out_dim:
+        w["K"] = args.out_dim
+    if args.batch:
+        w["B"] = args.batch
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    warmup = max(args.warmup, 3)
+    cfg = {"workload": f"{args.workload}: {w['note']}; D={w['D']} out_dim={w['K']} batch/GPU={w['B']} "
+                       f"crops={w['G']}+{w['C'] - w['G']}; EMA over {w['arch']} backbone + head",
+           "global_batch": w["B"] * world, "parallelism": f"dp{world}",
+           "l2": "per-step working set (logits + gradients > 1 GiB) exceeds the 126 MB L2; no explicit flush"}
+
+    if args.impl == "reference":
+        # The reference's own (eager PyTorch) path on this box's host cores; rank 0 only.
+        if rank != 0:
+            return
+        steps = min(args.steps, 10)
+        cb = cpu_baseline(w, args.cpu_sample_batch, steps, min(warmup, 3))
+        line = {"impl": "reference", "metric": "DINO head+loss+center+EMA step samples/sec", "value": cb["value"],
+                "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(warmup, 3),
+                "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": cfg,
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py (impl=ours) needs a CUDA device; there is no CPU fallback"
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    import dinomc_b200 as D
+    D._lib.check(D._lib.load().dmc_device_check(local_rank), "dmc_device_check")
+
+    step = Step(w, args.mode, rank, world, device)
+    ops = D.ops
+    for _ in range(warmup):
+        step.run()
+    torch.cuda.synchronize()
+
+    use_graph = bool(args.graph) and world == 1
+    graph = None
+    if use_graph:
+        # the whole step is stream-ordered libdinomc launches on fixed buffers: capture once, replay K times
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step.run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step.static_loss = step.run()
+        torch.cuda.synchronize()
+        run_value = graph.replay
+    else:
+        run_value = step.run
+
+    l0 = ops.launch_count
+    step.run()
+    launches_per_step = ops.launch_count - l0
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_total = timed(run_value, args.steps, world, device)
+    clocks = sampler.stop()
+    ms_step = ms_total / args.steps
+    value = w["B"] * world / (ms_step * 1e-3)
+
+    # end-to-end: host buffers in, loss out, through the public modules (eager launches)
+    for _ in range(3):
+        step.run_e2e()
+    ms_e2e = timed(step.run_e2e, args.steps, world, device) / args.steps
+    h2d = step.x_student_host.numel() * 4 + step.x_teacher_host.numel() * 4
+    e2e = {"value": w["B"] * world / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
+
+    # live per-kernel timing for the roofline object
+    peaks = load_peaks()
+    prof = per_kernel_times(step, min(args.steps, 20))
+    logit_bytes = 2 if args.mode == "bf16" else 4
+    flops, nbytes = roofline_model(w, step.P, logit_bytes)
+    t_roof_ms = max(flops / (peaks["bf16_tflops"] * 1e12), nbytes / (peaks["hbm_gbs"] * 1e9)) * 1e3
+    kernels = []
+    Ns, Nt, K = w["C"] * w["B"], w["G"] * w["B"], w["K"]
+    alg_bytes = {   # algorithmic bytes per launch of the HBM-bound kernels
+        "ce_bwd": logit_bytes * K * (2 * Ns + Nt),
+        "ce_fwd": logit_bytes * K * (Ns + Nt),
+        "teacher_stats_colsum": logit_bytes * K * Nt,
+        "ema": 12 * step.P,
+        "gemm_last_fwd_student": logit_bytes * K * Ns + 2 * BN * (K + Ns),
+        "gemm_last_wgrad": logit_bytes * K * Ns + 4 * K * BN,
+        "gemm_last_dgrad": logit_bytes * K * Ns + 2 * K * BN,
+    }
+    for name, (ms, calls) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        k = {"kernel": name, "ms_per_step": ms, "calls_per_step": calls}
+        if name in alg_bytes:
+            k["alg_GB"] = alg_bytes[name] / 1e9
+            k["GBps"] = alg_bytes[name] / 1e9 / (ms * 1e-3)
+            k["frac_of_hbm_peak"] = k["GBps"] / peaks["hbm_gbs"]
+        kernels.append(k)
+    dom = next((k for k in kernels if "GBps" in k), None)
+    roofline = None
+    if dom is not None:
+        roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["GBps"], "peak": peaks["hbm_gbs"],
+                    "unit": "GB/s", "frac": dom["frac_of_hbm_peak"], "traffic": None, "peak_source": peaks["source"],
+                    "step": {"t_roof_ms": t_roof_ms, "alg_GB": nbytes / 1e9, "alg_GFLOP": flops / 1e9,
+                             "frac_of_step_roofline": t_roof_ms / ms_step},
+                    "kernels": kernels[:12]}
+
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        c = cpu_baseline(w, args.cpu_sample_batch, 5, 2)
+        cb = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": "DINO head+loss+center+EMA step samples/sec", "value": value, "unit": "samples/s",
+                "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic", "config": cfg,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+                "launch_mode": "cuda_graph" if use_graph else "eager", "roofline": roofline, "cpu_baseline": cb,
+                "ema_params": step.P, "ema_tensors": step.n_tensors}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

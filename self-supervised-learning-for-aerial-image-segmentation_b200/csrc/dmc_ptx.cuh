@@ -121,14 +121,18 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---- descriptors -----------------------------------------------------------------------------
 // Shared-memory matrix descriptor (sm_100 "version 1"), 128-byte swizzle.
 //   bits [0,14)  start address >> 4          bits [16,30) leading-dim byte offset >> 4
-//   bits [32,46) stride-dim byte offset >> 4 bits [46,48) version = 1       bits [61,64) layout (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   bits [32,46) stride-dim byte offset >> 4 bits [46,48) version = 1
+//   bits [61,64) layout: 2 = SWIZZLE_128B (16-byte swizzle atoms, pattern repeats every 8 rows of 128 B),
+//                        1 = SWIZZLE_128B_BASE32B (32-byte atoms, repeats every 4 rows) -- the only layout
+//                            tcgen05 accepts for MN-major 32-bit (tf32) operands.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                         uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3fffu);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fffu) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fffu) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(layout_type) << 61;
   return d;
 }
 // Instruction descriptor for kind::f16 / kind::tf32, fp32 accumulate, dense.

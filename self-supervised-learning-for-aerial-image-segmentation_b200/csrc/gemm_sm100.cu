@@ -142,6 +142,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   constexpr int BOX_MN = kRowBytes / ESZ;        // MN-major box width in elements (64 / 32)
   constexpr uint32_t kBoxBytes = BLOCK_K * kRowBytes;   // one MN-major box: BLOCK_K k-rows x 128 B
   constexpr bool kTf32 = (ESZ == 4);
+  constexpr uint32_t kMnSbo = kTf32 ? 512 : 1024;        // MN-major stride between swizzle-pattern repeats along K
+  constexpr uint32_t kMnLayout = kTf32 ? 1 : 2;          // SWIZZLE_128B_BASE32B for tf32, SWIZZLE_128B for bf16
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -239,9 +241,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             // K-major: rows of 128 B, 8-row groups 1024 B apart (SBO); advance 32 B per MMA inside the swizzle row.
             // MN-major: boxes of BLOCK_K k-rows x 128 B; LBO = box stride along MN, SBO = 1024 B (8 k-rows);
             //           advance UMMA_K k-rows = UMMA_K * 128 B per MMA.
-            const uint64_t da = A_MN ? ptx::make_smem_desc_sw128(a_addr + k * (UMMA_K * kRowBytes), kBoxBytes, 1024)
+            //           32-bit operands must use the 32-byte-atom swizzle there (pattern repeats every 4 k-rows: SBO = 512 B).
+            const uint64_t da = A_MN ? ptx::make_smem_desc_sw128(a_addr + k * (UMMA_K * kRowBytes), kBoxBytes, kMnSbo, kMnLayout)
                                      : ptx::make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? ptx::make_smem_desc_sw128(b_addr + k * (UMMA_K * kRowBytes), kBoxBytes, 1024)
+            const uint64_t db = B_MN ? ptx::make_smem_desc_sw128(b_addr + k * (UMMA_K * kRowBytes), kBoxBytes, kMnSbo, kMnLayout)
                                      : ptx::make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
             ptx::umma<kTf32>(d_tmem, da, db, idesc, (vk > vk0 || k > 0) ? 1u : 0u);
           }
@@ -372,7 +375,8 @@ EncodeTiledFn get_encode_fn() {
 
 // Tensor map over a row-major matrix with `rows` rows of `cols` contiguous elements (row stride ld),
 // box = {box_cols (inner, 128 bytes), box_rows}, 128B swizzle, out-of-bounds elements read as zero.
-int make_tmap(CUtensorMap* tm, const void* base, int esz, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+int make_tmap(CUtensorMap* tm, const void* base, int esz, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+              bool atom32 = false) {
   EncodeTiledFn fn = get_encode_fn();
   DMC_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   DMC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "dmc_gemm: operand base pointer must be 16-byte aligned");
@@ -383,7 +387,8 @@ int make_tmap(CUtensorMap* tm, const void* base, int esz, int64_t rows, int64_t 
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DMC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
 }
@@ -476,11 +481,11 @@ extern "C" int dmc_gemm(const dmc_gemm_args* a, void* stream) {
   CUtensorMap tA0, tA1, tB0, tB1;
   int rc;
   auto mapA = [&](CUtensorMap* tm, const void* base) {
-    return a->a_mn_major ? make_tmap(tm, base, esz, a->K, a->M, a->lda, box_mn, block_k)      // stored [K,M]
+    return a->a_mn_major ? make_tmap(tm, base, esz, a->K, a->M, a->lda, box_mn, block_k, esz == 4)   // stored [K,M]
                          : make_tmap(tm, base, esz, a->M, a->K, a->lda, block_k, kBlockM);    // stored [M,K]
   };
   auto mapB = [&](CUtensorMap* tm, const void* base) {
-    return a->b_mn_major ? make_tmap(tm, base, esz, a->K, a->N, a->ldb, box_mn, block_k)      // stored [K,N]
+    return a->b_mn_major ? make_tmap(tm, base, esz, a->K, a->N, a->ldb, box_mn, block_k, esz == 4)   // stored [K,N]
                          : make_tmap(tm, base, esz, a->N, a->K, a->ldb, block_k, pl.block_n); // stored [N,K]
   };
   if ((rc = mapA(&tA0, a->A))) return rc;

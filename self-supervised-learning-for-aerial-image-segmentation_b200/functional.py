@@ -81,11 +81,11 @@ class MlpFn(torch.autograd.Function):
             bias = None if b is None else b.detach().float().contiguous()
             if li < n - 1:
                 z = torch.empty((rows, fo), dtype=sd, device=x.device)
-                h = mm(mode, acts[li], wop, rows, fo, fi, out_dtype=sd, bias=bias, act=L.ACT_GELU, aux=z)
+                h = mm(mode, acts[li], wop, rows, fo, fi, out_dtype=sd, bias=bias, act=L.ACT_GELU, aux=z, tag="gemm_mlp_fwd")
                 zs.append(z)
                 acts.append(prep(h, mode))
             else:
-                out = mm(mode, acts[li], wop, rows, fo, fi, out_dtype=torch.float32, bias=bias)
+                out = mm(mode, acts[li], wop, rows, fo, fi, out_dtype=torch.float32, bias=bias, tag="gemm_mlp_fwd")
         ctx.mode, ctx.n, ctx.rows = mode, n, rows
         ctx.acts, ctx.wops, ctx.zs = acts, wops, zs
         ctx.shapes = [tuple(wb[2 * li].shape) for li in range(n)]
@@ -104,16 +104,17 @@ class MlpFn(torch.autograd.Function):
             fo, fi = ctx.shapes[li]
             # wgrad: dW[fo,fi] = d^T . act   (both operands MN-major straight from their row-major storage)
             if ctx.needs_input_grad[2 + 2 * li]:
-                grads[2 * li] = mm(mode, d, ctx.acts[li], fo, fi, rows, a_mn=True, b_mn=True, out_dtype=torch.float32)
+                grads[2 * li] = mm(mode, d, ctx.acts[li], fo, fi, rows, a_mn=True, b_mn=True, out_dtype=torch.float32,
+                                   tag="gemm_mlp_wgrad")
             if ctx.has_bias[li] and ctx.needs_input_grad[3 + 2 * li]:
                 grads[2 * li + 1] = ops.colsum(d_full)
             if li > 0:
                 # dgrad with gelu'(z_{li-1}) fused: d_prev = (d . W) * gelu'(z)
                 d_full = mm(mode, d, ctx.wops[li], rows, fi, fo, b_mn=True, out_dtype=sd, act=L.ACT_GELU_BWD,
-                            aux=ctx.zs[li - 1])
+                            aux=ctx.zs[li - 1], tag="gemm_mlp_dgrad")
                 d = prep(d_full, mode)
             elif ctx.needs_input_grad[1]:
-                dx = mm(mode, d, ctx.wops[0], rows, fi, fo, b_mn=True, out_dtype=torch.float32)
+                dx = mm(mode, d, ctx.wops[0], rows, fi, fo, b_mn=True, out_dtype=torch.float32, tag="gemm_mlp_dgrad")
         return (None, dx, *grads)
 
 
@@ -139,7 +140,8 @@ class NormLastLayerFn(torch.autograd.Function):
             zop = Operand(zhat)
             w, _, scale, inv_vnorm = ops.weightnorm_fwd(v.detach(), g.detach().reshape(-1), "f32")
             wop = Operand(w)
-        logits = mm(mode, zop, wop, rows, K, dim, out_dtype=store_dtype(mode))
+        who = "student" if any(ctx.needs_input_grad) else "teacher"
+        logits = mm(mode, zop, wop, rows, K, dim, out_dtype=store_dtype(mode), tag="gemm_last_fwd_" + who)
         ctx.mode = mode
         ctx.zop, ctx.wop = zop, wop
         ctx.save_for_backward(zhat, inv_den, v.detach(), scale, inv_vnorm)
@@ -157,11 +159,11 @@ class NormLastLayerFn(torch.autograd.Function):
         dz = dg = dv = None
         if ctx.needs_input_grad[1]:
             # dgrad: contraction over out_dim (split-K), W read MN-major from its [K,dim] storage
-            dzhat = mm(mode, d, ctx.wop, rows, dim, K, b_mn=True, out_dtype=torch.float32)
+            dzhat = mm(mode, d, ctx.wop, rows, dim, K, b_mn=True, out_dtype=torch.float32, tag="gemm_last_dgrad")
             dz = ops.normalize_rows_bwd(dzhat, zhat, inv_den)
         if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
             # wgrad: dW[K,dim] = dlogits^T . zhat, both MN-major
-            dw = mm(mode, d, ctx.zop, K, dim, rows, a_mn=True, b_mn=True, out_dtype=torch.float32)
+            dw = mm(mode, d, ctx.zop, K, dim, rows, a_mn=True, b_mn=True, out_dtype=torch.float32, tag="gemm_last_wgrad")
             dv, dg = ops.weightnorm_bwd(dw, v, scale, inv_vnorm, want_dg=ctx.needs_input_grad[2])
             if not ctx.needs_input_grad[3]:
                 dv = None

@@ -25,6 +25,47 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# ---------------------------------------------------------------------------------------------
+# optional live profiling: CUDA events on the launching stream around every libdinomc call
+# ---------------------------------------------------------------------------------------------
+_prof_events = None
+
+
+def profile_begin():
+    global _prof_events
+    _prof_events = []
+
+
+def profile_end():
+    """Returns {op name: (total ms, calls)}; call after torch.cuda.synchronize()."""
+    global _prof_events
+    ev, _prof_events = _prof_events, None
+    out = {}
+    for name, e0, e1 in ev or []:
+        ms, n = out.get(name, (0.0, 0))
+        out[name] = (ms + e0.elapsed_time(e1), n + 1)
+    return out
+
+
+class _timed:
+    __slots__ = ("name", "e0")
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _prof_events is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if _prof_events is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _prof_events.append((self.name, self.e0, e1))
+        return False
+
+
 def _dt(t: torch.Tensor) -> int:
     if t.dtype == torch.float32:
         return L.DMC_F32
@@ -81,7 +122,8 @@ def tma_ok(t: torch.Tensor) -> bool:
 
 
 def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, A_lo=None, B_lo=None, out=None, out_dtype=torch.float32,
-         col_scale=None, bias=None, alpha=1.0, alpha_dev=None, act=L.ACT_NONE, aux=None, simt=False, split_k=0):
+         col_scale=None, bias=None, alpha=1.0, alpha_dev=None, act=L.ACT_NONE, aux=None, simt=False, split_k=0,
+         tag="gemm"):
     """D[M,N] = epilogue(sum_k A(m,k) B(n,k)).  A is stored [M,K] (a_mn=False) or [K,M] (a_mn=True);
     B is stored [N,K] (b_mn=False) or [K,N] (b_mn=True).  See dmc_gemm in include/dinomc.h."""
     lib = L.load()
@@ -112,14 +154,16 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, A_lo=None, B_lo=None, out=Non
         g.aux, g.ldaux, g.aux_dtype = aux.data_ptr(), aux.stride(0), _dt(aux)
     g.split_k = split_k
     if simt:
-        L.check(lib.dmc_gemm_simt(C.byref(g), _stream()), "dmc_gemm_simt")
+        with _timed(tag):
+            L.check(lib.dmc_gemm_simt(C.byref(g), _stream()), "dmc_gemm_simt")
         _count()
         return out
     nbytes = lib.dmc_gemm_workspace_bytes(M, N, K, g.in_dtype) if split_k == 0 else split_k * M * N * 4
     if nbytes:
         ws = workspace(nbytes, A.device)
         g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel()
-    L.check(lib.dmc_gemm(C.byref(g), _stream()), "dmc_gemm")
+    with _timed(tag):
+        L.check(lib.dmc_gemm(C.byref(g), _stream()), "dmc_gemm")
     _count(2 if nbytes else 1)
     return out
 
@@ -129,7 +173,8 @@ def split_tf32(x: torch.Tensor):
     _need_cuda(x)
     x = x.contiguous()
     hi, lo = torch.empty_like(x), torch.empty_like(x)
-    L.check(lib.dmc_split_tf32(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), _stream()), "dmc_split_tf32")
+    with _timed("split_tf32"):
+        L.check(lib.dmc_split_tf32(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), _stream()), "dmc_split_tf32")
     _count()
     return hi, lo
 
@@ -141,7 +186,8 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
         return x
     x = x.float().contiguous() if x.dtype != torch.float32 else x.contiguous()
     y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    L.check(lib.dmc_cast_f32_to_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "dmc_cast_f32_to_bf16")
+    with _timed("cast_bf16"):
+        L.check(lib.dmc_cast_f32_to_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "dmc_cast_f32_to_bf16")
     _count()
     return y
 
@@ -154,8 +200,9 @@ def colsum(X: torch.Tensor) -> torch.Tensor:
     out = torch.empty(N, dtype=torch.float32, device=X.device)
     nbytes = lib.dmc_colsum_workspace_bytes(M, N)
     ws = workspace(nbytes, X.device)
-    L.check(lib.dmc_colsum(X.data_ptr(), _dt(X), M, N, X.stride(0), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
-            "dmc_colsum")
+    with _timed("colsum"):
+        L.check(lib.dmc_colsum(X.data_ptr(), _dt(X), M, N, X.stride(0), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+                "dmc_colsum")
     _count(2)
     return out
 
@@ -172,8 +219,9 @@ def normalize_rows_fwd(z: torch.Tensor, eps=1e-12, want_bf16=False):
     zhat = torch.empty((n, dim), dtype=torch.float32, device=z.device)
     zb = torch.empty((n, dim), dtype=torch.bfloat16, device=z.device) if want_bf16 else None
     inv_den = torch.empty(n, dtype=torch.float32, device=z.device)
-    L.check(lib.dmc_normalize_rows_fwd(z.data_ptr(), _dt(z), n, dim, z.stride(0), eps, zhat.data_ptr(), _p(zb), None,
-                                       inv_den.data_ptr(), _stream()), "dmc_normalize_rows_fwd")
+    with _timed("normalize_fwd"):
+        L.check(lib.dmc_normalize_rows_fwd(z.data_ptr(), _dt(z), n, dim, z.stride(0), eps, zhat.data_ptr(), _p(zb), None,
+                                           inv_den.data_ptr(), _stream()), "dmc_normalize_rows_fwd")
     _count()
     return zhat, zb, inv_den
 
@@ -185,8 +233,9 @@ def normalize_rows_bwd(dzhat, zhat, inv_den, eps=1e-12, out_dtype=torch.float32)
     assert dzhat.dtype == torch.float32 and zhat.dtype == torch.float32
     n, dim = zhat.shape
     dz = torch.empty((n, dim), dtype=out_dtype, device=zhat.device)
-    L.check(lib.dmc_normalize_rows_bwd(dzhat.data_ptr(), zhat.data_ptr(), inv_den.data_ptr(), n, dim, eps, dz.data_ptr(),
-                                       _dt(dz), _stream()), "dmc_normalize_rows_bwd")
+    with _timed("normalize_bwd"):
+        L.check(lib.dmc_normalize_rows_bwd(dzhat.data_ptr(), zhat.data_ptr(), inv_den.data_ptr(), n, dim, eps, dz.data_ptr(),
+                                           _dt(dz), _stream()), "dmc_normalize_rows_bwd")
     _count()
     return dz
 
@@ -211,8 +260,9 @@ def weightnorm_fwd(v: torch.Tensor, g: torch.Tensor, mode: str):
         w_f32 = torch.empty((K, dim), dtype=torch.float32, device=dev)
         if mode == "tf32x3":
             w_lo = torch.empty((K, dim), dtype=torch.float32, device=dev)
-    L.check(lib.dmc_weightnorm_fwd(v.data_ptr(), g.data_ptr(), K, dim, _p(w_f32), _p(w_lo), _p(w_bf16), scale.data_ptr(),
-                                   inv_vnorm.data_ptr(), _stream()), "dmc_weightnorm_fwd")
+    with _timed("weightnorm_fwd"):
+        L.check(lib.dmc_weightnorm_fwd(v.data_ptr(), g.data_ptr(), K, dim, _p(w_f32), _p(w_lo), _p(w_bf16), scale.data_ptr(),
+                                       inv_vnorm.data_ptr(), _stream()), "dmc_weightnorm_fwd")
     _count()
     return (w_bf16, None, scale, inv_vnorm) if mode == "bf16" else (w_f32, w_lo, scale, inv_vnorm)
 
@@ -225,8 +275,9 @@ def weightnorm_bwd(dw, v, scale, inv_vnorm, want_dg: bool):
     K, dim = v.shape
     dv = torch.empty_like(v)
     dg = torch.empty((K, 1), dtype=torch.float32, device=v.device) if want_dg else None
-    L.check(lib.dmc_weightnorm_bwd(dw.data_ptr(), v.data_ptr(), scale.data_ptr(), inv_vnorm.data_ptr(), K, dim, dv.data_ptr(),
-                                   _p(dg), _stream()), "dmc_weightnorm_bwd")
+    with _timed("weightnorm_bwd"):
+        L.check(lib.dmc_weightnorm_bwd(dw.data_ptr(), v.data_ptr(), scale.data_ptr(), inv_vnorm.data_ptr(), K, dim, dv.data_ptr(),
+                                       _p(dg), _stream()), "dmc_weightnorm_bwd")
     _count()
     return dv, dg
 
@@ -246,9 +297,10 @@ def teacher_stats_colsum(t: torch.Tensor, center: torch.Tensor, inv_temp: float)
     colsum_ = torch.empty(K, dtype=torch.float32, device=t.device)
     nbytes = lib.dmc_teacher_workspace_bytes(Nt, K)
     ws = workspace(nbytes, t.device)
-    L.check(lib.dmc_teacher_stats_colsum(t.data_ptr(), _dt(t), Nt, K, t.stride(0), center.data_ptr(), inv_temp,
-                                         row_stats.data_ptr(), colsum_.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
-            "dmc_teacher_stats_colsum")
+    with _timed("teacher_stats_colsum"):
+        L.check(lib.dmc_teacher_stats_colsum(t.data_ptr(), _dt(t), Nt, K, t.stride(0), center.data_ptr(), inv_temp,
+                                             row_stats.data_ptr(), colsum_.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+                "dmc_teacher_stats_colsum")
     _count(2)
     return row_stats, colsum_
 
@@ -259,8 +311,9 @@ def center_update(center: torch.Tensor, colsum_: torch.Tensor, count: float, mom
     _need_cuda(center, colsum_)
     out = torch.empty_like(center)
     K = center.numel()
-    L.check(lib.dmc_center_update(center.data_ptr(), out.data_ptr(), colsum_.data_ptr(), K, float(count), float(momentum),
-                                  float(1 - momentum), _stream()), "dmc_center_update")
+    with _timed("center_update"):
+        L.check(lib.dmc_center_update(center.data_ptr(), out.data_ptr(), colsum_.data_ptr(), K, float(count), float(momentum),
+                                      float(1 - momentum), _stream()), "dmc_center_update")
     _count()
     return out
 
@@ -274,9 +327,10 @@ def ce_fwd(s, t, center, t_stats, B, C, G, inv_ts, inv_tt):
     loss = torch.empty((), dtype=torch.float32, device=s.device)
     nbytes = lib.dmc_ce_workspace_bytes(B, C, G, K)
     ws = workspace(nbytes, s.device)
-    L.check(lib.dmc_ce_fwd(s.data_ptr(), _dt(s), s.stride(0), t.data_ptr(), _dt(t), t.stride(0), center.data_ptr(),
-                           t_stats.data_ptr(), B, C, G, K, inv_ts, inv_tt, s_lse.data_ptr(), loss.data_ptr(),
-                           ws.data_ptr(), ws.numel(), _stream()), "dmc_ce_fwd")
+    with _timed("ce_fwd"):
+        L.check(lib.dmc_ce_fwd(s.data_ptr(), _dt(s), s.stride(0), t.data_ptr(), _dt(t), t.stride(0), center.data_ptr(),
+                               t_stats.data_ptr(), B, C, G, K, inv_ts, inv_tt, s_lse.data_ptr(), loss.data_ptr(),
+                               ws.data_ptr(), ws.numel(), _stream()), "dmc_ce_fwd")
     _count(2)
     return loss, s_lse
 
@@ -288,9 +342,10 @@ def ce_bwd(s, t, center, t_stats, s_lse, grad_out, B, C, G, inv_ts, inv_tt):
     K = s.shape[1]
     ds = torch.empty((s.shape[0], K), dtype=s.dtype, device=s.device)
     grad_out = grad_out.to(torch.float32).contiguous()
-    L.check(lib.dmc_ce_bwd(s.data_ptr(), _dt(s), s.stride(0), t.data_ptr(), _dt(t), t.stride(0), center.data_ptr(),
-                           t_stats.data_ptr(), s_lse.data_ptr(), grad_out.data_ptr(), B, C, G, K, inv_ts, inv_tt,
-                           ds.data_ptr(), _dt(ds), ds.stride(0), _stream()), "dmc_ce_bwd")
+    with _timed("ce_bwd"):
+        L.check(lib.dmc_ce_bwd(s.data_ptr(), _dt(s), s.stride(0), t.data_ptr(), _dt(t), t.stride(0), center.data_ptr(),
+                               t_stats.data_ptr(), s_lse.data_ptr(), grad_out.data_ptr(), B, C, G, K, inv_ts, inv_tt,
+                               ds.data_ptr(), _dt(ds), ds.stride(0), _stream()), "dmc_ce_bwd")
     _count()
     return ds
 
@@ -333,6 +388,7 @@ class EmaPlan:
     def run(self, m: float):
         lib = L.load()
         # m is float64 (momentum_schedule[it]); (1 - m) is formed in float64 like the reference, then both -> fp32
-        L.check(lib.dmc_ema_multi_tensor(self.plan.data_ptr(), self.n_chunks, float(m), float(1.0 - float(m)), _stream()),
-                "dmc_ema_multi_tensor")
+        with _timed("ema"):
+            L.check(lib.dmc_ema_multi_tensor(self.plan.data_ptr(), self.n_chunks, float(m), float(1.0 - float(m)), _stream()),
+                    "dmc_ema_multi_tensor")
         _count()

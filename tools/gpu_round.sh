@@ -1,15 +1,37 @@
 #!/usr/bin/env bash
-# One gpurun call: diagnostics + the GPU test suite, each step bounded by its own timeout.
-# Everything worth reading lands in gpurun_out/.
+# One gpurun call: diagnostics + the GPU test suite + bench, each step bounded by its own timeout.
+# Everything worth reading lands in gpurun_out/.  Usage: tools/gpu_round.sh [diag] [tests] [smoke] [bench] [ncu]
 mkdir -p gpurun_out
+STEPS="${*:-tests smoke bench}"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
-( timeout 900 python tools/diag_gemm.py ) > gpurun_out/diag_gemm.log 2>&1
-echo "diag rc=$?" >> gpurun_out/diag_gemm.log
-for f in test_gpu_gemm test_gpu_kernels test_gpu_modules; do
-  ( timeout 900 python -m pytest tests/$f.py -q -m gpu --tb=short -p no:cacheprovider ) > gpurun_out/$f.log 2>&1
-  echo "$f rc=$?" >> gpurun_out/$f.log
+nproc >> gpurun_out/gpu.txt
+for s in $STEPS; do
+case $s in
+diag)
+  ( timeout 900 python tools/diag_gemm.py ) > gpurun_out/diag_gemm.log 2>&1
+  echo "diag rc=$?" >> gpurun_out/diag_gemm.log; tail -n 40 gpurun_out/diag_gemm.log ;;
+tests)
+  for f in test_gpu_gemm test_gpu_kernels test_gpu_modules; do
+    ( timeout 900 python -m pytest tests/$f.py -q -m gpu --tb=short -p no:cacheprovider ) > gpurun_out/$f.log 2>&1
+    echo "$f rc=$?" >> gpurun_out/$f.log
+    echo "== $f"; tail -n 12 gpurun_out/$f.log
+  done ;;
+smoke)
+  ( timeout 300 python __graft_entry__.py smoke ) > gpurun_out/smoke.log 2>&1
+  echo "smoke rc=$?" >> gpurun_out/smoke.log; echo "== smoke"; tail -n 6 gpurun_out/smoke.log ;;
+bench)
+  ( timeout 900 python bench.py --steps 30 --warmup 5 ) > gpurun_out/bench_bf16.json 2> gpurun_out/bench_bf16.err
+  echo "== bench bf16 graph rc=$?"; tail -c 6000 gpurun_out/bench_bf16.json; tail -n 5 gpurun_out/bench_bf16.err
+  ( timeout 600 python bench.py --steps 30 --warmup 5 --graph 0 --no-cpu-baseline ) > gpurun_out/bench_bf16_eager.json 2> gpurun_out/bench_bf16_eager.err
+  echo "== bench bf16 eager rc=$?"; tail -c 3000 gpurun_out/bench_bf16_eager.json; tail -n 5 gpurun_out/bench_bf16_eager.err
+  ( timeout 600 python bench.py --steps 10 --warmup 3 --mode fp32 --no-cpu-baseline ) > gpurun_out/bench_fp32.json 2> gpurun_out/bench_fp32.err
+  echo "== bench fp32 rc=$?"; tail -c 3000 gpurun_out/bench_fp32.json; tail -n 5 gpurun_out/bench_fp32.err
+  ( timeout 600 python bench.py --impl reference --steps 5 --warmup 2 ) > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+  echo "== bench reference rc=$?"; tail -c 2000 gpurun_out/bench_ref.json; tail -n 5 gpurun_out/bench_ref.err ;;
+ncu)
+  ( timeout 600 python bench.py --steps 2 --warmup 3 --graph 0 --no-cpu-baseline > gpurun_out/ncu_plain.log 2>&1 ) &&
+  timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
+      python bench.py --steps 2 --warmup 3 --graph 0 --no-cpu-baseline > gpurun_out/ncu.log 2>&1
+  echo "== ncu launches rc=$?"; tail -n 3 gpurun_out/ncu.log; wc -l gpurun_out/launches.csv ;;
+esac
 done
-( timeout 300 python __graft_entry__.py smoke ) > gpurun_out/smoke.log 2>&1
-echo "smoke rc=$?" >> gpurun_out/smoke.log
-tail -n 30 gpurun_out/diag_gemm.log
-for f in test_gpu_gemm test_gpu_kernels test_gpu_modules smoke; do echo "== $f"; tail -n 15 gpurun_out/$f.log; done
