@@ -349,7 +349,7 @@ def main():
 
     # live per-kernel timing for the roofline object
     peaks = load_peaks()
-    prof = per_kernel_times(step, min(args.steps, 20))
+    prof = per_kernel_times(step, min(args.steps, 20))     # {op: (total ms, total calls)} over those steps
     logit_bytes = 2 if args.mode == "bf16" else 4
     flops, nbytes = roofline_model(w, step.P, logit_bytes)
     t_roof_ms = max(flops / (peaks["bf16_tflops"] * 1e12), nbytes / (peaks["hbm_gbs"] * 1e9)) * 1e3
@@ -364,7 +364,9 @@ def main():
         "gemm_last_wgrad": logit_bytes * K * Ns + 4 * K * BN,
         "gemm_last_dgrad": logit_bytes * K * Ns + 2 * K * BN,
     }
-    for name, (ms, calls) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+    prof_steps = min(args.steps, 20)
+    for name, (ms_tot, calls_tot) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        ms, calls = ms_tot / prof_steps, calls_tot / prof_steps
         k = {"kernel": name, "ms_per_step": ms, "calls_per_step": calls}
         if name in alg_bytes:
             k["alg_GB"] = alg_bytes[name] / 1e9

@@ -10,7 +10,7 @@
 // with x_v = s_v/tau_s, lse_v = logsumexp_k x_v, p_v = softmax(x_v), q_i = softmax((t_i - c)/tau_t),
 // Q = sum_i q_i, S = sum_v x_v, n_v = G - [v<G].  A CTA owns (sample b, column chunk): it loads the C
 // student and G teacher vectors of that chunk once, so every logit is read exactly once per pass and
-// the gradient is written exactly once.  HBM-bound streaming kernels: 128-bit loads, per-thread online
+// the gradient is written exactly once.  HBM-bound streaming kernels: packed 4-element loads, per-thread online
 // softmax statistics, warp-shuffle + shared-memory block reductions, deterministic partials (no atomics).
 #include <math.h>
 
@@ -20,7 +20,9 @@ namespace dmc {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kIters = 4;          // vectors per thread per row per CTA
+constexpr int kIters = 8;          // 4-element vectors per thread per row per CTA
+constexpr int kChunkCols = kThreads * 4 * kIters;   // 8192 columns per CTA
+constexpr int kMinBlocks = 3;      // CTAs per SM the register budget is tuned for (<= 85 registers/thread)
 
 struct CeArgs {
   const void* s; long long lds;
@@ -37,27 +39,27 @@ struct CeArgs {
   void* ds; long long ldds;
 };
 
-template <typename T>
-__device__ __forceinline__ void load_guard(const T* rowp, long long col, long long K, bool fast, float (&v)[Vec<T>::N]) {
+__device__ __forceinline__ void load_center4(const float* center, long long col, long long K, bool fast, float (&c)[4]) {
   if (fast) {
-    Vec<T>::load(rowp + col, v);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(center + col));
+    c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
   } else {
 #pragma unroll
-    for (int j = 0; j < Vec<T>::N; ++j) v[j] = (col + j < K) ? Vec<T>::load1(rowp + col + j) : 0.f;
+    for (int e = 0; e < 4; ++e) c[e] = (col + e < K) ? __ldg(center + col + e) : 0.f;
   }
 }
 
 // CT / GT: compile-time crop counts (0 = runtime, bounded by 16 / 4).
 template <typename T, int CT, int GT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 ce_fwd_kernel(const CeArgs a) {
-  constexpr int VEC = Vec<T>::N;
+  using Q4 = Quad<T>;
   constexpr int MAXC = CT ? CT : 16, MAXG = GT ? GT : 4;
   const int C = CT ? CT : a.C, G = GT ? GT : a.G;
   const long long b = blockIdx.y;
   const int chunk = blockIdx.x;
-  const long long col_begin = static_cast<long long>(chunk) * (kThreads * VEC * kIters);
-  const long long col_end = min(a.K, col_begin + kThreads * VEC * kIters);
+  const long long col_begin = static_cast<long long>(chunk) * kChunkCols;
+  const long long col_end = min(a.K, col_begin + kChunkCols);
   const T* s = static_cast<const T*>(a.s);
   const T* t = static_cast<const T*>(a.t);
 
@@ -70,62 +72,72 @@ ce_fwd_kernel(const CeArgs a) {
   for (int v = 0; v < MAXC; ++v) { m[v] = -INFINITY; l[v] = 0.f; }
   float cross = 0.f;
 
-  for (long long col = col_begin + threadIdx.x * VEC; col < col_end; col += kThreads * VEC) {
-    const bool fast = a.vec_ok && (col + VEC <= a.K);
-    float tv[MAXG][VEC], xv[MAXC][VEC];
-    // ---- load phase: all independent 128-bit loads first ----
-#pragma unroll
-    for (int i = 0; i < MAXG; ++i)
-      if (i < G) load_guard<T>(t + (i * a.B + b) * a.ldt, col, a.K, fast, tv[i]);
-#pragma unroll
-    for (int v = 0; v < MAXC; ++v)
-      if (v < C) load_guard<T>(s + (v * a.B + b) * a.lds, col, a.K, fast, xv[v]);
-    float cen[VEC];
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) cen[e] = (col + e < a.K) ? __ldg(a.center + col + e) : 0.f;
-    // ---- teacher probabilities ----
-    float Q[VEC];
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) Q[e] = 0.f;
+  for (long long col = col_begin + threadIdx.x * 4; col < col_end; col += kThreads * 4) {
+    const bool fast = a.vec_ok && (col + 4 <= a.K);
+    // ---- load phase: C + G independent packed loads in flight before any arithmetic ----
+    typename Q4::Raw rt[MAXG], rs[MAXC];
 #pragma unroll
     for (int i = 0; i < MAXG; ++i)
       if (i < G) {
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          float q = __expf((tv[i][e] - cen[e]) * a.inv_tt - tm[i]) * tinv[i];
-          if (!fast && col + e >= a.K) q = 0.f;
-          tv[i][e] = q;
-          Q[e] += q;
-        }
+        const T* p = t + (i * a.B + b) * a.ldt + col;
+        rt[i] = fast ? Q4::load(p) : Q4::load_guard(p, col, a.K);
       }
-    // ---- student rows ----
-    float S[VEC];
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) S[e] = 0.f;
 #pragma unroll
     for (int v = 0; v < MAXC; ++v)
       if (v < C) {
+        const T* p = s + (v * a.B + b) * a.lds + col;
+        rs[v] = fast ? Q4::load(p) : Q4::load_guard(p, col, a.K);
+      }
+    float cen[4];
+    load_center4(a.center, col, a.K, fast && ((reinterpret_cast<uintptr_t>(a.center) & 15) == 0), cen);
+    float Q[4] = {0.f, 0.f, 0.f, 0.f}, S[4] = {0.f, 0.f, 0.f, 0.f};
+    // ---- one student row at a time; the first G rows also have a teacher row of the same view ----
+#pragma unroll
+    for (int v = 0; v < MAXC; ++v) {
+      if (v < C) {
+        float x[4];
+        Q4::unpack(rs[v], x);
         float vm = -INFINITY;
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          const float x = xv[v][e] * a.inv_ts;
-          xv[v][e] = x;
-          S[e] += x;                                     // invalid columns: x = 0 and Q = 0 there
-          if (fast || col + e < a.K) vm = fmaxf(vm, x);
+        for (int e = 0; e < 4; ++e) {
+          x[e] *= a.inv_ts;
+          S[e] += x[e];                                    // padded columns: x = 0 and q = 0 there
+          if (fast || col + e < a.K) vm = fmaxf(vm, x[e]);
         }
         if (vm > m[v]) { l[v] *= __expf(m[v] - vm); m[v] = vm; }
         if (vm > -INFINITY) {
 #pragma unroll
-          for (int e = 0; e < VEC; ++e)
-            if (fast || col + e < a.K) l[v] += __expf(xv[v][e] - m[v]);
+          for (int e = 0; e < 4; ++e)
+            if (fast || col + e < a.K) l[v] += __expf(x[e] - m[v]);
         }
-        if (v < MAXG && v < G) {
+        if (v < MAXG && v < G) {                           // same-view pair is skipped: subtract q_v . x_v
+          float tq[4];
+          Q4::unpack(rt[v < MAXG ? v : 0], tq);
 #pragma unroll
-          for (int e = 0; e < VEC; ++e) cross = fmaf(-tv[v < MAXG ? v : 0][e], xv[v][e], cross);
+          for (int e = 0; e < 4; ++e) {
+            float q = __expf((tq[e] - cen[e]) * a.inv_tt - tm[v < MAXG ? v : 0]) * tinv[v < MAXG ? v : 0];
+            if (!fast && col + e >= a.K) q = 0.f;
+            Q[e] += q;
+            cross = fmaf(-q, x[e], cross);
+          }
+        }
+      }
+    }
+    // teacher views without a student row of the same index (only when G > C)
+#pragma unroll
+    for (int i = 0; i < MAXG; ++i)
+      if (i < G && i >= C) {
+        float tq[4];
+        Q4::unpack(rt[i], tq);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float q = __expf((tq[e] - cen[e]) * a.inv_tt - tm[i]) * tinv[i];
+          if (!fast && col + e >= a.K) q = 0.f;
+          Q[e] += q;
         }
       }
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) cross = fmaf(Q[e], S[e], cross);
+    for (int e = 0; e < 4; ++e) cross = fmaf(Q[e], S[e], cross);
   }
 
   // ---- block reduction: (m,l) per student row by online merge, cross by sum ----
@@ -189,14 +201,14 @@ ce_finalize_kernel(const float2* __restrict__ ws_s, const float* __restrict__ ws
 }
 
 template <typename T, int CT, int GT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 ce_bwd_kernel(const CeArgs a) {
-  constexpr int VEC = Vec<T>::N;
+  using Q4 = Quad<T>;
   constexpr int MAXC = CT ? CT : 16, MAXG = GT ? GT : 4;
   const int C = CT ? CT : a.C, G = GT ? GT : a.G;
   const long long b = blockIdx.y;
-  const long long col_begin = static_cast<long long>(blockIdx.x) * (kThreads * VEC * kIters);
-  const long long col_end = min(a.K, col_begin + kThreads * VEC * kIters);
+  const long long col_begin = static_cast<long long>(blockIdx.x) * kChunkCols;
+  const long long col_end = min(a.K, col_begin + kChunkCols);
   const T* s = static_cast<const T*>(a.s);
   const T* t = static_cast<const T*>(a.t);
   T* ds = static_cast<T*>(a.ds);
@@ -210,50 +222,55 @@ ce_bwd_kernel(const CeArgs a) {
   for (int v = 0; v < MAXC; ++v)
     if (v < C) lse[v] = a.s_lse[v * a.B + b];
 
-  for (long long col = col_begin + threadIdx.x * VEC; col < col_end; col += kThreads * VEC) {
-    const bool fast = a.vec_ok && (col + VEC <= a.K);
-    float tv[MAXG][VEC], xv[MAXC][VEC];
-#pragma unroll
-    for (int i = 0; i < MAXG; ++i)
-      if (i < G) load_guard<T>(t + (i * a.B + b) * a.ldt, col, a.K, fast, tv[i]);
-#pragma unroll
-    for (int v = 0; v < MAXC; ++v)
-      if (v < C) load_guard<T>(s + (v * a.B + b) * a.lds, col, a.K, fast, xv[v]);
-    float cen[VEC];
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) cen[e] = (col + e < a.K) ? __ldg(a.center + col + e) : 0.f;
-    float Q[VEC];
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) Q[e] = 0.f;
+  for (long long col = col_begin + threadIdx.x * 4; col < col_end; col += kThreads * 4) {
+    const bool fast = a.vec_ok && (col + 4 <= a.K);
+    typename Q4::Raw rt[MAXG], rs[MAXC];
 #pragma unroll
     for (int i = 0; i < MAXG; ++i)
       if (i < G) {
+        const T* p = t + (i * a.B + b) * a.ldt + col;
+        rt[i] = fast ? Q4::load(p) : Q4::load_guard(p, col, a.K);
+      }
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          const float q = __expf((tv[i][e] - cen[e]) * a.inv_tt - tm[i]) * tinv[i];
-          tv[i][e] = q;
-          Q[e] += q;
+    for (int v = 0; v < MAXC; ++v)
+      if (v < C) {
+        const T* p = s + (v * a.B + b) * a.lds + col;
+        rs[v] = fast ? Q4::load(p) : Q4::load_guard(p, col, a.K);
+      }
+    float cen[4];
+    load_center4(a.center, col, a.K, fast && ((reinterpret_cast<uintptr_t>(a.center) & 15) == 0), cen);
+    float q[MAXG][4], Q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < MAXG; ++i)
+      if (i < G) {
+        float tq[4];
+        Q4::unpack(rt[i], tq);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          q[i][e] = __expf((tq[e] - cen[e]) * a.inv_tt - tm[i]) * tinv[i];
+          Q[e] += q[i][e];
         }
       }
 #pragma unroll
     for (int v = 0; v < MAXC; ++v)
       if (v < C) {
         const float nv = static_cast<float>((v < G) ? (G - 1) : G);
-        float d[VEC];
+        float x[4], d[4];
+        Q4::unpack(rs[v], x);
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          const float p = __expf(fmaf(xv[v][e], a.inv_ts, -lse[v]));
+        for (int e = 0; e < 4; ++e) {
+          const float p = __expf(fmaf(x[e], a.inv_ts, -lse[v]));
           float qs = Q[e];
-          if (v < MAXG && v < G) qs -= tv[v < MAXG ? v : 0][e];
+          if (v < MAXG && v < G) qs -= q[v < MAXG ? v : 0][e];
           d[e] = scale * fmaf(nv, p, -qs);
         }
         T* dst = ds + (v * a.B + b) * a.ldds + col;
         if (fast) {
-          Vec<T>::store(dst, d);
+          Q4::store(dst, d);
         } else {
 #pragma unroll
-          for (int e = 0; e < VEC; ++e)
-            if (col + e < a.K) Vec<T>::store1(dst + e, d[e]);
+          for (int e = 0; e < 4; ++e)
+            if (col + e < a.K) Q4::store1(dst + e, d[e]);
         }
       }
   }
@@ -276,7 +293,7 @@ int launch_bwd(const CeArgs& a, dim3 grid, cudaStream_t st) {
   return 0;
 }
 
-int chunk_cols(int dtype) { return kThreads * (dtype == DMC_BF16 ? 8 : 4) * kIters; }
+int chunk_cols(int /*dtype*/) { return kChunkCols; }
 
 int check_common(const char* who, const void* s, int s_dtype, int64_t lds, const void* t, int t_dtype, int64_t ldt,
                  const float* center, const float* t_row_stats, int64_t B, int C, int G, int64_t K) {
@@ -316,8 +333,9 @@ extern "C" int dmc_ce_fwd(const void* s, int32_t s_dtype, int64_t lds, const voi
   a.s = s; a.lds = lds; a.t = t; a.ldt = ldt; a.center = center; a.t_stats = reinterpret_cast<const float2*>(t_row_stats);
   a.B = B; a.K = K; a.C = C; a.G = G; a.inv_ts = inv_student_temp; a.inv_tt = inv_teacher_temp;
   a.nchunks = static_cast<int>(ceil_div(K, chunk_cols(s_dtype)));
-  a.vec_ok = ((reinterpret_cast<uintptr_t>(s) & 15) == 0) && ((reinterpret_cast<uintptr_t>(t) & 15) == 0) &&
-             ((lds * esz) % 16 == 0) && ((ldt * esz) % 16 == 0);
+  const int va = 4 * esz;     // bytes per packed 4-element access
+  a.vec_ok = ((reinterpret_cast<uintptr_t>(s) % va) == 0) && ((reinterpret_cast<uintptr_t>(t) % va) == 0) &&
+             ((lds * esz) % va == 0) && ((ldt * esz) % va == 0);
   const size_t s_bytes = (static_cast<size_t>(C) * B * a.nchunks * sizeof(float2) + 255) & ~static_cast<size_t>(255);
   a.ws_s = static_cast<float2*>(workspace);
   a.ws_x = reinterpret_cast<float*>(static_cast<char*>(workspace) + s_bytes);
@@ -343,9 +361,10 @@ extern "C" int dmc_ce_bwd(const void* s, int32_t s_dtype, int64_t lds, const voi
   a.s = s; a.lds = lds; a.t = t; a.ldt = ldt; a.center = center; a.t_stats = reinterpret_cast<const float2*>(t_row_stats);
   a.B = B; a.K = K; a.C = C; a.G = G; a.inv_ts = inv_student_temp; a.inv_tt = inv_teacher_temp;
   a.nchunks = static_cast<int>(ceil_div(K, chunk_cols(s_dtype)));
-  a.vec_ok = ((reinterpret_cast<uintptr_t>(s) & 15) == 0) && ((reinterpret_cast<uintptr_t>(t) & 15) == 0) &&
-             ((reinterpret_cast<uintptr_t>(ds) & 15) == 0) && ((lds * esz) % 16 == 0) && ((ldt * esz) % 16 == 0) &&
-             ((ldds * esz) % 16 == 0);
+  const int va = 4 * esz;
+  a.vec_ok = ((reinterpret_cast<uintptr_t>(s) % va) == 0) && ((reinterpret_cast<uintptr_t>(t) % va) == 0) &&
+             ((reinterpret_cast<uintptr_t>(ds) % va) == 0) && ((lds * esz) % va == 0) && ((ldt * esz) % va == 0) &&
+             ((ldds * esz) % va == 0);
   a.s_lse = s_lse; a.gout = grad_out;
   const int n_terms = G * C - (G < C ? G : C);
   a.coef = static_cast<float>(static_cast<double>(inv_student_temp) / (static_cast<double>(n_terms) * static_cast<double>(B)));

@@ -101,6 +101,52 @@ template <> struct Vec<__nv_bfloat16> {
   __device__ static __forceinline__ void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 };
 
+// Four consecutive logits per thread: one 128-bit (fp32) or 64-bit (bf16) streaming load, kept packed ("raw")
+// in registers until the row is processed -- keeps the register footprint of the multi-row loss kernels small.
+__device__ __forceinline__ uint2 ld_stream_u2(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_u2(void* p, const uint2& v) {
+  asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+template <typename T> struct Quad;
+template <> struct Quad<float> {
+  using Raw = uint4;
+  __device__ static __forceinline__ Raw load(const float* p) { return ld_stream_u4(p); }
+  __device__ static __forceinline__ Raw load_guard(const float* p, long long col, long long K) {
+    Raw r;
+    r.x = (col + 0 < K) ? __float_as_uint(p[0]) : 0u; r.y = (col + 1 < K) ? __float_as_uint(p[1]) : 0u;
+    r.z = (col + 2 < K) ? __float_as_uint(p[2]) : 0u; r.w = (col + 3 < K) ? __float_as_uint(p[3]) : 0u;
+    return r;
+  }
+  __device__ static __forceinline__ void unpack(const Raw& r, float (&v)[4]) {
+    v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+  }
+  __device__ static __forceinline__ void store(float* p, const float (&v)[4]) {
+    st_stream_u4(p, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
+  }
+  __device__ static __forceinline__ void store1(float* p, float v) { *p = v; }
+};
+template <> struct Quad<__nv_bfloat16> {
+  using Raw = uint2;
+  __device__ static __forceinline__ Raw load(const __nv_bfloat16* p) { return ld_stream_u2(p); }
+  __device__ static __forceinline__ Raw load_guard(const __nv_bfloat16* p, long long col, long long K) {
+    const unsigned short* q = reinterpret_cast<const unsigned short*>(p);
+    const uint32_t a = (col + 0 < K) ? q[0] : 0u, b = (col + 1 < K) ? q[1] : 0u;
+    const uint32_t c = (col + 2 < K) ? q[2] : 0u, d = (col + 3 < K) ? q[3] : 0u;
+    return make_uint2(a | (b << 16), c | (d << 16));
+  }
+  __device__ static __forceinline__ void unpack(const Raw& r, float (&v)[4]) {
+    v[0] = bf16_lo(r.x); v[1] = bf16_hi(r.x); v[2] = bf16_lo(r.y); v[3] = bf16_hi(r.y);
+  }
+  __device__ static __forceinline__ void store(__nv_bfloat16* p, const float (&v)[4]) {
+    st_stream_u2(p, make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3])));
+  }
+  __device__ static __forceinline__ void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
 // online softmax statistic merge: (m, l) <- (m, l) (+) (m2, l2), l = sum exp(x - m)
 __device__ __forceinline__ void online_merge(float& m, float& l, float m2, float l2) {
   float mn = fmaxf(m, m2);

@@ -15,10 +15,17 @@
 //               overlaps the MMAs of the next tile thanks to the double-buffered accumulator.
 // Three mbarrier pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue).
 //
+// Output path: the epilogue warps write the converted tile into 128B-swizzled smem staging buffers and one
+// lane issues a TMA store (cp.async.bulk.tensor, coalesced 128-byte rows, clipped at the matrix edge).
+// "B-resident" schedule (short contractions, e.g. the last layer's K = 256): every CTA owns a contiguous range
+// of tiles ordered n-tile-major, keeps the whole B (weight) tile of its current n-tile in smem and streams only
+// the A tiles, which cuts the L2->smem operand traffic from 3x to ~1x the output bytes.
+//
 // Operands may be K-major or MN-major (tcgen05 reads both through the smem matrix descriptor), in
 // bf16 (kind::f16) or fp32-as-TF32 (kind::tf32) with an optional 3-pass hi/lo split ("3xTF32").
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "dmc_common.cuh"
 #include "dmc_ptx.cuh"
@@ -44,6 +51,8 @@ struct GemmDev {
   int splits, vk_per_split;
   int stages;
   uint32_t b_bytes;   // block_n * 128
+  int resident;       // 1: B-resident schedule (contiguous tile ranges, B slabs loaded once per n-tile)
+  int tma_store;      // 1: epilogue stores D through smem staging + TMA
   // epilogue
   void* D; long long ldd; int out_dtype;
   float* partial;     // split-K partial sums [splits][M][N] (raw accumulators) or nullptr
@@ -68,8 +77,8 @@ __device__ __forceinline__ void store_elem(void* p, long long idx, int dtype, fl
 
 // Apply the epilogue to `n` (<= 32) consecutive columns [col0, col0+n) of one row and store them.
 // `acc` holds raw fp32 accumulators.  vec_ok: all pointers/strides allow 16-byte accesses.
-__device__ __forceinline__ void epilogue_store_row(const Epilogue& e, float (&acc)[32], long long row, int col0, int n,
-                                                   bool vec_ok) {
+__device__ __forceinline__ void epilogue_math(const Epilogue& e, float (&acc)[32], long long row, int col0, int n,
+                                              bool vec_ok) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     if (j < n) {
@@ -115,6 +124,11 @@ __device__ __forceinline__ void epilogue_store_row(const Epilogue& e, float (&ac
       for (int j = 0; j < n; ++j) acc[j] *= gelu_grad_f(load_elem(e.aux, row * e.ldaux + col0 + j, e.aux_dtype));
     }
   }
+}
+
+__device__ __forceinline__ void epilogue_store_row(const Epilogue& e, float (&acc)[32], long long row, int col0, int n,
+                                                   bool vec_ok) {
+  epilogue_math(e, acc, row, col0, n, vec_ok);
   if (vec_ok && n == 32) {
     if (e.out_dtype == DMC_BF16) {
       uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.D) + row * e.ldd + col0);
@@ -132,11 +146,14 @@ __device__ __forceinline__ void epilogue_store_row(const Epilogue& e, float (&ac
   }
 }
 
+constexpr int kStagingBytesPerWarp = 2 * 4096;   // two 32-row x 128-byte boxes per epilogue warp
+constexpr int kStagingBytes = 4 * kStagingBytesPerWarp;
+
 template <int ESZ, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
-               const GemmDev p) {
+               const __grid_constant__ CUtensorMap tmD, const GemmDev p) {
   constexpr int BLOCK_K = kRowBytes / ESZ;       // elements per k-block (64 bf16 / 32 tf32)
   constexpr int UMMA_K = 32 / ESZ;               // elements per tcgen05.mma (16 / 8)
   constexpr int BOX_MN = kRowBytes / ESZ;        // MN-major box width in elements (64 / 32)
@@ -149,11 +166,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);   // 1024-B aligned (SWIZZLE_128B atoms)
 
-  const uint32_t stage_bytes = kABytes + p.b_bytes;
-  uint8_t* tiles = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
+  // smem carve-up: [resident B slabs][stage ring][epilogue staging][barriers]
+  const uint32_t stage_bytes = p.resident ? kABytes : (kABytes + p.b_bytes);
+  const uint32_t res_bytes = p.resident ? static_cast<uint32_t>(p.vk_total) * p.b_bytes : 0u;
+  uint8_t* b_res = smem;
+  uint8_t* tiles = smem + res_bytes;
+  uint8_t* staging = tiles + static_cast<size_t>(p.stages) * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + (p.tma_store ? kStagingBytes : 0));
   uint64_t* empty_bar = full_bar + kMaxStages;
-  uint64_t* tmem_full = empty_bar + kMaxStages;
+  uint64_t* bfull_bar = empty_bar + kMaxStages;          // resident B slabs (<= kMaxStages of them)
+  uint64_t* bempty_bar = bfull_bar + kMaxStages;
+  uint64_t* tmem_full = bempty_bar + kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -163,7 +186,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA0); ptx::prefetch_tensormap(&tmB0);
     ptx::prefetch_tensormap(&tmA1); ptx::prefetch_tensormap(&tmB1);
-    for (int i = 0; i < p.stages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+    if (p.tma_store) ptx::prefetch_tensormap(&tmD);
+    for (int i = 0; i < kMaxStages; ++i) {
+      ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1);
+      ptx::mbar_init(&bfull_bar[i], 1); ptx::mbar_init(&bempty_bar[i], 1);
+    }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], 4); }
     ptx::fence_barrier_init();
   }
@@ -176,13 +203,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  // Work enumeration.  Work item w -> (mt = w % m_tiles, nt = (w / m_tiles) % n_tiles, split = w / (m_tiles n_tiles)).
+  // round-robin: w = blockIdx.x, +gridDim.x, ...   resident: a contiguous range (same n-tile for consecutive items).
   const int num_work = p.m_tiles * p.n_tiles * p.splits;
+  int w_begin, w_end, w_step;
+  if (p.resident) {
+    w_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * num_work / gridDim.x);
+    w_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * num_work / gridDim.x);
+    w_step = 1;
+  } else {
+    w_begin = blockIdx.x; w_end = num_work; w_step = gridDim.x;
+  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      int prev_nt = -1; uint32_t b_gen = 0;
+      for (int w = w_begin; w < w_end; w += w_step) {
         const int mt = w % p.m_tiles;
         const int rest = w / p.m_tiles;
         const int nt = rest % p.n_tiles;
@@ -190,15 +228,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int m0 = mt * kBlockM, n0 = nt * p.block_n;
         const int vk0 = sp * p.vk_per_split;
         const int vk1 = min(vk0 + p.vk_per_split, p.vk_total);
+        const bool load_b = p.resident && (nt != prev_nt);
         for (int vk = vk0; vk < vk1; ++vk) {
           const int pass = vk / p.kb_total;
           const int k0 = (vk - pass * p.kb_total) * BLOCK_K;
           const CUtensorMap* ta = (pass == 2) ? &tmA1 : &tmA0;   // passes: hi*hi, hi*lo, lo*hi
           const CUtensorMap* tb = (pass == 1) ? &tmB1 : &tmB0;
+          uint8_t* sA = tiles + static_cast<size_t>(stage) * stage_bytes;
+          uint8_t* sB = p.resident ? (b_res + static_cast<size_t>(vk) * p.b_bytes) : (sA + kABytes);
+          uint64_t* bar_b = p.resident ? &bfull_bar[vk] : &full_bar[stage];
+          if (load_b) {                                           // new n-tile: refill slab vk once the MMAs
+            ptx::mbar_wait(&bempty_bar[vk], (b_gen & 1u) ^ 1u);   // that read its previous contents have retired
+            ptx::mbar_arrive_expect_tx(&bfull_bar[vk], p.b_bytes);
+          }
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
           ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-          uint8_t* sA = tiles + static_cast<size_t>(stage) * stage_bytes;
-          uint8_t* sB = sA + kABytes;
+          if (!p.resident || load_b) {
+            if constexpr (!B_MN) {
+              ptx::tma_load_2d(sB, tb, bar_b, k0, n0);                           // box {BLOCK_K, block_n}
+            } else {
+              for (int j = 0; j < p.block_n / BOX_MN; ++j)
+                ptx::tma_load_2d(sB + j * kBoxBytes, tb, bar_b, n0 + j * BOX_MN, k0);
+            }
+          }
           if constexpr (!A_MN) {
             ptx::tma_load_2d(sA, ta, &full_bar[stage], k0, m0);                 // box {BLOCK_K, 128}
           } else {
@@ -206,14 +258,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             for (int j = 0; j < kBlockM / BOX_MN; ++j)                            // boxes {BOX_MN, BLOCK_K}
               ptx::tma_load_2d(sA + j * kBoxBytes, ta, &full_bar[stage], m0 + j * BOX_MN, k0);
           }
-          if constexpr (!B_MN) {
-            ptx::tma_load_2d(sB, tb, &full_bar[stage], k0, n0);                 // box {BLOCK_K, block_n}
-          } else {
-            for (int j = 0; j < p.block_n / BOX_MN; ++j)
-              ptx::tma_load_2d(sB + j * kBoxBytes, tb, &full_bar[stage], n0 + j * BOX_MN, k0);
-          }
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
+        if (load_b) { ++b_gen; prev_nt = nt; }
       }
     }
   } else if (warp == 1) {
@@ -222,20 +269,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const uint32_t idesc = ptx::make_instr_desc(kTf32 ? 2u : 1u, A_MN, B_MN, kBlockM, static_cast<uint32_t>(p.block_n));
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
-        const int sp = (w / p.m_tiles) / p.n_tiles;
+      int prev_nt = -1; uint32_t b_gen = 0;
+      for (int w = w_begin; w < w_end; w += w_step, ++it) {
+        const int rest = w / p.m_tiles;
+        const int nt = rest % p.n_tiles;
+        const int sp = rest / p.n_tiles;
         const int vk0 = sp * p.vk_per_split;
         const int vk1 = min(vk0 + p.vk_per_split, p.vk_total);
+        const bool new_b = p.resident && (nt != prev_nt);
+        // last tile of this CTA that uses the resident B of this n-tile -> release the slabs afterwards
+        const bool last_of_nt = p.resident && ((w + 1 >= w_end) || (((w + 1) / p.m_tiles) % p.n_tiles != nt));
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1u;
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);      // epilogue has drained this accumulator
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccCols);
         for (int vk = vk0; vk < vk1; ++vk) {
+          if (new_b) ptx::mbar_wait(&bfull_bar[vk], b_gen & 1u);
           ptx::mbar_wait(&full_bar[stage], phase);              // TMA bytes have landed
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(tiles + static_cast<size_t>(stage) * stage_bytes);
-          const uint32_t b_addr = a_addr + kABytes;
+          const uint32_t b_addr = p.resident ? ptx::smem_u32(b_res + static_cast<size_t>(vk) * p.b_bytes) : (a_addr + kABytes);
 #pragma unroll
           for (int k = 0; k < kMmaPerKBlock; ++k) {
             // K-major: rows of 128 B, 8-row groups 1024 B apart (SBO); advance 32 B per MMA inside the swizzle row.
@@ -249,9 +303,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             ptx::umma<kTf32>(d_tmem, da, db, idesc, (vk > vk0 || k > 0) ? 1u : 0u);
           }
           ptx::umma_commit(&empty_bar[stage]);                  // frees the smem stage when these MMAs retire
+          if (last_of_nt) ptx::umma_commit(&bempty_bar[vk]);    // ... and the resident B slab
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
         ptx::umma_commit(&tmem_full[acc]);                      // accumulator complete -> epilogue
+        if (new_b) { ++b_gen; prev_nt = nt; }
       }
     }
     __syncwarp();
@@ -262,12 +318,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (p.alpha_dev) e.alpha *= __ldg(p.alpha_dev);
     const int out_esz = (p.out_dtype == DMC_BF16) ? 2 : 4;
     bool vec_ok = ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) && ((p.ldd * out_esz) % 16 == 0);
+    bool aux_vec_ok = true;
     if (p.aux) {
       const int aux_esz = (p.aux_dtype == DMC_BF16) ? 2 : 4;
-      vec_ok = vec_ok && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) && ((p.ldaux * aux_esz) % 16 == 0);
+      aux_vec_ok = ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) && ((p.ldaux * aux_esz) % 16 == 0);
     }
+    uint8_t* my_staging = staging + (warp - 2) * kStagingBytesPerWarp;
+    const int chunks_per_box = (p.out_dtype == DMC_BF16) ? 2 : 1;   // 32-column chunks per 128-byte-wide box
+    uint32_t n_boxes = 0;                                            // boxes this warp has stored so far
     int it = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+    for (int w = w_begin; w < w_end; w += w_step, ++it) {
       const int mt = w % p.m_tiles;
       const int rest = w / p.m_tiles;
       const int nt = rest % p.n_tiles;
@@ -275,7 +335,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int n0 = nt * p.block_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      const long long row = static_cast<long long>(mt) * kBlockM + q * 32 + lane;
+      const int row0 = mt * kBlockM + q * 32;
+      const long long row = static_cast<long long>(row0) + lane;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc * kAccCols) + (static_cast<uint32_t>(q * 32) << 16);
@@ -290,11 +351,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
         }
         const int n = min(32, ncols - c);
-        if (row < p.M && n > 0) {
-          float v[32];
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.partial) {                                      // split-K: raw partial sums, epilogue runs in the reducer
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.partial) {                                        // split-K: raw partial sums, epilogue runs in the reducer
+          if (row < p.M && n > 0) {
             float* dst = p.partial + (static_cast<long long>(sp) * p.M + row) * p.N + n0 + c;
             if (n == 32 && (p.N % 4 == 0)) {
 #pragma unroll
@@ -302,12 +363,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             } else {
               for (int j = 0; j < n; ++j) dst[j] = v[j];
             }
-          } else {
-            epilogue_store_row(e, v, row, n0 + c, n, vec_ok);
+          }
+        } else if (!p.tma_store) {
+          if (row < p.M && n > 0) epilogue_store_row(e, v, row, n0 + c, n, vec_ok && aux_vec_ok);
+        } else {
+          // ---- smem-staged TMA store.  Box = 32 rows x 128 bytes (64 bf16 / 32 fp32 columns), 128B-swizzled:
+          //      16-byte chunk j of row r lives at r*128 + ((j ^ (r & 7)) << 4)  -> conflict-free warp stores.
+          if (n > 0) {
+            if (row < p.M) epilogue_math(e, v, row, n0 + c, n, aux_vec_ok);
+            const int sub = (c >> 5) % chunks_per_box;          // which half of the box this chunk fills
+            uint8_t* buf = my_staging + (n_boxes & 1u) * 4096;
+            if (sub == 0 && n_boxes >= 2) {                     // buffer was handed to TMA two boxes ago
+              if (lane == 0) ptx::tma_store_wait_read<1>();
+              __syncwarp();
+            }
+            uint8_t* rowp = buf + lane * 128;
+            if (p.out_dtype == DMC_BF16) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 pk = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                            pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+                *reinterpret_cast<uint4*>(rowp + ((((sub << 2) + j) ^ (lane & 7)) << 4)) = pk;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            const bool box_done = (sub == chunks_per_box - 1) || (c + 32 >= ncols);
+            if (box_done) {
+              ptx::fence_proxy_async();                         // generic-proxy smem writes -> visible to the TMA engine
+              __syncwarp();
+              if (lane == 0) {
+                ptx::tma_store_2d(&tmD, buf, n0 + c - sub * 32, row0);
+                ptx::tma_store_commit();
+              }
+              ++n_boxes;
+            }
           }
         }
       }
     }
+    if (p.tma_store && lane == 0) ptx::tma_store_wait_all<0>();  // all bulk stores complete before the CTA exits
   }
 
   ptx::tc_fence_before();
@@ -394,11 +491,21 @@ int make_tmap(CUtensorMap* tm, const void* base, int esz, int64_t rows, int64_t 
 }
 
 struct Plan {
-  int block_n, m_tiles, n_tiles, kb_total, passes, vk_total, splits, vk_per_split, stages;
+  int block_n, m_tiles, n_tiles, kb_total, passes, vk_total, splits, vk_per_split, stages, resident, tma_store;
   size_t smem_bytes, workspace_bytes;
 };
 
-Plan make_plan(int64_t M, int64_t N, int64_t K, int in_dtype, bool three_pass, int forced_split) {
+// DMC_GEMM_FLAGS (debug / A-B measurements): bit 0 = no TMA-store epilogue, bit 1 = no B-resident schedule.
+int debug_flags() {
+  static int flags = -1;
+  if (flags < 0) {
+    const char* e = getenv("DMC_GEMM_FLAGS");
+    flags = e ? atoi(e) : 0;
+  }
+  return flags;
+}
+
+Plan make_plan(int64_t M, int64_t N, int64_t K, int in_dtype, bool three_pass, int forced_split, bool store_ok = false) {
   Plan pl{};
   const int esz = (in_dtype == DMC_BF16) ? 2 : 4;
   const int block_k = kRowBytes / esz;
@@ -422,23 +529,33 @@ Plan make_plan(int64_t M, int64_t N, int64_t K, int in_dtype, bool three_pass, i
   if (splits < 1) splits = 1;
   pl.vk_per_split = static_cast<int>(ceil_div(pl.vk_total, splits));
   pl.splits = static_cast<int>(ceil_div(pl.vk_total, pl.vk_per_split));   // every split owns >= 1 k-block
-  const size_t stage_bytes = kABytes + static_cast<size_t>(pl.block_n) * kRowBytes;
-  const size_t budget = 227 * 1024 - 1024 /*alignment slack*/ - 256 /*barriers*/;
+  const size_t b_bytes = static_cast<size_t>(pl.block_n) * kRowBytes;
+  pl.tma_store = (store_ok && pl.splits == 1 && !(debug_flags() & 1)) ? 1 : 0;
+  const size_t kBarrierBytes = 512;
+  size_t budget = 227 * 1024 - 1024 /*alignment slack*/ - kBarrierBytes - (pl.tma_store ? kStagingBytes : 0);
+  // B-resident schedule: the whole contraction's worth of B for one n-tile stays in smem (<= 8 slabs, <= 128 KiB),
+  // leaving >= 4 A-only stages.  Pays off when several m-tiles share an n-tile.
+  const size_t res_bytes = static_cast<size_t>(pl.vk_total) * b_bytes;
+  pl.resident = (pl.splits == 1 && pl.vk_total <= kMaxStages && pl.m_tiles >= 2 && !(debug_flags() & 2) &&
+                 res_bytes + 4 * kABytes <= budget) ? 1 : 0;
+  const size_t stage_bytes = pl.resident ? kABytes : (kABytes + b_bytes);
+  if (pl.resident) budget -= res_bytes;
   int stages = static_cast<int>(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   pl.stages = stages;
-  pl.smem_bytes = static_cast<size_t>(stages) * stage_bytes + 256 + 1024;
+  pl.smem_bytes = (pl.resident ? res_bytes : 0) + static_cast<size_t>(stages) * stage_bytes +
+                  (pl.tma_store ? kStagingBytes : 0) + kBarrierBytes + 1024;
   pl.workspace_bytes = pl.splits > 1 ? static_cast<size_t>(pl.splits) * M * N * sizeof(float) : 0;
   return pl;
 }
 
 template <int ESZ, bool A_MN, bool B_MN>
 int launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
-              const GemmDev& dev, size_t smem_bytes, int grid, cudaStream_t st) {
+              const CUtensorMap& td, const GemmDev& dev, size_t smem_bytes, int grid, cudaStream_t st) {
   auto kern = gemm_tc_kernel<ESZ, A_MN, B_MN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
   if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(gemm_tc_kernel)");
-  kern<<<grid, kThreads, smem_bytes, st>>>(a0, a1, b0, b1, dev);
+  kern<<<grid, kThreads, smem_bytes, st>>>(a0, a1, b0, b1, td, dev);
   DMC_LAUNCH_CHECK("gemm_tc_kernel launch");
   return 0;
 }
@@ -471,14 +588,16 @@ extern "C" int dmc_gemm(const dmc_gemm_args* a, void* stream) {
   const int block_k = kRowBytes / esz, box_mn = kRowBytes / esz;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-  Plan pl = make_plan(a->M, a->N, a->K, a->in_dtype, three, a->split_k);
+  const int out_esz = (a->out_dtype == DMC_BF16) ? 2 : 4;
+  const bool store_ok = ((reinterpret_cast<uintptr_t>(a->D) & 15) == 0) && ((a->ldd * out_esz) % 16 == 0);
+  Plan pl = make_plan(a->M, a->N, a->K, a->in_dtype, three, a->split_k, store_ok);
   if (pl.splits > 1) {
     DMC_REQUIRE(a->workspace != nullptr && a->workspace_bytes >= pl.workspace_bytes,
                 "dmc_gemm: split-K needs a workspace of %zu bytes (got %zu)", pl.workspace_bytes, a->workspace_bytes);
     DMC_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace) & 15) == 0, "dmc_gemm: workspace must be 16-byte aligned");
   }
 
-  CUtensorMap tA0, tA1, tB0, tB1;
+  CUtensorMap tA0, tA1, tB0, tB1, tD;
   int rc;
   auto mapA = [&](CUtensorMap* tm, const void* base) {
     return a->a_mn_major ? make_tmap(tm, base, esz, a->K, a->M, a->lda, box_mn, block_k, esz == 4)   // stored [K,M]
@@ -492,12 +611,18 @@ extern "C" int dmc_gemm(const dmc_gemm_args* a, void* stream) {
   if ((rc = mapB(&tB0, a->B))) return rc;
   if ((rc = mapA(&tA1, three ? a->A_lo : a->A))) return rc;
   if ((rc = mapB(&tB1, three ? a->B_lo : a->B))) return rc;
+  if (pl.tma_store) {            // output boxes: 32 rows x 128 bytes, same 128B swizzle as the staging writes
+    if ((rc = make_tmap(&tD, a->D, out_esz, a->M, a->N, a->ldd, kRowBytes / out_esz, 32))) return rc;
+  } else {
+    tD = tA0;
+  }
 
   GemmDev d{};
   d.M = static_cast<int>(a->M); d.N = static_cast<int>(a->N);
   d.block_n = pl.block_n; d.m_tiles = pl.m_tiles; d.n_tiles = pl.n_tiles;
   d.kb_total = pl.kb_total; d.vk_total = pl.vk_total; d.splits = pl.splits; d.vk_per_split = pl.vk_per_split;
   d.stages = pl.stages; d.b_bytes = static_cast<uint32_t>(pl.block_n) * kRowBytes;
+  d.resident = pl.resident; d.tma_store = pl.tma_store;
   d.D = a->D; d.ldd = a->ldd; d.out_dtype = a->out_dtype;
   d.partial = pl.splits > 1 ? static_cast<float*>(a->workspace) : nullptr;
   d.col_scale = a->col_scale; d.bias = a->bias; d.alpha_dev = a->alpha_dev; d.alpha = a->alpha;
@@ -507,10 +632,10 @@ extern "C" int dmc_gemm(const dmc_gemm_args* a, void* stream) {
   const int grid = num_work < kNumSMs ? num_work : kNumSMs;
   const bool amn = a->a_mn_major != 0, bmn = a->b_mn_major != 0;
 #define DMC_DISPATCH(ESZ_)                                                                                   \
-  (amn ? (bmn ? launch_tc<ESZ_, true, true>(tA0, tA1, tB0, tB1, d, pl.smem_bytes, grid, st)                  \
-              : launch_tc<ESZ_, true, false>(tA0, tA1, tB0, tB1, d, pl.smem_bytes, grid, st))                \
-       : (bmn ? launch_tc<ESZ_, false, true>(tA0, tA1, tB0, tB1, d, pl.smem_bytes, grid, st)                 \
-              : launch_tc<ESZ_, false, false>(tA0, tA1, tB0, tB1, d, pl.smem_bytes, grid, st)))
+  (amn ? (bmn ? launch_tc<ESZ_, true, true>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st)                  \
+              : launch_tc<ESZ_, true, false>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st))                \
+       : (bmn ? launch_tc<ESZ_, false, true>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st)                 \
+              : launch_tc<ESZ_, false, false>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st)))
   rc = (esz == 2) ? DMC_DISPATCH(2) : DMC_DISPATCH(4);
 #undef DMC_DISPATCH
   if (rc) return rc;

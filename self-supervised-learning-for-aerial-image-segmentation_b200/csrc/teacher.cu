@@ -5,8 +5,9 @@
 //   main_dino_mc.py:470-473  center EMA                                  -> dmc_center_update
 //
 // teacher_pass_kernel reads every teacher logit exactly once and produces BOTH reductions: each warp
-// walks rows of a 1024-column chunk, a lane keeps its 32 columns' running sums in registers (column
-// direction) and reduces max / sum-exp across the warp with shuffles (row direction).  Partials go to a
+// walks rows of a 512-column chunk four rows at a time (16 packed loads in flight per lane), a lane keeps
+// its 16 columns' running sums in registers (column direction) and reduces max / sum-exp across the warp
+// with shuffles (row direction).  Partials go to a
 // small workspace and are merged in a fixed order (deterministic, no atomics).
 // HBM-bound: algorithmic bytes = Nt*K*sizeof(logit) read; everything else is O(Nt + K).
 #include <math.h>
@@ -16,90 +17,88 @@
 namespace dmc {
 namespace {
 
-constexpr int kChunk = 1024;     // columns per CTA
+constexpr int kChunk = 512;      // columns per CTA: a lane owns 4 vectors of 4 consecutive columns
 constexpr int kWarps = 8;
+constexpr int kRowsInFlight = 4; // rows a warp loads before it starts reducing (16 packed loads in flight per lane)
+constexpr int kNV = kChunk / (32 * 4);
 
 template <typename T>
-__device__ __forceinline__ void load_guard(const T* rowp, long long col, long long K, bool vec_ok, float* v) {
-  constexpr int N = Vec<T>::N;
-  if (vec_ok && col + N <= K) {
-    float tmp[N];
-    Vec<T>::load(rowp + col, tmp);
-#pragma unroll
-    for (int j = 0; j < N; ++j) v[j] = tmp[j];
-  } else {
-#pragma unroll
-    for (int j = 0; j < N; ++j) v[j] = (col + j < K) ? Vec<T>::load1(rowp + col + j) : 0.f;
-  }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, 2)
 teacher_pass_kernel(const T* __restrict__ t, long long Nt, long long K, long long ld, const float* __restrict__ center,
                     float inv_temp, float2* __restrict__ ws_stats, float* __restrict__ ws_colsum, int rows_per_block,
                     int nchunks, bool vec_ok) {
-  constexpr int VEC = Vec<T>::N;
-  constexpr int NV = 32 / VEC;                        // vectors per lane per row
-  __shared__ __align__(16) float sm[kWarps][kChunk];  // 32 KiB: per-warp column sums
+  using Q4 = Quad<T>;
+  __shared__ __align__(16) float sm[kWarps][kChunk];  // 16 KiB: per-warp column sums
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.x;
   const long long col0 = static_cast<long long>(chunk) * kChunk;
-  const bool full = (col0 + kChunk <= K);
+  const bool full = vec_ok && (col0 + kChunk <= K);
 
-  float cen[32], cs[32];
+  float cen[kNV][4], cs[kNV][4];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const long long c = col0 + (i * 32 + lane) * VEC;
+  for (int i = 0; i < kNV; ++i) {
+    const long long c = col0 + (i * 32 + lane) * 4;
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      cen[i * VEC + e] = (c + e < K) ? __ldg(center + c + e) : 0.f;
-      cs[i * VEC + e] = 0.f;
+    for (int e = 0; e < 4; ++e) {
+      cen[i][e] = (c + e < K) ? __ldg(center + c + e) : 0.f;
+      cs[i][e] = 0.f;
     }
   }
   const long long r_begin = static_cast<long long>(blockIdx.y) * rows_per_block;
   const long long r_end = min(r_begin + rows_per_block, Nt);
-  for (long long r = r_begin + warp; r < r_end; r += kWarps) {
-    float x[32];
-    const T* rowp = t + r * ld;
+  for (long long r0 = r_begin + warp * kRowsInFlight; r0 < r_end; r0 += kWarps * kRowsInFlight) {
+    typename Q4::Raw raw[kRowsInFlight][kNV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) load_guard<T>(rowp, col0 + (i * 32 + lane) * VEC, K, vec_ok, &x[i * VEC]);
-    float m = -INFINITY;
+    for (int j = 0; j < kRowsInFlight; ++j) {
+      const long long r = r0 + j;
+      if (r < r_end) {
+        const T* rowp = t + r * ld;
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        const int j = i * VEC + e;
-        cs[j] += x[j];
-        float y = (x[j] - cen[j]) * inv_temp;
-        if (!full && (col0 + (i * 32 + lane) * VEC + e >= K)) y = -INFINITY;
-        x[j] = y;
-        m = fmaxf(m, y);
+        for (int i = 0; i < kNV; ++i) {
+          const long long c = col0 + (i * 32 + lane) * 4;
+          raw[j][i] = full ? Q4::load(rowp + c) : Q4::load_guard(rowp + c, c, K);
+        }
       }
-    m = warp_max(m);
-    float l = 0.f;
+    }
 #pragma unroll
-    for (int j = 0; j < 32; ++j) l += __expf(x[j] - m);
-    l = warp_sum(l);
-    if (lane == 0) ws_stats[r * nchunks + chunk] = make_float2(m, l);
+    for (int j = 0; j < kRowsInFlight; ++j) {
+      const long long r = r0 + j;
+      if (r < r_end) {                                   // warp-uniform
+        float y[kNV][4];
+        float m = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < kNV; ++i) {
+          float x[4];
+          Q4::unpack(raw[j][i], x);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            cs[i][e] += x[e];
+            float v = (x[e] - cen[i][e]) * inv_temp;
+            if (!full && (col0 + (i * 32 + lane) * 4 + e >= K)) v = -INFINITY;
+            y[i][e] = v;
+            m = fmaxf(m, v);
+          }
+        }
+        m = warp_max(m);
+        float l = 0.f;
+#pragma unroll
+        for (int i = 0; i < kNV; ++i)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) l += __expf(y[i][e] - m);
+        l = warp_sum(l);
+        if (lane == 0) ws_stats[r * nchunks + chunk] = make_float2(m, l);
+      }
+    }
   }
 #pragma unroll
-  for (int i = 0; i < NV; ++i)
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) sm[warp][(i * 32 + lane) * VEC + e] = cs[i * VEC + e];
+  for (int i = 0; i < kNV; ++i)
+    *reinterpret_cast<float4*>(&sm[warp][(i * 32 + lane) * 4]) = make_float4(cs[i][0], cs[i][1], cs[i][2], cs[i][3]);
   __syncthreads();
-  {
-    const int c = threadIdx.x * 4;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = threadIdx.x; c < kChunk; c += kWarps * 32) {
+    float acc = 0.f;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-      const float4 v = *reinterpret_cast<const float4*>(&sm[w][c]);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    }
-    float* dst = ws_colsum + static_cast<long long>(blockIdx.y) * K + col0 + c;
-    if (col0 + c + 0 < K) dst[0] = acc.x;
-    if (col0 + c + 1 < K) dst[1] = acc.y;
-    if (col0 + c + 2 < K) dst[2] = acc.z;
-    if (col0 + c + 3 < K) dst[3] = acc.w;
+    for (int w = 0; w < kWarps; ++w) acc += sm[w][c];
+    if (col0 + c < K) ws_colsum[static_cast<long long>(blockIdx.y) * K + col0 + c] = acc;
   }
 }
 
@@ -146,12 +145,13 @@ struct TeacherPlan { int nchunks, nrb, rows_per_block; size_t stats_bytes, colsu
 TeacherPlan teacher_plan(int64_t Nt, int64_t K) {
   TeacherPlan p{};
   p.nchunks = static_cast<int>(ceil_div(K, kChunk));
-  int64_t nrb = ceil_div(4 * kNumSMs, p.nchunks);
-  const int64_t max_rb = ceil_div(Nt, kWarps);
+  const int64_t rows_unit = kWarps * kRowsInFlight;
+  int64_t nrb = ceil_div(8 * kNumSMs, p.nchunks);
+  const int64_t max_rb = ceil_div(Nt, rows_unit);
   if (nrb > max_rb) nrb = max_rb;
   if (nrb < 1) nrb = 1;
   int64_t rpb = ceil_div(Nt, nrb);
-  rpb = ceil_div(rpb, kWarps) * kWarps;
+  rpb = ceil_div(rpb, rows_unit) * rows_unit;
   p.rows_per_block = static_cast<int>(rpb);
   p.nrb = static_cast<int>(ceil_div(Nt, rpb));
   p.stats_bytes = (static_cast<size_t>(Nt) * p.nchunks * sizeof(float2) + 255) & ~static_cast<size_t>(255);
@@ -184,7 +184,7 @@ extern "C" int dmc_teacher_stats_colsum(const void* t, int32_t dtype, int64_t Nt
   float2* ws_stats = static_cast<float2*>(workspace);
   float* ws_colsum = reinterpret_cast<float*>(static_cast<char*>(workspace) + p.stats_bytes);
   const int esz = dtype == DMC_BF16 ? 2 : 4;
-  const bool vec_ok = ((reinterpret_cast<uintptr_t>(t) & 15) == 0) && ((ld * esz) % 16 == 0);
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(t) % (4 * esz)) == 0) && ((ld * esz) % (4 * esz) == 0);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid((unsigned)p.nchunks, (unsigned)p.nrb);
   if (dtype == DMC_BF16)

@@ -28,6 +28,20 @@ bench)
   echo "== bench fp32 rc=$?"; tail -c 3000 gpurun_out/bench_fp32.json; tail -n 5 gpurun_out/bench_fp32.err
   ( timeout 600 python bench.py --impl reference --steps 5 --warmup 2 ) > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
   echo "== bench reference rc=$?"; tail -c 2000 gpurun_out/bench_ref.json; tail -n 5 gpurun_out/bench_ref.err ;;
+ab)
+  for fl in 0 1 2 3; do
+    ( DMC_GEMM_FLAGS=$fl timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline ) > gpurun_out/bench_flags$fl.json 2> gpurun_out/bench_flags$fl.err
+    echo "== bench flags=$fl rc=$?"; python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/bench_flags$fl.json"))
+    print("value", round(d["value"]), "ms", round(d["ms_per_step"], 4), "e2e", round(d["e2e"]["value"]))
+    for k in d["roofline"]["kernels"]:
+        print("   %-26s %.4f ms  x%.0f %s" % (k["kernel"], k["ms_per_step"], k["calls_per_step"], ("%.0f GB/s" % k["GBps"]) if "GBps" in k else ""))
+except Exception as e:
+    print("parse failed", e)
+PY
+  done ;;
 ncu)
   ( timeout 600 python bench.py --steps 2 --warmup 3 --graph 0 --no-cpu-baseline > gpurun_out/ncu_plain.log 2>&1 ) &&
   timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
