@@ -64,6 +64,7 @@ struct Epilogue {
   const float* col_scale; const float* bias; float alpha; int act;
   void* aux; long long ldaux; int aux_dtype;
   void* D; long long ldd; int out_dtype;
+  int N;
 };
 
 __device__ __forceinline__ float load_elem(const void* p, long long idx, int dtype) {
@@ -75,23 +76,26 @@ __device__ __forceinline__ void store_elem(void* p, long long idx, int dtype, fl
   else reinterpret_cast<float*>(p)[idx] = v;
 }
 
-// Apply the epilogue to `n` (<= 32) consecutive columns [col0, col0+n) of one row and store them.
-// `acc` holds raw fp32 accumulators.  vec_ok: all pointers/strides allow 16-byte accesses.
+// Epilogue arithmetic on the 32 consecutive columns [col0, col0+32) of one row (raw fp32 accumulators in,
+// finished values out).  Every option sits behind ONE warp-uniform branch so the common plain case costs
+// nothing; columns >= N are computed on clamped vector entries and never stored.  `n` = valid columns.
 __device__ __forceinline__ void epilogue_math(const Epilogue& e, float (&acc)[32], long long row, int col0, int n,
-                                              bool vec_ok) {
+                                              bool aux_vec_ok) {
+  if (e.col_scale != nullptr) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    if (j < n) {
-      float v = acc[j];
-      if (e.col_scale) v *= __ldg(e.col_scale + col0 + j);
-      v *= e.alpha;
-      if (e.bias) v += __ldg(e.bias + col0 + j);
-      acc[j] = v;
-    }
+    for (int j = 0; j < 32; ++j) acc[j] *= __ldg(e.col_scale + min(col0 + j, e.N - 1));
+  }
+  if (e.alpha != 1.0f) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] *= e.alpha;
+  }
+  if (e.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] += __ldg(e.bias + min(col0 + j, e.N - 1));
   }
   if (e.act == DMC_ACT_GELU) {
-    if (e.aux) {
-      if (vec_ok && n == 32) {
+    if (e.aux != nullptr) {                                  // save the pre-activation for backward
+      if (aux_vec_ok && n == 32) {
         if (e.aux_dtype == DMC_BF16) {
           uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.aux) + row * e.ldaux + col0);
 #pragma unroll
@@ -104,31 +108,35 @@ __device__ __forceinline__ void epilogue_math(const Epilogue& e, float (&acc)[32
           for (int j = 0; j < 8; ++j) p[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
         }
       } else {
-        for (int j = 0; j < n; ++j) store_elem(e.aux, row * e.ldaux + col0 + j, e.aux_dtype, acc[j]);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < n) store_elem(e.aux, row * e.ldaux + col0 + j, e.aux_dtype, acc[j]);
       }
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] = gelu_f(acc[j]);
   } else if (e.act == DMC_ACT_GELU_BWD) {
-    if (vec_ok && n == 32 && e.aux_dtype == DMC_BF16) {
+    if (aux_vec_ok && n == 32 && e.aux_dtype == DMC_BF16) {
       const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.aux) + row * e.ldaux + col0);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        uint4 w = p[j];
+        const uint4 w = p[j];
         acc[8 * j + 0] *= gelu_grad_f(bf16_lo(w.x)); acc[8 * j + 1] *= gelu_grad_f(bf16_hi(w.x));
         acc[8 * j + 2] *= gelu_grad_f(bf16_lo(w.y)); acc[8 * j + 3] *= gelu_grad_f(bf16_hi(w.y));
         acc[8 * j + 4] *= gelu_grad_f(bf16_lo(w.z)); acc[8 * j + 5] *= gelu_grad_f(bf16_hi(w.z));
         acc[8 * j + 6] *= gelu_grad_f(bf16_lo(w.w)); acc[8 * j + 7] *= gelu_grad_f(bf16_hi(w.w));
       }
     } else {
-      for (int j = 0; j < n; ++j) acc[j] *= gelu_grad_f(load_elem(e.aux, row * e.ldaux + col0 + j, e.aux_dtype));
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < n) acc[j] *= gelu_grad_f(load_elem(e.aux, row * e.ldaux + col0 + j, e.aux_dtype));
     }
   }
 }
 
+// Direct (non-TMA) store of one row's 32-column chunk; used for unaligned outputs only.
 __device__ __forceinline__ void epilogue_store_row(const Epilogue& e, float (&acc)[32], long long row, int col0, int n,
                                                    bool vec_ok) {
-  epilogue_math(e, acc, row, col0, n, vec_ok);
   if (vec_ok && n == 32) {
     if (e.out_dtype == DMC_BF16) {
       uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.D) + row * e.ldd + col0);
@@ -142,7 +150,9 @@ __device__ __forceinline__ void epilogue_store_row(const Epilogue& e, float (&ac
       for (int j = 0; j < 8; ++j) p[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
     }
   } else {
-    for (int j = 0; j < n; ++j) store_elem(e.D, row * e.ldd + col0 + j, e.out_dtype, acc[j]);
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < n) store_elem(e.D, row * e.ldd + col0 + j, e.out_dtype, acc[j]);
   }
 }
 
@@ -314,7 +324,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;                                     // TMEM lane quadrant this warp may access
-    Epilogue e{p.col_scale, p.bias, p.alpha, p.act, p.aux, p.ldaux, p.aux_dtype, p.D, p.ldd, p.out_dtype};
+    Epilogue e{p.col_scale, p.bias, p.alpha, p.act, p.aux, p.ldaux, p.aux_dtype, p.D, p.ldd, p.out_dtype, p.N};
     if (p.alpha_dev) e.alpha *= __ldg(p.alpha_dev);
     const int out_esz = (p.out_dtype == DMC_BF16) ? 2 : 4;
     bool vec_ok = ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) && ((p.ldd * out_esz) % 16 == 0);
@@ -341,67 +351,76 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc * kAccCols) + (static_cast<uint32_t>(q * 32) << 16);
       const int ncols = min(p.block_n, p.N - n0);
-      for (int c = 0; c < p.block_n; c += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(t_addr + c, r);
-        ptx::tmem_ld_wait();
-        if (c + 32 >= p.block_n) {                              // last read of this accumulator: hand it back
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
-        }
+      // One 32-column chunk: accumulators -> epilogue -> split-K partials | direct store | smem staging + TMA store.
+      auto process = [&](uint32_t (&r)[32], int c) {
         const int n = min(32, ncols - c);
+        if (n <= 0) return;                                     // whole chunk beyond N (warp-uniform)
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         if (p.partial) {                                        // split-K: raw partial sums, epilogue runs in the reducer
-          if (row < p.M && n > 0) {
+          if (row < p.M) {
             float* dst = p.partial + (static_cast<long long>(sp) * p.M + row) * p.N + n0 + c;
             if (n == 32 && (p.N % 4 == 0)) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             } else {
-              for (int j = 0; j < n; ++j) dst[j] = v[j];
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < n) dst[j] = v[j];
             }
           }
-        } else if (!p.tma_store) {
-          if (row < p.M && n > 0) epilogue_store_row(e, v, row, n0 + c, n, vec_ok && aux_vec_ok);
-        } else {
-          // ---- smem-staged TMA store.  Box = 32 rows x 128 bytes (64 bf16 / 32 fp32 columns), 128B-swizzled:
-          //      16-byte chunk j of row r lives at r*128 + ((j ^ (r & 7)) << 4)  -> conflict-free warp stores.
-          if (n > 0) {
-            if (row < p.M) epilogue_math(e, v, row, n0 + c, n, aux_vec_ok);
-            const int sub = (c >> 5) % chunks_per_box;          // which half of the box this chunk fills
-            uint8_t* buf = my_staging + (n_boxes & 1u) * 4096;
-            if (sub == 0 && n_boxes >= 2) {                     // buffer was handed to TMA two boxes ago
-              if (lane == 0) ptx::tma_store_wait_read<1>();
-              __syncwarp();
-            }
-            uint8_t* rowp = buf + lane * 128;
-            if (p.out_dtype == DMC_BF16) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 pk = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                            pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-                *reinterpret_cast<uint4*>(rowp + ((((sub << 2) + j) ^ (lane & 7)) << 4)) = pk;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-            const bool box_done = (sub == chunks_per_box - 1) || (c + 32 >= ncols);
-            if (box_done) {
-              ptx::fence_proxy_async();                         // generic-proxy smem writes -> visible to the TMA engine
-              __syncwarp();
-              if (lane == 0) {
-                ptx::tma_store_2d(&tmD, buf, n0 + c - sub * 32, row0);
-                ptx::tma_store_commit();
-              }
-              ++n_boxes;
-            }
-          }
+          return;
         }
+        if (row < p.M) epilogue_math(e, v, row, n0 + c, n, aux_vec_ok);
+        if (!p.tma_store) {
+          if (row < p.M) epilogue_store_row(e, v, row, n0 + c, n, vec_ok);
+          return;
+        }
+        // ---- smem-staged TMA store.  Box = 32 rows x 128 bytes (64 bf16 / 32 fp32 columns), 128B-swizzled:
+        //      16-byte chunk j of row r lives at r*128 + ((j ^ (r & 7)) << 4)  -> conflict-free warp stores.
+        const int sub = (c >> 5) % chunks_per_box;              // which half of the box this chunk fills
+        uint8_t* buf = my_staging + (n_boxes & 1u) * 4096;
+        if (sub == 0 && n_boxes >= 2) {                         // buffer was handed to TMA two boxes ago
+          if (lane == 0) ptx::tma_store_wait_read<1>();
+          __syncwarp();
+        }
+        uint8_t* rowp = buf + lane * 128;
+        if (p.out_dtype == DMC_BF16) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 pk = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                        pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+            *reinterpret_cast<uint4*>(rowp + ((((sub << 2) + j) ^ (lane & 7)) << 4)) = pk;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        const bool box_done = (sub == chunks_per_box - 1) || (c + 32 >= ncols);
+        if (box_done) {
+          ptx::fence_proxy_async();                             // generic-proxy smem writes -> visible to the TMA engine
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmD, buf, n0 + c - sub * 32, row0);
+            ptx::tma_store_commit();
+          }
+          ++n_boxes;
+        }
+      };
+      for (int c = 0; c < p.block_n; c += 64) {                 // block_n is a multiple of 64
+        uint32_t ra[32], rb[32];
+        ptx::tmem_ld_32x32(t_addr + c, ra);                     // two TMEM loads in flight per wait
+        ptx::tmem_ld_32x32(t_addr + c + 32, rb);
+        ptx::tmem_ld_wait();
+        if (c + 64 >= p.block_n) {                              // last read of this accumulator: hand it back
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+        }
+        process(ra, c);
+        process(rb, c + 32);
       }
     }
     if (p.tma_store && lane == 0) ptx::tma_store_wait_all<0>();  // all bulk stores complete before the CTA exits
@@ -641,7 +660,8 @@ extern "C" int dmc_gemm(const dmc_gemm_args* a, void* stream) {
   if (rc) return rc;
 
   if (pl.splits > 1) {
-    Epilogue e{a->col_scale, a->bias, a->alpha, a->act, a->aux, a->ldaux, a->aux_dtype, a->D, a->ldd, a->out_dtype};
+    Epilogue e{a->col_scale, a->bias, a->alpha, a->act, a->aux, a->ldaux, a->aux_dtype, a->D, a->ldd, a->out_dtype,
+               static_cast<int>(a->N)};
     const long long groups = a->M * ((a->N + 3) / 4);
     const int blocks = static_cast<int>(ceil_div(groups, 256));
     splitk_reduce_kernel<<<blocks, 256, 0, st>>>(static_cast<const float*>(a->workspace), pl.splits, a->M,
