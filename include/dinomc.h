@@ -130,8 +130,9 @@ int dmc_weightnorm_bwd(const float* dw, const float* v, const float* scale, cons
  * (the layout MultiCropWrapper guarantees, utils/utils.py:627-646).  Logits are F32 or BF16.
  * ------------------------------------------------------------------------------------------- */
 /* One pass over the teacher logits t [Nt,K] (main_dino_mc.py:446 and :468): per-row statistics of
- * softmax((t - center) * inv_temp) as row_stats[Nt][2] = {row max, 1/sum exp} and the per-GPU batch
- * column sum colsum[K] = sum_rows t (input of the center all-reduce). */
+ * softmax((t - center) * inv_temp), kept in the base-2 domain the loss kernels compute in:
+ * row_stats[Nt][2] = {max_k y2, 1 / sum_k 2^(y2 - max)} with y2 = (t - center) * inv_temp * log2(e);
+ * and the per-GPU batch column sum colsum[K] = sum_rows t (input of the center all-reduce). */
 size_t dmc_teacher_workspace_bytes(int64_t Nt, int64_t K);
 int dmc_teacher_stats_colsum(const void* t, int32_t dtype, int64_t Nt, int64_t K, int64_t ld,
                              const float* center, float inv_temp, float* row_stats, float* colsum,

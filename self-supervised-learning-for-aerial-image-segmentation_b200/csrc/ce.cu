@@ -49,11 +49,96 @@ __device__ __forceinline__ void load_center4(const float* center, long long col,
   }
 }
 
+// Per-thread running softmax statistics of the student rows, in the base-2 domain:
+//   m[v] = max of the RAW logits seen so far, l[v] = sum 2^{(x - m[v]) * c2},  c2 = log2(e)/tau_s.
+template <int MAXC>
+struct RowStats {
+  float m[MAXC], l[MAXC];
+};
+
+// One 4-column vector of all C student and G teacher rows of sample b.  FAST: the vector is fully inside K and
+// aligned (packed loads, no per-element guards); !FAST: the ragged last vector of a row.
+template <typename T, int MAXC, int MAXG, bool FAST>
+__device__ __forceinline__ void ce_fwd_vector(const CeArgs& a, const T* s, const T* t, long long b, long long col, int C, int G,
+                                              const float (&tmc)[MAXG], const float (&tinv)[MAXG], float c2, float ct,
+                                              RowStats<MAXC>& st, float& cross) {
+  using Q4 = Quad<T>;
+  // ---- load phase: C + G independent packed loads in flight before any arithmetic ----
+  typename Q4::Raw rt[MAXG], rs[MAXC];
+#pragma unroll
+  for (int i = 0; i < MAXG; ++i)
+    if (i < G) {
+      const T* p = t + (i * a.B + b) * a.ldt + col;
+      rt[i] = FAST ? Q4::load(p) : Q4::load_guard(p, col, a.K);
+    }
+#pragma unroll
+  for (int v = 0; v < MAXC; ++v)
+    if (v < C) {
+      const T* p = s + (v * a.B + b) * a.lds + col;
+      rs[v] = FAST ? Q4::load(p) : Q4::load_guard(p, col, a.K);
+    }
+  float cen[4];
+  load_center4(a.center, col, a.K, FAST && ((reinterpret_cast<uintptr_t>(a.center) & 15) == 0), cen);
+  float Q[4] = {0.f, 0.f, 0.f, 0.f}, S[4] = {0.f, 0.f, 0.f, 0.f};     // S = sum_v RAW student logits
+  float qx = 0.f;                                                       // sum_{v<G} q_v . s_v (raw)
+#pragma unroll
+  for (int v = 0; v < MAXC; ++v) {
+    if (v < C) {
+      float x[4];
+      Q4::unpack(rs[v], x);
+      float vm;
+      if (FAST) {
+        vm = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3]));
+      } else {
+        vm = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (col + e < a.K) vm = fmaxf(vm, x[e]);
+      }
+      if (vm > st.m[v]) { st.l[v] *= ex2((st.m[v] - vm) * c2); st.m[v] = vm; }     // rare after the first vectors
+      const float mb = -st.m[v] * c2;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        S[e] += x[e];                                                   // padded columns hold 0 and q = 0 there
+        const float p = ex2(fmaf(x[e], c2, mb));
+        st.l[v] += (FAST || col + e < a.K) ? p : 0.f;
+      }
+      if (v < MAXG && v < G) {                                          // same-view pair is skipped: subtract q_v . x_v
+        float tq[4];
+        Q4::unpack(rt[v < MAXG ? v : 0], tq);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float q = ex2(fmaf(tq[e] - cen[e], ct, tmc[v < MAXG ? v : 0])) * tinv[v < MAXG ? v : 0];
+          if (!FAST && col + e >= a.K) q = 0.f;
+          Q[e] += q;
+          qx = fmaf(q, x[e], qx);
+        }
+      }
+    }
+  }
+  // teacher views without a student row of the same index (only when G > C)
+#pragma unroll
+  for (int i = 0; i < MAXG; ++i)
+    if (i < G && i >= C) {
+      float tq[4];
+      Q4::unpack(rt[i], tq);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float q = ex2(fmaf(tq[e] - cen[e], ct, tmc[i])) * tinv[i];
+        if (!FAST && col + e >= a.K) q = 0.f;
+        Q[e] += q;
+      }
+    }
+  float qs = -qx;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) qs = fmaf(Q[e], S[e], qs);
+  cross = fmaf(qs, a.inv_ts, cross);                                    // raw logits -> x = s / tau_s
+}
+
 // CT / GT: compile-time crop counts (0 = runtime, bounded by 16 / 4).
 template <typename T, int CT, int GT>
-__global__ void __launch_bounds__(kThreads, kMinBlocks)
+__global__ void __launch_bounds__(kThreads, 2)
 ce_fwd_kernel(const CeArgs a) {
-  using Q4 = Quad<T>;
   constexpr int MAXC = CT ? CT : 16, MAXG = GT ? GT : 4;
   const int C = CT ? CT : a.C, G = GT ? GT : a.G;
   const long long b = blockIdx.y;
@@ -62,97 +147,38 @@ ce_fwd_kernel(const CeArgs a) {
   const long long col_end = min(a.K, col_begin + kChunkCols);
   const T* s = static_cast<const T*>(a.s);
   const T* t = static_cast<const T*>(a.t);
+  const float c2 = a.inv_ts * kLog2e, ct = a.inv_tt * kLog2e;
 
-  float tm[MAXG], tinv[MAXG];
+  float tmc[MAXG], tinv[MAXG];                        // -(row max in the base-2 domain) and 1/sum of the teacher rows of sample b
 #pragma unroll
-  for (int i = 0; i < MAXG; ++i)
-    if (i < G) { const float2 st = a.t_stats[i * a.B + b]; tm[i] = st.x; tinv[i] = st.y; }
-  float m[MAXC], l[MAXC];
+  for (int i = 0; i < MAXG; ++i) {
+    tmc[i] = 0.f; tinv[i] = 0.f;
+    if (i < G) { const float2 st = a.t_stats[i * a.B + b]; tmc[i] = -st.x; tinv[i] = st.y; }
+  }
+  RowStats<MAXC> st;
 #pragma unroll
-  for (int v = 0; v < MAXC; ++v) { m[v] = -INFINITY; l[v] = 0.f; }
+  for (int v = 0; v < MAXC; ++v) { st.m[v] = -INFINITY; st.l[v] = 0.f; }
   float cross = 0.f;
 
   for (long long col = col_begin + threadIdx.x * 4; col < col_end; col += kThreads * 4) {
-    const bool fast = a.vec_ok && (col + 4 <= a.K);
-    // ---- load phase: C + G independent packed loads in flight before any arithmetic ----
-    typename Q4::Raw rt[MAXG], rs[MAXC];
-#pragma unroll
-    for (int i = 0; i < MAXG; ++i)
-      if (i < G) {
-        const T* p = t + (i * a.B + b) * a.ldt + col;
-        rt[i] = fast ? Q4::load(p) : Q4::load_guard(p, col, a.K);
-      }
-#pragma unroll
-    for (int v = 0; v < MAXC; ++v)
-      if (v < C) {
-        const T* p = s + (v * a.B + b) * a.lds + col;
-        rs[v] = fast ? Q4::load(p) : Q4::load_guard(p, col, a.K);
-      }
-    float cen[4];
-    load_center4(a.center, col, a.K, fast && ((reinterpret_cast<uintptr_t>(a.center) & 15) == 0), cen);
-    float Q[4] = {0.f, 0.f, 0.f, 0.f}, S[4] = {0.f, 0.f, 0.f, 0.f};
-    // ---- one student row at a time; the first G rows also have a teacher row of the same view ----
-#pragma unroll
-    for (int v = 0; v < MAXC; ++v) {
-      if (v < C) {
-        float x[4];
-        Q4::unpack(rs[v], x);
-        float vm = -INFINITY;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          x[e] *= a.inv_ts;
-          S[e] += x[e];                                    // padded columns: x = 0 and q = 0 there
-          if (fast || col + e < a.K) vm = fmaxf(vm, x[e]);
-        }
-        if (vm > m[v]) { l[v] *= __expf(m[v] - vm); m[v] = vm; }
-        if (vm > -INFINITY) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (fast || col + e < a.K) l[v] += __expf(x[e] - m[v]);
-        }
-        if (v < MAXG && v < G) {                           // same-view pair is skipped: subtract q_v . x_v
-          float tq[4];
-          Q4::unpack(rt[v < MAXG ? v : 0], tq);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float q = __expf((tq[e] - cen[e]) * a.inv_tt - tm[v < MAXG ? v : 0]) * tinv[v < MAXG ? v : 0];
-            if (!fast && col + e >= a.K) q = 0.f;
-            Q[e] += q;
-            cross = fmaf(-q, x[e], cross);
-          }
-        }
-      }
-    }
-    // teacher views without a student row of the same index (only when G > C)
-#pragma unroll
-    for (int i = 0; i < MAXG; ++i)
-      if (i < G && i >= C) {
-        float tq[4];
-        Q4::unpack(rt[i], tq);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float q = __expf((tq[e] - cen[e]) * a.inv_tt - tm[i]) * tinv[i];
-          if (!fast && col + e >= a.K) q = 0.f;
-          Q[e] += q;
-        }
-      }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) cross = fmaf(Q[e], S[e], cross);
+    if (a.vec_ok && (col + 4 <= a.K)) ce_fwd_vector<T, MAXC, MAXG, true>(a, s, t, b, col, C, G, tmc, tinv, c2, ct, st, cross);
+    else ce_fwd_vector<T, MAXC, MAXG, false>(a, s, t, b, col, C, G, tmc, tinv, c2, ct, st, cross);
   }
 
-  // ---- block reduction: (m,l) per student row by online merge, cross by sum ----
+  // ---- block reduction: (m,l) per student row by online merge (natural-log domain), cross by sum ----
   __shared__ float red[kThreads / 32][2 * MAXC + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int v = 0; v < MAXC; ++v)
     if (v < C) {
+      float mv = st.m[v] * a.inv_ts, lv = st.l[v];                      // max of x = s/tau_s; l is already sum e^{x - max}
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        const float m2 = __shfl_xor_sync(0xffffffffu, m[v], o);
-        const float l2 = __shfl_xor_sync(0xffffffffu, l[v], o);
-        online_merge(m[v], l[v], m2, l2);
+        const float m2 = __shfl_xor_sync(0xffffffffu, mv, o);
+        const float l2 = __shfl_xor_sync(0xffffffffu, lv, o);
+        online_merge(mv, lv, m2, l2);
       }
-      if (lane == 0) { red[warp][2 * v] = m[v]; red[warp][2 * v + 1] = l[v]; }
+      if (lane == 0) { red[warp][2 * v] = mv; red[warp][2 * v + 1] = lv; }
     }
   cross = warp_sum(cross);
   if (lane == 0) red[warp][2 * MAXC] = cross;
@@ -200,10 +226,65 @@ ce_finalize_kernel(const float2* __restrict__ ws_s, const float* __restrict__ ws
   }
 }
 
+template <typename T, int MAXC, int MAXG, bool FAST>
+__device__ __forceinline__ void ce_bwd_vector(const CeArgs& a, const T* s, const T* t, T* ds, long long b, long long col, int C,
+                                              int G, const float (&tmc)[MAXG], const float (&tinv)[MAXG],
+                                              const float (&lse2)[MAXC], float c2, float ct, float scale) {
+  using Q4 = Quad<T>;
+  typename Q4::Raw rt[MAXG], rs[MAXC];
+#pragma unroll
+  for (int i = 0; i < MAXG; ++i)
+    if (i < G) {
+      const T* p = t + (i * a.B + b) * a.ldt + col;
+      rt[i] = FAST ? Q4::load(p) : Q4::load_guard(p, col, a.K);
+    }
+#pragma unroll
+  for (int v = 0; v < MAXC; ++v)
+    if (v < C) {
+      const T* p = s + (v * a.B + b) * a.lds + col;
+      rs[v] = FAST ? Q4::load(p) : Q4::load_guard(p, col, a.K);
+    }
+  float cen[4];
+  load_center4(a.center, col, a.K, FAST && ((reinterpret_cast<uintptr_t>(a.center) & 15) == 0), cen);
+  float q[MAXG][4], Q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < MAXG; ++i)
+    if (i < G) {
+      float tq[4];
+      Q4::unpack(rt[i], tq);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        q[i][e] = ex2(fmaf(tq[e] - cen[e], ct, tmc[i])) * tinv[i];
+        Q[e] += q[i][e];
+      }
+    }
+#pragma unroll
+  for (int v = 0; v < MAXC; ++v)
+    if (v < C) {
+      const float nvs = scale * static_cast<float>((v < G) ? (G - 1) : G);
+      float x[4], d[4];
+      Q4::unpack(rs[v], x);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float p = ex2(fmaf(x[e], c2, lse2[v]));                   // softmax(s/tau_s)
+        float qs = Q[e];
+        if (v < MAXG && v < G) qs -= q[v < MAXG ? v : 0][e];
+        d[e] = fmaf(nvs, p, -scale * qs);
+      }
+      T* dst = ds + (v * a.B + b) * a.ldds + col;
+      if (FAST) {
+        Q4::store(dst, d);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (col + e < a.K) Q4::store1(dst + e, d[e]);
+      }
+    }
+}
+
 template <typename T, int CT, int GT>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 ce_bwd_kernel(const CeArgs a) {
-  using Q4 = Quad<T>;
   constexpr int MAXC = CT ? CT : 16, MAXG = GT ? GT : 4;
   const int C = CT ? CT : a.C, G = GT ? GT : a.G;
   const long long b = blockIdx.y;
@@ -213,66 +294,22 @@ ce_bwd_kernel(const CeArgs a) {
   const T* t = static_cast<const T*>(a.t);
   T* ds = static_cast<T*>(a.ds);
   const float scale = a.coef * __ldg(a.gout);
+  const float c2 = a.inv_ts * kLog2e, ct = a.inv_tt * kLog2e;
 
-  float tm[MAXG], tinv[MAXG], lse[MAXC];
+  float tmc[MAXG], tinv[MAXG], lse2[MAXC];
 #pragma unroll
-  for (int i = 0; i < MAXG; ++i)
-    if (i < G) { const float2 st = a.t_stats[i * a.B + b]; tm[i] = st.x; tinv[i] = st.y; }
+  for (int i = 0; i < MAXG; ++i) {
+    tmc[i] = 0.f; tinv[i] = 0.f;
+    if (i < G) { const float2 st = a.t_stats[i * a.B + b]; tmc[i] = -st.x; tinv[i] = st.y; }
+  }
 #pragma unroll
-  for (int v = 0; v < MAXC; ++v)
-    if (v < C) lse[v] = a.s_lse[v * a.B + b];
-
+  for (int v = 0; v < MAXC; ++v) {
+    lse2[v] = 0.f;
+    if (v < C) lse2[v] = -a.s_lse[v * a.B + b] * kLog2e;
+  }
   for (long long col = col_begin + threadIdx.x * 4; col < col_end; col += kThreads * 4) {
-    const bool fast = a.vec_ok && (col + 4 <= a.K);
-    typename Q4::Raw rt[MAXG], rs[MAXC];
-#pragma unroll
-    for (int i = 0; i < MAXG; ++i)
-      if (i < G) {
-        const T* p = t + (i * a.B + b) * a.ldt + col;
-        rt[i] = fast ? Q4::load(p) : Q4::load_guard(p, col, a.K);
-      }
-#pragma unroll
-    for (int v = 0; v < MAXC; ++v)
-      if (v < C) {
-        const T* p = s + (v * a.B + b) * a.lds + col;
-        rs[v] = fast ? Q4::load(p) : Q4::load_guard(p, col, a.K);
-      }
-    float cen[4];
-    load_center4(a.center, col, a.K, fast && ((reinterpret_cast<uintptr_t>(a.center) & 15) == 0), cen);
-    float q[MAXG][4], Q[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int i = 0; i < MAXG; ++i)
-      if (i < G) {
-        float tq[4];
-        Q4::unpack(rt[i], tq);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          q[i][e] = __expf((tq[e] - cen[e]) * a.inv_tt - tm[i]) * tinv[i];
-          Q[e] += q[i][e];
-        }
-      }
-#pragma unroll
-    for (int v = 0; v < MAXC; ++v)
-      if (v < C) {
-        const float nv = static_cast<float>((v < G) ? (G - 1) : G);
-        float x[4], d[4];
-        Q4::unpack(rs[v], x);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float p = __expf(fmaf(x[e], a.inv_ts, -lse[v]));
-          float qs = Q[e];
-          if (v < MAXG && v < G) qs -= q[v < MAXG ? v : 0][e];
-          d[e] = scale * fmaf(nv, p, -qs);
-        }
-        T* dst = ds + (v * a.B + b) * a.ldds + col;
-        if (fast) {
-          Q4::store(dst, d);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (col + e < a.K) Q4::store1(dst + e, d[e]);
-        }
-      }
+    if (a.vec_ok && (col + 4 <= a.K)) ce_bwd_vector<T, MAXC, MAXG, true>(a, s, t, ds, b, col, C, G, tmc, tinv, lse2, c2, ct, scale);
+    else ce_bwd_vector<T, MAXC, MAXG, false>(a, s, t, ds, b, col, C, G, tmc, tinv, lse2, c2, ct, scale);
   }
 }
 

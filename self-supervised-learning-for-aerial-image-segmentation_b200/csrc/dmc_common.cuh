@@ -48,6 +48,15 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// 2^x on the SFU as a single MUFU.EX2 (flush-to-zero: no denormal fix-up sequence around it).  The softmax
+// kernels work in the base-2 domain: exp(a*x - m) = ex2(fma(x, a*log2e, -m*log2e)) -> one FFMA + one MUFU.
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+
 // exact (erf) GELU of nn.GELU() and its derivative
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_grad_f(float x) {
@@ -150,8 +159,17 @@ template <> struct Quad<__nv_bfloat16> {
 // online softmax statistic merge: (m, l) <- (m, l) (+) (m2, l2), l = sum exp(x - m)
 __device__ __forceinline__ void online_merge(float& m, float& l, float m2, float l2) {
   float mn = fmaxf(m, m2);
-  float a = (m == -INFINITY) ? 0.f : __expf(m - mn);
-  float b = (m2 == -INFINITY) ? 0.f : __expf(m2 - mn);
+  float a = (m == -INFINITY) ? 0.f : ex2((m - mn) * kLog2e);
+  float b = (m2 == -INFINITY) ? 0.f : ex2((m2 - mn) * kLog2e);
+  l = l * a + l2 * b;
+  m = mn;
+}
+
+// same merge for statistics kept in the base-2 domain: l = sum 2^(y - m)
+__device__ __forceinline__ void online_merge2(float& m, float& l, float m2, float l2) {
+  float mn = fmaxf(m, m2);
+  float a = (m == -INFINITY) ? 0.f : ex2(m - mn);
+  float b = (m2 == -INFINITY) ? 0.f : ex2(m2 - mn);
   l = l * a + l2 * b;
   m = mn;
 }

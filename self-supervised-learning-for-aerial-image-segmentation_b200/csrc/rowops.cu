@@ -67,14 +67,47 @@ normalize_bwd_kernel(const float* __restrict__ dzhat, const float* __restrict__ 
   }
 }
 
+// Vector path (dim % 4 == 0, 16-byte aligned rows): each lane owns float4 #lane, #lane+32, ... of its row; the
+// usual bottleneck width (256) keeps the whole row in registers between the two passes.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 weightnorm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, long long K, int dim,
                       float* __restrict__ w_f32, float* __restrict__ w_lo, __nv_bfloat16* __restrict__ w_bf16,
-                      float* __restrict__ scale, float* __restrict__ inv_vnorm) {
+                      float* __restrict__ scale, float* __restrict__ inv_vnorm, bool vec_ok) {
   const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= K) return;
   const int lane = threadIdx.x & 31;
   const float* vr = v + row * dim;
+  if (vec_ok) {
+    const float4* v4 = reinterpret_cast<const float4*>(vr);
+    const int nv = dim >> 2;
+    float4 keep[2];
+    float ss = 0.f;
+    for (int i = lane, j = 0; i < nv; i += 32, ++j) {
+      const float4 x = __ldg(v4 + i);
+      if (j < 2) keep[j] = x;
+      ss = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, ss))));
+    }
+    ss = warp_sum(ss);
+    const float nrm = sqrtf(ss);
+    const float sc = g[row] / nrm;
+    if (lane == 0) { scale[row] = sc; inv_vnorm[row] = 1.0f / nrm; }
+    for (int i = lane, j = 0; i < nv; i += 32, ++j) {
+      const float4 x = (j < 2) ? keep[j] : __ldg(v4 + i);
+      const float w[4] = {x.x * sc, x.y * sc, x.z * sc, x.w * sc};
+      const long long o = row * dim + 4 * i;
+      if (w_lo) {
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { hi[e] = tf32_round(w[e]); lo[e] = tf32_round(w[e] - hi[e]); }
+        if (w_f32) *reinterpret_cast<float4*>(w_f32 + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(w_lo + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      } else if (w_f32) {
+        *reinterpret_cast<float4*>(w_f32 + o) = make_float4(w[0], w[1], w[2], w[3]);
+      }
+      if (w_bf16) *reinterpret_cast<uint2*>(w_bf16 + o) = make_uint2(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]));
+    }
+    return;
+  }
   float ss = 0.f;
   for (int c = lane; c < dim; c += 32) { float x = vr[c]; ss = fmaf(x, x, ss); }
   ss = warp_sum(ss);
@@ -97,11 +130,34 @@ weightnorm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, 
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 weightnorm_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v, const float* __restrict__ scale,
-                      const float* __restrict__ inv_vnorm, long long K, int dim, float* __restrict__ dv, float* __restrict__ dg) {
+                      const float* __restrict__ inv_vnorm, long long K, int dim, float* __restrict__ dv, float* __restrict__ dg,
+                      bool vec_ok) {
   const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= K) return;
   const int lane = threadIdx.x & 31;
   const float iv = inv_vnorm[row], sc = scale[row];
+  if (vec_ok) {
+    const float4* dw4 = reinterpret_cast<const float4*>(dw + row * dim);
+    const float4* v4 = reinterpret_cast<const float4*>(v + row * dim);
+    float4* dv4 = reinterpret_cast<float4*>(dv + row * dim);
+    const int nv = dim >> 2;
+    float4 kd[2], kv[2];
+    float dot = 0.f;
+    for (int i = lane, j = 0; i < nv; i += 32, ++j) {
+      const float4 a = __ldg(dw4 + i), b = __ldg(v4 + i);
+      if (j < 2) { kd[j] = a; kv[j] = b; }
+      dot = fmaf(a.x, b.x * iv, fmaf(a.y, b.y * iv, fmaf(a.z, b.z * iv, fmaf(a.w, b.w * iv, dot))));
+    }
+    dot = warp_sum(dot);
+    if (dg && lane == 0) dg[row] = dot;
+    for (int i = lane, j = 0; i < nv; i += 32, ++j) {
+      const float4 a = (j < 2) ? kd[j] : __ldg(dw4 + i);
+      const float4 b = (j < 2) ? kv[j] : __ldg(v4 + i);
+      dv4[i] = make_float4(sc * (a.x - dot * (b.x * iv)), sc * (a.y - dot * (b.y * iv)), sc * (a.z - dot * (b.z * iv)),
+                           sc * (a.w - dot * (b.w * iv)));
+    }
+    return;
+  }
   float dot = 0.f;
   for (int c = lane; c < dim; c += 32) dot = fmaf(dw[row * dim + c], v[row * dim + c] * iv, dot);
   dot = warp_sum(dot);                                 // dW . v_hat
@@ -212,8 +268,10 @@ extern "C" int dmc_weightnorm_fwd(const float* v, const float* g, int64_t K, int
                                   void* w_bf16, float* scale, float* inv_vnorm, void* stream) {
   DMC_REQUIRE(v && g && scale && inv_vnorm, "dmc_weightnorm_fwd: null pointer");
   DMC_REQUIRE(K > 0 && dim > 0 && dim < (1 << 30), "dmc_weightnorm_fwd: bad shape");
+  auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool vec_ok = (dim % 4 == 0) && al16(v) && al16(w_f32) && al16(w_lo) && al16(w_bf16);
   weightnorm_fwd_kernel<<<(unsigned)ceil_div(K, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      v, g, K, (int)dim, w_f32, w_lo, static_cast<__nv_bfloat16*>(w_bf16), scale, inv_vnorm);
+      v, g, K, (int)dim, w_f32, w_lo, static_cast<__nv_bfloat16*>(w_bf16), scale, inv_vnorm, vec_ok);
   DMC_LAUNCH_CHECK("weightnorm_fwd_kernel launch");
   return 0;
 }
@@ -222,8 +280,10 @@ extern "C" int dmc_weightnorm_bwd(const float* dw, const float* v, const float* 
                                   int64_t K, int64_t dim, float* dv, float* dg, void* stream) {
   DMC_REQUIRE(dw && v && scale && inv_vnorm && dv, "dmc_weightnorm_bwd: null pointer");
   DMC_REQUIRE(K > 0 && dim > 0 && dim < (1 << 30), "dmc_weightnorm_bwd: bad shape");
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool vec_ok = (dim % 4 == 0) && al16(dw) && al16(v) && al16(dv);
   weightnorm_bwd_kernel<<<(unsigned)ceil_div(K, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      dw, v, scale, inv_vnorm, K, (int)dim, dv, dg);
+      dw, v, scale, inv_vnorm, K, (int)dim, dv, dg, vec_ok);
   DMC_LAUNCH_CHECK("weightnorm_bwd_kernel launch");
   return 0;
 }

@@ -1,6 +1,6 @@
 // teacher.cu -- fused teacher kernels of DINOLoss.
 //
-//   main_dino_mc.py:446   softmax((teacher_output - center) / temp)     -> per-row (max, 1/sum exp)
+//   main_dino_mc.py:446   softmax((teacher_output - center) / temp)     -> per-row (max * log2(e), 1/sum exp)
 //   main_dino_mc.py:468   torch.sum(teacher_output, dim=0)              -> per-GPU batch column sum
 //   main_dino_mc.py:470-473  center EMA                                  -> dmc_center_update
 //
@@ -19,76 +19,90 @@ namespace {
 
 constexpr int kChunk = 512;      // columns per CTA: a lane owns 4 vectors of 4 consecutive columns
 constexpr int kWarps = 8;
-constexpr int kRowsInFlight = 4; // rows a warp loads before it starts reducing (16 packed loads in flight per lane)
+constexpr int kRowsInFlight = 4; // max rows a warp loads before it starts reducing (<= 16 packed loads in flight per lane)
 constexpr int kNV = kChunk / (32 * 4);
+
+// FULL: the whole 512-column chunk lies inside K and is aligned (packed loads, no per-element guards).
+template <typename T> struct RowsInFlight { static constexpr int value = 16 / sizeof(T) / 2; };   // 4 (bf16) / 2 (fp32)
+
+template <typename T, bool FULL>
+__device__ __forceinline__ void teacher_rows(const T* __restrict__ t, long long K, long long ld, long long col0, int lane,
+                                             long long r0, long long r_end, const float (&cb)[kNV][4], float ct,
+                                             float (&cs)[kNV][4], float2* __restrict__ ws_stats, int nchunks, int chunk) {
+  using Q4 = Quad<T>;
+  constexpr int RIF = RowsInFlight<T>::value;
+  typename Q4::Raw raw[RIF][kNV];
+#pragma unroll
+  for (int j = 0; j < RIF; ++j) {
+    const long long r = r0 + j;
+    if (r < r_end) {
+      const T* rowp = t + r * ld;
+#pragma unroll
+      for (int i = 0; i < kNV; ++i) {
+        const long long c = col0 + (i * 32 + lane) * 4;
+        raw[j][i] = FULL ? Q4::load(rowp + c) : Q4::load_guard(rowp + c, c, K);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < RIF; ++j) {
+    const long long r = r0 + j;
+    if (r < r_end) {                                     // warp-uniform
+      float y[kNV][4];
+      float m = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < kNV; ++i) {
+        float x[4];
+        Q4::unpack(raw[j][i], x);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          cs[i][e] += x[e];
+          float v = fmaf(x[e], ct, cb[i][e]);            // (t - center) / temp * log2(e)
+          if (!FULL && (col0 + (i * 32 + lane) * 4 + e >= K)) v = -INFINITY;
+          y[i][e] = v;
+          m = fmaxf(m, v);
+        }
+      }
+      m = warp_max(m);
+      float l = 0.f;
+#pragma unroll
+      for (int i = 0; i < kNV; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) l += ex2(y[i][e] - m);
+      l = warp_sum(l);
+      if (lane == 0) ws_stats[r * nchunks + chunk] = make_float2(m, l);
+    }
+  }
+}
 
 template <typename T>
 __global__ void __launch_bounds__(kWarps * 32, 2)
 teacher_pass_kernel(const T* __restrict__ t, long long Nt, long long K, long long ld, const float* __restrict__ center,
                     float inv_temp, float2* __restrict__ ws_stats, float* __restrict__ ws_colsum, int rows_per_block,
                     int nchunks, bool vec_ok) {
-  using Q4 = Quad<T>;
   __shared__ __align__(16) float sm[kWarps][kChunk];  // 16 KiB: per-warp column sums
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.x;
   const long long col0 = static_cast<long long>(chunk) * kChunk;
   const bool full = vec_ok && (col0 + kChunk <= K);
+  const float ct = inv_temp * kLog2e;
 
-  float cen[kNV][4], cs[kNV][4];
+  float cb[kNV][4], cs[kNV][4];                        // cb = -center * ct (folded into one FFMA per logit)
 #pragma unroll
   for (int i = 0; i < kNV; ++i) {
     const long long c = col0 + (i * 32 + lane) * 4;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      cen[i][e] = (c + e < K) ? __ldg(center + c + e) : 0.f;
+      cb[i][e] = (c + e < K) ? -__ldg(center + c + e) * ct : 0.f;
       cs[i][e] = 0.f;
     }
   }
   const long long r_begin = static_cast<long long>(blockIdx.y) * rows_per_block;
   const long long r_end = min(r_begin + rows_per_block, Nt);
-  for (long long r0 = r_begin + warp * kRowsInFlight; r0 < r_end; r0 += kWarps * kRowsInFlight) {
-    typename Q4::Raw raw[kRowsInFlight][kNV];
-#pragma unroll
-    for (int j = 0; j < kRowsInFlight; ++j) {
-      const long long r = r0 + j;
-      if (r < r_end) {
-        const T* rowp = t + r * ld;
-#pragma unroll
-        for (int i = 0; i < kNV; ++i) {
-          const long long c = col0 + (i * 32 + lane) * 4;
-          raw[j][i] = full ? Q4::load(rowp + c) : Q4::load_guard(rowp + c, c, K);
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < kRowsInFlight; ++j) {
-      const long long r = r0 + j;
-      if (r < r_end) {                                   // warp-uniform
-        float y[kNV][4];
-        float m = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < kNV; ++i) {
-          float x[4];
-          Q4::unpack(raw[j][i], x);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            cs[i][e] += x[e];
-            float v = (x[e] - cen[i][e]) * inv_temp;
-            if (!full && (col0 + (i * 32 + lane) * 4 + e >= K)) v = -INFINITY;
-            y[i][e] = v;
-            m = fmaxf(m, v);
-          }
-        }
-        m = warp_max(m);
-        float l = 0.f;
-#pragma unroll
-        for (int i = 0; i < kNV; ++i)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) l += __expf(y[i][e] - m);
-        l = warp_sum(l);
-        if (lane == 0) ws_stats[r * nchunks + chunk] = make_float2(m, l);
-      }
-    }
+  constexpr int RIF = RowsInFlight<T>::value;
+  for (long long r0 = r_begin + warp * RIF; r0 < r_end; r0 += kWarps * RIF) {
+    if (full) teacher_rows<T, true>(t, K, ld, col0, lane, r0, r_end, cb, ct, cs, ws_stats, nchunks, chunk);
+    else teacher_rows<T, false>(t, K, ld, col0, lane, r0, r_end, cb, ct, cs, ws_stats, nchunks, chunk);
   }
 #pragma unroll
   for (int i = 0; i < kNV; ++i)
@@ -111,16 +125,16 @@ teacher_finalize_kernel(const float2* __restrict__ ws_stats, const float* __rest
     const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
     if (r >= Nt) return;
     const int lane = threadIdx.x & 31;
-    float m = -INFINITY, l = 0.f;
+    float m = -INFINITY, l = 0.f;                    // base-2 domain: l = sum 2^(y2 - m)
     for (int c = lane; c < nchunks; c += 32) {
       const float2 p = ws_stats[r * nchunks + c];
-      online_merge(m, l, p.x, p.y);
+      online_merge2(m, l, p.x, p.y);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
       const float l2 = __shfl_xor_sync(0xffffffffu, l, o);
-      online_merge(m, l, m2, l2);
+      online_merge2(m, l, m2, l2);
     }
     if (lane == 0) row_stats[r] = make_float2(m, 1.0f / l);
   } else {
