@@ -8,6 +8,7 @@ Python identifier).  Public surface mirrors the reference:
     DINOLoss(out_dim, ncrops, warmup_teacher_temp, teacher_temp, warmup_teacher_temp_epochs, nepochs,
              teacher_crops_number=2, student_temp=0.1, center_momentum=0.9)
     ema_update_(teacher_params, student_params, m)
+    StepGraph(fn)      # capture a whole step into a CUDA graph and replay it
     dropin.install()   # patch the reference's modules in place
 
 All compute goes through libdinomc.so (hand-written CUDA behind the C ABI in include/dinomc.h).
@@ -16,8 +17,9 @@ kernels raises.
 """
 from . import _lib, functional, ops  # noqa: F401
 from .ema import ema_update_  # noqa: F401
+from .graph import StepGraph  # noqa: F401
 from .head import DINOHead, get_default_precision, set_default_precision  # noqa: F401
 from .loss import DINOLoss  # noqa: F401
 
-__all__ = ["DINOHead", "DINOLoss", "ema_update_", "set_default_precision", "get_default_precision",
+__all__ = ["DINOHead", "DINOLoss", "ema_update_", "StepGraph", "set_default_precision", "get_default_precision",
            "ops", "functional"]

@@ -7,12 +7,13 @@
 // N = out_dim = 65536, K = bottleneck = 256), its dgrad (contraction over out_dim, split-K) and wgrad
 // (MN-major operands straight from the row-major gradient), and the MLP Linears (:291).
 //
-// Structure (one CTA per SM, 192 threads):
+// Structure (one CTA per SM, 320 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor tiles into a ring of 128B-swizzled smem stages
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=block_n, K=32 bytes/row)
 //               into one of two TMEM accumulators (2 x 256 fp32 columns = all 512 TMEM columns)
-//   warps 2..5  epilogue: tcgen05.ld the finished accumulator, apply scale/bias/activation, store;
-//               overlaps the MMAs of the next tile thanks to the double-buffered accumulator.
+//   warps 2..9  epilogue: tcgen05.ld the finished accumulator (two warps per TMEM lane quadrant, one per half of
+//               the tile's columns), apply scale/bias/activation, store; overlaps the MMAs of the next tile
+//               thanks to the double-buffered accumulator.
 // Three mbarrier pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue).
 //
 // Output path: the epilogue warps write the converted tile into 128B-swizzled smem staging buffers and one
@@ -39,7 +40,8 @@ constexpr int kMaxStages = 8;
 constexpr int kMmaPerKBlock = 4;        // 128 B / 32 B: four tcgen05.mma per k-block
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 256;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;           // two epilogue warps per TMEM lane quadrant (one per half of the tile columns)
+constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr uint32_t kABytes = kBlockM * kRowBytes;  // 16 KiB per stage for A
 
 struct GemmDev {
@@ -156,10 +158,12 @@ __device__ __forceinline__ void epilogue_store_row(const Epilogue& e, float (&ac
   }
 }
 
-constexpr int kStagingBytesPerWarp = 2 * 4096;   // two 32-row x 128-byte boxes per epilogue warp
-constexpr int kStagingBytes = 4 * kStagingBytesPerWarp;
+constexpr int kStagingBytesPerWarp = 4096;       // one 32-row x 128-byte box per epilogue warp
+constexpr int kStagingBytes = kEpiWarps * kStagingBytesPerWarp;
 
-template <int ESZ, bool A_MN, bool B_MN>
+// PLAIN: the epilogue is only "scale by alpha, convert, store" (no column scale / bias / activation / aux):
+// compiled separately so the hot last-layer kernels carry none of the optional epilogue code.
+template <int ESZ, bool A_MN, bool B_MN, bool PLAIN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -201,7 +205,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1);
       ptx::mbar_init(&bfull_bar[i], 1); ptx::mbar_init(&bempty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], kEpiWarps); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {               // this warp owns the TMEM allocation (alloc + dealloc)
@@ -322,8 +326,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;                                     // TMEM lane quadrant this warp may access
+    const int ew = warp - 2;
+    const int half = ew >> 2;                                   // which half of the tile's columns this warp drains
+    const int c_begin = (p.block_n >= 128) ? half * (p.block_n >> 1) : 0;
+    const int c_end = (p.block_n >= 128) ? c_begin + (p.block_n >> 1) : (half == 0 ? p.block_n : 0);
     Epilogue e{p.col_scale, p.bias, p.alpha, p.act, p.aux, p.ldaux, p.aux_dtype, p.D, p.ldd, p.out_dtype, p.N};
     if (p.alpha_dev) e.alpha *= __ldg(p.alpha_dev);
     const int out_esz = (p.out_dtype == DMC_BF16) ? 2 : 4;
@@ -333,7 +341,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int aux_esz = (p.aux_dtype == DMC_BF16) ? 2 : 4;
       aux_vec_ok = ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) && ((p.ldaux * aux_esz) % 16 == 0);
     }
-    uint8_t* my_staging = staging + (warp - 2) * kStagingBytesPerWarp;
+    uint8_t* my_staging = staging + ew * kStagingBytesPerWarp;
     const int chunks_per_box = (p.out_dtype == DMC_BF16) ? 2 : 1;   // 32-column chunks per 128-byte-wide box
     uint32_t n_boxes = 0;                                            // boxes this warp has stored so far
     int it = 0;
@@ -372,7 +380,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
           return;
         }
-        if (row < p.M) epilogue_math(e, v, row, n0 + c, n, aux_vec_ok);
+        if constexpr (PLAIN) {
+          if (e.alpha != 1.0f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= e.alpha;
+          }
+        } else {
+          if (row < p.M) epilogue_math(e, v, row, n0 + c, n, aux_vec_ok);
+        }
         if (!p.tma_store) {
           if (row < p.M) epilogue_store_row(e, v, row, n0 + c, n, vec_ok);
           return;
@@ -380,9 +395,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // ---- smem-staged TMA store.  Box = 32 rows x 128 bytes (64 bf16 / 32 fp32 columns), 128B-swizzled:
         //      16-byte chunk j of row r lives at r*128 + ((j ^ (r & 7)) << 4)  -> conflict-free warp stores.
         const int sub = (c >> 5) % chunks_per_box;              // which half of the box this chunk fills
-        uint8_t* buf = my_staging + (n_boxes & 1u) * 4096;
-        if (sub == 0 && n_boxes >= 2) {                         // buffer was handed to TMA two boxes ago
-          if (lane == 0) ptx::tma_store_wait_read<1>();
+        uint8_t* buf = my_staging;
+        if (sub == 0 && n_boxes >= 1) {                         // the previous box's TMA store must have read the buffer
+          if (lane == 0) ptx::tma_store_wait_read<0>();
           __syncwarp();
         }
         uint8_t* rowp = buf + lane * 128;
@@ -409,18 +424,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           ++n_boxes;
         }
       };
-      for (int c = 0; c < p.block_n; c += 64) {                 // block_n is a multiple of 64
+      for (int c = c_begin; c < c_end; c += 64) {               // this warp's column range, 64 columns at a time
         uint32_t ra[32], rb[32];
         ptx::tmem_ld_32x32(t_addr + c, ra);                     // two TMEM loads in flight per wait
         ptx::tmem_ld_32x32(t_addr + c + 32, rb);
         ptx::tmem_ld_wait();
-        if (c + 64 >= p.block_n) {                              // last read of this accumulator: hand it back
+        if (c + 64 >= c_end) {                                  // this warp's last read of the accumulator: hand it back
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
         }
         process(ra, c);
         process(rb, c + 32);
+      }
+      if (c_begin >= c_end) {                                   // nothing to drain (block_n == 64, upper half): still release
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
       }
     }
     if (p.tma_store && lane == 0) ptx::tma_store_wait_all<0>();  // all bulk stores complete before the CTA exits
@@ -528,8 +548,14 @@ Plan make_plan(int64_t M, int64_t N, int64_t K, int in_dtype, bool three_pass, i
   Plan pl{};
   const int esz = (in_dtype == DMC_BF16) ? 2 : 4;
   const int block_k = kRowBytes / esz;
-  pl.block_n = N >= 256 ? 256 : (N > 64 ? 128 : 64);
-  if (N > 128 && N < 256) pl.block_n = 256;
+  // Tile width: as wide as possible (fewest re-reads of A), but for short contractions prefer enough tiles to fill
+  // the 148 SMs over a split-K pass; long contractions keep the wide tile and split K instead (A is read once).
+  const int64_t mt = ceil_div(M, kBlockM);
+  int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  if (K < 8192 && forced_split == 0) {
+    while (bn > 64 && mt * ceil_div(N, bn) < 100) bn >>= 1;
+  }
+  pl.block_n = bn;
   pl.m_tiles = static_cast<int>(ceil_div(M, kBlockM));
   pl.n_tiles = static_cast<int>(ceil_div(N, pl.block_n));
   pl.kb_total = static_cast<int>(ceil_div(K, block_k));
@@ -568,10 +594,10 @@ Plan make_plan(int64_t M, int64_t N, int64_t K, int in_dtype, bool three_pass, i
   return pl;
 }
 
-template <int ESZ, bool A_MN, bool B_MN>
+template <int ESZ, bool A_MN, bool B_MN, bool PLAIN>
 int launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
               const CUtensorMap& td, const GemmDev& dev, size_t smem_bytes, int grid, cudaStream_t st) {
-  auto kern = gemm_tc_kernel<ESZ, A_MN, B_MN>;
+  auto kern = gemm_tc_kernel<ESZ, A_MN, B_MN, PLAIN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
   if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(gemm_tc_kernel)");
   kern<<<grid, kThreads, smem_bytes, st>>>(a0, a1, b0, b1, td, dev);
@@ -650,12 +676,15 @@ extern "C" int dmc_gemm(const dmc_gemm_args* a, void* stream) {
   const int num_work = pl.m_tiles * pl.n_tiles * pl.splits;
   const int grid = num_work < kNumSMs ? num_work : kNumSMs;
   const bool amn = a->a_mn_major != 0, bmn = a->b_mn_major != 0;
-#define DMC_DISPATCH(ESZ_)                                                                                   \
-  (amn ? (bmn ? launch_tc<ESZ_, true, true>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st)                  \
-              : launch_tc<ESZ_, true, false>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st))                \
-       : (bmn ? launch_tc<ESZ_, false, true>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st)                 \
-              : launch_tc<ESZ_, false, false>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st)))
+const bool plain = (a->col_scale == nullptr && a->bias == nullptr && a->act == DMC_ACT_NONE);
+#define DMC_LAUNCH(ESZ_, AMN_, BMN_)                                                                          \
+  (plain ? launch_tc<ESZ_, AMN_, BMN_, true>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st)              \
+         : launch_tc<ESZ_, AMN_, BMN_, false>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st))
+#define DMC_DISPATCH(ESZ_)                                                                                    \
+  (amn ? (bmn ? DMC_LAUNCH(ESZ_, true, true) : DMC_LAUNCH(ESZ_, true, false))                                 \
+       : (bmn ? DMC_LAUNCH(ESZ_, false, true) : DMC_LAUNCH(ESZ_, false, false)))
   rc = (esz == 2) ? DMC_DISPATCH(2) : DMC_DISPATCH(4);
+#undef DMC_LAUNCH
 #undef DMC_DISPATCH
   if (rc) return rc;
 

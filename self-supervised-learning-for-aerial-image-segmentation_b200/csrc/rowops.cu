@@ -192,24 +192,39 @@ cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, lon
 }
 
 // Column sum in two deterministic steps: [row_splits][N] partials, then a fixed-order reduction.
+// A thread owns 4 consecutive columns (one packed load per row), a block = 32 column groups x 8 row lanes.
+template <typename T>
 __global__ void __launch_bounds__(256)
-colsum_partial_kernel(const void* __restrict__ X, int dtype, long long M, int N, long long ld, int rows_per_split,
+colsum_partial_kernel(const T* __restrict__ X, long long M, int N, long long ld, int rows_per_split, bool vec_ok,
                       float* __restrict__ partial) {
-  __shared__ float red[8][33];
+  using Q4 = Quad<T>;
+  __shared__ float red[8][32][5];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int col = blockIdx.x * 32 + cx;
+  const long long col = (static_cast<long long>(blockIdx.x) * 32 + cx) * 4;
   const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_split;
   const long long r1 = min(r0 + rows_per_split, M);
-  float s = 0.f;
-  if (col < N)
-    for (long long r = r0 + ry; r < r1; r += 8) s += ld_in(X, r * ld + col, dtype);
-  red[ry][cx] = s;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  if (col < N) {
+    const bool fast = vec_ok && (col + 4 <= N);
+    for (long long r = r0 + ry; r < r1; r += 8) {
+      float x[4];
+      const T* p = X + r * ld + col;
+      Q4::unpack(fast ? Q4::load(p) : Q4::load_guard(p, col, N), x);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[e] += x[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) red[ry][cx][e] = s[e];
   __syncthreads();
   if (ry == 0 && col < N) {
-    float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][cx];
-    partial[static_cast<long long>(blockIdx.y) * N + col] = t;
+    for (int e = 0; e < 4; ++e) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += red[i][cx][e];
+      if (col + e < N) partial[static_cast<long long>(blockIdx.y) * N + col + e] = t;
+    }
   }
 }
 __global__ void __launch_bounds__(256)
@@ -222,9 +237,9 @@ colsum_final_kernel(const float* __restrict__ partial, int splits, int N, float*
 }
 
 int colsum_splits(int64_t M, int64_t N) {
-  const int64_t col_blocks = ceil_div(N, 32);
-  int64_t s = ceil_div(2 * kNumSMs, col_blocks);
-  if (s > ceil_div(M, 8)) s = ceil_div(M, 8);
+  const int64_t col_blocks = ceil_div(N, 128);
+  int64_t s = ceil_div(4 * kNumSMs, col_blocks);
+  if (s > ceil_div(M, 16)) s = ceil_div(M, 16);
   if (s < 1) s = 1;
   if (s > 1024) s = 1024;
   return static_cast<int>(s);
@@ -315,8 +330,15 @@ extern "C" int dmc_colsum(const void* X, int32_t dtype, int64_t M, int64_t N, in
   const int splits = colsum_splits(M, N);
   DMC_REQUIRE(workspace_bytes >= static_cast<size_t>(splits) * N * sizeof(float), "dmc_colsum: workspace too small");
   const int rows_per_split = static_cast<int>(ceil_div(M, splits));
-  dim3 grid((unsigned)ceil_div(N, 32), (unsigned)splits);
-  colsum_partial_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, dtype, M, (int)N, ld, rows_per_split, static_cast<float*>(workspace));
+  dim3 grid((unsigned)ceil_div(N, 128), (unsigned)splits);
+  const int esz = dtype == DMC_BF16 ? 2 : 4;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(X) % (4 * esz)) == 0) && ((ld * esz) % (4 * esz) == 0);
+  if (dtype == DMC_BF16)
+    colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16*>(X), M, (int)N, ld,
+                                                                                rows_per_split, vec_ok, static_cast<float*>(workspace));
+  else
+    colsum_partial_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const float*>(X), M, (int)N, ld, rows_per_split,
+                                                                        vec_ok, static_cast<float*>(workspace));
   DMC_LAUNCH_CHECK("colsum_partial_kernel launch");
   colsum_final_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, (cudaStream_t)stream>>>(static_cast<const float*>(workspace), splits, (int)N, out);
   DMC_LAUNCH_CHECK("colsum_final_kernel launch");
