@@ -54,6 +54,7 @@ struct GemmDev {
   int stages;
   uint32_t b_bytes;   // block_n * 128
   int resident;       // 1: B-resident schedule (contiguous tile ranges, B slabs loaded once per n-tile)
+  int dual;           // 1: "dual-M": a work item is 256 rows = two accumulators that share every B k-block
   int tma_store;      // 1: epilogue stores D through smem staging + TMA
   // epilogue
   void* D; long long ldd; int out_dtype;
@@ -181,7 +182,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);   // 1024-B aligned (SWIZZLE_128B atoms)
 
   // smem carve-up: [resident B slabs][stage ring][epilogue staging][barriers]
-  const uint32_t stage_bytes = p.resident ? kABytes : (kABytes + p.b_bytes);
+  const uint32_t a_stage_bytes = p.dual ? 2u * kABytes : kABytes;   // dual-M: two 128-row A tiles per stage
+  const uint32_t stage_bytes = p.resident ? a_stage_bytes : (a_stage_bytes + p.b_bytes);
+  const int tile_m = p.dual ? 2 * kBlockM : kBlockM;
   const uint32_t res_bytes = p.resident ? static_cast<uint32_t>(p.vk_total) * p.b_bytes : 0u;
   uint8_t* b_res = smem;
   uint8_t* tiles = smem + res_bytes;
@@ -239,7 +242,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int rest = w / p.m_tiles;
         const int nt = rest % p.n_tiles;
         const int sp = rest / p.n_tiles;
-        const int m0 = mt * kBlockM, n0 = nt * p.block_n;
+        const int m0 = mt * tile_m, n0 = nt * p.block_n;
         const int vk0 = sp * p.vk_per_split;
         const int vk1 = min(vk0 + p.vk_per_split, p.vk_total);
         const bool load_b = p.resident && (nt != prev_nt);
@@ -249,7 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const CUtensorMap* ta = (pass == 2) ? &tmA1 : &tmA0;   // passes: hi*hi, hi*lo, lo*hi
           const CUtensorMap* tb = (pass == 1) ? &tmB1 : &tmB0;
           uint8_t* sA = tiles + static_cast<size_t>(stage) * stage_bytes;
-          uint8_t* sB = p.resident ? (b_res + static_cast<size_t>(vk) * p.b_bytes) : (sA + kABytes);
+          uint8_t* sB = p.resident ? (b_res + static_cast<size_t>(vk) * p.b_bytes) : (sA + a_stage_bytes);
           uint64_t* bar_b = p.resident ? &bfull_bar[vk] : &full_bar[stage];
           if (load_b) {                                           // new n-tile: refill slab vk once the MMAs
             ptx::mbar_wait(&bempty_bar[vk], (b_gen & 1u) ^ 1u);   // that read its previous contents have retired
@@ -265,12 +268,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 ptx::tma_load_2d(sB + j * kBoxBytes, tb, bar_b, n0 + j * BOX_MN, k0);
             }
           }
-          if constexpr (!A_MN) {
-            ptx::tma_load_2d(sA, ta, &full_bar[stage], k0, m0);                 // box {BLOCK_K, 128}
-          } else {
+          for (int h = 0; h <= p.dual; ++h) {                                     // one or two 128-row A tiles
+            uint8_t* sAh = sA + h * kABytes;
+            const int mh = m0 + h * kBlockM;
+            if constexpr (!A_MN) {
+              ptx::tma_load_2d(sAh, ta, &full_bar[stage], k0, mh);              // box {BLOCK_K, 128}
+            } else {
 #pragma unroll
-            for (int j = 0; j < kBlockM / BOX_MN; ++j)                            // boxes {BOX_MN, BLOCK_K}
-              ptx::tma_load_2d(sA + j * kBoxBytes, ta, &full_bar[stage], m0 + j * BOX_MN, k0);
+              for (int j = 0; j < kBlockM / BOX_MN; ++j)                          // boxes {BOX_MN, BLOCK_K}
+                ptx::tma_load_2d(sAh + j * kBoxBytes, ta, &full_bar[stage], mh + j * BOX_MN, k0);
+            }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
@@ -293,8 +300,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const bool new_b = p.resident && (nt != prev_nt);
         // last tile of this CTA that uses the resident B of this n-tile -> release the slabs afterwards
         const bool last_of_nt = p.resident && ((w + 1 >= w_end) || (((w + 1) / p.m_tiles) % p.n_tiles != nt));
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1u;
+        // single-M: two accumulators ping-pong between MMA and epilogue; dual-M: both belong to this work item
+        const int acc = p.dual ? 0 : (it & 1);
+        const uint32_t acc_phase = p.dual ? (it & 1u) : ((it >> 1) & 1u);
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);      // epilogue has drained this accumulator
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccCols);
@@ -303,7 +311,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           ptx::mbar_wait(&full_bar[stage], phase);              // TMA bytes have landed
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(tiles + static_cast<size_t>(stage) * stage_bytes);
-          const uint32_t b_addr = p.resident ? ptx::smem_u32(b_res + static_cast<size_t>(vk) * p.b_bytes) : (a_addr + kABytes);
+          const uint32_t b_addr = p.resident ? ptx::smem_u32(b_res + static_cast<size_t>(vk) * p.b_bytes) : (a_addr + a_stage_bytes);
 #pragma unroll
           for (int k = 0; k < kMmaPerKBlock; ++k) {
             // K-major: rows of 128 B, 8-row groups 1024 B apart (SBO); advance 32 B per MMA inside the swizzle row.
@@ -315,6 +323,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const uint64_t db = B_MN ? ptx::make_smem_desc_sw128(b_addr + k * (UMMA_K * kRowBytes), kBoxBytes, kMnSbo, kMnLayout)
                                      : ptx::make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
             ptx::umma<kTf32>(d_tmem, da, db, idesc, (vk > vk0 || k > 0) ? 1u : 0u);
+            if (p.dual) {                                       // rows 128..255 of the item: same B, second accumulator
+              const uint64_t da1 = A_MN ? ptx::make_smem_desc_sw128(a_addr + kABytes + k * (UMMA_K * kRowBytes), kBoxBytes, kMnSbo, kMnLayout)
+                                        : ptx::make_smem_desc_sw128(a_addr + kABytes + k * 32, 16, 1024);
+              ptx::umma<kTf32>(d_tmem + kAccCols, da1, db, idesc, (vk > vk0 || k > 0) ? 1u : 0u);
+            }
           }
           ptx::umma_commit(&empty_bar[stage]);                  // frees the smem stage when these MMAs retire
           if (last_of_nt) ptx::umma_commit(&bempty_bar[vk]);    // ... and the resident B slab
@@ -351,14 +364,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int nt = rest % p.n_tiles;
       const int sp = rest / p.n_tiles;
       const int n0 = nt * p.block_n;
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1u;
-      const int row0 = mt * kBlockM + q * 32;
-      const long long row = static_cast<long long>(row0) + lane;
+      const int acc = p.dual ? 0 : (it & 1);
+      const uint32_t acc_phase = p.dual ? (it & 1u) : ((it >> 1) & 1u);
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
-      const uint32_t t_addr = tmem_base + static_cast<uint32_t>(acc * kAccCols) + (static_cast<uint32_t>(q * 32) << 16);
       const int ncols = min(p.block_n, p.N - n0);
+      for (int h = 0; h <= p.dual; ++h) {                       // dual-M: drain both accumulators of the item
+      const int row0 = mt * tile_m + h * kBlockM + q * 32;
+      const long long row = static_cast<long long>(row0) + lane;
+      const uint32_t t_addr = tmem_base + static_cast<uint32_t>((acc + h) * kAccCols) + (static_cast<uint32_t>(q * 32) << 16);
+      const bool last_h = (h == p.dual);
       // One 32-column chunk: accumulators -> epilogue -> split-K partials | direct store | smem staging + TMA store.
       auto process = [&](uint32_t (&r)[32], int c) {
         const int n = min(32, ncols - c);
@@ -429,7 +444,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         ptx::tmem_ld_32x32(t_addr + c, ra);                     // two TMEM loads in flight per wait
         ptx::tmem_ld_32x32(t_addr + c + 32, rb);
         ptx::tmem_ld_wait();
-        if (c + 64 >= c_end) {                                  // this warp's last read of the accumulator: hand it back
+        if (last_h && c + 64 >= c_end) {                        // this warp's last read of the accumulator(s): hand back
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
@@ -437,11 +452,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         process(ra, c);
         process(rb, c + 32);
       }
-      if (c_begin >= c_end) {                                   // nothing to drain (block_n == 64, upper half): still release
+      if (last_h && c_begin >= c_end) {                         // nothing to drain (block_n == 64, upper half): still release
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
       }
+      }  // h
     }
     if (p.tma_store && lane == 0) ptx::tma_store_wait_all<0>();  // all bulk stores complete before the CTA exits
   }
@@ -530,11 +546,12 @@ int make_tmap(CUtensorMap* tm, const void* base, int esz, int64_t rows, int64_t 
 }
 
 struct Plan {
-  int block_n, m_tiles, n_tiles, kb_total, passes, vk_total, splits, vk_per_split, stages, resident, tma_store;
+  int block_n, m_tiles, n_tiles, kb_total, passes, vk_total, splits, vk_per_split, stages, resident, tma_store, dual;
   size_t smem_bytes, workspace_bytes;
 };
 
-// DMC_GEMM_FLAGS (debug / A-B measurements): bit 0 = no TMA-store epilogue, bit 1 = no B-resident schedule.
+// DMC_GEMM_FLAGS (debug / A-B measurements): bit 0 = no TMA-store epilogue, bit 1 = no B-resident schedule,
+// bit 2 = no dual-M work items.
 int debug_flags() {
   static int flags = -1;
   if (flags < 0) {
@@ -556,11 +573,19 @@ Plan make_plan(int64_t M, int64_t N, int64_t K, int in_dtype, bool three_pass, i
     while (bn > 64 && mt * ceil_div(N, bn) < 100) bn >>= 1;
   }
   pl.block_n = bn;
-  pl.m_tiles = static_cast<int>(ceil_div(M, kBlockM));
   pl.n_tiles = static_cast<int>(ceil_div(N, pl.block_n));
   pl.kb_total = static_cast<int>(ceil_div(K, block_k));
   pl.passes = three_pass ? 3 : 1;
   pl.vk_total = pl.kb_total * pl.passes;
+  // dual-M: 256-row work items whose two accumulators share every B k-block from smem (a third less L2->smem
+  // operand traffic).  Costs the MMA/epilogue overlap between items, so only for long contractions, and only
+  // when there are still enough items to fill the machine (or K is split anyway).
+  pl.dual = 0;
+  if (!(debug_flags() & 4) && M > kBlockM && pl.vk_total >= 16) {
+    const int64_t items = ceil_div(M, 2 * kBlockM) * pl.n_tiles;
+    if (K >= 8192 || items >= kNumSMs) pl.dual = 1;
+  }
+  pl.m_tiles = static_cast<int>(ceil_div(M, pl.dual ? 2 * kBlockM : kBlockM));
   const int tiles = pl.m_tiles * pl.n_tiles;
   int splits = 1;
   if (forced_split >= 1) {
@@ -581,9 +606,9 @@ Plan make_plan(int64_t M, int64_t N, int64_t K, int in_dtype, bool three_pass, i
   // B-resident schedule: the whole contraction's worth of B for one n-tile stays in smem (<= 8 slabs, <= 128 KiB),
   // leaving >= 4 A-only stages.  Pays off when several m-tiles share an n-tile.
   const size_t res_bytes = static_cast<size_t>(pl.vk_total) * b_bytes;
-  pl.resident = (pl.splits == 1 && pl.vk_total <= kMaxStages && pl.m_tiles >= 2 && !(debug_flags() & 2) &&
+  pl.resident = (pl.splits == 1 && pl.vk_total <= kMaxStages && pl.m_tiles >= 2 && !pl.dual && !(debug_flags() & 2) &&
                  res_bytes + 4 * kABytes <= budget) ? 1 : 0;
-  const size_t stage_bytes = pl.resident ? kABytes : (kABytes + b_bytes);
+  const size_t stage_bytes = pl.resident ? kABytes : ((pl.dual ? 2 : 1) * kABytes + b_bytes);
   if (pl.resident) budget -= res_bytes;
   int stages = static_cast<int>(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
@@ -667,7 +692,7 @@ extern "C" int dmc_gemm(const dmc_gemm_args* a, void* stream) {
   d.block_n = pl.block_n; d.m_tiles = pl.m_tiles; d.n_tiles = pl.n_tiles;
   d.kb_total = pl.kb_total; d.vk_total = pl.vk_total; d.splits = pl.splits; d.vk_per_split = pl.vk_per_split;
   d.stages = pl.stages; d.b_bytes = static_cast<uint32_t>(pl.block_n) * kRowBytes;
-  d.resident = pl.resident; d.tma_store = pl.tma_store;
+  d.resident = pl.resident; d.tma_store = pl.tma_store; d.dual = pl.dual;
   d.D = a->D; d.ldd = a->ldd; d.out_dtype = a->out_dtype;
   d.partial = pl.splits > 1 ? static_cast<float*>(a->workspace) : nullptr;
   d.col_scale = a->col_scale; d.bias = a->bias; d.alpha_dev = a->alpha_dev; d.alpha = a->alpha;
