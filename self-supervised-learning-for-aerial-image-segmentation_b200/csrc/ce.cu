@@ -56,36 +56,45 @@ struct RowStats {
   float m[MAXC], l[MAXC];
 };
 
-// One 4-column vector of all C student and G teacher rows of sample b.  FAST: the vector is fully inside K and
-// aligned (packed loads, no per-element guards); !FAST: the ragged last vector of a row.
+// The packed logits of one 4-column vector: C student rows + G teacher rows of sample b, plus the center.
+template <typename T, int MAXC, int MAXG>
+struct CeVec {
+  typename Quad<T>::Raw rs[MAXC], rt[MAXG];
+  float cen[4];
+};
+
+// FAST: the vector is fully inside K and aligned (packed loads, no per-element guards); !FAST: ragged row end.
 template <typename T, int MAXC, int MAXG, bool FAST>
-__device__ __forceinline__ void ce_fwd_vector(const CeArgs& a, const T* s, const T* t, long long b, long long col, int C, int G,
-                                              const float (&tmc)[MAXG], const float (&tinv)[MAXG], float c2, float ct,
-                                              RowStats<MAXC>& st, float& cross) {
+__device__ __forceinline__ void ce_load(const CeArgs& a, const T* s, const T* t, long long b, long long col, int C, int G,
+                                        CeVec<T, MAXC, MAXG>& v) {
   using Q4 = Quad<T>;
-  // ---- load phase: C + G independent packed loads in flight before any arithmetic ----
-  typename Q4::Raw rt[MAXG], rs[MAXC];
 #pragma unroll
   for (int i = 0; i < MAXG; ++i)
     if (i < G) {
       const T* p = t + (i * a.B + b) * a.ldt + col;
-      rt[i] = FAST ? Q4::load(p) : Q4::load_guard(p, col, a.K);
+      v.rt[i] = FAST ? Q4::load(p) : Q4::load_guard(p, col, a.K);
     }
 #pragma unroll
-  for (int v = 0; v < MAXC; ++v)
-    if (v < C) {
-      const T* p = s + (v * a.B + b) * a.lds + col;
-      rs[v] = FAST ? Q4::load(p) : Q4::load_guard(p, col, a.K);
+  for (int r = 0; r < MAXC; ++r)
+    if (r < C) {
+      const T* p = s + (r * a.B + b) * a.lds + col;
+      v.rs[r] = FAST ? Q4::load(p) : Q4::load_guard(p, col, a.K);
     }
-  float cen[4];
-  load_center4(a.center, col, a.K, FAST && ((reinterpret_cast<uintptr_t>(a.center) & 15) == 0), cen);
+  load_center4(a.center, col, a.K, FAST && ((reinterpret_cast<uintptr_t>(a.center) & 15) == 0), v.cen);
+}
+
+template <typename T, int MAXC, int MAXG, bool FAST>
+__device__ __forceinline__ void ce_fwd_compute(const CeArgs& a, const CeVec<T, MAXC, MAXG>& in, long long col, int C, int G,
+                                               const float (&tmc)[MAXG], const float (&tinv)[MAXG], float c2, float ct,
+                                               RowStats<MAXC>& st, float& cross) {
+  using Q4 = Quad<T>;
   float Q[4] = {0.f, 0.f, 0.f, 0.f}, S[4] = {0.f, 0.f, 0.f, 0.f};     // S = sum_v RAW student logits
   float qx = 0.f;                                                       // sum_{v<G} q_v . s_v (raw)
 #pragma unroll
   for (int v = 0; v < MAXC; ++v) {
     if (v < C) {
       float x[4];
-      Q4::unpack(rs[v], x);
+      Q4::unpack(in.rs[v], x);
       float vm;
       if (FAST) {
         vm = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3]));
@@ -105,10 +114,10 @@ __device__ __forceinline__ void ce_fwd_vector(const CeArgs& a, const T* s, const
       }
       if (v < MAXG && v < G) {                                          // same-view pair is skipped: subtract q_v . x_v
         float tq[4];
-        Q4::unpack(rt[v < MAXG ? v : 0], tq);
+        Q4::unpack(in.rt[v < MAXG ? v : 0], tq);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          float q = ex2(fmaf(tq[e] - cen[e], ct, tmc[v < MAXG ? v : 0])) * tinv[v < MAXG ? v : 0];
+          float q = ex2(fmaf(tq[e] - in.cen[e], ct, tmc[v < MAXG ? v : 0])) * tinv[v < MAXG ? v : 0];
           if (!FAST && col + e >= a.K) q = 0.f;
           Q[e] += q;
           qx = fmaf(q, x[e], qx);
@@ -121,10 +130,10 @@ __device__ __forceinline__ void ce_fwd_vector(const CeArgs& a, const T* s, const
   for (int i = 0; i < MAXG; ++i)
     if (i < G && i >= C) {
       float tq[4];
-      Q4::unpack(rt[i], tq);
+      Q4::unpack(in.rt[i], tq);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        float q = ex2(fmaf(tq[e] - cen[e], ct, tmc[i])) * tinv[i];
+        float q = ex2(fmaf(tq[e] - in.cen[e], ct, tmc[i])) * tinv[i];
         if (!FAST && col + e >= a.K) q = 0.f;
         Q[e] += q;
       }
@@ -160,9 +169,27 @@ ce_fwd_kernel(const CeArgs a) {
   for (int v = 0; v < MAXC; ++v) { st.m[v] = -INFINITY; st.l[v] = 0.f; }
   float cross = 0.f;
 
-  for (long long col = col_begin + threadIdx.x * 4; col < col_end; col += kThreads * 4) {
-    if (a.vec_ok && (col + 4 <= a.K)) ce_fwd_vector<T, MAXC, MAXG, true>(a, s, t, b, col, C, G, tmc, tinv, c2, ct, st, cross);
-    else ce_fwd_vector<T, MAXC, MAXG, false>(a, s, t, b, col, C, G, tmc, tinv, c2, ct, st, cross);
+  constexpr long long kStride = kThreads * 4;
+  long long col = col_begin + threadIdx.x * 4;
+  if (a.vec_ok) {
+    // Software pipeline over the full vectors: the C+G loads of vector i+1 are in flight while vector i is reduced.
+    const long long full_end = min(col_end, (a.K / 4) * 4);
+    CeVec<T, MAXC, MAXG> va, vb;
+    if (col < full_end) ce_load<T, MAXC, MAXG, true>(a, s, t, b, col, C, G, va);
+    while (col < full_end) {
+      const long long c1 = col + kStride, c2n = col + 2 * kStride;
+      if (c1 < full_end) ce_load<T, MAXC, MAXG, true>(a, s, t, b, c1, C, G, vb);
+      ce_fwd_compute<T, MAXC, MAXG, true>(a, va, col, C, G, tmc, tinv, c2, ct, st, cross);
+      if (c1 >= full_end) { col = c1; break; }
+      if (c2n < full_end) ce_load<T, MAXC, MAXG, true>(a, s, t, b, c2n, C, G, va);
+      ce_fwd_compute<T, MAXC, MAXG, true>(a, vb, c1, C, G, tmc, tinv, c2, ct, st, cross);
+      col = c2n;
+    }
+  }
+  for (; col < col_end; col += kStride) {              // ragged row end / unaligned tensors
+    CeVec<T, MAXC, MAXG> v;
+    ce_load<T, MAXC, MAXG, false>(a, s, t, b, col, C, G, v);
+    ce_fwd_compute<T, MAXC, MAXG, false>(a, v, col, C, G, tmc, tinv, c2, ct, st, cross);
   }
 
   // ---- block reduction: (m,l) per student row by online merge (natural-log domain), cross by sum ----

@@ -77,34 +77,35 @@ weightnorm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, 
   if (row >= K) return;
   const int lane = threadIdx.x & 31;
   const float* vr = v + row * dim;
-  if (vec_ok) {
+  if (vec_ok && dim == 256) {                          // the DINO bottleneck width: whole row in registers
     const float4* v4 = reinterpret_cast<const float4*>(vr);
-    const int nv = dim >> 2;
-    float4 keep[2];
-    float ss = 0.f;
-    for (int i = lane, j = 0; i < nv; i += 32, ++j) {
-      const float4 x = __ldg(v4 + i);
-      if (j < 2) keep[j] = x;
-      ss = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, ss))));
-    }
+    const float4 x0 = __ldg(v4 + lane), x1 = __ldg(v4 + lane + 32);
+    float ss = x0.x * x0.x;
+    ss = fmaf(x0.y, x0.y, ss); ss = fmaf(x0.z, x0.z, ss); ss = fmaf(x0.w, x0.w, ss);
+    ss = fmaf(x1.x, x1.x, ss); ss = fmaf(x1.y, x1.y, ss); ss = fmaf(x1.z, x1.z, ss); ss = fmaf(x1.w, x1.w, ss);
     ss = warp_sum(ss);
     const float nrm = sqrtf(ss);
     const float sc = g[row] / nrm;
     if (lane == 0) { scale[row] = sc; inv_vnorm[row] = 1.0f / nrm; }
-    for (int i = lane, j = 0; i < nv; i += 32, ++j) {
-      const float4 x = (j < 2) ? keep[j] : __ldg(v4 + i);
-      const float w[4] = {x.x * sc, x.y * sc, x.z * sc, x.w * sc};
-      const long long o = row * dim + 4 * i;
-      if (w_lo) {
-        float hi[4], lo[4];
+    const float w[8] = {x0.x * sc, x0.y * sc, x0.z * sc, x0.w * sc, x1.x * sc, x1.y * sc, x1.z * sc, x1.w * sc};
+    const long long o0 = row * 256 + 4 * lane, o1 = o0 + 128;
+    if (w_lo) {
+      float hi[8], lo[8];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { hi[e] = tf32_round(w[e]); lo[e] = tf32_round(w[e] - hi[e]); }
-        if (w_f32) *reinterpret_cast<float4*>(w_f32 + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(w_lo + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-      } else if (w_f32) {
-        *reinterpret_cast<float4*>(w_f32 + o) = make_float4(w[0], w[1], w[2], w[3]);
+      for (int e = 0; e < 8; ++e) { hi[e] = tf32_round(w[e]); lo[e] = tf32_round(w[e] - hi[e]); }
+      if (w_f32) {
+        *reinterpret_cast<float4*>(w_f32 + o0) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(w_f32 + o1) = make_float4(hi[4], hi[5], hi[6], hi[7]);
       }
-      if (w_bf16) *reinterpret_cast<uint2*>(w_bf16 + o) = make_uint2(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]));
+      *reinterpret_cast<float4*>(w_lo + o0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      *reinterpret_cast<float4*>(w_lo + o1) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+    } else if (w_f32) {
+      *reinterpret_cast<float4*>(w_f32 + o0) = make_float4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<float4*>(w_f32 + o1) = make_float4(w[4], w[5], w[6], w[7]);
+    }
+    if (w_bf16) {
+      *reinterpret_cast<uint2*>(w_bf16 + o0) = make_uint2(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]));
+      *reinterpret_cast<uint2*>(w_bf16 + o1) = make_uint2(pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
     }
     return;
   }
@@ -136,26 +137,20 @@ weightnorm_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v,
   if (row >= K) return;
   const int lane = threadIdx.x & 31;
   const float iv = inv_vnorm[row], sc = scale[row];
-  if (vec_ok) {
-    const float4* dw4 = reinterpret_cast<const float4*>(dw + row * dim);
-    const float4* v4 = reinterpret_cast<const float4*>(v + row * dim);
-    float4* dv4 = reinterpret_cast<float4*>(dv + row * dim);
-    const int nv = dim >> 2;
-    float4 kd[2], kv[2];
-    float dot = 0.f;
-    for (int i = lane, j = 0; i < nv; i += 32, ++j) {
-      const float4 a = __ldg(dw4 + i), b = __ldg(v4 + i);
-      if (j < 2) { kd[j] = a; kv[j] = b; }
-      dot = fmaf(a.x, b.x * iv, fmaf(a.y, b.y * iv, fmaf(a.z, b.z * iv, fmaf(a.w, b.w * iv, dot))));
-    }
+  if (vec_ok && dim == 256) {
+    const float4* dw4 = reinterpret_cast<const float4*>(dw + row * 256);
+    const float4* v4 = reinterpret_cast<const float4*>(v + row * 256);
+    float4* dv4 = reinterpret_cast<float4*>(dv + row * 256);
+    const float4 a0 = __ldg(dw4 + lane), a1 = __ldg(dw4 + lane + 32);
+    float4 b0 = __ldg(v4 + lane), b1 = __ldg(v4 + lane + 32);
+    b0.x *= iv; b0.y *= iv; b0.z *= iv; b0.w *= iv; b1.x *= iv; b1.y *= iv; b1.z *= iv; b1.w *= iv;   // v_hat
+    float dot = a0.x * b0.x;
+    dot = fmaf(a0.y, b0.y, dot); dot = fmaf(a0.z, b0.z, dot); dot = fmaf(a0.w, b0.w, dot);
+    dot = fmaf(a1.x, b1.x, dot); dot = fmaf(a1.y, b1.y, dot); dot = fmaf(a1.z, b1.z, dot); dot = fmaf(a1.w, b1.w, dot);
     dot = warp_sum(dot);
     if (dg && lane == 0) dg[row] = dot;
-    for (int i = lane, j = 0; i < nv; i += 32, ++j) {
-      const float4 a = (j < 2) ? kd[j] : __ldg(dw4 + i);
-      const float4 b = (j < 2) ? kv[j] : __ldg(v4 + i);
-      dv4[i] = make_float4(sc * (a.x - dot * (b.x * iv)), sc * (a.y - dot * (b.y * iv)), sc * (a.z - dot * (b.z * iv)),
-                           sc * (a.w - dot * (b.w * iv)));
-    }
+    dv4[lane] = make_float4(sc * (a0.x - dot * b0.x), sc * (a0.y - dot * b0.y), sc * (a0.z - dot * b0.z), sc * (a0.w - dot * b0.w));
+    dv4[lane + 32] = make_float4(sc * (a1.x - dot * b1.x), sc * (a1.y - dot * b1.y), sc * (a1.z - dot * b1.z), sc * (a1.w - dot * b1.w));
     return;
   }
   float dot = 0.f;

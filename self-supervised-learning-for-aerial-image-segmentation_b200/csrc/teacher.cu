@@ -48,7 +48,6 @@ __device__ __forceinline__ void teacher_rows(const T* __restrict__ t, long long 
   for (int j = 0; j < RIF; ++j) {
     const long long r = r0 + j;
     if (r < r_end) {                                     // warp-uniform
-      float y[kNV][4];
       float m = -INFINITY;
 #pragma unroll
       for (int i = 0; i < kNV; ++i) {
@@ -59,16 +58,22 @@ __device__ __forceinline__ void teacher_rows(const T* __restrict__ t, long long 
           cs[i][e] += x[e];
           float v = fmaf(x[e], ct, cb[i][e]);            // (t - center) / temp * log2(e)
           if (!FULL && (col0 + (i * 32 + lane) * 4 + e >= K)) v = -INFINITY;
-          y[i][e] = v;
           m = fmaxf(m, v);
         }
       }
       m = warp_max(m);
       float l = 0.f;
 #pragma unroll
-      for (int i = 0; i < kNV; ++i)
+      for (int i = 0; i < kNV; ++i) {                    // second pass over the packed registers (one FFMA to redo)
+        float x[4];
+        Q4::unpack(raw[j][i], x);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) l += ex2(y[i][e] - m);
+        for (int e = 0; e < 4; ++e) {
+          float v = fmaf(x[e], ct, cb[i][e]) - m;
+          if (!FULL && (col0 + (i * 32 + lane) * 4 + e >= K)) v = -INFINITY;
+          l += ex2(v);
+        }
+      }
       l = warp_sum(l);
       if (lane == 0) ws_stats[r * nchunks + chunk] = make_float2(m, l);
     }
