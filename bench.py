@@ -267,6 +267,7 @@ def main():
     ap.add_argument("--out-dim", type=int, default=None)
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--graph", type=int, default=1, help="replay the N=1 step from a CUDA graph (0 = eager launches)")
+    ap.add_argument("--overlap", type=int, default=1, help="teacher head forward on a side stream, overlapping the student's")
     ap.add_argument("--cpu-sample-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -310,6 +311,7 @@ def main():
     import dinomc_b200 as D
     D._lib.check(D._lib.load().dmc_device_check(local_rank), "dmc_device_check")
 
+    D.set_teacher_overlap(bool(args.overlap))
     step = Step(w, args.mode, rank, world, device)
     ops = D.ops
     for _ in range(warmup):
@@ -393,7 +395,7 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic", "config": cfg,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-                "launch_mode": "cuda_graph" if use_graph else "eager", "roofline": roofline, "cpu_baseline": cb,
+                "launch_mode": "cuda_graph" if use_graph else "eager", "teacher_overlap": bool(args.overlap), "roofline": roofline, "cpu_baseline": cb,
                 "ema_params": step.P, "ema_tensors": step.n_tensors}
         print(json.dumps(line))
     if world > 1:

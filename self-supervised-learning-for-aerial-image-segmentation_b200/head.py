@@ -28,6 +28,41 @@ def get_default_precision() -> str:
     return _default_precision
 
 
+# ---------------------------------------------------------------------------------------------
+# optional: run no-grad (teacher) head forwards on a side stream so they overlap the student's head
+# ---------------------------------------------------------------------------------------------
+_teacher_overlap = False
+_side_streams = {}
+
+
+def set_teacher_overlap(enabled: bool):
+    """When enabled, a DINOHead called under torch.no_grad() (the teacher, main_dino_mc.py:264-265,373) enqueues
+    its kernels on a per-device side stream and returns immediately; the logits carry a CUDA event that
+    dinomc_b200.DINOLoss waits for before reading them.  The teacher head then runs concurrently with the
+    student head's forward instead of in front of it.  Contract: such logits must only be consumed by
+    dinomc_b200.DINOLoss (any other consumer must first call `dinomc_b200.wait_ready(logits)`)."""
+    global _teacher_overlap
+    _teacher_overlap = bool(enabled)
+
+
+def wait_ready(t):
+    """Make the current stream wait for a tensor produced by an overlapped (side-stream) head forward."""
+    ev = getattr(t, "_dmc_ready_event", None)
+    if ev is not None:
+        torch.cuda.current_stream(t.device).wait_event(ev)
+        t._dmc_ready_event = None
+    return t
+
+
+def _side_stream(device):
+    key = torch.device(device).index
+    st = _side_streams.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _side_streams[key] = st
+    return st
+
+
 def _trunc_normal_(tensor, mean=0., std=1., a=-2., b=2.):
     """Same sampling procedure as utils/utils.py:529-567 (inverse-CDF of a truncated uniform), so that a
     given torch RNG state yields the same weights as the reference's trunc_normal_."""
@@ -108,6 +143,21 @@ class DINOHead(nn.Module):
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError("dinomc_b200.DINOHead runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if _teacher_overlap and not torch.is_grad_enabled():
+            cur = torch.cuda.current_stream(x.device)
+            side = _side_stream(x.device)
+            side.wait_stream(cur)                       # inputs (features, EMA'd weights) are ready on `cur`
+            with torch.cuda.stream(side):
+                out = self._forward(x)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            x.record_stream(side)
+            out.record_stream(cur)
+            out._dmc_ready_event = ev
+            return out
+        return self._forward(x)
+
+    def _forward(self, x):
         mode = self._mode()
         with torch.autocast("cuda", enabled=False):
             if self.use_bn:

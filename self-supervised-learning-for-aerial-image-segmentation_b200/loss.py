@@ -12,6 +12,7 @@ import torch.nn as nn
 
 from . import functional as Fn
 from . import ops
+from .head import wait_ready
 
 
 class DINOLoss(nn.Module):
@@ -46,6 +47,7 @@ class DINOLoss(nn.Module):
         if teacher_output.shape[0] // G != B:
             raise ValueError("student and teacher batches differ")
         temp = float(self.teacher_temp_schedule[epoch])
+        wait_ready(teacher_output)              # no-op unless the teacher head ran on the overlap side stream
         s, t = self._common(student_output, teacher_output.detach())
         loss, colsum = Fn.DinoLossFn.apply(s, t, self.center, 1.0 / self.student_temp, 1.0 / temp, B, C, G)
         self._update_center_from_colsum(colsum, teacher_output.shape[0])
@@ -64,6 +66,7 @@ class DINOLoss(nn.Module):
     @torch.no_grad()
     def update_center(self, teacher_output):
         """Public API of the reference (main_dino_mc.py:463-473) for callers that use it directly."""
+        wait_ready(teacher_output)
         t = teacher_output.detach()
         t = t if t.dtype == torch.bfloat16 else t.float()
         _, colsum = ops.teacher_stats_colsum(t, self.center.reshape(-1), 1.0)

@@ -216,3 +216,32 @@ def test_headline_size_properties(mode):
     assert all(torch.equal(a, b) for a, b in zip(before, tp))
     D.ema_update_(tp, sp, 0.0)
     assert all(torch.equal(a.detach(), b.detach()) for a, b in zip(tp, sp))
+
+
+def test_teacher_overlap_side_stream(golden):
+    """Teacher head on the side stream (set_teacher_overlap): same numbers, DINOLoss waits for the event."""
+    if golden.name != "mc_wide":
+        pytest.skip("one case is enough")
+    import dinomc_b200 as D
+    D.set_teacher_overlap(True)
+    try:
+        _, student, teacher, loss_mod = _build(golden, "fp32")
+        c, ref = golden.cfg, golden.ref64
+        xs = torch.from_numpy(golden.inputs["x_student"]).cuda().requires_grad_(True)
+        xt = torch.from_numpy(golden.inputs["x_teacher"]).cuda()
+        for _ in range(3):                                     # repeated steps exercise stream/allocator reuse
+            loss_mod.center.copy_(torch.from_numpy(golden.inputs["center0"]))
+            with torch.no_grad():
+                t_out = teacher(xt)
+            assert getattr(t_out, "_dmc_ready_event", None) is not None
+            s_out = student(xs)
+            loss = loss_mod(s_out, t_out, c["epoch"])
+            xs.grad = None
+            loss.backward()
+        assert abs(float(loss.detach()) - float(ref["loss1"])) / abs(float(ref["loss1"])) < 1e-5
+        assert rel_err(xs.grad.cpu().numpy(), ref["grad.x"]) < 1e-5
+        assert rel_err(loss_mod.center.cpu().numpy(), ref["center1"]) < 1e-6
+        D.wait_ready(t_out)
+        assert rel_err(t_out.float().cpu().numpy(), ref["teacher_logits"]) < 1e-5
+    finally:
+        D.set_teacher_overlap(False)

@@ -42,6 +42,17 @@ except Exception as e:
     print("parse failed", e)
 PY
   done ;;
+multi)
+  NG=$(nvidia-smi -L | wc -l)
+  for n in 2 4 8; do
+    if [ $n -le $NG ]; then
+      ( timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $n --steps 20 --warmup 5 ) > gpurun_out/bench_n$n.json 2> gpurun_out/bench_n$n.err
+      echo "== bench N=$n rc=$?"; tail -c 1500 gpurun_out/bench_n$n.json; grep -v Warning gpurun_out/bench_n$n.err | tail -n 8
+    fi
+  done ;;
+profstep)
+  ( timeout 600 python tools/prof_step.py bf16 ) > gpurun_out/prof_step_bf16.txt 2>&1
+  echo "== prof_step rc=$?"; grep -v Warning gpurun_out/prof_step_bf16.txt | tail -45 ;;
 gemmbench)
   ( timeout 600 python tools/gemm_bench.py ) > gpurun_out/gemm_bench.log 2>&1
   echo "== gemm_bench rc=$?"; cat gpurun_out/gemm_bench.log ;;

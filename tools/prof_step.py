@@ -1,0 +1,35 @@
+"""Warm per-kernel device times of one step, from the CUPTI activity records torch.profiler collects while the
+step runs back to back (no replay, no cache flush).  Diagnostic only: bench.py never reports these numbers."""
+import collections
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from torch.profiler import ProfilerActivity, profile
+
+import bench
+
+mode = sys.argv[1] if len(sys.argv) > 1 else "bf16"
+w = dict(bench.WORKLOADS["cfg2"])
+dev = torch.device("cuda", 0)
+step = bench.Step(w, mode, 0, 1, dev)
+for _ in range(5):
+    step.run()
+torch.cuda.synchronize()
+N = 10
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(N):
+        step.run()
+    torch.cuda.synchronize()
+agg, cnt = collections.Counter(), collections.Counter()
+for ev in prof.events():
+    if ev.device_type == torch.autograd.DeviceType.CUDA:
+        name = ev.name.replace("void ", "").replace("dmc::(anonymous namespace)::", "")
+        name = name.split("(")[0][:70]
+        agg[name] += ev.device_time / N if hasattr(ev, "device_time") else ev.cuda_time / N
+        cnt[name] += 1
+tot = sum(agg.values())
+print(f"sum of kernel time per step: {tot:.1f} us")
+for n, v in agg.most_common(40):
+    print(f"{n:72s} x{cnt[n] / N:<4.1f} {v:8.1f} us {100 * v / tot:5.1f}%")
