@@ -131,7 +131,7 @@ class ClockSampler:
 class Step:
     """Owns the modules/buffers of one rank and runs one whole step on the current stream."""
 
-    def __init__(self, w, mode, rank, world, device):
+    def __init__(self, w, mode, rank, world, device, ddp=False):
         import dinomc_b200 as D
         self.D, self.w, self.world, self.device = D, w, world, device
         torch.manual_seed(0)                                          # identical weights on every rank
@@ -153,9 +153,14 @@ class Step:
         self.P = sum(t.numel() for t in self.ema_student)
         self.n_tensors = len(self.ema_student)
         self.model = self.student
+        self.reducer = None
         if world > 1:
-            from torch.nn.parallel import DistributedDataParallel as DDP
-            self.model = DDP(self.student, device_ids=[device.index])  # main_dino_mc.py:260
+            if ddp:
+                from torch.nn.parallel import DistributedDataParallel as DDP
+                self.model = DDP(self.student, device_ids=[device.index])  # main_dino_mc.py:260
+            else:
+                # same exchange (mean of the head gradients over ranks), graph-capturable, overlapped with bwd + EMA
+                self.reducer = D.GradAllReduce(self.student.parameters())
         gs = torch.Generator(device="cpu").manual_seed(1234 + rank)
         gt = torch.Generator(device="cpu").manual_seed(4321 + rank)
         self.x_student_host = torch.randn(C * B, Din, generator=gs).pin_memory()
@@ -177,6 +182,8 @@ class Step:
         loss = self.loss_mod(s_out, t_out, 0)
         loss.backward()
         self.D.ema_update_(self.ema_teacher, self.ema_student, self.m)
+        if self.reducer is not None:
+            self.reducer.wait()
         return loss
 
     def run_e2e(self, graph=None):
@@ -267,6 +274,7 @@ def main():
     ap.add_argument("--out-dim", type=int, default=None)
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--graph", type=int, default=1, help="replay the N=1 step from a CUDA graph (0 = eager launches)")
+    ap.add_argument("--ddp", type=int, default=0, help="N>1: wrap the student head in torch DDP (eager) instead of GradAllReduce")
     ap.add_argument("--overlap", type=int, default=1, help="teacher head forward on a side stream, overlapping the student's")
     ap.add_argument("--cpu-sample-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -284,6 +292,7 @@ def main():
     cfg = {"workload": f"{args.workload}: {w['note']}; D={w['D']} out_dim={w['K']} batch/GPU={w['B']} "
                        f"crops={w['G']}+{w['C'] - w['G']}; EMA over {w['arch']} backbone + head",
            "global_batch": w["B"] * world, "parallelism": f"dp{world}",
+           "grad_allreduce": ("none (1 GPU)" if world == 1 else ("torch DDP" if args.ddp else "dinomc_b200.GradAllReduce (NCCL, side stream)")),
            "l2": "per-step working set (logits + gradients > 1 GiB) exceeds the 126 MB L2; no explicit flush"}
 
     if args.impl == "reference":
@@ -312,20 +321,27 @@ def main():
     D._lib.check(D._lib.load().dmc_device_check(local_rank), "dmc_device_check")
 
     D.set_teacher_overlap(bool(args.overlap))
-    step = Step(w, args.mode, rank, world, device)
+    step = Step(w, args.mode, rank, world, device, ddp=bool(args.ddp))
     ops = D.ops
     for _ in range(warmup):
         step.run()
     torch.cuda.synchronize()
 
-    use_graph = bool(args.graph) and world == 1
+    use_graph = bool(args.graph) and not (world > 1 and args.ddp)
     graph = None
+    run_value = step.run
     if use_graph:
-        # the whole step is stream-ordered libdinomc launches on fixed buffers: capture once, replay K times
-        graph = D.StepGraph(step.run, warmup=3)
-        run_value = graph.replay
-    else:
-        run_value = step.run
+        # the whole step is stream-ordered libdinomc launches (+ NCCL all-reduces when N > 1) on fixed buffers:
+        # capture once, replay K times
+        try:
+            graph = D.StepGraph(step.run, warmup=3, capture_error_mode="thread_local" if world > 1 else "global")
+            run_value = graph.replay
+        except Exception as e:          # noqa: BLE001 -- e.g. a collective that refuses capture: fall back to eager
+            if world == 1:
+                raise
+            print(f"[rank {rank}] CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
+            use_graph, graph = False, None
+            torch.cuda.synchronize()
 
     l0 = ops.launch_count
     step.run()

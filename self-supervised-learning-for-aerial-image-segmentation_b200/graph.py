@@ -15,7 +15,7 @@ import torch
 
 
 class StepGraph:
-    def __init__(self, fn, warmup: int = 3):
+    def __init__(self, fn, warmup: int = 3, capture_error_mode: str = "global"):
         """`fn()` must read its inputs from fixed (static) device tensors; its return value (tensor or tuple of
         tensors) is kept as the static output of the graph."""
         self.fn = fn
@@ -27,7 +27,7 @@ class StepGraph:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
             self.out = fn()
         torch.cuda.synchronize()
 

@@ -1,0 +1,82 @@
+"""GPU, >= 2 devices, NCCL: the data-parallel exchanges of the path on real hardware -- the center all-reduce
+inside DINOLoss (main_dino_mc.py:469) and the gradient mean over ranks (DDP's job at main_dino_mc.py:260,
+here dinomc_b200.GradAllReduce).  Skipped on single-GPU boxes; the CPU/gloo twin is test_multirank_cpu.py."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import dinomc_b200 as D
+        torch.manual_seed(0)                                   # identical weights on both ranks
+        Din, K, B, C, G = 64, 1024, 4, 8, 2
+        head = D.DINOHead(Din, K, hidden_dim=128, bottleneck_dim=64).cuda()
+        teacher = D.DINOHead(Din, K, hidden_dim=128, bottleneck_dim=64).cuda()
+        head.precision = teacher.precision = "fp32"
+        loss_mod = D.DINOLoss(K, C, 0.04, 0.04, 0, 10, teacher_crops_number=G).cuda()
+        g = torch.Generator().manual_seed(100 + rank)          # different data per rank
+        xs = torch.randn(C * B, Din, generator=g).cuda()
+        xt = torch.randn(G * B, Din, generator=g).cuda()
+        with torch.no_grad():
+            t_out = teacher(xt)
+        # local (un-reduced) gradients first
+        loss = loss_mod(head(xs), t_out, 0)
+        loss.backward()
+        local = {n: p.grad.clone() for n, p in head.named_parameters() if p.grad is not None}
+        center_after = loss_mod.center.clone()
+        for p in head.parameters():
+            p.grad = None
+        # the same step with the reducer: gradients become the mean over ranks
+        red = D.GradAllReduce(head.parameters())
+        loss_mod.center.zero_()
+        loss2 = loss_mod(head(xs), t_out, 0)
+        loss2.backward()
+        red.wait()
+        torch.cuda.synchronize()
+        reduced = {n: p.grad.clone() for n, p in head.named_parameters() if p.grad is not None}
+        torch.save({"local": {k: v.cpu() for k, v in local.items()}, "reduced": {k: v.cpu() for k, v in reduced.items()},
+                    "center": center_after.cpu(), "t_out": t_out.cpu(), "loss": float(loss.detach())},
+                   os.path.join(out_dir, f"rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_center_and_gradient_exchange_two_gpus(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from oracle import np_oracle as O
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r = [torch.load(os.path.join(tmp_path, f"rank{i}.pt")) for i in range(2)]
+    assert r[0]["loss"] != r[1]["loss"]                                        # different data per rank
+    for name in r[0]["local"]:
+        mean = (r[0]["local"][name].double() + r[1]["local"][name].double()) / 2
+        for i in range(2):
+            err = (r[i]["reduced"][name].double() - mean).abs().max() / mean.abs().max()
+            assert err < 1e-6, (name, float(err))
+        assert torch.equal(r[0]["reduced"][name], r[1]["reduced"][name])       # replicas stay bit-identical
+    outs = [x["t_out"].double().numpy() for x in r]
+    ref = O.update_center(np.zeros((1, outs[0].shape[1])), outs[0], 0.9, world_size=2, all_rank_outputs=outs)
+    for i in range(2):
+        assert np.abs(r[i]["center"].double().numpy() - ref).max() / np.abs(ref).max() < 1e-6
+    assert torch.equal(r[0]["center"], r[1]["center"])
