@@ -183,7 +183,8 @@ class Step:
         loss.backward()
         self.D.ema_update_(self.ema_teacher, self.ema_student, self.m)
         if self.reducer is not None:
-            self.reducer.wait()
+            self.reducer.wait()             # averaged gradients are complete at the end of the step ...
+            self.loss_mod.sync_center()     # ... and so is the all-reduced center
         return loss
 
     def run_e2e(self, graph=None):
@@ -275,6 +276,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--graph", type=int, default=1, help="replay the N=1 step from a CUDA graph (0 = eager launches)")
     ap.add_argument("--ddp", type=int, default=0, help="N>1: wrap the student head in torch DDP (eager) instead of GradAllReduce")
+    ap.add_argument("--reserve-sms", type=int, default=20, help="N>1: SMs the persistent GEMM grids leave to NCCL")
     ap.add_argument("--overlap", type=int, default=1, help="teacher head forward on a side stream, overlapping the student's")
     ap.add_argument("--cpu-sample-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -321,6 +323,9 @@ def main():
     D._lib.check(D._lib.load().dmc_device_check(local_rank), "dmc_device_check")
 
     D.set_teacher_overlap(bool(args.overlap))
+    if world > 1 and not args.ddp:
+        D.set_async_center(True)
+        D.ops.gemm_max_ctas = 148 - args.reserve_sms      # leave SMs to the concurrent NCCL all-reduce kernels
     step = Step(w, args.mode, rank, world, device, ddp=bool(args.ddp))
     ops = D.ops
     for _ in range(warmup):
@@ -415,8 +420,12 @@ def main():
                 "ema_params": step.P, "ema_tensors": step.n_tensors}
         print(json.dumps(line))
     if world > 1:
+        # leave without tearing NCCL down: destroying communicators that CUDA graphs still reference can hang
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -84,6 +84,8 @@ typedef struct dmc_gemm_args {
   void* aux;        int64_t ldaux; int32_t aux_dtype;
   int32_t split_k;         /* 0 = let the library choose, >= 1 = forced */
   void* workspace;  size_t workspace_bytes; /* needed when split_k != 1, see query */
+  int32_t max_ctas;        /* 0 = one persistent CTA per SM (148); > 0 = cap, e.g. to leave SMs to a concurrent
+                              NCCL all-reduce kernel (the persistent CTAs would otherwise queue behind it) */
 } dmc_gemm_args;
 
 /* Upper bound of the split-K workspace dmc_gemm may need for this problem. */

@@ -20,8 +20,8 @@ from .ema import ema_update_  # noqa: F401
 from .graph import StepGraph  # noqa: F401
 from .head import (DINOHead, get_default_precision, set_default_precision, set_teacher_overlap,  # noqa: F401
                    wait_ready)
-from .loss import DINOLoss  # noqa: F401
+from .loss import DINOLoss, set_async_center  # noqa: F401
 from .reducer import GradAllReduce  # noqa: F401
 
-__all__ = ["DINOHead", "DINOLoss", "ema_update_", "StepGraph", "GradAllReduce", "set_teacher_overlap", "wait_ready", "set_default_precision", "get_default_precision",
+__all__ = ["DINOHead", "DINOLoss", "ema_update_", "StepGraph", "GradAllReduce", "set_teacher_overlap", "set_async_center", "wait_ready", "set_default_precision", "get_default_precision",
            "ops", "functional"]

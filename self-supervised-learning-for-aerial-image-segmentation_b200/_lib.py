@@ -31,6 +31,7 @@ class GemmArgs(C.Structure):
         ("aux", vp), ("ldaux", i64), ("aux_dtype", i32),
         ("split_k", i32),
         ("workspace", vp), ("workspace_bytes", sz),
+        ("max_ctas", i32),
     ]
 
 

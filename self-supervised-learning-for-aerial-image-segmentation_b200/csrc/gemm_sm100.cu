@@ -699,7 +699,8 @@ extern "C" int dmc_gemm(const dmc_gemm_args* a, void* stream) {
   d.act = a->act; d.aux = a->aux; d.ldaux = a->ldaux; d.aux_dtype = a->aux_dtype;
 
   const int num_work = pl.m_tiles * pl.n_tiles * pl.splits;
-  const int grid = num_work < kNumSMs ? num_work : kNumSMs;
+  const int cap = (a->max_ctas > 0 && a->max_ctas < kNumSMs) ? a->max_ctas : kNumSMs;
+  const int grid = num_work < cap ? num_work : cap;
   const bool amn = a->a_mn_major != 0, bmn = a->b_mn_major != 0;
 const bool plain = (a->col_scale == nullptr && a->bias == nullptr && a->act == DMC_ACT_NONE);
 #define DMC_LAUNCH(ESZ_, AMN_, BMN_)                                                                          \

@@ -15,6 +15,18 @@ from . import ops
 from .head import wait_ready
 
 
+_async_center = False
+
+
+def set_async_center(enabled: bool):
+    """Multi-GPU only.  When enabled, the center exchange (column-sum all-reduce + EMA, main_dino_mc.py:468-473)
+    runs on a side stream and the next `DINOLoss.forward` waits for it, taking the latency-bound 256 KiB
+    all-reduce off the step's critical path (its result is first needed by the NEXT step's teacher softmax).
+    Code that reads `loss.center` directly in between must call `loss.sync_center()` first."""
+    global _async_center
+    _async_center = bool(enabled)
+
+
 class DINOLoss(nn.Module):
     def __init__(self, out_dim, ncrops, warmup_teacher_temp, teacher_temp, warmup_teacher_temp_epochs, nepochs,
                  teacher_crops_number=2, student_temp=0.1, center_momentum=0.9):
@@ -24,6 +36,8 @@ class DINOLoss(nn.Module):
         self.ncrops = ncrops
         self.teacher_crops_number = teacher_crops_number
         self.register_buffer("center", torch.zeros(1, out_dim))
+        self._center_event = None
+        self._comm_stream = None
         # same schedule construction as main_dino_mc.py:431-435
         self.teacher_temp_schedule = np.concatenate((
             np.linspace(warmup_teacher_temp, teacher_temp, warmup_teacher_temp_epochs),
@@ -47,19 +61,43 @@ class DINOLoss(nn.Module):
         if teacher_output.shape[0] // G != B:
             raise ValueError("student and teacher batches differ")
         temp = float(self.teacher_temp_schedule[epoch])
+        self.sync_center()
         wait_ready(teacher_output)              # no-op unless the teacher head ran on the overlap side stream
         s, t = self._common(student_output, teacher_output.detach())
         loss, colsum = Fn.DinoLossFn.apply(s, t, self.center, 1.0 / self.student_temp, 1.0 / temp, B, C, G)
         self._update_center_from_colsum(colsum, teacher_output.shape[0])
         return loss
 
+    def sync_center(self):
+        """Make the current stream wait for an in-flight asynchronous center exchange (no-op otherwise)."""
+        if self._center_event is not None:
+            torch.cuda.current_stream().wait_event(self._center_event)
+            self._center_event = None
+
     @torch.no_grad()
     def _update_center_from_colsum(self, colsum, n_rows):
         world = 1
         if dist.is_available() and dist.is_initialized():
             world = dist.get_world_size()
-            if world > 1:
-                dist.all_reduce(colsum)                 # main_dino_mc.py:469 (65536 fp32 = 256 KiB over NCCL)
+        if world > 1 and _async_center:
+            cur = torch.cuda.current_stream()
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream()
+            comm = self._comm_stream
+            comm.wait_stream(cur)                       # colsum and the old center were produced on `cur`
+            with torch.cuda.stream(comm):
+                dist.all_reduce(colsum)                 # main_dino_mc.py:469
+                new_center = ops.center_update(self.center, colsum, n_rows * world, self.center_momentum)
+            colsum.record_stream(comm)
+            self.center.record_stream(comm)
+            new_center.record_stream(cur)
+            ev = torch.cuda.Event()
+            ev.record(comm)
+            self._center_event = ev
+            self.center = new_center
+            return
+        if world > 1:
+            dist.all_reduce(colsum)                     # main_dino_mc.py:469 (65536 fp32 = 256 KiB over NCCL)
         # rebinding the buffer (like the reference, :473) keeps the old tensor alive for backward
         self.center = ops.center_update(self.center, colsum, n_rows * world, self.center_momentum)
 

@@ -15,6 +15,10 @@ from . import _lib as L
 # kernel launches issued through this module (bench.py reports it as `gpu_launches`)
 launch_count = 0
 
+# Cap on the persistent GEMM grid (0 = all 148 SMs).  Data-parallel runs set it below 148 so that a concurrent
+# NCCL all-reduce kernel finds free SMs instead of queueing behind (or stalling) the one-CTA-per-SM GEMMs.
+gemm_max_ctas = 0
+
 
 def _count(n=1):
     global launch_count
@@ -153,6 +157,7 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, A_lo=None, B_lo=None, out=Non
     if aux is not None:
         g.aux, g.ldaux, g.aux_dtype = aux.data_ptr(), aux.stride(0), _dt(aux)
     g.split_k = split_k
+    g.max_ctas = gemm_max_ctas
     if simt:
         with _timed(tag):
             L.check(lib.dmc_gemm_simt(C.byref(g), _stream()), "dmc_gemm_simt")
