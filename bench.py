@@ -131,7 +131,7 @@ class ClockSampler:
 class Step:
     """Owns the modules/buffers of one rank and runs one whole step on the current stream."""
 
-    def __init__(self, w, mode, rank, world, device, ddp=False):
+    def __init__(self, w, mode, rank, world, device, ddp=False, reserve_sms=16):
         import dinomc_b200 as D
         self.D, self.w, self.world, self.device = D, w, world, device
         torch.manual_seed(0)                                          # identical weights on every rank
@@ -160,7 +160,7 @@ class Step:
                 self.model = DDP(self.student, device_ids=[device.index])  # main_dino_mc.py:260
             else:
                 # same exchange (mean of the head gradients over ranks), graph-capturable, overlapped with bwd + EMA
-                self.reducer = D.GradAllReduce(self.student.parameters())
+                self.reducer = D.GradAllReduce(self.student.parameters(), reserve_sms=reserve_sms)
         gs = torch.Generator(device="cpu").manual_seed(1234 + rank)
         gt = torch.Generator(device="cpu").manual_seed(4321 + rank)
         self.x_student_host = torch.randn(C * B, Din, generator=gs).pin_memory()
@@ -184,7 +184,7 @@ class Step:
         self.D.ema_update_(self.ema_teacher, self.ema_student, self.m)
         if self.reducer is not None:
             self.reducer.wait()             # averaged gradients are complete at the end of the step ...
-            self.loss_mod.sync_center()     # ... and so is the all-reduced center
+        self.loss_mod.sync_center()         # ... and so is the all-reduced center (no-op unless it ran asynchronously)
         return loss
 
     def run_e2e(self, graph=None):
@@ -276,7 +276,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--graph", type=int, default=1, help="replay the N=1 step from a CUDA graph (0 = eager launches)")
     ap.add_argument("--ddp", type=int, default=0, help="N>1: wrap the student head in torch DDP (eager) instead of GradAllReduce")
-    ap.add_argument("--reserve-sms", type=int, default=20, help="N>1: SMs the persistent GEMM grids leave to NCCL")
+    ap.add_argument("--reserve-sms", type=int, default=16, help="N>1: SMs the backward GEMM grids leave to NCCL")
     ap.add_argument("--overlap", type=int, default=1, help="teacher head forward on a side stream, overlapping the student's")
     ap.add_argument("--cpu-sample-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -325,8 +325,7 @@ def main():
     D.set_teacher_overlap(bool(args.overlap))
     if world > 1 and not args.ddp:
         D.set_async_center(True)
-        D.ops.gemm_max_ctas = 148 - args.reserve_sms      # leave SMs to the concurrent NCCL all-reduce kernels
-    step = Step(w, args.mode, rank, world, device, ddp=bool(args.ddp))
+    step = Step(w, args.mode, rank, world, device, ddp=bool(args.ddp), reserve_sms=args.reserve_sms)
     ops = D.ops
     for _ in range(warmup):
         step.run()

@@ -94,6 +94,11 @@ class MlpFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
+        with ops.backward_cap():
+            return MlpFn._backward(ctx, dy)
+
+    @staticmethod
+    def _backward(ctx, dy):
         mode, n, rows = ctx.mode, ctx.n, ctx.rows
         sd = store_dtype(mode)
         grads = [None] * (2 * n)
@@ -157,16 +162,20 @@ class NormLastLayerFn(torch.autograd.Function):
             dlogits = dlogits.to(store_dtype(mode))
         d = prep(dlogits, mode) if mode != "bf16" else Operand(ops._rows2d(dlogits))
         dz = dg = dv = None
-        if ctx.needs_input_grad[1]:
-            # dgrad: contraction over out_dim (split-K), W read MN-major from its [K,dim] storage
-            dzhat = mm(mode, d, ctx.wop, rows, dim, K, b_mn=True, out_dtype=torch.float32, tag="gemm_last_dgrad")
-            dz = ops.normalize_rows_bwd(dzhat, zhat, inv_den)
-        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
-            # wgrad: dW[K,dim] = dlogits^T . zhat, both MN-major
-            dw = mm(mode, d, ctx.zop, K, dim, rows, a_mn=True, b_mn=True, out_dtype=torch.float32, tag="gemm_last_wgrad")
-            dv, dg = ops.weightnorm_bwd(dw, v, scale, inv_vnorm, want_dg=ctx.needs_input_grad[2])
-            if not ctx.needs_input_grad[3]:
-                dv = None
+        with ops.backward_cap():
+            if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+                # wgrad first: dW[K,dim] = dlogits^T . zhat (both MN-major).  dv is the largest gradient of the step
+                # (K x 256 fp32); marking it ready here lets its all-reduce overlap the dgrad and the MLP backward.
+                dw = mm(mode, d, ctx.zop, K, dim, rows, a_mn=True, b_mn=True, out_dtype=torch.float32, tag="gemm_last_wgrad")
+                dv, dg = ops.weightnorm_bwd(dw, v, scale, inv_vnorm, want_dg=ctx.needs_input_grad[2])
+                if not ctx.needs_input_grad[3]:
+                    dv = None
+                else:
+                    ops.mark_ready(dv)
+            if ctx.needs_input_grad[1]:
+                # dgrad: contraction over out_dim (split-K), W read MN-major from its [K,dim] storage
+                dzhat = mm(mode, d, ctx.wop, rows, dim, K, b_mn=True, out_dtype=torch.float32, tag="gemm_last_dgrad")
+                dz = ops.normalize_rows_bwd(dzhat, zhat, inv_den)
         return None, dz, dg, dv
 
 

@@ -26,10 +26,13 @@ class StepGraph:
                 fn()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        from .loss import drop_pending_events
+        drop_pending_events()                   # everything has completed: no stale cross-stream events into the capture
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
             self.out = fn()
         torch.cuda.synchronize()
+        drop_pending_events()                   # events recorded inside the capture are not usable outside it
 
     def replay(self):
         self.graph.replay()

@@ -15,7 +15,17 @@ from . import ops
 from .head import wait_ready
 
 
+import weakref
+
 _async_center = False
+_instances = weakref.WeakSet()          # live DINOLoss modules (StepGraph drops their pending events before capture)
+
+
+def drop_pending_events():
+    """After a device-wide synchronize: forget events of completed asynchronous center exchanges.  An event
+    recorded inside one CUDA-graph capture must not be waited on from eager code or from another capture."""
+    for m in list(_instances):
+        m._center_event = None
 
 
 def set_async_center(enabled: bool):
@@ -38,6 +48,7 @@ class DINOLoss(nn.Module):
         self.register_buffer("center", torch.zeros(1, out_dim))
         self._center_event = None
         self._comm_stream = None
+        _instances.add(self)
         # same schedule construction as main_dino_mc.py:431-435
         self.teacher_temp_schedule = np.concatenate((
             np.linspace(warmup_teacher_temp, teacher_temp, warmup_teacher_temp_epochs),

@@ -18,6 +18,35 @@ launch_count = 0
 # Cap on the persistent GEMM grid (0 = all 148 SMs).  Data-parallel runs set it below 148 so that a concurrent
 # NCCL all-reduce kernel finds free SMs instead of queueing behind (or stalling) the one-CTA-per-SM GEMMs.
 gemm_max_ctas = 0
+backward_max_ctas = 0        # same cap, applied only inside the backward Functions (set by GradAllReduce)
+
+# data_ptr -> CUDA event recorded right after the kernel that produced a gradient buffer; lets the gradient
+# all-reduce start as soon as that buffer is final instead of when its autograd node returns.
+ready_events = {}
+
+
+class backward_cap:
+    """Context manager: GEMMs launched inside use `backward_max_ctas` as their persistent-grid cap."""
+
+    def __enter__(self):
+        global gemm_max_ctas
+        self.saved = gemm_max_ctas
+        if backward_max_ctas:
+            gemm_max_ctas = backward_max_ctas
+
+    def __exit__(self, *exc):
+        global gemm_max_ctas
+        gemm_max_ctas = self.saved
+        return False
+
+
+def mark_ready(t: torch.Tensor):
+    """Record "this buffer is final" on the current stream (see ready_events)."""
+    ev = torch.cuda.Event()
+    ev.record()
+    if len(ready_events) > 64:
+        ready_events.clear()
+    ready_events[t.data_ptr()] = ev
 
 
 def _count(n=1):

@@ -1,37 +1,80 @@
 """Gradient all-reduce for the data-parallel step (the exchange DDP performs at main_dino_mc.py:260).
 
-`GradAllReduce` averages each parameter's gradient over the ranks as soon as autograd has accumulated it,
-on a dedicated communication stream, so the NCCL transfers (89 MB of head gradients at K = 65536) overlap the
-rest of the backward pass and the EMA update.  Unlike `DistributedDataParallel` it keeps no Python-side
-reducer state between steps, which makes the whole step (collectives included) capturable in one CUDA graph
-(`StepGraph`).  `torch.distributed` (NCCL over NVLink / NVSwitch) does the transport.
+`GradAllReduce` averages each parameter's gradient over the ranks on a dedicated communication stream so the
+NCCL transfers (89 MB of head gradients at K = 65536) overlap the rest of the backward pass and the EMA update:
+
+  * a large gradient (the weight-normed last layer's dv, 64 MB) is reduced the moment the kernel that produced
+    it has finished (`ops.mark_ready` event), not when its autograd node returns;
+  * the small gradients are batched into one coalesced NCCL launch once all of them exist;
+  * while a reducer is active the persistent GEMM grids of the backward pass leave `reserve_sms` SMs free, so the
+    NCCL kernel neither queues behind a one-CTA-per-SM GEMM nor starves its tail CTAs.
+
+Unlike `DistributedDataParallel` it keeps no Python-side reducer state between steps, which makes the whole step
+(collectives included) capturable in one CUDA graph (`StepGraph`).  `torch.distributed` (NCCL over NVLink /
+NVSwitch) does the transport.
 """
 from __future__ import annotations
 
 import torch
 import torch.distributed as dist
 
+from . import ops
+
+_BIG = 32 << 20      # bytes: gradients at least this large get their own all-reduce
+
 
 class GradAllReduce:
-    def __init__(self, params, group=None):
+    def __init__(self, params, group=None, reserve_sms: int = 16):
         self.group = group
         self.params = [p for p in params if p.requires_grad]
         self.comm = torch.cuda.Stream()
+        self._pending = []
+        self._seen = 0
         self._handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
         self.bytes_per_step = sum(p.numel() * p.element_size() for p in self.params)
+        if reserve_sms > 0:
+            ops.backward_max_ctas = 148 - reserve_sms
 
     def _hook(self, p):
-        cur = torch.cuda.current_stream()
-        self.comm.wait_stream(cur)                       # the gradient was produced on `cur`
-        with torch.cuda.stream(self.comm):
-            dist.all_reduce(p.grad, op=dist.ReduceOp.AVG, group=self.group)
-        p.grad.record_stream(self.comm)
+        g = p.grad
+        self._seen += 1
+        if g.numel() * g.element_size() >= _BIG:
+            ev = ops.ready_events.pop(g.data_ptr(), None)
+            if ev is not None:
+                self.comm.wait_event(ev)                 # start as soon as the producing kernel is done
+            else:
+                self.comm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm):
+                dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
+            g.record_stream(self.comm)
+        else:
+            self._pending.append(g)
+        if self._seen == len(self.params):
+            self._flush()
+
+    def _flush(self):
+        if self._pending:
+            self.comm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm):
+                try:
+                    with dist._coalescing_manager(group=self.group, device=self._pending[0].device, async_ops=False):
+                        for g in self._pending:
+                            dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
+                except (AttributeError, TypeError, RuntimeError):
+                    for g in self._pending:
+                        dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
+            for g in self._pending:
+                g.record_stream(self.comm)
+            self._pending = []
+        self._seen = 0
 
     def wait(self):
         """Join: later work on the current stream sees the averaged gradients."""
+        self._flush()
         torch.cuda.current_stream().wait_stream(self.comm)
 
     def remove(self):
         for h in self._handles:
             h.remove()
         self._handles = []
+        ops.backward_max_ctas = 0
