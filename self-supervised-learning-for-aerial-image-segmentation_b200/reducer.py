@@ -21,6 +21,7 @@ import torch.distributed as dist
 from . import ops
 
 _BIG = 32 << 20      # bytes: gradients at least this large get their own all-reduce
+_FLUSH = 16 << 20    # bytes: pending small gradients are sent as one coalesced all-reduce once they reach this
 
 
 class GradAllReduce:
@@ -29,6 +30,7 @@ class GradAllReduce:
         self.params = [p for p in params if p.requires_grad]
         self.comm = torch.cuda.Stream()
         self._pending = []
+        self._pending_bytes = 0
         self._seen = 0
         self._handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
         self.bytes_per_step = sum(p.numel() * p.element_size() for p in self.params)
@@ -49,7 +51,8 @@ class GradAllReduce:
             g.record_stream(self.comm)
         else:
             self._pending.append(g)
-        if self._seen == len(self.params):
+            self._pending_bytes += g.numel() * g.element_size()
+        if self._seen == len(self.params) or self._pending_bytes >= _FLUSH:
             self._flush()
 
     def _flush(self):
@@ -66,11 +69,14 @@ class GradAllReduce:
             for g in self._pending:
                 g.record_stream(self.comm)
             self._pending = []
-        self._seen = 0
+            self._pending_bytes = 0
+        if self._seen >= len(self.params):
+            self._seen = 0
 
     def wait(self):
         """Join: later work on the current stream sees the averaged gradients."""
         self._flush()
+        self._seen = 0
         torch.cuda.current_stream().wait_stream(self.comm)
 
     def remove(self):
