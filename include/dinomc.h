@@ -86,7 +86,17 @@ typedef struct dmc_gemm_args {
   void* workspace;  size_t workspace_bytes; /* needed when split_k != 1, see query */
   int32_t max_ctas;        /* 0 = one persistent CTA per SM (148); > 0 = cap, e.g. to leave SMs to a concurrent
                               NCCL all-reduce kernel (the persistent CTAs would otherwise queue behind it) */
+  /* Optional statistics of the STORED output, fused into the epilogue (last-layer forward; plain epilogue,
+   * K-major operands, N > 128).  With y2 = (D[m,n] - stat_center[n]) * stat_scale * log2(e):
+   *   stat_row_partials[m][part] = { max_n y2, sum_n 2^(y2 - max) } over column part `part` (128 columns each,
+   *   dmc_gemm_stats_parts(N) parts per row) -- merged by dmc_teacher_finalize / dmc_lse_finalize;
+   *   stat_colsum_partials[g][n] = sum of D over the rows of 32-row group g (NULL = not wanted).
+   * This replaces DINOLoss's separate statistics passes over the logits (main_dino_mc.py:446,456,468). */
+  float stat_scale; const float* stat_center; float* stat_row_partials; float* stat_colsum_partials;
 } dmc_gemm_args;
+
+/* Number of 128-column parts per row that the fused statistics produce for an N-column output. */
+int64_t dmc_gemm_stats_parts(int64_t N);
 
 /* Upper bound of the split-K workspace dmc_gemm may need for this problem. */
 size_t dmc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int32_t in_dtype);
@@ -139,6 +149,11 @@ size_t dmc_teacher_workspace_bytes(int64_t Nt, int64_t K);
 int dmc_teacher_stats_colsum(const void* t, int32_t dtype, int64_t Nt, int64_t K, int64_t ld,
                              const float* center, float inv_temp, float* row_stats, float* colsum,
                              void* workspace, size_t workspace_bytes, void* stream);
+/* Same outputs as dmc_teacher_stats_colsum, but from the partials the last-layer GEMM's epilogue already wrote
+ * (dmc_gemm_args.stat_row_partials [Nt][parts] and stat_colsum_partials [row_groups][K]): no pass over the logits. */
+int dmc_teacher_finalize(const float* row_partials, const float* colsum_partials, int64_t Nt, int64_t K, int64_t parts,
+                         int64_t row_groups, float* row_stats, float* colsum, void* stream);
+
 /* center_out = center_in * momentum + (colsum / count) * one_minus_momentum  (main_dino_mc.py:470-473)
  * with the reference's fp32 roundings: true division by count (= Nt * world_size), separate multiplies and
  * add (no FMA).  center_out may alias center_in.  `momentum` and `one_minus_momentum` are passed
@@ -160,6 +175,19 @@ int dmc_ce_bwd(const void* s, int32_t s_dtype, int64_t lds, const void* t, int32
                const float* center, const float* t_row_stats, const float* s_lse, const float* grad_out,
                int64_t B, int32_t C, int32_t G, int64_t K, float inv_student_temp, float inv_teacher_temp,
                void* ds, int32_t ds_dtype, int64_t ldds, void* stream);
+
+/* lse[m] = logsumexp_n (D[m,n] * scale) from the GEMM epilogue's stat_row_partials [M][parts] (computed with
+ * stat_scale = scale = 1/tau_s and no center). */
+int dmc_lse_finalize(const float* row_partials, int64_t M, int64_t parts, float* lse, void* stream);
+/* Fused forward + backward of the crop-pair cross-entropy for rows whose log-sum-exp is already known: ONE pass
+ * over the logits writes loss[1] and ds = dL/ds for an upstream gradient of exactly 1 (dmc_scale_inplace_if
+ * rescales when autograd later delivers something else).  Workspace as for dmc_ce_fwd. */
+int dmc_ce_fused(const void* s, int32_t s_dtype, int64_t lds, const void* t, int32_t t_dtype, int64_t ldt,
+                 const float* center, const float* t_row_stats, const float* s_lse, int64_t B, int32_t C, int32_t G,
+                 int64_t K, float inv_student_temp, float inv_teacher_temp, void* ds, int32_t ds_dtype, int64_t ldds,
+                 float* loss, void* workspace, size_t workspace_bytes, void* stream);
+/* x *= (*scale / expected) unless the device scalar *scale == expected (then it costs one 4-byte read per CTA). */
+int dmc_scale_inplace_if(void* x, int32_t dtype, int64_t n, const float* scale, float expected, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * EMA teacher update (main_dino_mc.py:403-406):  p_k = fp32(p_k * m) + fp32((1-m) * p_q) for every

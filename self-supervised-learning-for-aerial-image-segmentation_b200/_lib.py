@@ -32,6 +32,7 @@ class GemmArgs(C.Structure):
         ("split_k", i32),
         ("workspace", vp), ("workspace_bytes", sz),
         ("max_ctas", i32),
+        ("stat_scale", f32), ("stat_center", vp), ("stat_row_partials", vp), ("stat_colsum_partials", vp),
     ]
 
 
@@ -41,6 +42,7 @@ SIGNATURES = {
     "dmc_last_error_string": (C.c_char_p, []),
     "dmc_device_check": (C.c_int, [C.c_int]),
     "dmc_gemm_workspace_bytes": (sz, [i64, i64, i64, i32]),
+    "dmc_gemm_stats_parts": (i64, [i64]),
     "dmc_gemm": (C.c_int, [C.POINTER(GemmArgs), vp]),
     "dmc_gemm_simt": (C.c_int, [C.POINTER(GemmArgs), vp]),
     "dmc_split_tf32": (C.c_int, [vp, vp, vp, i64, vp]),
@@ -53,6 +55,10 @@ SIGNATURES = {
     "dmc_weightnorm_bwd": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp, vp]),
     "dmc_teacher_workspace_bytes": (sz, [i64, i64]),
     "dmc_teacher_stats_colsum": (C.c_int, [vp, i32, i64, i64, i64, vp, f32, vp, vp, vp, sz, vp]),
+    "dmc_teacher_finalize": (C.c_int, [vp, vp, i64, i64, i64, i64, vp, vp, vp]),
+    "dmc_lse_finalize": (C.c_int, [vp, i64, i64, vp, vp]),
+    "dmc_ce_fused": (C.c_int, [vp, i32, i64, vp, i32, i64, vp, vp, vp, i64, i32, i32, i64, f32, f32, vp, i32, i64, vp, vp, sz, vp]),
+    "dmc_scale_inplace_if": (C.c_int, [vp, i32, i64, vp, f32, vp]),
     "dmc_center_update": (C.c_int, [vp, vp, vp, i64, f32, f32, f32, vp]),
     "dmc_ce_workspace_bytes": (sz, [i64, i32, i32, i64]),
     "dmc_ce_fwd": (C.c_int, [vp, i32, i64, vp, i32, i64, vp, vp, i64, i32, i32, i64, f32, f32, vp, vp, vp, sz, vp]),

@@ -340,6 +340,167 @@ ce_bwd_kernel(const CeArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fused loss + gradient pass.  When the per-row log-sum-exp of the student logits is already known (the GEMM
+// epilogue produced it, dmc_gemm stat_row_partials -> dmc_lse_finalize), ONE pass over the logits yields both the
+// loss's cross term and the gradient (for an upstream gradient of 1; dmc_scale_inplace_if rescales otherwise),
+// i.e. the forward statistics pass over [N_s + N_t, K] disappears.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, int MAXC, int MAXG, bool FAST>
+__device__ __forceinline__ void ce_fused_vector(const CeArgs& a, const T* s, const T* t, T* ds, long long b, long long col, int C,
+                                                int G, const float (&tmc)[MAXG], const float (&tinv)[MAXG],
+                                                const float (&lse2)[MAXC], float c2, float ct, float scale, float& cross) {
+  using Q4 = Quad<T>;
+  CeVec<T, MAXC, MAXG> in;
+  ce_load<T, MAXC, MAXG, FAST>(a, s, t, b, col, C, G, in);
+  float q[MAXG][4], Q[4] = {0.f, 0.f, 0.f, 0.f}, S[4] = {0.f, 0.f, 0.f, 0.f};
+  float qx = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXG; ++i)
+    if (i < G) {
+      float tq[4];
+      Q4::unpack(in.rt[i], tq);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float qv = ex2(fmaf(tq[e] - in.cen[e], ct, tmc[i])) * tinv[i];
+        if (!FAST && col + e >= a.K) qv = 0.f;
+        q[i][e] = qv;
+        Q[e] += qv;
+      }
+    }
+#pragma unroll
+  for (int v = 0; v < MAXC; ++v)
+    if (v < C) {
+      const float nvs = scale * static_cast<float>((v < G) ? (G - 1) : G);
+      float x[4], d[4];
+      Q4::unpack(in.rs[v], x);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        S[e] += x[e];
+        const float p = ex2(fmaf(x[e], c2, lse2[v]));                   // softmax(s/tau_s)
+        float qs = Q[e];
+        if (v < MAXG && v < G) { qs -= q[v < MAXG ? v : 0][e]; qx = fmaf(q[v < MAXG ? v : 0][e], x[e], qx); }
+        d[e] = fmaf(nvs, p, -scale * qs);
+      }
+      T* dst = ds + (v * a.B + b) * a.ldds + col;
+      if (FAST) {
+        Q4::store(dst, d);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (col + e < a.K) Q4::store1(dst + e, d[e]);
+      }
+    }
+  float qs = -qx;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) qs = fmaf(Q[e], S[e], qs);
+  cross = fmaf(qs, a.inv_ts, cross);
+}
+
+template <typename T, int CT, int GT>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
+ce_fused_kernel(const CeArgs a) {
+  constexpr int MAXC = CT ? CT : 16, MAXG = GT ? GT : 4;
+  const int C = CT ? CT : a.C, G = GT ? GT : a.G;
+  const long long b = blockIdx.y;
+  const int chunk = blockIdx.x;
+  const long long col_begin = static_cast<long long>(chunk) * kChunkCols;
+  const long long col_end = min(a.K, col_begin + kChunkCols);
+  const T* s = static_cast<const T*>(a.s);
+  const T* t = static_cast<const T*>(a.t);
+  T* ds = static_cast<T*>(a.ds);
+  const float scale = a.coef;
+  const float c2 = a.inv_ts * kLog2e, ct = a.inv_tt * kLog2e;
+  float tmc[MAXG], tinv[MAXG], lse2[MAXC];
+#pragma unroll
+  for (int i = 0; i < MAXG; ++i) {
+    tmc[i] = 0.f; tinv[i] = 0.f;
+    if (i < G) { const float2 st = a.t_stats[i * a.B + b]; tmc[i] = -st.x; tinv[i] = st.y; }
+  }
+#pragma unroll
+  for (int v = 0; v < MAXC; ++v) {
+    lse2[v] = 0.f;
+    if (v < C) lse2[v] = -a.s_lse[v * a.B + b] * kLog2e;
+  }
+  float cross = 0.f;
+  for (long long col = col_begin + threadIdx.x * 4; col < col_end; col += kThreads * 4) {
+    if (a.vec_ok && (col + 4 <= a.K)) ce_fused_vector<T, MAXC, MAXG, true>(a, s, t, ds, b, col, C, G, tmc, tinv, lse2, c2, ct, scale, cross);
+    else ce_fused_vector<T, MAXC, MAXG, false>(a, s, t, ds, b, col, C, G, tmc, tinv, lse2, c2, ct, scale, cross);
+  }
+  __shared__ float red[kThreads / 32];
+  cross = warp_sum(cross);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cross;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float c = 0.f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) c += red[w];
+    a.ws_x[b * a.nchunks + chunk] = c;
+  }
+}
+
+// loss = ( sum_rows n_v lse - sum cross partials ) / (n B), from final per-row lse values (fixed order).
+__global__ void __launch_bounds__(1024)
+ce_finalize_lse_kernel(const float* __restrict__ s_lse, const float* __restrict__ ws_x, long long B, int C, int G, int nchunks,
+                       float* __restrict__ loss) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  const long long rows = static_cast<long long>(C) * B;
+  for (long long r = threadIdx.x; r < rows; r += blockDim.x) {
+    const int v = static_cast<int>(r / B);
+    acc += static_cast<double>((v < G) ? (G - 1) : G) * static_cast<double>(s_lse[r]);
+  }
+  for (long long i = threadIdx.x; i < B * nchunks; i += blockDim.x) acc -= static_cast<double>(ws_x[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+    const int n_terms = G * C - (G < C ? G : C);
+    loss[0] = static_cast<float>(tot / (static_cast<double>(n_terms) * static_cast<double>(B)));
+  }
+}
+
+// lse[m] = (max2 + log2(sum)) * ln2 from the GEMM epilogue's per-part (max2, sum) pairs.  One warp per row.
+__global__ void __launch_bounds__(256)
+lse_finalize_kernel(const float2* __restrict__ partials, long long M, int parts, float* __restrict__ lse) {
+  const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= M) return;
+  const int lane = threadIdx.x & 31;
+  float m = -INFINITY, l = 0.f;
+  for (int c = lane; c < parts; c += 32) { const float2 p = partials[r * parts + c]; online_merge2(m, l, p.x, p.y); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+    const float l2 = __shfl_xor_sync(0xffffffffu, l, o);
+    online_merge2(m, l, m2, l2);
+  }
+  if (lane == 0) lse[r] = (m + log2f(l)) * 0.6931471805599453f;
+}
+
+// x *= (*scale / expected) unless *scale == expected (then every CTA exits after one 4-byte read).
+template <typename T>
+__global__ void __launch_bounds__(256)
+scale_if_kernel(T* __restrict__ x, long long n, const float* __restrict__ scale, float expected) {
+  const float sc = __ldg(scale);
+  if (sc == expected) return;
+  const float f = sc / expected;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    Vec<T>::store1(x + i, Vec<T>::load1(x + i) * f);
+}
+
+template <typename T>
+int launch_fused(const CeArgs& a, dim3 grid, cudaStream_t st) {
+  if (a.C == 8 && a.G == 2) ce_fused_kernel<T, 8, 2><<<grid, kThreads, 0, st>>>(a);
+  else if (a.C == 9 && a.G == 3) ce_fused_kernel<T, 9, 3><<<grid, kThreads, 0, st>>>(a);
+  else ce_fused_kernel<T, 0, 0><<<grid, kThreads, 0, st>>>(a);
+  DMC_LAUNCH_CHECK("ce_fused_kernel launch");
+  return 0;
+}
+
 template <typename T>
 int launch_fwd(const CeArgs& a, dim3 grid, cudaStream_t st) {
   if (a.C == 8 && a.G == 2) ce_fwd_kernel<T, 8, 2><<<grid, kThreads, 0, st>>>(a);
@@ -436,4 +597,56 @@ extern "C" int dmc_ce_bwd(const void* s, int32_t s_dtype, int64_t lds, const voi
   dim3 grid((unsigned)a.nchunks, (unsigned)B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return (s_dtype == DMC_BF16) ? launch_bwd<__nv_bfloat16>(a, grid, st) : launch_bwd<float>(a, grid, st);
+}
+
+extern "C" int dmc_lse_finalize(const float* row_partials, int64_t M, int64_t parts, float* lse, void* stream) {
+  DMC_REQUIRE(row_partials && lse && M > 0 && parts > 0 && parts < (1 << 30), "dmc_lse_finalize: bad arguments");
+  lse_finalize_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float2*>(row_partials), M, (int)parts, lse);
+  DMC_LAUNCH_CHECK("lse_finalize_kernel launch");
+  return 0;
+}
+
+extern "C" int dmc_ce_fused(const void* s, int32_t s_dtype, int64_t lds, const void* t, int32_t t_dtype, int64_t ldt,
+                            const float* center, const float* t_row_stats, const float* s_lse, int64_t B, int32_t C, int32_t G,
+                            int64_t K, float inv_student_temp, float inv_teacher_temp, void* ds, int32_t ds_dtype, int64_t ldds,
+                            float* loss, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common("dmc_ce_fused", s, s_dtype, lds, t, t_dtype, ldt, center, t_row_stats, B, C, G, K);
+  if (rc) return rc;
+  DMC_REQUIRE(s_lse && ds && loss && workspace, "dmc_ce_fused: null pointer");
+  DMC_REQUIRE(ds_dtype == s_dtype && ldds >= K, "dmc_ce_fused: gradient must have the logits' dtype and ld >= K");
+  DMC_REQUIRE(workspace_bytes >= dmc_ce_workspace_bytes(B, C, G, K), "dmc_ce_fused: workspace too small");
+  const int esz = s_dtype == DMC_BF16 ? 2 : 4;
+  CeArgs a{};
+  a.s = s; a.lds = lds; a.t = t; a.ldt = ldt; a.center = center; a.t_stats = reinterpret_cast<const float2*>(t_row_stats);
+  a.B = B; a.K = K; a.C = C; a.G = G; a.inv_ts = inv_student_temp; a.inv_tt = inv_teacher_temp;
+  a.nchunks = static_cast<int>(ceil_div(K, chunk_cols(s_dtype)));
+  const int va = 4 * esz;
+  a.vec_ok = ((reinterpret_cast<uintptr_t>(s) % va) == 0) && ((reinterpret_cast<uintptr_t>(t) % va) == 0) &&
+             ((reinterpret_cast<uintptr_t>(ds) % va) == 0) && ((lds * esz) % va == 0) && ((ldt * esz) % va == 0) &&
+             ((ldds * esz) % va == 0);
+  a.s_lse = s_lse;
+  const int n_terms = G * C - (G < C ? G : C);
+  a.coef = static_cast<float>(static_cast<double>(inv_student_temp) / (static_cast<double>(n_terms) * static_cast<double>(B)));
+  a.ds = ds; a.ldds = ldds;
+  a.ws_x = static_cast<float*>(workspace);
+  dim3 grid((unsigned)a.nchunks, (unsigned)B);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = (s_dtype == DMC_BF16) ? launch_fused<__nv_bfloat16>(a, grid, st) : launch_fused<float>(a, grid, st);
+  if (rc) return rc;
+  ce_finalize_lse_kernel<<<1, 1024, 0, st>>>(s_lse, a.ws_x, B, C, G, a.nchunks, loss);
+  DMC_LAUNCH_CHECK("ce_finalize_lse_kernel launch");
+  return 0;
+}
+
+extern "C" int dmc_scale_inplace_if(void* x, int32_t dtype, int64_t n, const float* scale, float expected, void* stream) {
+  DMC_REQUIRE(x && scale && n > 0 && expected != 0.f, "dmc_scale_inplace_if: bad arguments");
+  DMC_REQUIRE(dtype == DMC_F32 || dtype == DMC_BF16, "dmc_scale_inplace_if: bad dtype");
+  const int blocks = kNumSMs * 8;
+  if (dtype == DMC_BF16)
+    scale_if_kernel<__nv_bfloat16><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<__nv_bfloat16*>(x), n, scale, expected);
+  else
+    scale_if_kernel<float><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<float*>(x), n, scale, expected);
+  DMC_LAUNCH_CHECK("scale_if_kernel launch");
+  return 0;
 }

@@ -55,6 +55,11 @@ struct GemmDev {
   uint32_t b_bytes;   // block_n * 128
   int resident;       // 1: B-resident schedule (contiguous tile ranges, B slabs loaded once per n-tile)
   int dual;           // 1: "dual-M": a work item is 256 rows = two accumulators that share every B k-block
+  // fused output statistics (EPI == 2): softmax row partials and 32-row column sums of the stored values
+  float stat_sc2;               // stat_scale * log2(e)
+  const float* stat_center;     // [N] or nullptr
+  float2* stat_row_partials;    // [M][2 * n_tiles]
+  float* stat_colsum_partials;  // [ceil(M/32)][N] or nullptr
   int tma_store;      // 1: epilogue stores D through smem staging + TMA
   // epilogue
   void* D; long long ldd; int out_dtype;
@@ -162,9 +167,13 @@ __device__ __forceinline__ void epilogue_store_row(const Epilogue& e, float (&ac
 constexpr int kStagingBytesPerWarp = 4096;       // one 32-row x 128-byte box per epilogue warp
 constexpr int kStagingBytes = kEpiWarps * kStagingBytesPerWarp;
 
-// PLAIN: the epilogue is only "scale by alpha, convert, store" (no column scale / bias / activation / aux):
-// compiled separately so the hot last-layer kernels carry none of the optional epilogue code.
-template <int ESZ, bool A_MN, bool B_MN, bool PLAIN>
+// EPI 0: full epilogue (column scale / bias / activation / aux).
+// EPI 1: "plain" -- scale by alpha, convert, store; compiled separately so the hot last-layer kernels carry none of
+//        the optional epilogue code.
+// EPI 2: plain + fused statistics of the stored (rounded) logits: per row and 128-column part the online-softmax
+//        pair (max, sum 2^(y - max)) of y = (D - center) * scale * log2e, and per 32-row group the column sums.
+//        This is what lets DINOLoss skip its separate statistics passes over the logits.
+template <int ESZ, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -374,6 +383,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const long long row = static_cast<long long>(row0) + lane;
       const uint32_t t_addr = tmem_base + static_cast<uint32_t>((acc + h) * kAccCols) + (static_cast<uint32_t>(q * 32) << 16);
       const bool last_h = (h == p.dual);
+      float st_m = -INFINITY, st_l = 0.f;                       // EPI 2: this row's softmax partial over [c_begin, c_end)
       // One 32-column chunk: accumulators -> epilogue -> split-K partials | direct store | smem staging + TMA store.
       auto process = [&](uint32_t (&r)[32], int c) {
         const int n = min(32, ncols - c);
@@ -395,7 +405,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
           return;
         }
-        if constexpr (PLAIN) {
+        if constexpr (EPI >= 1) {
           if (e.alpha != 1.0f) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= e.alpha;
@@ -422,11 +432,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const uint4 pk = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
                                         pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
             *reinterpret_cast<uint4*>(rowp + ((((sub << 2) + j) ^ (lane & 7)) << 4)) = pk;
+            if constexpr (EPI == 2) {                           // statistics see exactly the values that are stored
+              v[8 * j + 0] = bf16_lo(pk.x); v[8 * j + 1] = bf16_hi(pk.x); v[8 * j + 2] = bf16_lo(pk.y); v[8 * j + 3] = bf16_hi(pk.y);
+              v[8 * j + 4] = bf16_lo(pk.z); v[8 * j + 5] = bf16_hi(pk.z); v[8 * j + 6] = bf16_lo(pk.w); v[8 * j + 7] = bf16_hi(pk.w);
+            }
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        if constexpr (EPI == 2) {
+          // online softmax partial of this thread's row over its 32 columns (base-2 domain)
+          float y[32];
+          float cm = -INFINITY;
+          if (p.stat_center != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float cb = -__ldg(p.stat_center + min(n0 + c + j, p.N - 1)) * p.stat_sc2;
+              y[j] = (j < n) ? fmaf(v[j], p.stat_sc2, cb) : -INFINITY;
+              cm = fmaxf(cm, y[j]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              y[j] = (j < n) ? v[j] * p.stat_sc2 : -INFINITY;
+              cm = fmaxf(cm, y[j]);
+            }
+          }
+          if (cm > st_m) { st_l *= ex2(st_m - cm); st_m = cm; }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) st_l += ex2(y[j] - st_m);
         }
         const bool box_done = (sub == chunks_per_box - 1) || (c + 32 >= ncols);
         if (box_done) {
@@ -437,6 +473,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             ptx::tma_store_commit();
           }
           ++n_boxes;
+          if constexpr (EPI == 2) {
+            if (p.stat_colsum_partials != nullptr && row0 < p.M) {
+              // column sums over this warp's 32 rows, read back from the staged (swizzled) box: lane j owns the
+              // 32-bit word j of every 128-byte row -> conflict-free; 2 bf16 columns or 1 fp32 column per lane.
+              const int nrows = min(32, p.M - row0);
+              float s0 = 0.f, s1 = 0.f;
+              for (int r = 0; r < nrows; ++r) {
+                const uint32_t wv = *reinterpret_cast<const uint32_t*>(buf + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+                if (p.out_dtype == DMC_BF16) { s0 += bf16_lo(wv); s1 += bf16_hi(wv); }
+                else s0 += __uint_as_float(wv);
+              }
+              float* dst = p.stat_colsum_partials + static_cast<long long>(row0 >> 5) * p.N;
+              const int cbox = n0 + c - sub * 32;
+              if (p.out_dtype == DMC_BF16) {
+                if (cbox + 2 * lane < p.N) dst[cbox + 2 * lane] = s0;
+                if (cbox + 2 * lane + 1 < p.N) dst[cbox + 2 * lane + 1] = s1;
+              } else {
+                if (cbox + lane < p.N) dst[cbox + lane] = s0;
+              }
+            }
+          }
         }
       };
       for (int c = c_begin; c < c_end; c += 64) {               // this warp's column range, 64 columns at a time
@@ -451,6 +508,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         process(ra, c);
         process(rb, c + 32);
+      }
+      if constexpr (EPI == 2) {
+        if (row < p.M && c_begin < c_end)
+          p.stat_row_partials[row * (2 * p.n_tiles) + 2 * nt + half] = make_float2(st_m, st_l);
       }
       if (last_h && c_begin >= c_end) {                         // nothing to drain (block_n == 64, upper half): still release
         ptx::tc_fence_before();
@@ -619,10 +680,10 @@ Plan make_plan(int64_t M, int64_t N, int64_t K, int in_dtype, bool three_pass, i
   return pl;
 }
 
-template <int ESZ, bool A_MN, bool B_MN, bool PLAIN>
+template <int ESZ, bool A_MN, bool B_MN, int EPI>
 int launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
               const CUtensorMap& td, const GemmDev& dev, size_t smem_bytes, int grid, cudaStream_t st) {
-  auto kern = gemm_tc_kernel<ESZ, A_MN, B_MN, PLAIN>;
+  auto kern = gemm_tc_kernel<ESZ, A_MN, B_MN, EPI>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
   if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(gemm_tc_kernel)");
   kern<<<grid, kThreads, smem_bytes, st>>>(a0, a1, b0, b1, td, dev);
@@ -634,6 +695,8 @@ int launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b
 }  // namespace dmc
 
 using namespace dmc;
+
+extern "C" int64_t dmc_gemm_stats_parts(int64_t N) { return N > 0 ? 2 * ceil_div(N, 256) : 0; }
 
 extern "C" size_t dmc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int32_t in_dtype) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
@@ -693,6 +756,14 @@ extern "C" int dmc_gemm(const dmc_gemm_args* a, void* stream) {
   d.kb_total = pl.kb_total; d.vk_total = pl.vk_total; d.splits = pl.splits; d.vk_per_split = pl.vk_per_split;
   d.stages = pl.stages; d.b_bytes = static_cast<uint32_t>(pl.block_n) * kRowBytes;
   d.resident = pl.resident; d.tma_store = pl.tma_store; d.dual = pl.dual;
+  d.stat_sc2 = a->stat_scale * 1.4426950408889634f; d.stat_center = a->stat_center;
+  d.stat_row_partials = reinterpret_cast<float2*>(a->stat_row_partials); d.stat_colsum_partials = a->stat_colsum_partials;
+  if (a->stat_row_partials != nullptr) {
+    DMC_REQUIRE(a->col_scale == nullptr && a->bias == nullptr && a->act == DMC_ACT_NONE && !a->a_mn_major && !a->b_mn_major,
+                "dmc_gemm: fused statistics need a plain epilogue and K-major operands");
+    DMC_REQUIRE(pl.tma_store && pl.block_n == 256 && !pl.dual && pl.splits == 1,
+                "dmc_gemm: fused statistics need N >= 129, an aligned output and an unsplit contraction");
+  }
   d.D = a->D; d.ldd = a->ldd; d.out_dtype = a->out_dtype;
   d.partial = pl.splits > 1 ? static_cast<float*>(a->workspace) : nullptr;
   d.col_scale = a->col_scale; d.bias = a->bias; d.alpha_dev = a->alpha_dev; d.alpha = a->alpha;
@@ -703,13 +774,19 @@ extern "C" int dmc_gemm(const dmc_gemm_args* a, void* stream) {
   const int grid = num_work < cap ? num_work : cap;
   const bool amn = a->a_mn_major != 0, bmn = a->b_mn_major != 0;
 const bool plain = (a->col_scale == nullptr && a->bias == nullptr && a->act == DMC_ACT_NONE);
+  const bool stats = (a->stat_row_partials != nullptr);
 #define DMC_LAUNCH(ESZ_, AMN_, BMN_)                                                                          \
-  (plain ? launch_tc<ESZ_, AMN_, BMN_, true>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st)              \
-         : launch_tc<ESZ_, AMN_, BMN_, false>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st))
+  (plain ? launch_tc<ESZ_, AMN_, BMN_, 1>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st)                 \
+         : launch_tc<ESZ_, AMN_, BMN_, 0>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st))
 #define DMC_DISPATCH(ESZ_)                                                                                    \
   (amn ? (bmn ? DMC_LAUNCH(ESZ_, true, true) : DMC_LAUNCH(ESZ_, true, false))                                 \
        : (bmn ? DMC_LAUNCH(ESZ_, false, true) : DMC_LAUNCH(ESZ_, false, false)))
-  rc = (esz == 2) ? DMC_DISPATCH(2) : DMC_DISPATCH(4);
+  if (stats) {          // last-layer forward only: K-major operands
+    rc = (esz == 2) ? launch_tc<2, false, false, 2>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st)
+                    : launch_tc<4, false, false, 2>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st);
+  } else {
+    rc = (esz == 2) ? DMC_DISPATCH(2) : DMC_DISPATCH(4);
+  }
 #undef DMC_LAUNCH
 #undef DMC_DISPATCH
   if (rc) return rc;

@@ -229,3 +229,17 @@ extern "C" int dmc_center_update(const float* center_in, float* center_out, cons
   DMC_LAUNCH_CHECK("center_update_kernel launch");
   return 0;
 }
+
+extern "C" int dmc_teacher_finalize(const float* row_partials, const float* colsum_partials, int64_t Nt, int64_t K, int64_t parts,
+                                    int64_t row_groups, float* row_stats, float* colsum, void* stream) {
+  DMC_REQUIRE(row_partials && colsum_partials && row_stats && colsum, "dmc_teacher_finalize: null pointer");
+  DMC_REQUIRE(Nt > 0 && K > 0 && parts > 0 && row_groups > 0 && parts < (1 << 30) && row_groups < (1 << 30),
+              "dmc_teacher_finalize: bad shape");
+  const int row_blocks = static_cast<int>(ceil_div(Nt, 8));
+  const int col_blocks = static_cast<int>(ceil_div(K, 256));
+  teacher_finalize_kernel<<<row_blocks + col_blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float2*>(row_partials), colsum_partials, Nt, K, (int)parts, (int)row_groups, row_blocks,
+      reinterpret_cast<float2*>(row_stats), colsum);
+  DMC_LAUNCH_CHECK("teacher_finalize_kernel launch");
+  return 0;
+}

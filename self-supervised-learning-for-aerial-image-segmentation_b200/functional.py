@@ -16,6 +16,28 @@ from . import ops
 
 MODES = ("bf16", "fp32", "fp32_simt")
 
+# ---------------------------------------------------------------------------------------------------------
+# Fused logit statistics.  The last-layer GEMM can emit, from its epilogue, the softmax statistics DINOLoss
+# needs (student log-sum-exp partials; teacher softmax partials + column sums), which removes the loss's own
+# statistics passes over the logits.  The head does not know the temperatures or the center -- they belong to
+# DINOLoss -- so the most recently used DINOLoss registers itself here (weak reference) and the head asks it.
+# Everything is validated again inside DINOLoss.forward; on any mismatch the separate passes run instead.
+# ---------------------------------------------------------------------------------------------------------
+import weakref
+
+fused_stats_enabled = True
+_loss_ref = None          # weakref to the DINOLoss whose temperatures / center the heads should use
+last_stats = None         # stats record of the most recent NormLastLayerFn.forward (picked up by DINOHead)
+
+
+def register_loss(loss_module):
+    global _loss_ref
+    _loss_ref = weakref.ref(loss_module)
+
+
+def _current_loss():
+    return _loss_ref() if _loss_ref is not None else None
+
 
 class Operand:
     """A GEMM operand in the representation a mode needs: bf16 tensor, (hi, lo) TF32 pair, or plain fp32."""
@@ -146,7 +168,23 @@ class NormLastLayerFn(torch.autograd.Function):
             w, _, scale, inv_vnorm = ops.weightnorm_fwd(v.detach(), g.detach().reshape(-1), "f32")
             wop = Operand(w)
         who = "student" if any(ctx.needs_input_grad) else "teacher"
-        logits = mm(mode, zop, wop, rows, K, dim, out_dtype=store_dtype(mode), tag="gemm_last_fwd_" + who)
+        global last_stats
+        last_stats = None
+        stats = None
+        loss_mod = _current_loss() if (fused_stats_enabled and mode != "fp32_simt" and K > 128) else None
+        if loss_mod is not None:
+            parts = ops.gemm_stats_parts(K)
+            rp = torch.empty((rows, parts, 2), dtype=torch.float32, device=z.device)
+            if who == "student":
+                stats = dict(kind="student", scale=1.0 / loss_mod.student_temp, center=None, row_partials=rp)
+            else:
+                loss_mod.sync_center()
+                cen = loss_mod.center
+                stats = dict(kind="teacher", scale=loss_mod._last_inv_tt, center=cen.reshape(-1), row_partials=rp,
+                             colsum_partials=torch.empty(((rows + 31) // 32, K), dtype=torch.float32, device=z.device),
+                             center_ptr=cen.data_ptr(), center_version=cen._version)
+        logits = mm(mode, zop, wop, rows, K, dim, out_dtype=store_dtype(mode), tag="gemm_last_fwd_" + who, stats=stats)
+        last_stats = stats
         ctx.mode = mode
         ctx.zop, ctx.wop = zop, wop
         ctx.save_for_backward(zhat, inv_den, v.detach(), scale, inv_vnorm)
@@ -181,15 +219,31 @@ class NormLastLayerFn(torch.autograd.Function):
 
 class DinoLossFn(torch.autograd.Function):
     """DINOLoss.forward (main_dino_mc.py:437-459) on the OLD center.  forward(student, teacher, center,
-    inv_ts, inv_tt, B, C, G) -> (loss, colsum); colsum = per-GPU batch column sum of the teacher logits
-    (input of update_center), produced by the same pass that computes the teacher softmax statistics."""
+    inv_ts, inv_tt, B, C, G, s_pre, t_pre) -> (loss, colsum); colsum = per-GPU batch column sum of the teacher
+    logits (input of update_center).
+
+    Two routes.  Plain: teacher pass (row statistics + column sums), forward pass (student log-sum-exp + loss),
+    and in backward one pass that writes the gradient.  Fused (when the last-layer GEMM epilogue already produced
+    the statistics, `s_pre` / `t_pre`): no teacher pass, and a single pass computes the loss AND the gradient for
+    an upstream gradient of 1 -- backward only rescales if autograd delivers something else."""
 
     @staticmethod
-    def forward(ctx, s, t, center, inv_ts, inv_tt, B, C, G):
+    def forward(ctx, s, t, center, inv_ts, inv_tt, B, C, G, s_pre, t_pre):
         s_d, t_d = s.detach(), t.detach()
         center = center.detach().reshape(-1)
-        t_stats, colsum = ops.teacher_stats_colsum(t_d, center, inv_tt)
-        loss, s_lse = ops.ce_fwd(s_d, t_d, center, t_stats, B, C, G, inv_ts, inv_tt)
+        K = s_d.shape[1]
+        if t_pre is not None:
+            t_stats, colsum = ops.teacher_finalize(t_pre["row_partials"], t_pre["colsum_partials"], t_d.shape[0], K)
+        else:
+            t_stats, colsum = ops.teacher_stats_colsum(t_d, center, inv_tt)
+        ctx.fused = bool(s_pre is not None and ctx.needs_input_grad[0])
+        ctx.used = False
+        if ctx.fused:
+            s_lse = ops.lse_finalize(s_pre["row_partials"])
+            loss, ds = ops.ce_fused(s_d, t_d, center, t_stats, s_lse, B, C, G, inv_ts, inv_tt)
+            ctx.ds = ds
+        else:
+            loss, s_lse = ops.ce_fwd(s_d, t_d, center, t_stats, B, C, G, inv_ts, inv_tt)
         ctx.save_for_backward(s_d, t_d, center, t_stats, s_lse)
         ctx.cfg = (B, C, G, inv_ts, inv_tt)
         ctx.mark_non_differentiable(colsum)
@@ -199,5 +253,10 @@ class DinoLossFn(torch.autograd.Function):
     def backward(ctx, gloss, _gcolsum):
         s, t, center, t_stats, s_lse = ctx.saved_tensors
         B, C, G, inv_ts, inv_tt = ctx.cfg
-        ds = ops.ce_bwd(s, t, center, t_stats, s_lse, gloss, B, C, G, inv_ts, inv_tt)
-        return ds, None, None, None, None, None, None, None
+        if ctx.fused and not ctx.used:
+            ctx.used = True
+            ds = ops.scale_inplace_if(ctx.ds, gloss, 1.0)     # no-op kernel when the upstream gradient is 1
+            ctx.ds = None
+        else:
+            ds = ops.ce_bwd(s, t, center, t_stats, s_lse, gloss, B, C, G, inv_ts, inv_tt)
+        return ds, None, None, None, None, None, None, None, None, None

@@ -170,4 +170,8 @@ class DINOHead(nn.Module):
                 for lin in linears:
                     wb += [lin.weight, lin.bias]
                 z = Fn.MlpFn.apply(mode, x, *wb)
-            return Fn.NormLastLayerFn.apply(mode, z, self.last_layer.weight_g, self.last_layer.weight_v)
+            out = Fn.NormLastLayerFn.apply(mode, z, self.last_layer.weight_g, self.last_layer.weight_v)
+            if Fn.last_stats is not None:       # statistics the GEMM epilogue produced for dinomc_b200.DINOLoss
+                out._dmc_stats = Fn.last_stats
+                Fn.last_stats = None
+            return out

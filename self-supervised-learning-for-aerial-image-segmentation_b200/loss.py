@@ -54,6 +54,9 @@ class DINOLoss(nn.Module):
             np.linspace(warmup_teacher_temp, teacher_temp, warmup_teacher_temp_epochs),
             np.ones(nepochs - warmup_teacher_temp_epochs) * teacher_temp,
         ))
+        # temperature the teacher head's fused statistics assume until the first forward tells otherwise
+        self._last_inv_tt = 1.0 / float(self.teacher_temp_schedule[0]) if len(self.teacher_temp_schedule) else 25.0
+        Fn.register_loss(self)
 
     @staticmethod
     def _common(student_output, teacher_output):
@@ -75,7 +78,21 @@ class DINOLoss(nn.Module):
         self.sync_center()
         wait_ready(teacher_output)              # no-op unless the teacher head ran on the overlap side stream
         s, t = self._common(student_output, teacher_output.detach())
-        loss, colsum = Fn.DinoLossFn.apply(s, t, self.center, 1.0 / self.student_temp, 1.0 / temp, B, C, G)
+        inv_ts, inv_tt = 1.0 / self.student_temp, 1.0 / temp
+        # statistics the heads' GEMM epilogues may have attached to the logits; re-validated here
+        s_pre = getattr(student_output, "_dmc_stats", None) if s is student_output else None
+        if s_pre is not None and not (s_pre.get("kind") == "student" and s_pre["scale"] == inv_ts
+                                      and s_pre["row_partials"].shape[0] == s.shape[0]):
+            s_pre = None
+        t_pre = getattr(teacher_output, "_dmc_stats", None) if t.data_ptr() == teacher_output.data_ptr() else None
+        if t_pre is not None and not (t_pre.get("kind") == "teacher" and t_pre["scale"] == inv_tt
+                                      and t_pre["center_ptr"] == self.center.data_ptr()
+                                      and t_pre["center_version"] == self.center._version
+                                      and t_pre["row_partials"].shape[0] == t.shape[0]):
+            t_pre = None
+        self._last_inv_tt = inv_tt
+        Fn.register_loss(self)
+        loss, colsum = Fn.DinoLossFn.apply(s, t, self.center, inv_ts, inv_tt, B, C, G, s_pre, t_pre)
         self._update_center_from_colsum(colsum, teacher_output.shape[0])
         return loss
 

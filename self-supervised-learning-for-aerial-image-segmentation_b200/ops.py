@@ -156,7 +156,7 @@ def tma_ok(t: torch.Tensor) -> bool:
 
 def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, A_lo=None, B_lo=None, out=None, out_dtype=torch.float32,
          col_scale=None, bias=None, alpha=1.0, alpha_dev=None, act=L.ACT_NONE, aux=None, simt=False, split_k=0,
-         tag="gemm"):
+         tag="gemm", stats=None):
     """D[M,N] = epilogue(sum_k A(m,k) B(n,k)).  A is stored [M,K] (a_mn=False) or [K,M] (a_mn=True);
     B is stored [N,K] (b_mn=False) or [K,N] (b_mn=True).  See dmc_gemm in include/dinomc.h."""
     lib = L.load()
@@ -187,6 +187,11 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, A_lo=None, B_lo=None, out=Non
         g.aux, g.ldaux, g.aux_dtype = aux.data_ptr(), aux.stride(0), _dt(aux)
     g.split_k = split_k
     g.max_ctas = gemm_max_ctas
+    if stats is not None:        # fused softmax / column-sum statistics of the stored output (see dmc_gemm_args)
+        g.stat_scale = float(stats["scale"])
+        g.stat_center = _p(stats.get("center"))
+        g.stat_row_partials = stats["row_partials"].data_ptr()
+        g.stat_colsum_partials = _p(stats.get("colsum_partials"))
     if simt:
         with _timed(tag):
             L.check(lib.dmc_gemm_simt(C.byref(g), _stream()), "dmc_gemm_simt")
@@ -200,6 +205,63 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, A_lo=None, B_lo=None, out=Non
         L.check(lib.dmc_gemm(C.byref(g), _stream()), "dmc_gemm")
     _count(2 if nbytes else 1)
     return out
+
+
+def gemm_stats_parts(N: int) -> int:
+    return int(L.load().dmc_gemm_stats_parts(N))
+
+
+def teacher_finalize(row_partials, colsum_partials, Nt, K):
+    """(row_stats [Nt,2], colsum [K]) from the partials the last-layer GEMM epilogue wrote."""
+    lib = L.load()
+    row_stats = torch.empty((Nt, 2), dtype=torch.float32, device=row_partials.device)
+    colsum_ = torch.empty(K, dtype=torch.float32, device=row_partials.device)
+    with _timed("teacher_finalize"):
+        L.check(lib.dmc_teacher_finalize(row_partials.data_ptr(), colsum_partials.data_ptr(), Nt, K, row_partials.shape[1],
+                                         colsum_partials.shape[0], row_stats.data_ptr(), colsum_.data_ptr(), _stream()),
+                "dmc_teacher_finalize")
+    _count()
+    return row_stats, colsum_
+
+
+def lse_finalize(row_partials):
+    lib = L.load()
+    M, parts = row_partials.shape[0], row_partials.shape[1]
+    lse = torch.empty(M, dtype=torch.float32, device=row_partials.device)
+    with _timed("lse_finalize"):
+        L.check(lib.dmc_lse_finalize(row_partials.data_ptr(), M, parts, lse.data_ptr(), _stream()), "dmc_lse_finalize")
+    _count()
+    return lse
+
+
+def ce_fused(s, t, center, t_stats, s_lse, B, C, G, inv_ts, inv_tt):
+    """One pass: (loss, ds for an upstream gradient of 1)."""
+    lib = L.load()
+    s, t = _rows2d(s), _rows2d(t)
+    _need_cuda(s, t, center, t_stats, s_lse)
+    K = s.shape[1]
+    ds = torch.empty((s.shape[0], K), dtype=s.dtype, device=s.device)
+    loss = torch.empty((), dtype=torch.float32, device=s.device)
+    nbytes = lib.dmc_ce_workspace_bytes(B, C, G, K)
+    ws = workspace(nbytes, s.device)
+    with _timed("ce_fused"):
+        L.check(lib.dmc_ce_fused(s.data_ptr(), _dt(s), s.stride(0), t.data_ptr(), _dt(t), t.stride(0), center.data_ptr(),
+                                 t_stats.data_ptr(), s_lse.data_ptr(), B, C, G, K, inv_ts, inv_tt, ds.data_ptr(), _dt(ds),
+                                 ds.stride(0), loss.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "dmc_ce_fused")
+    _count(2)
+    return loss, ds
+
+
+def scale_inplace_if(x, scale_dev, expected=1.0):
+    lib = L.load()
+    _need_cuda(x, scale_dev)
+    assert x.is_contiguous()
+    scale_dev = scale_dev.to(torch.float32).contiguous()
+    with _timed("scale_if"):
+        L.check(lib.dmc_scale_inplace_if(x.data_ptr(), _dt(x), x.numel(), scale_dev.data_ptr(), float(expected), _stream()),
+                "dmc_scale_inplace_if")
+    _count()
+    return x
 
 
 def split_tf32(x: torch.Tensor):

@@ -245,3 +245,43 @@ def test_teacher_overlap_side_stream(golden):
         assert rel_err(t_out.float().cpu().numpy(), ref["teacher_logits"]) < 1e-5
     finally:
         D.set_teacher_overlap(False)
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-5), ("bf16", 2e-2)])
+def test_fused_statistics_route_matches_plain_route(mode, tol):
+    """The GEMM-epilogue statistics + single-pass loss/gradient route against the separate-passes route, on a shape
+    where the fused route is taken (out_dim > 128), incl. a ragged out_dim and an upstream gradient != 1."""
+    import dinomc_b200 as D
+    Fn = D.functional
+    torch.manual_seed(3)
+    Din, K, B, C, G = 64, 1000, 6, 8, 2
+    student = D.DINOHead(Din, K, hidden_dim=128, bottleneck_dim=64).cuda()
+    teacher = D.DINOHead(Din, K, hidden_dim=128, bottleneck_dim=64).cuda()
+    student.precision = teacher.precision = mode
+    xs = torch.randn(C * B, Din, device="cuda")
+    xt = torch.randn(G * B, Din, device="cuda")
+    res = {}
+    for fused in (True, False):
+        Fn.fused_stats_enabled = fused
+        try:
+            loss_mod = D.DINOLoss(K, C, 0.04, 0.07, 3, 10, teacher_crops_number=G).cuda()
+            loss_mod.center.normal_(0, 0.2, generator=torch.Generator(device="cuda").manual_seed(5))
+            x = xs.clone().requires_grad_(True)
+            for epoch in (0, 0, 1):                       # epoch 1 changes the teacher temperature -> one fallback step
+                with torch.no_grad():
+                    t_out = teacher(xt)
+                s_out = student(x)
+                assert (getattr(s_out, "_dmc_stats", None) is not None) == fused
+                loss = loss_mod(s_out, t_out, epoch)
+                for p in student.parameters():
+                    p.grad = None
+                x.grad = None
+                (loss * 3.0).backward()                   # upstream gradient 3: exercises the rescale kernel
+            res[fused] = (float(loss.detach()), x.grad.clone(), student.last_layer.weight_v.grad.clone(),
+                          loss_mod.center.clone())
+        finally:
+            Fn.fused_stats_enabled = True
+    lf, lp = res[True][0], res[False][0]
+    assert abs(lf - lp) / abs(lp) < tol
+    for a, b in zip(res[True][1:], res[False][1:]):
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < tol
