@@ -93,6 +93,8 @@ typedef struct dmc_gemm_args {
    *   stat_colsum_partials[g][n] = sum of D over the rows of 32-row group g (NULL = not wanted).
    * This replaces DINOLoss's separate statistics passes over the logits (main_dino_mc.py:446,456,468). */
   float stat_scale; const float* stat_center; float* stat_row_partials; float* stat_colsum_partials;
+  const float* stat_bound; /* optional device scalar b >= max |D| (e.g. the largest weight-norm gain when the rows of A
+                              are unit vectors): lets the epilogue skip the running max (used only without a center) */
 } dmc_gemm_args;
 
 /* Number of 128-column parts per row that the fused statistics produce for an N-column output. */
@@ -131,7 +133,8 @@ int dmc_normalize_rows_bwd(const float* dzhat, const float* zhat, const float* i
  * output row k of v [K,dim].  Writes any non-NULL of w_f32 (tf32-rounded when w_lo is given) / w_lo /
  * w_bf16, and scale[K] = g_k/||v_k||, inv_vnorm[K] = 1/||v_k|| (saved for backward). */
 int dmc_weightnorm_fwd(const float* v, const float* g, int64_t K, int64_t dim,
-                       float* w_f32, float* w_lo, void* w_bf16, float* scale, float* inv_vnorm, void* stream);
+                       float* w_f32, float* w_lo, void* w_bf16, float* scale, float* inv_vnorm, float* gmax, void* stream);
+/* gmax (optional device scalar) receives max_k |g_k|, the bound of every logit when the activations are unit rows. */
 /* Backward: dv = scale * (dw - (dw . vhat) vhat), dg = dw . vhat (dg may be NULL: frozen gain,
  * utils/vision_transformer.py:281-282). */
 int dmc_weightnorm_bwd(const float* dw, const float* v, const float* scale, const float* inv_vnorm,

@@ -33,6 +33,7 @@ class GemmArgs(C.Structure):
         ("workspace", vp), ("workspace_bytes", sz),
         ("max_ctas", i32),
         ("stat_scale", f32), ("stat_center", vp), ("stat_row_partials", vp), ("stat_colsum_partials", vp),
+        ("stat_bound", vp),
     ]
 
 
@@ -51,7 +52,7 @@ SIGNATURES = {
     "dmc_colsum": (C.c_int, [vp, i32, i64, i64, i64, vp, vp, sz, vp]),
     "dmc_normalize_rows_fwd": (C.c_int, [vp, i32, i64, i64, i64, f32, vp, vp, vp, vp, vp]),
     "dmc_normalize_rows_bwd": (C.c_int, [vp, vp, vp, i64, i64, f32, vp, i32, vp]),
-    "dmc_weightnorm_fwd": (C.c_int, [vp, vp, i64, i64, vp, vp, vp, vp, vp, vp]),
+    "dmc_weightnorm_fwd": (C.c_int, [vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp]),
     "dmc_weightnorm_bwd": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp, vp]),
     "dmc_teacher_workspace_bytes": (sz, [i64, i64]),
     "dmc_teacher_stats_colsum": (C.c_int, [vp, i32, i64, i64, i64, vp, f32, vp, vp, vp, sz, vp]),

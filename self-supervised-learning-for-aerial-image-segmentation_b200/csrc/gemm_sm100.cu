@@ -60,6 +60,7 @@ struct GemmDev {
   const float* stat_center;     // [N] or nullptr
   float2* stat_row_partials;    // [M][2 * n_tiles]
   float* stat_colsum_partials;  // [ceil(M/32)][N] or nullptr
+  const float* stat_bound;      // device scalar b with |D| <= b, or nullptr
   int tma_store;      // 1: epilogue stores D through smem staging + TMA
   // epilogue
   void* D; long long ldd; int out_dtype;
@@ -366,6 +367,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     uint8_t* my_staging = staging + ew * kStagingBytesPerWarp;
     const int chunks_per_box = (p.out_dtype == DMC_BF16) ? 2 : 1;   // 32-column chunks per 128-byte-wide box
     uint32_t n_boxes = 0;                                            // boxes this warp has stored so far
+    // EPI 2, bounded logits: with |D| <= bound (device scalar: max gain of the weight-normed rows) and no center, every
+    // y2 lies in [-shift, shift]; summing 2^(y2 - shift) directly is safe while 2*shift stays inside fp32's exponent range.
+    bool stat_fixed = false;
+    float stat_shift = 0.f;
+    if constexpr (EPI == 2) {
+      if (p.stat_bound != nullptr && p.stat_center == nullptr) {
+        stat_shift = fabsf(__ldg(p.stat_bound) * p.stat_sc2) * 1.01f + 0.05f;
+        stat_fixed = (stat_shift < 55.f);
+      }
+    }
     int it = 0;
     for (int w = w_begin; w < w_end; w += w_step, ++it) {
       const int mt = w % p.m_tiles;
@@ -383,7 +394,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const long long row = static_cast<long long>(row0) + lane;
       const uint32_t t_addr = tmem_base + static_cast<uint32_t>((acc + h) * kAccCols) + (static_cast<uint32_t>(q * 32) << 16);
       const bool last_h = (h == p.dual);
-      float st_m = -INFINITY, st_l = 0.f;                       // EPI 2: this row's softmax partial over [c_begin, c_end)
+      float st_m = stat_fixed ? stat_shift : -INFINITY, st_l = 0.f;   // EPI 2: this row's softmax partial over [c_begin, c_end)
       // One 32-column chunk: accumulators -> epilogue -> split-K partials | direct store | smem staging + TMA store.
       auto process = [&](uint32_t (&r)[32], int c) {
         const int n = min(32, ncols - c);
@@ -443,26 +454,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
         if constexpr (EPI == 2) {
-          // online softmax partial of this thread's row over its 32 columns (base-2 domain)
-          float y[32];
-          float cm = -INFINITY;
-          if (p.stat_center != nullptr) {
+          // softmax partial of this thread's row over its 32 columns (base-2 domain), four independent chains
+          if (stat_fixed) {
+            // |y2| <= stat_shift is known (rows and weights are unit / g-bounded): no running max, 3 instr/logit
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float cb = -__ldg(p.stat_center + min(n0 + c + j, p.N - 1)) * p.stat_sc2;
-              y[j] = (j < n) ? fmaf(v[j], p.stat_sc2, cb) : -INFINITY;
-              cm = fmaxf(cm, y[j]);
+            for (int j = 0; j < 32; j += 4) {
+              a0 += (j + 0 < n) ? ex2(fmaf(v[j + 0], p.stat_sc2, -stat_shift)) : 0.f;
+              a1 += (j + 1 < n) ? ex2(fmaf(v[j + 1], p.stat_sc2, -stat_shift)) : 0.f;
+              a2 += (j + 2 < n) ? ex2(fmaf(v[j + 2], p.stat_sc2, -stat_shift)) : 0.f;
+              a3 += (j + 3 < n) ? ex2(fmaf(v[j + 3], p.stat_sc2, -stat_shift)) : 0.f;
             }
+            st_l += (a0 + a1) + (a2 + a3);
           } else {
+            float y[32];
+            float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+            if (p.stat_center != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              y[j] = (j < n) ? v[j] * p.stat_sc2 : -INFINITY;
-              cm = fmaxf(cm, y[j]);
+              for (int j = 0; j < 32; ++j) {
+                const float cb = -__ldg(p.stat_center + min(n0 + c + j, p.N - 1)) * p.stat_sc2;
+                y[j] = (j < n) ? fmaf(v[j], p.stat_sc2, cb) : -INFINITY;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) y[j] = (j < n) ? v[j] * p.stat_sc2 : -INFINITY;
             }
-          }
-          if (cm > st_m) { st_l *= ex2(st_m - cm); st_m = cm; }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) st_l += ex2(y[j] - st_m);
+            for (int j = 0; j < 32; j += 4) {
+              m0 = fmaxf(m0, y[j]); m1 = fmaxf(m1, y[j + 1]); m2 = fmaxf(m2, y[j + 2]); m3 = fmaxf(m3, y[j + 3]);
+            }
+            const float cm = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+            if (cm > st_m) { st_l *= ex2(st_m - cm); st_m = cm; }
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              a0 += ex2(y[j] - st_m); a1 += ex2(y[j + 1] - st_m); a2 += ex2(y[j + 2] - st_m); a3 += ex2(y[j + 3] - st_m);
+            }
+            st_l += (a0 + a1) + (a2 + a3);
+          }
         }
         const bool box_done = (sub == chunks_per_box - 1) || (c + 32 >= ncols);
         if (box_done) {
@@ -622,7 +651,8 @@ int debug_flags() {
   return flags;
 }
 
-Plan make_plan(int64_t M, int64_t N, int64_t K, int in_dtype, bool three_pass, int forced_split, bool store_ok = false) {
+Plan make_plan(int64_t M, int64_t N, int64_t K, int in_dtype, bool three_pass, int forced_split, bool store_ok = false,
+               bool want_stats = false) {
   Plan pl{};
   const int esz = (in_dtype == DMC_BF16) ? 2 : 4;
   const int block_k = kRowBytes / esz;
@@ -630,9 +660,10 @@ Plan make_plan(int64_t M, int64_t N, int64_t K, int in_dtype, bool three_pass, i
   // the 148 SMs over a split-K pass; long contractions keep the wide tile and split K instead (A is read once).
   const int64_t mt = ceil_div(M, kBlockM);
   int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
-  if (K < 8192 && forced_split == 0) {
+  if (K < 8192 && forced_split == 0 && !want_stats) {
     while (bn > 64 && mt * ceil_div(N, bn) < 100) bn >>= 1;
   }
+  if (want_stats) { bn = 256; forced_split = 1; }         // statistics parts are defined on 256-wide unsplit tiles
   pl.block_n = bn;
   pl.n_tiles = static_cast<int>(ceil_div(N, pl.block_n));
   pl.kb_total = static_cast<int>(ceil_div(K, block_k));
@@ -642,7 +673,7 @@ Plan make_plan(int64_t M, int64_t N, int64_t K, int in_dtype, bool three_pass, i
   // operand traffic).  Costs the MMA/epilogue overlap between items, so only for long contractions, and only
   // when there are still enough items to fill the machine (or K is split anyway).
   pl.dual = 0;
-  if (!(debug_flags() & 4) && M > kBlockM && pl.vk_total >= 16) {
+  if (!(debug_flags() & 4) && M > kBlockM && pl.vk_total >= 16 && !want_stats) {
     const int64_t items = ceil_div(M, 2 * kBlockM) * pl.n_tiles;
     if (K >= 8192 || items >= kNumSMs) pl.dual = 1;
   }
@@ -723,7 +754,7 @@ extern "C" int dmc_gemm(const dmc_gemm_args* a, void* stream) {
 
   const int out_esz = (a->out_dtype == DMC_BF16) ? 2 : 4;
   const bool store_ok = ((reinterpret_cast<uintptr_t>(a->D) & 15) == 0) && ((a->ldd * out_esz) % 16 == 0);
-  Plan pl = make_plan(a->M, a->N, a->K, a->in_dtype, three, a->split_k, store_ok);
+  Plan pl = make_plan(a->M, a->N, a->K, a->in_dtype, three, a->split_k, store_ok, a->stat_row_partials != nullptr);
   if (pl.splits > 1) {
     DMC_REQUIRE(a->workspace != nullptr && a->workspace_bytes >= pl.workspace_bytes,
                 "dmc_gemm: split-K needs a workspace of %zu bytes (got %zu)", pl.workspace_bytes, a->workspace_bytes);
@@ -758,11 +789,12 @@ extern "C" int dmc_gemm(const dmc_gemm_args* a, void* stream) {
   d.resident = pl.resident; d.tma_store = pl.tma_store; d.dual = pl.dual;
   d.stat_sc2 = a->stat_scale * 1.4426950408889634f; d.stat_center = a->stat_center;
   d.stat_row_partials = reinterpret_cast<float2*>(a->stat_row_partials); d.stat_colsum_partials = a->stat_colsum_partials;
+  d.stat_bound = a->stat_bound;
   if (a->stat_row_partials != nullptr) {
     DMC_REQUIRE(a->col_scale == nullptr && a->bias == nullptr && a->act == DMC_ACT_NONE && !a->a_mn_major && !a->b_mn_major,
                 "dmc_gemm: fused statistics need a plain epilogue and K-major operands");
     DMC_REQUIRE(pl.tma_store && pl.block_n == 256 && !pl.dual && pl.splits == 1,
-                "dmc_gemm: fused statistics need N >= 129, an aligned output and an unsplit contraction");
+                "dmc_gemm: fused statistics need a 16-byte aligned output (pointer and row stride)");
   }
   d.D = a->D; d.ldd = a->ldd; d.out_dtype = a->out_dtype;
   d.partial = pl.splits > 1 ? static_cast<float*>(a->workspace) : nullptr;

@@ -72,11 +72,13 @@ normalize_bwd_kernel(const float* __restrict__ dzhat, const float* __restrict__ 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 weightnorm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, long long K, int dim,
                       float* __restrict__ w_f32, float* __restrict__ w_lo, __nv_bfloat16* __restrict__ w_bf16,
-                      float* __restrict__ scale, float* __restrict__ inv_vnorm, bool vec_ok) {
+                      float* __restrict__ scale, float* __restrict__ inv_vnorm, bool vec_ok, float* __restrict__ gmax) {
   const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= K) return;
   const int lane = threadIdx.x & 31;
   const float* vr = v + row * dim;
+  if (gmax != nullptr && lane == 0)       // non-negative floats order like their bit patterns
+    atomicMax(reinterpret_cast<int*>(gmax), __float_as_int(fabsf(g[row])));
   if (vec_ok && dim == 256) {                          // the DINO bottleneck width: whole row in registers
     const float4* v4 = reinterpret_cast<const float4*>(vr);
     const float4 x0 = __ldg(v4 + lane), x1 = __ldg(v4 + lane + 32);
@@ -275,13 +277,17 @@ extern "C" int dmc_normalize_rows_bwd(const float* dzhat, const float* zhat, con
 }
 
 extern "C" int dmc_weightnorm_fwd(const float* v, const float* g, int64_t K, int64_t dim, float* w_f32, float* w_lo,
-                                  void* w_bf16, float* scale, float* inv_vnorm, void* stream) {
+                                  void* w_bf16, float* scale, float* inv_vnorm, float* gmax, void* stream) {
   DMC_REQUIRE(v && g && scale && inv_vnorm, "dmc_weightnorm_fwd: null pointer");
   DMC_REQUIRE(K > 0 && dim > 0 && dim < (1 << 30), "dmc_weightnorm_fwd: bad shape");
   auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const bool vec_ok = (dim % 4 == 0) && al16(v) && al16(w_f32) && al16(w_lo) && al16(w_bf16);
+  if (gmax != nullptr) {
+    cudaError_t e = cudaMemsetAsync(gmax, 0, sizeof(float), (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_status(e, "cudaMemsetAsync(gmax)");
+  }
   weightnorm_fwd_kernel<<<(unsigned)ceil_div(K, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      v, g, K, (int)dim, w_f32, w_lo, static_cast<__nv_bfloat16*>(w_bf16), scale, inv_vnorm, vec_ok);
+      v, g, K, (int)dim, w_f32, w_lo, static_cast<__nv_bfloat16*>(w_bf16), scale, inv_vnorm, vec_ok, gmax);
   DMC_LAUNCH_CHECK("weightnorm_fwd_kernel launch");
   return 0;
 }

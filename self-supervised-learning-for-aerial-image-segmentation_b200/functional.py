@@ -176,7 +176,8 @@ class NormLastLayerFn(torch.autograd.Function):
             parts = ops.gemm_stats_parts(K)
             rp = torch.empty((rows, parts, 2), dtype=torch.float32, device=z.device)
             if who == "student":
-                stats = dict(kind="student", scale=1.0 / loss_mod.student_temp, center=None, row_partials=rp)
+                stats = dict(kind="student", scale=1.0 / loss_mod.student_temp, center=None, row_partials=rp,
+                             bound=ops.last_gmax[0])
             else:
                 loss_mod.sync_center()
                 cen = loss_mod.center

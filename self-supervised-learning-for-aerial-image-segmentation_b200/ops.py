@@ -192,6 +192,7 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, A_lo=None, B_lo=None, out=Non
         g.stat_center = _p(stats.get("center"))
         g.stat_row_partials = stats["row_partials"].data_ptr()
         g.stat_colsum_partials = _p(stats.get("colsum_partials"))
+        g.stat_bound = _p(stats.get("bound"))
     if simt:
         with _timed(tag):
             L.check(lib.dmc_gemm_simt(C.byref(g), _stream()), "dmc_gemm_simt")
@@ -336,6 +337,9 @@ def normalize_rows_bwd(dzhat, zhat, inv_den, eps=1e-12, out_dtype=torch.float32)
     return dz
 
 
+last_gmax = [None]      # device scalar max|g| of the most recent weightnorm_fwd (read by NormLastLayerFn for the GEMM)
+
+
 def weightnorm_fwd(v: torch.Tensor, g: torch.Tensor, mode: str):
     """mode 'bf16' -> (w_bf16, None); 'tf32x3' -> (w_hi, w_lo); 'f32' -> (w_f32, None).
     Also returns scale[K] = g/||v|| and inv_vnorm[K]."""
@@ -349,6 +353,7 @@ def weightnorm_fwd(v: torch.Tensor, g: torch.Tensor, mode: str):
     dev = v.device
     scale = torch.empty(K, dtype=torch.float32, device=dev)
     inv_vnorm = torch.empty(K, dtype=torch.float32, device=dev)
+    gmax = torch.empty((), dtype=torch.float32, device=dev)      # max |g|: bound of the logits of unit rows
     w_f32 = w_lo = w_bf16 = None
     if mode == "bf16":
         w_bf16 = torch.empty((K, dim), dtype=torch.bfloat16, device=dev)
@@ -358,8 +363,9 @@ def weightnorm_fwd(v: torch.Tensor, g: torch.Tensor, mode: str):
             w_lo = torch.empty((K, dim), dtype=torch.float32, device=dev)
     with _timed("weightnorm_fwd"):
         L.check(lib.dmc_weightnorm_fwd(v.data_ptr(), g.data_ptr(), K, dim, _p(w_f32), _p(w_lo), _p(w_bf16), scale.data_ptr(),
-                                       inv_vnorm.data_ptr(), _stream()), "dmc_weightnorm_fwd")
+                                       inv_vnorm.data_ptr(), gmax.data_ptr(), _stream()), "dmc_weightnorm_fwd")
     _count()
+    last_gmax[0] = gmax
     return (w_bf16, None, scale, inv_vnorm) if mode == "bf16" else (w_f32, w_lo, scale, inv_vnorm)
 
 

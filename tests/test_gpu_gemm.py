@@ -153,3 +153,43 @@ def test_gemm_argument_errors():
     B_odd = torch.zeros(128, 20, dtype=torch.bfloat16, device="cuda")[:, :12]
     with pytest.raises(RuntimeError, match="16 bytes"):
         ops.gemm(A_odd, B_odd, 128, 128, 12)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("M,N,K", [(200, 1000, 64), (512, 4096, 256), (40, 264, 128)])
+def test_gemm_fused_statistics(M, N, K, dtype):
+    """EPI 2: softmax row partials (+ center) and 32-row column sums of the STORED output, merged by
+    dmc_lse_finalize / dmc_teacher_finalize, against numpy on the stored output."""
+    ops, _ = _ops()
+    g = torch.Generator().manual_seed(11)
+    A = torch.nn.functional.normalize(torch.randn(M, K, generator=g), dim=-1)      # unit rows, like the head's zhat
+    B = torch.nn.functional.normalize(torch.randn(N, K, generator=g), dim=-1) * 1.5  # rows of norm g = 1.5
+    if dtype == torch.bfloat16:
+        Ad, Bd, kw = A.bfloat16().cuda(), B.bfloat16().cuda(), {}
+    else:
+        Ah, Al = ops.split_tf32(A.cuda())
+        Bh, Bl = ops.split_tf32(B.cuda())
+        Ad, Bd, kw = Ah, Bh, dict(A_lo=Al, B_lo=Bl)
+    parts = ops.gemm_stats_parts(N)
+    center = (torch.randn(N, generator=g) * 0.2).cuda()
+    bound = torch.tensor(1.5, device="cuda")
+    for use_center, use_bound in ((False, True), (False, False), (True, False)):
+        rp = torch.zeros(M, parts, 2, device="cuda")
+        cp = torch.zeros((M + 31) // 32, N, device="cuda")
+        scale = 10.0 if not use_center else 25.0
+        stats = dict(scale=scale, center=center if use_center else None, row_partials=rp, colsum_partials=cp,
+                     bound=bound if use_bound else None)
+        D = ops.gemm(Ad, Bd, M, N, K, out_dtype=dtype, stats=stats, **kw)
+        torch.cuda.synchronize()
+        Dn = D.double().cpu().numpy()                                  # the stored (rounded) values
+        y = (Dn - (center.double().cpu().numpy() if use_center else 0.0)) * scale
+        ref_lse = np.log(np.exp(y - y.max(-1, keepdims=True)).sum(-1)) + y.max(-1)
+        lse = ops.lse_finalize(rp)
+        assert rel_err(lse.cpu().numpy(), ref_lse) < 2e-6
+        stats_t, colsum = ops.teacher_finalize(rp, cp, M, N)
+        assert rel_err(colsum.cpu().numpy(), Dn.sum(0)) < 1e-5
+        m2 = y.max(-1) * np.log2(np.e)
+        if not use_bound:
+            assert rel_err(stats_t[:, 0].cpu().numpy(), m2) < 1e-6
+        l_ref = np.exp2(y * np.log2(np.e) - stats_t[:, 0].double().cpu().numpy()[:, None]).sum(-1)
+        assert rel_err(stats_t[:, 1].cpu().numpy(), 1.0 / l_ref) < 1e-5
