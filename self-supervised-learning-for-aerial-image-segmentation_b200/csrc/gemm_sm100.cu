@@ -399,9 +399,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       auto process = [&](uint32_t (&r)[32], int c) {
         const int n = min(32, ncols - c);
         if (n <= 0) return;                                     // whole chunk beyond N (warp-uniform)
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        float (&v)[32] = reinterpret_cast<float (&)[32]>(r);    // accumulators in place (EPI 2 leaves the stored values here)
         if (p.partial) {                                        // split-K: raw partial sums, epilogue runs in the reducer
           if (row < p.M) {
             float* dst = p.partial + (static_cast<long long>(sp) * p.M + row) * p.N + n0 + c;
@@ -453,46 +451,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
-        if constexpr (EPI == 2) {
-          // softmax partial of this thread's row over its 32 columns (base-2 domain), four independent chains
-          if (stat_fixed) {
-            // |y2| <= stat_shift is known (rows and weights are unit / g-bounded): no running max, 3 instr/logit
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              a0 += (j + 0 < n) ? ex2(fmaf(v[j + 0], p.stat_sc2, -stat_shift)) : 0.f;
-              a1 += (j + 1 < n) ? ex2(fmaf(v[j + 1], p.stat_sc2, -stat_shift)) : 0.f;
-              a2 += (j + 2 < n) ? ex2(fmaf(v[j + 2], p.stat_sc2, -stat_shift)) : 0.f;
-              a3 += (j + 3 < n) ? ex2(fmaf(v[j + 3], p.stat_sc2, -stat_shift)) : 0.f;
-            }
-            st_l += (a0 + a1) + (a2 + a3);
-          } else {
-            float y[32];
-            float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-            if (p.stat_center != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float cb = -__ldg(p.stat_center + min(n0 + c + j, p.N - 1)) * p.stat_sc2;
-                y[j] = (j < n) ? fmaf(v[j], p.stat_sc2, cb) : -INFINITY;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) y[j] = (j < n) ? v[j] * p.stat_sc2 : -INFINITY;
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              m0 = fmaxf(m0, y[j]); m1 = fmaxf(m1, y[j + 1]); m2 = fmaxf(m2, y[j + 2]); m3 = fmaxf(m3, y[j + 3]);
-            }
-            const float cm = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-            if (cm > st_m) { st_l *= ex2(st_m - cm); st_m = cm; }
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              a0 += ex2(y[j] - st_m); a1 += ex2(y[j + 1] - st_m); a2 += ex2(y[j + 2] - st_m); a3 += ex2(y[j + 3] - st_m);
-            }
-            st_l += (a0 + a1) + (a2 + a3);
-          }
-        }
         const bool box_done = (sub == chunks_per_box - 1) || (c + 32 >= ncols);
         if (box_done) {
           ptx::fence_proxy_async();                             // generic-proxy smem writes -> visible to the TMA engine
@@ -525,6 +483,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
         }
       };
+      // EPI 2: softmax partial of this thread's row over the 32 columns of chunk c (base-2 domain, four independent
+      // chains).  Runs AFTER the chunk pair has been staged and its TMA store issued, so the SFU work overlaps the
+      // store's shared-memory read instead of sitting in front of it.
+      auto chunk_stats = [&](uint32_t (&r)[32], int c) {
+        const int n = min(32, ncols - c);
+        if (n <= 0) return;
+        float (&v)[32] = reinterpret_cast<float (&)[32]>(r);
+        if (stat_fixed) {
+          // |y2| <= stat_shift is known (rows and weights are unit / g-bounded): no running max, 3 instr/logit
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            a0 += (j + 0 < n) ? ex2(fmaf(v[j + 0], p.stat_sc2, -stat_shift)) : 0.f;
+            a1 += (j + 1 < n) ? ex2(fmaf(v[j + 1], p.stat_sc2, -stat_shift)) : 0.f;
+            a2 += (j + 2 < n) ? ex2(fmaf(v[j + 2], p.stat_sc2, -stat_shift)) : 0.f;
+            a3 += (j + 3 < n) ? ex2(fmaf(v[j + 3], p.stat_sc2, -stat_shift)) : 0.f;
+          }
+          st_l += (a0 + a1) + (a2 + a3);
+        } else {
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+          if (p.stat_center != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float cb = -__ldg(p.stat_center + min(n0 + c + j, p.N - 1)) * p.stat_sc2;
+              v[j] = (j < n) ? fmaf(v[j], p.stat_sc2, cb) : -INFINITY;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (j < n) ? v[j] * p.stat_sc2 : -INFINITY;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            m0 = fmaxf(m0, v[j]); m1 = fmaxf(m1, v[j + 1]); m2 = fmaxf(m2, v[j + 2]); m3 = fmaxf(m3, v[j + 3]);
+          }
+          const float cm = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+          if (cm > st_m) { st_l *= ex2(st_m - cm); st_m = cm; }
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            a0 += ex2(v[j] - st_m); a1 += ex2(v[j + 1] - st_m); a2 += ex2(v[j + 2] - st_m); a3 += ex2(v[j + 3] - st_m);
+          }
+          st_l += (a0 + a1) + (a2 + a3);
+        }
+      };
       for (int c = c_begin; c < c_end; c += 64) {               // this warp's column range, 64 columns at a time
         uint32_t ra[32], rb[32];
         ptx::tmem_ld_32x32(t_addr + c, ra);                     // two TMEM loads in flight per wait
@@ -537,6 +539,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         process(ra, c);
         process(rb, c + 32);
+        if constexpr (EPI == 2) {
+          chunk_stats(ra, c);
+          chunk_stats(rb, c + 32);
+        }
       }
       if constexpr (EPI == 2) {
         if (row < p.M && c_begin < c_end)

@@ -77,8 +77,10 @@ weightnorm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, 
   if (row >= K) return;
   const int lane = threadIdx.x & 31;
   const float* vr = v + row * dim;
-  if (gmax != nullptr && lane == 0)       // non-negative floats order like their bit patterns
-    atomicMax(reinterpret_cast<int*>(gmax), __float_as_int(fabsf(g[row])));
+  if (gmax != nullptr && lane == 0) {     // non-negative floats order like their bit patterns; almost every warp skips
+    const int gi = __float_as_int(fabsf(g[row]));
+    if (gi > *reinterpret_cast<volatile int*>(gmax)) atomicMax(reinterpret_cast<int*>(gmax), gi);
+  }
   if (vec_ok && dim == 256) {                          // the DINO bottleneck width: whole row in registers
     const float4* v4 = reinterpret_cast<const float4*>(vr);
     const float4 x0 = __ldg(v4 + lane), x1 = __ldg(v4 + lane + 32);
