@@ -7,13 +7,14 @@
 // N = out_dim = 65536, K = bottleneck = 256), its dgrad (contraction over out_dim, split-K) and wgrad
 // (MN-major operands straight from the row-major gradient), and the MLP Linears (:291).
 //
-// Structure (one CTA per SM, 320 threads):
+// Structure (one CTA per SM, 576 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor tiles into a ring of 128B-swizzled smem stages
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=block_n, K=32 bytes/row)
 //               into one of two TMEM accumulators (2 x 256 fp32 columns = all 512 TMEM columns)
-//   warps 2..9  epilogue: tcgen05.ld the finished accumulator (two warps per TMEM lane quadrant, one per half of
-//               the tile's columns), apply scale/bias/activation, store; overlaps the MMAs of the next tile
-//               thanks to the double-buffered accumulator.
+//   warps 2..17 epilogue: tcgen05.ld the finished accumulator (four warps per TMEM lane quadrant, one per 64-column
+//               quarter of the tile: the epilogue is a latency chain, so it is spread over many warps), apply
+//               scale/bias/activation, store; overlaps the MMAs of the next tile thanks to the double-buffered
+//               accumulator.
 // Three mbarrier pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue).
 //
 // Output path: the epilogue warps write the converted tile into 128B-swizzled smem staging buffers and one
@@ -40,7 +41,7 @@ constexpr int kMaxStages = 8;
 constexpr int kMmaPerKBlock = 4;        // 128 B / 32 B: four tcgen05.mma per k-block
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 256;
-constexpr int kEpiWarps = 8;           // two epilogue warps per TMEM lane quadrant (one per half of the tile columns)
+constexpr int kEpiWarps = 16;          // four epilogue warps per TMEM lane quadrant (one per 64-column quarter of the tile)
 constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr uint32_t kABytes = kBlockM * kRowBytes;  // 16 KiB per stage for A
 
@@ -58,7 +59,7 @@ struct GemmDev {
   // fused output statistics (EPI == 2): softmax row partials and 32-row column sums of the stored values
   float stat_sc2;               // stat_scale * log2(e)
   const float* stat_center;     // [N] or nullptr
-  float2* stat_row_partials;    // [M][2 * n_tiles]
+  float2* stat_row_partials;    // [M][4 * n_tiles]
   float* stat_colsum_partials;  // [ceil(M/32)][N] or nullptr
   const float* stat_bound;      // device scalar b with |D| <= b, or nullptr
   int tma_store;      // 1: epilogue stores D through smem staging + TMA
@@ -349,12 +350,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (warps 2..9) =====================
+    // ===================== epilogue (warps 2..17) =====================
     const int q = warp & 3;                                     // TMEM lane quadrant this warp may access
     const int ew = warp - 2;
-    const int half = ew >> 2;                                   // which half of the tile's columns this warp drains
-    const int c_begin = (p.block_n >= 128) ? half * (p.block_n >> 1) : 0;
-    const int c_end = (p.block_n >= 128) ? c_begin + (p.block_n >> 1) : (half == 0 ? p.block_n : 0);
+    const int quarter = ew >> 2;                                // which 64-column quarter of the tile this warp drains
+    const int c_begin = min(quarter * 64, p.block_n);
+    const int c_end = min(c_begin + 64, p.block_n);             // empty for the upper quarters of narrow tiles
     Epilogue e{p.col_scale, p.bias, p.alpha, p.act, p.aux, p.ldaux, p.aux_dtype, p.D, p.ldd, p.out_dtype, p.N};
     if (p.alpha_dev) e.alpha *= __ldg(p.alpha_dev);
     const int out_esz = (p.out_dtype == DMC_BF16) ? 2 : 4;
@@ -490,8 +491,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int n = min(32, ncols - c);
         if (n <= 0) return;
         float (&v)[32] = reinterpret_cast<float (&)[32]>(r);
-        if (stat_fixed) {
+        if (stat_fixed && n == 32) {
           // |y2| <= stat_shift is known (rows and weights are unit / g-bounded): no running max, 3 instr/logit
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            a0 += ex2(fmaf(v[j + 0], p.stat_sc2, -stat_shift));
+            a1 += ex2(fmaf(v[j + 1], p.stat_sc2, -stat_shift));
+            a2 += ex2(fmaf(v[j + 2], p.stat_sc2, -stat_shift));
+            a3 += ex2(fmaf(v[j + 3], p.stat_sc2, -stat_shift));
+          }
+          st_l += (a0 + a1) + (a2 + a3);
+        } else if (stat_fixed) {
           float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -546,7 +557,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
       if constexpr (EPI == 2) {
         if (row < p.M && c_begin < c_end)
-          p.stat_row_partials[row * (2 * p.n_tiles) + 2 * nt + half] = make_float2(st_m, st_l);
+          p.stat_row_partials[row * (4 * p.n_tiles) + 4 * nt + quarter] = make_float2(st_m, st_l);
       }
       if (last_h && c_begin >= c_end) {                         // nothing to drain (block_n == 64, upper half): still release
         ptx::tc_fence_before();
@@ -733,7 +744,7 @@ int launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b
 
 using namespace dmc;
 
-extern "C" int64_t dmc_gemm_stats_parts(int64_t N) { return N > 0 ? 2 * ceil_div(N, 256) : 0; }
+extern "C" int64_t dmc_gemm_stats_parts(int64_t N) { return N > 0 ? 4 * ceil_div(N, 256) : 0; }
 
 extern "C" size_t dmc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int32_t in_dtype) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;

@@ -77,10 +77,7 @@ weightnorm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, 
   if (row >= K) return;
   const int lane = threadIdx.x & 31;
   const float* vr = v + row * dim;
-  if (gmax != nullptr && lane == 0) {     // non-negative floats order like their bit patterns; almost every warp skips
-    const int gi = __float_as_int(fabsf(g[row]));
-    if (gi > *reinterpret_cast<volatile int*>(gmax)) atomicMax(reinterpret_cast<int*>(gmax), gi);
-  }
+  (void)gmax;
   if (vec_ok && dim == 256) {                          // the DINO bottleneck width: whole row in registers
     const float4* v4 = reinterpret_cast<const float4*>(vr);
     const float4 x0 = __ldg(v4 + lane), x1 = __ldg(v4 + lane + 32);
@@ -164,6 +161,21 @@ weightnorm_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v,
   for (int c = lane; c < dim; c += 32) {
     const long long o = row * dim + c;
     dv[o] = sc * (dw[o] - dot * (v[o] * iv));
+  }
+}
+
+// gmax = max_k |g_k| (single block; K floats are a few hundred KB at most).
+__global__ void __launch_bounds__(1024)
+absmax_kernel(const float* __restrict__ g, long long K, float* __restrict__ out) {
+  __shared__ float red[32];
+  float m = 0.f;
+  for (long long i = threadIdx.x; i < K; i += 1024) m = fmaxf(m, fabsf(g[i]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = warp_max(red[threadIdx.x]);
+    if (threadIdx.x == 0) *out = m;
   }
 }
 
@@ -285,8 +297,8 @@ extern "C" int dmc_weightnorm_fwd(const float* v, const float* g, int64_t K, int
   auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const bool vec_ok = (dim % 4 == 0) && al16(v) && al16(w_f32) && al16(w_lo) && al16(w_bf16);
   if (gmax != nullptr) {
-    cudaError_t e = cudaMemsetAsync(gmax, 0, sizeof(float), (cudaStream_t)stream);
-    if (e != cudaSuccess) return cuda_status(e, "cudaMemsetAsync(gmax)");
+    absmax_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(g, K, gmax);
+    DMC_LAUNCH_CHECK("absmax_kernel launch");
   }
   weightnorm_fwd_kernel<<<(unsigned)ceil_div(K, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
       v, g, K, (int)dim, w_f32, w_lo, static_cast<__nv_bfloat16*>(w_bf16), scale, inv_vnorm, vec_ok, gmax);

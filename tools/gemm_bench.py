@@ -9,6 +9,8 @@ SHAPES = {
     # name: (M, N, K, a_mn, b_mn, in dtype, out dtype)
     "last_fwd_student": (2048, 65536, 256, False, False, torch.bfloat16, torch.bfloat16),
     "last_fwd_teacher": (512, 65536, 256, False, False, torch.bfloat16, torch.bfloat16),
+    "last_fwd_student_bound_stats": (2048, 65536, 256, False, False, torch.bfloat16, torch.bfloat16),
+    "last_fwd_student_max_stats": (2048, 65536, 256, False, False, torch.bfloat16, torch.bfloat16),
     "last_dgrad": (2048, 256, 65536, False, True, torch.bfloat16, torch.float32),
     "last_wgrad": (65536, 256, 2048, True, True, torch.bfloat16, torch.float32),
     "mlp_fwd1": (2048, 2048, 384, False, False, torch.bfloat16, torch.bfloat16),
@@ -23,13 +25,24 @@ def run(name, iters=10):
     A = torch.randn((K, M) if a_mn else (M, K), device="cuda").to(dt)
     B = torch.randn((K, N) if b_mn else (N, K), device="cuda").to(dt)
     out = torch.empty(M, N, dtype=odt, device="cuda")
+    stats = None
+    if name.endswith("_stats"):
+        A = torch.nn.functional.normalize(A.float(), dim=-1).to(dt)
+        B = torch.nn.functional.normalize(B.float(), dim=-1).to(dt)
+        stats = dict(scale=10.0, center=None, row_partials=torch.empty(M, ops.gemm_stats_parts(N), 2, device="cuda"),
+                     bound=torch.tensor(1.0, device="cuda") if "bound" in name else None)
+    if stats is not None:
+        import functools
+        ops_gemm = functools.partial(ops.gemm, stats=stats)
+    else:
+        ops_gemm = ops.gemm
     for _ in range(3):
-        ops.gemm(A, B, M, N, K, a_mn=a_mn, b_mn=b_mn, out=out)
+        ops_gemm(A, B, M, N, K, a_mn=a_mn, b_mn=b_mn, out=out)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        ops.gemm(A, B, M, N, K, a_mn=a_mn, b_mn=b_mn, out=out)
+        ops_gemm(A, B, M, N, K, a_mn=a_mn, b_mn=b_mn, out=out)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters

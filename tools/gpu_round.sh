@@ -56,6 +56,11 @@ profstep)
 gemmbench)
   ( timeout 600 python tools/gemm_bench.py ) > gpurun_out/gemm_bench.log 2>&1
   echo "== gemm_bench rc=$?"; cat gpurun_out/gemm_bench.log ;;
+ncustats)
+  ( timeout 300 python tools/gemm_bench.py last_fwd_student_bound_stats > gpurun_out/ncustats_plain.log 2>&1 ) &&
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 3 -c 1 -f -o gpurun_out/prof_gemm_stats \
+      python tools/gemm_bench.py last_fwd_student_bound_stats > gpurun_out/ncustats.log 2>&1
+  echo "== ncu stats gemm rc=$?"; cat gpurun_out/ncustats_plain.log; ls -la gpurun_out/prof_gemm_stats.ncu-rep ;;
 ncugemm)
   ( timeout 300 python tools/gemm_bench.py last_fwd_student > gpurun_out/ncugemm_plain.log 2>&1 ) &&
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 3 -c 1 -f -o gpurun_out/prof_gemm_last_fwd \
