@@ -88,7 +88,7 @@ typedef struct dmc_gemm_args {
                               NCCL all-reduce kernel (the persistent CTAs would otherwise queue behind it) */
   /* Optional statistics of the STORED output, fused into the epilogue (last-layer forward; plain epilogue,
    * K-major operands, N > 128).  With y2 = (D[m,n] - stat_center[n]) * stat_scale * log2(e):
-   *   stat_row_partials[m][part] = { max_n y2, sum_n 2^(y2 - max) } over column part `part` (64 columns each,
+   *   stat_row_partials[m][part] = { max_n y2, sum_n 2^(y2 - max) } over column part `part` (128 columns each,
    *   dmc_gemm_stats_parts(N) parts per row) -- merged by dmc_teacher_finalize / dmc_lse_finalize;
    *   stat_colsum_partials[g][n] = sum of D over the rows of 32-row group g (NULL = not wanted).
    * This replaces DINOLoss's separate statistics passes over the logits (main_dino_mc.py:446,456,468). */
@@ -97,7 +97,7 @@ typedef struct dmc_gemm_args {
                               are unit vectors): lets the epilogue skip the running max (used only without a center) */
 } dmc_gemm_args;
 
-/* Number of 64-column parts per row that the fused statistics produce for an N-column output. */
+/* Number of 128-column parts per row that the fused statistics produce for an N-column output. */
 int64_t dmc_gemm_stats_parts(int64_t N);
 
 /* Upper bound of the split-K workspace dmc_gemm may need for this problem. */

@@ -7,14 +7,13 @@
 // N = out_dim = 65536, K = bottleneck = 256), its dgrad (contraction over out_dim, split-K) and wgrad
 // (MN-major operands straight from the row-major gradient), and the MLP Linears (:291).
 //
-// Structure (one CTA per SM, 576 threads):
+// Structure (one CTA per SM, 320 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor tiles into a ring of 128B-swizzled smem stages
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=block_n, K=32 bytes/row)
 //               into one of two TMEM accumulators (2 x 256 fp32 columns = all 512 TMEM columns)
-//   warps 2..17 epilogue: tcgen05.ld the finished accumulator (four warps per TMEM lane quadrant, one per 64-column
-//               quarter of the tile: the epilogue is a latency chain, so it is spread over many warps), apply
-//               scale/bias/activation, store; overlaps the MMAs of the next tile thanks to the double-buffered
-//               accumulator.
+//   warps 2..9  epilogue: tcgen05.ld the finished accumulator (two warps per TMEM lane quadrant, one per half of
+//               the tile's columns), apply scale/bias/activation, store; overlaps the MMAs of the next tile
+//               thanks to the double-buffered accumulator.
 // Three mbarrier pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue).
 //
 // Output path: the epilogue warps write the converted tile into 128B-swizzled smem staging buffers and one
@@ -41,7 +40,9 @@ constexpr int kMaxStages = 8;
 constexpr int kMmaPerKBlock = 4;        // 128 B / 32 B: four tcgen05.mma per k-block
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 256;
-constexpr int kEpiWarps = 16;          // four epilogue warps per TMEM lane quadrant (one per 64-column quarter of the tile)
+constexpr int kEpiWarps = 8;           // two epilogue warps per TMEM lane quadrant (one per half of the tile columns);
+                                       // 16 warps (register cap 96, 3 smem stages) measured slower
+constexpr int kColGroups = kEpiWarps / 4;   // column groups per tile = statistics parts per tile
 constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr uint32_t kABytes = kBlockM * kRowBytes;  // 16 KiB per stage for A
 
@@ -59,9 +60,10 @@ struct GemmDev {
   // fused output statistics (EPI == 2): softmax row partials and 32-row column sums of the stored values
   float stat_sc2;               // stat_scale * log2(e)
   const float* stat_center;     // [N] or nullptr
-  float2* stat_row_partials;    // [M][4 * n_tiles]
+  float2* stat_row_partials;    // [M][kColGroups * n_tiles]
   float* stat_colsum_partials;  // [ceil(M/32)][N] or nullptr
   const float* stat_bound;      // device scalar b with |D| <= b, or nullptr
+  int dbg;                      // DMC_GEMM_FLAGS >> 3 (timing experiments only): 1 = no TMA store issue, 2 = no staging writes, 4 = no TMEM loads
   int tma_store;      // 1: epilogue stores D through smem staging + TMA
   // epilogue
   void* D; long long ldd; int out_dtype;
@@ -350,12 +352,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (warps 2..17) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;                                     // TMEM lane quadrant this warp may access
     const int ew = warp - 2;
-    const int quarter = ew >> 2;                                // which 64-column quarter of the tile this warp drains
-    const int c_begin = min(quarter * 64, p.block_n);
-    const int c_end = min(c_begin + 64, p.block_n);             // empty for the upper quarters of narrow tiles
+    const int quarter = ew >> 2;                                // which column group of the tile this warp drains
+    const int cols_per_group = max(64, p.block_n / kColGroups);
+    const int c_begin = min(quarter * cols_per_group, p.block_n);
+    const int c_end = min(c_begin + cols_per_group, p.block_n); // empty for the upper groups of narrow tiles
     Epilogue e{p.col_scale, p.bias, p.alpha, p.act, p.aux, p.ldaux, p.aux_dtype, p.D, p.ldd, p.out_dtype, p.N};
     if (p.alpha_dev) e.alpha *= __ldg(p.alpha_dev);
     const int out_esz = (p.out_dtype == DMC_BF16) ? 2 : 4;
@@ -431,6 +434,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         //      16-byte chunk j of row r lives at r*128 + ((j ^ (r & 7)) << 4)  -> conflict-free warp stores.
         const int sub = (c >> 5) % chunks_per_box;              // which half of the box this chunk fills
         uint8_t* buf = my_staging;
+        if (p.dbg & 2) return;
         if (sub == 0 && n_boxes >= 1) {                         // the previous box's TMA store must have read the buffer
           if (lane == 0) ptx::tma_store_wait_read<0>();
           __syncwarp();
@@ -456,7 +460,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (box_done) {
           ptx::fence_proxy_async();                             // generic-proxy smem writes -> visible to the TMA engine
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && !(p.dbg & 1)) {
             ptx::tma_store_2d(&tmD, buf, n0 + c - sub * 32, row0);
             ptx::tma_store_commit();
           }
@@ -540,9 +544,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       };
       for (int c = c_begin; c < c_end; c += 64) {               // this warp's column range, 64 columns at a time
         uint32_t ra[32], rb[32];
-        ptx::tmem_ld_32x32(t_addr + c, ra);                     // two TMEM loads in flight per wait
-        ptx::tmem_ld_32x32(t_addr + c + 32, rb);
-        ptx::tmem_ld_wait();
+        if (!(p.dbg & 4)) {
+          ptx::tmem_ld_32x32(t_addr + c, ra);                   // two TMEM loads in flight per wait
+          ptx::tmem_ld_32x32(t_addr + c + 32, rb);
+          ptx::tmem_ld_wait();
+        }
         if (last_h && c + 64 >= c_end) {                        // this warp's last read of the accumulator(s): hand back
           ptx::tc_fence_before();
           __syncwarp();
@@ -557,7 +563,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
       if constexpr (EPI == 2) {
         if (row < p.M && c_begin < c_end)
-          p.stat_row_partials[row * (4 * p.n_tiles) + 4 * nt + quarter] = make_float2(st_m, st_l);
+          p.stat_row_partials[row * (kColGroups * p.n_tiles) + kColGroups * nt + quarter] = make_float2(st_m, st_l);
       }
       if (last_h && c_begin >= c_end) {                         // nothing to drain (block_n == 64, upper half): still release
         ptx::tc_fence_before();
@@ -744,7 +750,7 @@ int launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b
 
 using namespace dmc;
 
-extern "C" int64_t dmc_gemm_stats_parts(int64_t N) { return N > 0 ? 4 * ceil_div(N, 256) : 0; }
+extern "C" int64_t dmc_gemm_stats_parts(int64_t N) { return N > 0 ? kColGroups * ceil_div(N, 256) : 0; }
 
 extern "C" size_t dmc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int32_t in_dtype) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
@@ -807,6 +813,7 @@ extern "C" int dmc_gemm(const dmc_gemm_args* a, void* stream) {
   d.stat_sc2 = a->stat_scale * 1.4426950408889634f; d.stat_center = a->stat_center;
   d.stat_row_partials = reinterpret_cast<float2*>(a->stat_row_partials); d.stat_colsum_partials = a->stat_colsum_partials;
   d.stat_bound = a->stat_bound;
+  d.dbg = debug_flags() >> 3;
   if (a->stat_row_partials != nullptr) {
     DMC_REQUIRE(a->col_scale == nullptr && a->bias == nullptr && a->act == DMC_ACT_NONE && !a->a_mn_major && !a->b_mn_major,
                 "dmc_gemm: fused statistics need a plain epilogue and K-major operands");
