@@ -177,7 +177,11 @@ constexpr int kStagingBytes = kEpiWarps * kStagingBytesPerWarp;
 // EPI 2: plain + fused statistics of the stored (rounded) logits: per row and 128-column part the online-softmax
 //        pair (max, sum 2^(y - max)) of y = (D - center) * scale * log2e, and per 32-row group the column sums.
 //        This is what lets DINOLoss skip its separate statistics passes over the logits.
-template <int ESZ, bool A_MN, bool B_MN, int EPI>
+// CG2: CTA pair (cluster of 2, tcgen05 cta_group::2).  One work item is 256 rows x block_n columns: each CTA of the
+//      pair owns 128 rows of A and of the accumulator and loads only HALF of the B tile; the leader CTA's single MMA
+//      thread drives both tensor cores (M = 256) reading both B halves.  A third less shared-memory fill per unit of
+//      MMA work than the single-CTA tile, which is what bounds the long-K GEMMs.
+template <int ESZ, bool A_MN, bool B_MN, int EPI, bool CG2>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -195,9 +199,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);   // 1024-B aligned (SWIZZLE_128B atoms)
 
   // smem carve-up: [resident B slabs][stage ring][epilogue staging][barriers]
+  const uint32_t cta_rank = CG2 ? ptx::cluster_ctarank() : 0u;      // rank in the CTA pair (0 = MMA leader)
+  const uint32_t b_cta_bytes = CG2 ? (p.b_bytes >> 1) : p.b_bytes;  // CTA pair: this CTA holds half of the B tile
   const uint32_t a_stage_bytes = p.dual ? 2u * kABytes : kABytes;   // dual-M: two 128-row A tiles per stage
-  const uint32_t stage_bytes = p.resident ? a_stage_bytes : (a_stage_bytes + p.b_bytes);
-  const int tile_m = p.dual ? 2 * kBlockM : kBlockM;
+  const uint32_t stage_bytes = p.resident ? a_stage_bytes : (a_stage_bytes + b_cta_bytes);
+  const int tile_m = (p.dual || CG2) ? 2 * kBlockM : kBlockM;
   const uint32_t res_bytes = p.resident ? static_cast<uint32_t>(p.vk_total) * p.b_bytes : 0u;
   uint8_t* b_res = smem;
   uint8_t* tiles = smem + res_bytes;
@@ -221,15 +227,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1);
       ptx::mbar_init(&bfull_bar[i], 1); ptx::mbar_init(&bempty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], kEpiWarps); }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tmem_full[i], 1);
+      ptx::mbar_init(&tmem_empty[i], CG2 ? 2 * kEpiWarps : kEpiWarps);   // pair: both CTAs' epilogues release the leader
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {               // this warp owns the TMEM allocation (alloc + dealloc)
-    ptx::tmem_alloc(tmem_ptr, kTmemCols);
-    ptx::tmem_relinquish();
+    if constexpr (CG2) { ptx::tmem_alloc_pair(tmem_ptr, kTmemCols); ptx::tmem_relinquish_pair(); }
+    else { ptx::tmem_alloc(tmem_ptr, kTmemCols); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (CG2) ptx::cluster_sync();       // barrier inits and TMEM of both CTAs are in place before any remote signal
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -237,7 +247,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   // round-robin: w = blockIdx.x, +gridDim.x, ...   resident: a contiguous range (same n-tile for consecutive items).
   const int num_work = p.m_tiles * p.n_tiles * p.splits;
   int w_begin, w_end, w_step;
-  if (p.resident) {
+  if constexpr (CG2) {
+    w_begin = blockIdx.x >> 1; w_end = num_work; w_step = gridDim.x >> 1;    // both CTAs of a pair walk the same items
+  } else if (p.resident) {
     w_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * num_work / gridDim.x);
     w_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * num_work / gridDim.x);
     w_step = 1;
@@ -255,7 +267,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int rest = w / p.m_tiles;
         const int nt = rest % p.n_tiles;
         const int sp = rest / p.n_tiles;
-        const int m0 = mt * tile_m, n0 = nt * p.block_n;
+        const int m0 = mt * tile_m + (CG2 ? static_cast<int>(cta_rank) * kBlockM : 0);
+        const int n0 = nt * p.block_n + (CG2 ? static_cast<int>(cta_rank) * (p.block_n >> 1) : 0);
+        const int nb_rows = CG2 ? (p.block_n >> 1) : p.block_n;       // B rows (N extent) this CTA loads
         const int vk0 = sp * p.vk_per_split;
         const int vk1 = min(vk0 + p.vk_per_split, p.vk_total);
         const bool load_b = p.resident && (nt != prev_nt);
@@ -272,6 +286,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             ptx::mbar_arrive_expect_tx(&bfull_bar[vk], p.b_bytes);
           }
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if constexpr (CG2) {
+            // Pair: both CTAs fill their own smem but report the bytes to the LEADER's full barrier, which therefore
+            // expects both CTAs' stage bytes.
+            const uint32_t lead_full = ptx::mapa(ptx::smem_u32(&full_bar[stage]), 0);
+            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2u * stage_bytes);
+            if constexpr (!B_MN) {
+              ptx::tma_load_2d_pair(sB, tb, lead_full, k0, n0);                  // box {BLOCK_K, block_n / 2}
+            } else {
+              for (int j = 0; j < nb_rows / BOX_MN; ++j)
+                ptx::tma_load_2d_pair(sB + j * kBoxBytes, tb, lead_full, n0 + j * BOX_MN, k0);
+            }
+            if constexpr (!A_MN) {
+              ptx::tma_load_2d_pair(sA, ta, lead_full, k0, m0);                  // box {BLOCK_K, 128}
+            } else {
+#pragma unroll
+              for (int j = 0; j < kBlockM / BOX_MN; ++j)
+                ptx::tma_load_2d_pair(sA + j * kBoxBytes, ta, lead_full, m0 + j * BOX_MN, k0);
+            }
+          } else {
           ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
           if (!p.resident || load_b) {
             if constexpr (!B_MN) {
@@ -292,15 +325,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 ptx::tma_load_2d(sAh + j * kBoxBytes, ta, &full_bar[stage], mh + j * BOX_MN, k0);
             }
           }
+          }
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
         if (load_b) { ++b_gen; prev_nt = nt; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = ptx::make_instr_desc(kTf32 ? 2u : 1u, A_MN, B_MN, kBlockM, static_cast<uint32_t>(p.block_n));
+    // ===================== MMA issuer (pair: leader CTA only) =====================
+    if (lane == 0 && cta_rank == 0) {
+      const uint32_t idesc = ptx::make_instr_desc(kTf32 ? 2u : 1u, A_MN, B_MN, CG2 ? 2 * kBlockM : kBlockM,
+                                                  static_cast<uint32_t>(p.block_n));
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       int prev_nt = -1; uint32_t b_gen = 0;
@@ -335,18 +370,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                      : ptx::make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
             const uint64_t db = B_MN ? ptx::make_smem_desc_sw128(b_addr + k * (UMMA_K * kRowBytes), kBoxBytes, kMnSbo, kMnLayout)
                                      : ptx::make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            ptx::umma<kTf32>(d_tmem, da, db, idesc, (vk > vk0 || k > 0) ? 1u : 0u);
+            if constexpr (CG2) ptx::umma_pair<kTf32>(d_tmem, da, db, idesc, (vk > vk0 || k > 0) ? 1u : 0u);
+            else ptx::umma<kTf32>(d_tmem, da, db, idesc, (vk > vk0 || k > 0) ? 1u : 0u);
             if (p.dual) {                                       // rows 128..255 of the item: same B, second accumulator
               const uint64_t da1 = A_MN ? ptx::make_smem_desc_sw128(a_addr + kABytes + k * (UMMA_K * kRowBytes), kBoxBytes, kMnSbo, kMnLayout)
                                         : ptx::make_smem_desc_sw128(a_addr + kABytes + k * 32, 16, 1024);
               ptx::umma<kTf32>(d_tmem + kAccCols, da1, db, idesc, (vk > vk0 || k > 0) ? 1u : 0u);
             }
           }
-          ptx::umma_commit(&empty_bar[stage]);                  // frees the smem stage when these MMAs retire
-          if (last_of_nt) ptx::umma_commit(&bempty_bar[vk]);    // ... and the resident B slab
+          if constexpr (CG2) {
+            ptx::umma_commit_pair(&empty_bar[stage]);           // frees the stage in BOTH CTAs when these MMAs retire
+          } else {
+            ptx::umma_commit(&empty_bar[stage]);                // frees the smem stage when these MMAs retire
+            if (last_of_nt) ptx::umma_commit(&bempty_bar[vk]);  // ... and the resident B slab
+          }
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        ptx::umma_commit(&tmem_full[acc]);                      // accumulator complete -> epilogue
+        if constexpr (CG2) ptx::umma_commit_pair(&tmem_full[acc]);   // accumulator complete -> both CTAs' epilogues
+        else ptx::umma_commit(&tmem_full[acc]);                 // accumulator complete -> epilogue
         if (new_b) { ++b_gen; prev_nt = nt; }
       }
     }
@@ -394,7 +435,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       ptx::tc_fence_after();
       const int ncols = min(p.block_n, p.N - n0);
       for (int h = 0; h <= p.dual; ++h) {                       // dual-M: drain both accumulators of the item
-      const int row0 = mt * tile_m + h * kBlockM + q * 32;
+      const int row0 = mt * tile_m + (CG2 ? static_cast<int>(cta_rank) : h) * kBlockM + q * 32;
       const long long row = static_cast<long long>(row0) + lane;
       const uint32_t t_addr = tmem_base + static_cast<uint32_t>((acc + h) * kAccCols) + (static_cast<uint32_t>(q * 32) << 16);
       const bool last_h = (h == p.dual);
@@ -552,7 +593,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (last_h && c + 64 >= c_end) {                        // this warp's last read of the accumulator(s): hand back
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+          if (lane == 0) {
+            if constexpr (CG2) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tmem_empty[acc]), 0));   // leader's barrier
+            else ptx::mbar_arrive(&tmem_empty[acc]);
+          }
         }
         process(ra, c);
         process(rb, c + 32);
@@ -568,7 +612,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (last_h && c_begin >= c_end) {                         // nothing to drain (block_n == 64, upper half): still release
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) {
+          if constexpr (CG2) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tmem_empty[acc]), 0));
+          else ptx::mbar_arrive(&tmem_empty[acc]);
+        }
       }
       }  // h
     }
@@ -577,9 +624,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (CG2) ptx::cluster_sync();       // the peer may still signal our barriers / the leader still writes our TMEM
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (CG2) ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
+    else ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -659,12 +708,12 @@ int make_tmap(CUtensorMap* tm, const void* base, int esz, int64_t rows, int64_t 
 }
 
 struct Plan {
-  int block_n, m_tiles, n_tiles, kb_total, passes, vk_total, splits, vk_per_split, stages, resident, tma_store, dual;
+  int block_n, m_tiles, n_tiles, kb_total, passes, vk_total, splits, vk_per_split, stages, resident, tma_store, dual, cg2;
   size_t smem_bytes, workspace_bytes;
 };
 
 // DMC_GEMM_FLAGS (debug / A-B measurements): bit 0 = no TMA-store epilogue, bit 1 = no B-resident schedule,
-// bit 2 = no dual-M work items.
+// bit 2 = no dual-M work items, bits 3-5 = epilogue ablations (timing only), bit 6 = no CTA pairs (cta_group::1 only).
 int debug_flags() {
   static int flags = -1;
   if (flags < 0) {
@@ -681,10 +730,13 @@ Plan make_plan(int64_t M, int64_t N, int64_t K, int in_dtype, bool three_pass, i
   const int block_k = kRowBytes / esz;
   // Tile width: as wide as possible (fewest re-reads of A), but for short contractions prefer enough tiles to fill
   // the 148 SMs over a split-K pass; long contractions keep the wide tile and split K instead (A is read once).
-  const int64_t mt = ceil_div(M, kBlockM);
+  // CTA pairs (cta_group::2) whenever there is more than one 128-row tile: 256-row items, half a B tile per CTA.
+  pl.cg2 = (M > kBlockM && !(debug_flags() & 64)) ? 1 : 0;
+  const int units = pl.cg2 ? kNumSMs / 2 : kNumSMs;                 // schedulable units: CTA pairs or CTAs
+  const int64_t mt = ceil_div(M, pl.cg2 ? 2 * kBlockM : kBlockM);
   int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
   if (K < 8192 && forced_split == 0 && !want_stats) {
-    while (bn > 64 && mt * ceil_div(N, bn) < 100) bn >>= 1;
+    while (bn > 64 && mt * ceil_div(N, bn) < (units * 2) / 3) bn >>= 1;
   }
   if (want_stats) { bn = 256; forced_split = 1; }         // statistics parts are defined on 256-wide unsplit tiles
   pl.block_n = bn;
@@ -692,21 +744,19 @@ Plan make_plan(int64_t M, int64_t N, int64_t K, int in_dtype, bool three_pass, i
   pl.kb_total = static_cast<int>(ceil_div(K, block_k));
   pl.passes = three_pass ? 3 : 1;
   pl.vk_total = pl.kb_total * pl.passes;
-  // dual-M: 256-row work items whose two accumulators share every B k-block from smem (a third less L2->smem
-  // operand traffic).  Costs the MMA/epilogue overlap between items, so only for long contractions, and only
-  // when there are still enough items to fill the machine (or K is split anyway).
+  // dual-M (single-CTA kernels only): 256-row work items whose two accumulators share every B k-block from smem.
   pl.dual = 0;
-  if (!(debug_flags() & 4) && M > kBlockM && pl.vk_total >= 16 && !want_stats) {
+  if (!pl.cg2 && !(debug_flags() & 4) && M > kBlockM && pl.vk_total >= 16 && !want_stats) {
     const int64_t items = ceil_div(M, 2 * kBlockM) * pl.n_tiles;
     if (K >= 8192 || items >= kNumSMs) pl.dual = 1;
   }
-  pl.m_tiles = static_cast<int>(ceil_div(M, pl.dual ? 2 * kBlockM : kBlockM));
+  pl.m_tiles = static_cast<int>(ceil_div(M, (pl.dual || pl.cg2) ? 2 * kBlockM : kBlockM));
   const int tiles = pl.m_tiles * pl.n_tiles;
   int splits = 1;
   if (forced_split >= 1) {
     splits = forced_split;
-  } else if (tiles * 2 <= kNumSMs) {                       // under half a wave: split the contraction
-    splits = kNumSMs / tiles;
+  } else if (tiles * 2 <= units) {                         // under half a wave: split the contraction
+    splits = units / tiles;
     const int max_by_k = pl.vk_total / 4 > 0 ? pl.vk_total / 4 : 1;   // keep >= 4 k-blocks per split
     if (splits > max_by_k) splits = max_by_k;
   }
@@ -721,9 +771,9 @@ Plan make_plan(int64_t M, int64_t N, int64_t K, int in_dtype, bool three_pass, i
   // B-resident schedule: the whole contraction's worth of B for one n-tile stays in smem (<= 8 slabs, <= 128 KiB),
   // leaving >= 4 A-only stages.  Pays off when several m-tiles share an n-tile.
   const size_t res_bytes = static_cast<size_t>(pl.vk_total) * b_bytes;
-  pl.resident = (pl.splits == 1 && pl.vk_total <= kMaxStages && pl.m_tiles >= 2 && !pl.dual && !(debug_flags() & 2) &&
+  pl.resident = (pl.splits == 1 && pl.vk_total <= kMaxStages && pl.m_tiles >= 2 && !pl.dual && !pl.cg2 && !(debug_flags() & 2) &&
                  res_bytes + 4 * kABytes <= budget) ? 1 : 0;
-  const size_t stage_bytes = pl.resident ? kABytes : ((pl.dual ? 2 : 1) * kABytes + b_bytes);
+  const size_t stage_bytes = pl.resident ? kABytes : ((pl.dual ? 2 : 1) * kABytes + (pl.cg2 ? b_bytes / 2 : b_bytes));
   if (pl.resident) budget -= res_bytes;
   int stages = static_cast<int>(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
@@ -734,15 +784,36 @@ Plan make_plan(int64_t M, int64_t N, int64_t K, int in_dtype, bool three_pass, i
   return pl;
 }
 
-template <int ESZ, bool A_MN, bool B_MN, int EPI>
-int launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
-              const CUtensorMap& td, const GemmDev& dev, size_t smem_bytes, int grid, cudaStream_t st) {
-  auto kern = gemm_tc_kernel<ESZ, A_MN, B_MN, EPI>;
+template <int ESZ, bool A_MN, bool B_MN, int EPI, bool CG2>
+int launch_tc2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
+               const CUtensorMap& td, const GemmDev& dev, size_t smem_bytes, int grid, cudaStream_t st) {
+  auto kern = gemm_tc_kernel<ESZ, A_MN, B_MN, EPI, CG2>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
   if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(gemm_tc_kernel)");
-  kern<<<grid, kThreads, smem_bytes, st>>>(a0, a1, b0, b1, td, dev);
+  if constexpr (CG2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, a0, a1, b0, b1, td, dev);
+    if (e != cudaSuccess) return cuda_status(e, "cudaLaunchKernelEx(gemm_tc_kernel, cluster 2)");
+  } else {
+    kern<<<grid, kThreads, smem_bytes, st>>>(a0, a1, b0, b1, td, dev);
+  }
   DMC_LAUNCH_CHECK("gemm_tc_kernel launch");
   return 0;
+}
+
+template <int ESZ, bool A_MN, bool B_MN, int EPI>
+int launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
+              const CUtensorMap& td, const GemmDev& dev, size_t smem_bytes, int grid, cudaStream_t st, bool cg2) {
+  return cg2 ? launch_tc2<ESZ, A_MN, B_MN, EPI, true>(a0, a1, b0, b1, td, dev, smem_bytes, grid, st)
+             : launch_tc2<ESZ, A_MN, B_MN, EPI, false>(a0, a1, b0, b1, td, dev, smem_bytes, grid, st);
 }
 
 }  // namespace
@@ -792,7 +863,7 @@ extern "C" int dmc_gemm(const dmc_gemm_args* a, void* stream) {
   };
   auto mapB = [&](CUtensorMap* tm, const void* base) {
     return a->b_mn_major ? make_tmap(tm, base, esz, a->K, a->N, a->ldb, box_mn, block_k, esz == 4)   // stored [K,N]
-                         : make_tmap(tm, base, esz, a->N, a->K, a->ldb, block_k, pl.block_n); // stored [N,K]
+                         : make_tmap(tm, base, esz, a->N, a->K, a->ldb, block_k, pl.cg2 ? pl.block_n / 2 : pl.block_n); // [N,K]
   };
   if ((rc = mapA(&tA0, a->A))) return rc;
   if ((rc = mapB(&tB0, a->B))) return rc;
@@ -827,19 +898,23 @@ extern "C" int dmc_gemm(const dmc_gemm_args* a, void* stream) {
 
   const int num_work = pl.m_tiles * pl.n_tiles * pl.splits;
   const int cap = (a->max_ctas > 0 && a->max_ctas < kNumSMs) ? a->max_ctas : kNumSMs;
-  const int grid = num_work < cap ? num_work : cap;
+  int grid = num_work < cap ? num_work : cap;
+  if (pl.cg2) {                                   // CTA pairs: one cluster of 2 per work item slot
+    const int pairs_cap = cap / 2;
+    grid = 2 * (num_work < pairs_cap ? num_work : pairs_cap);
+  }
   const bool amn = a->a_mn_major != 0, bmn = a->b_mn_major != 0;
 const bool plain = (a->col_scale == nullptr && a->bias == nullptr && a->act == DMC_ACT_NONE);
   const bool stats = (a->stat_row_partials != nullptr);
 #define DMC_LAUNCH(ESZ_, AMN_, BMN_)                                                                          \
-  (plain ? launch_tc<ESZ_, AMN_, BMN_, 1>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st)                 \
-         : launch_tc<ESZ_, AMN_, BMN_, 0>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st))
+  (plain ? launch_tc<ESZ_, AMN_, BMN_, 1>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st, pl.cg2)                 \
+         : launch_tc<ESZ_, AMN_, BMN_, 0>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st, pl.cg2))
 #define DMC_DISPATCH(ESZ_)                                                                                    \
   (amn ? (bmn ? DMC_LAUNCH(ESZ_, true, true) : DMC_LAUNCH(ESZ_, true, false))                                 \
        : (bmn ? DMC_LAUNCH(ESZ_, false, true) : DMC_LAUNCH(ESZ_, false, false)))
   if (stats) {          // last-layer forward only: K-major operands
-    rc = (esz == 2) ? launch_tc<2, false, false, 2>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st)
-                    : launch_tc<4, false, false, 2>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st);
+    rc = (esz == 2) ? launch_tc<2, false, false, 2>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st, pl.cg2)
+                    : launch_tc<4, false, false, 2>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st, pl.cg2);
   } else {
     rc = (esz == 2) ? DMC_DISPATCH(2) : DMC_DISPATCH(4);
   }
