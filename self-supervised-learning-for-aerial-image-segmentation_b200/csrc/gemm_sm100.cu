@@ -713,7 +713,7 @@ struct Plan {
 };
 
 // DMC_GEMM_FLAGS (debug / A-B measurements): bit 0 = no TMA-store epilogue, bit 1 = no B-resident schedule,
-// bit 2 = no dual-M work items, bits 3-5 = epilogue ablations (timing only), bit 6 = no CTA pairs (cta_group::1 only).
+// bit 2 = no dual-M work items, bits 3-5 = epilogue ablations (timing only), bit 6 = use CTA pairs (cta_group::2) where M > 128.
 int debug_flags() {
   static int flags = -1;
   if (flags < 0) {
@@ -730,13 +730,16 @@ Plan make_plan(int64_t M, int64_t N, int64_t K, int in_dtype, bool three_pass, i
   const int block_k = kRowBytes / esz;
   // Tile width: as wide as possible (fewest re-reads of A), but for short contractions prefer enough tiles to fill
   // the 148 SMs over a split-K pass; long contractions keep the wide tile and split K instead (A is read once).
-  // CTA pairs (cta_group::2) whenever there is more than one 128-row tile: 256-row items, half a B tile per CTA.
-  pl.cg2 = (M > kBlockM && !(debug_flags() & 64)) ? 1 : 0;
+  // CTA pairs (cta_group::2): 256-row items, half a B tile per CTA.  Correct in every layout (tests run both), but on
+  // these shapes measured slower than the single-CTA schedule (8192^3: 1.11 vs 1.43 PFLOP/s), so it is opt-in:
+  // DMC_GEMM_FLAGS bit 6.
+  pl.cg2 = (M > kBlockM && (debug_flags() & 64)) ? 1 : 0;
   const int units = pl.cg2 ? kNumSMs / 2 : kNumSMs;                 // schedulable units: CTA pairs or CTAs
   const int64_t mt = ceil_div(M, pl.cg2 ? 2 * kBlockM : kBlockM);
-  int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  int bn = N > 128 ? 256 : ((N > 64 || pl.cg2) ? 128 : 64);
   if (K < 8192 && forced_split == 0 && !want_stats) {
-    while (bn > 64 && mt * ceil_div(N, bn) < (units * 2) / 3) bn >>= 1;
+    const int bn_min = pl.cg2 ? 128 : 64;       // a CTA pair splits the B tile in two: each half needs >= one 64-wide box
+    while (bn > bn_min && mt * ceil_div(N, bn) < (units * 2) / 3) bn >>= 1;
   }
   if (want_stats) { bn = 256; forced_split = 1; }         // statistics parts are defined on 256-wide unsplit tiles
   pl.block_n = bn;

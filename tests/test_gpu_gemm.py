@@ -193,3 +193,34 @@ def test_gemm_fused_statistics(M, N, K, dtype):
             assert rel_err(stats_t[:, 0].cpu().numpy(), m2) < 1e-6
         l_ref = np.exp2(y * np.log2(np.e) - stats_t[:, 0].double().cpu().numpy()[:, None]).sum(-1)
         assert rel_err(stats_t[:, 1].cpu().numpy(), 1.0 / l_ref) < 1e-5
+
+
+def test_gemm_cta_pair_mode_subprocess():
+    """The opt-in CTA-pair (tcgen05 cta_group::2) schedule gives the same results (own process: the mode is read once
+    from DMC_GEMM_FLAGS)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import sys, torch, numpy as np
+sys.path.insert(0, %r)
+import dinomc_b200
+ops = dinomc_b200.ops
+worst = 0.0
+for (M, N, K, a_mn, b_mn) in [(256, 512, 256, False, False), (300, 320, 136, False, True), (512, 256, 1000, True, True),
+                              (2048, 256, 4096, False, True), (1024, 2048, 384, True, False)]:
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn(M, K, generator=g).bfloat16().float(); B = torch.randn(N, K, generator=g).bfloat16().float()
+    Ast = (A.t().contiguous() if a_mn else A).bfloat16().cuda(); Bst = (B.t().contiguous() if b_mn else B).bfloat16().cuda()
+    D = ops.gemm(Ast, Bst, M, N, K, a_mn=a_mn, b_mn=b_mn)
+    torch.cuda.synchronize()
+    ref = A.double().numpy() @ B.double().numpy().T
+    worst = max(worst, float(np.abs(D.cpu().double().numpy() - ref).max() / np.abs(ref).max()))
+print("WORST", worst)
+""" % root
+    env = dict(os.environ, DMC_GEMM_FLAGS="64")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    worst = float(r.stdout.strip().split("WORST")[-1])
+    assert worst < 2e-5

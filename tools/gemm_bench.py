@@ -13,6 +13,8 @@ SHAPES = {
     "last_fwd_student_max_stats": (2048, 65536, 256, False, False, torch.bfloat16, torch.bfloat16),
     "last_dgrad": (2048, 256, 65536, False, True, torch.bfloat16, torch.float32),
     "last_wgrad": (65536, 256, 2048, True, True, torch.bfloat16, torch.float32),
+    "big8192": (8192, 8192, 8192, False, False, torch.bfloat16, torch.bfloat16),
+    "big4096": (4096, 4096, 4096, False, False, torch.bfloat16, torch.bfloat16),
     "mlp_fwd1": (2048, 2048, 384, False, False, torch.bfloat16, torch.bfloat16),
     "mlp_fwd2": (2048, 2048, 2048, False, False, torch.bfloat16, torch.bfloat16),
     "mlp_fwd3": (2048, 256, 2048, False, False, torch.bfloat16, torch.float32),
