@@ -112,6 +112,10 @@ int dmc_gemm_simt(const dmc_gemm_args* args, void* stream);
 int dmc_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
 /* fp32 -> bf16 (round to nearest even). */
 int dmc_cast_f32_to_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
+/* The same for up to 8 tensors in ONE launch (the bf16 operand copies of a head forward: features + Linear weights).
+ * The three arrays are HOST arrays of `count` entries. */
+int dmc_cast_f32_to_bf16_batch(const float* const* srcs_host, void* const* dsts_host, const int64_t* ns_host,
+                               int32_t count, void* stream);
 /* out[n] = sum_m X[m,n]   (bias gradients of the MLP Linears).  X is F32 or BF16. */
 size_t dmc_colsum_workspace_bytes(int64_t M, int64_t N);
 int dmc_colsum(const void* X, int32_t dtype, int64_t M, int64_t N, int64_t ld, float* out,

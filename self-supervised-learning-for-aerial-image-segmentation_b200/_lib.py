@@ -48,6 +48,7 @@ SIGNATURES = {
     "dmc_gemm_simt": (C.c_int, [C.POINTER(GemmArgs), vp]),
     "dmc_split_tf32": (C.c_int, [vp, vp, vp, i64, vp]),
     "dmc_cast_f32_to_bf16": (C.c_int, [vp, vp, i64, vp]),
+    "dmc_cast_f32_to_bf16_batch": (C.c_int, [C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), i32, vp]),
     "dmc_colsum_workspace_bytes": (sz, [i64, i64]),
     "dmc_colsum": (C.c_int, [vp, i32, i64, i64, i64, vp, vp, sz, vp]),
     "dmc_normalize_rows_fwd": (C.c_int, [vp, i32, i64, i64, i64, f32, vp, vp, vp, vp, vp]),

@@ -758,7 +758,7 @@ Plan make_plan(int64_t M, int64_t N, int64_t K, int in_dtype, bool three_pass, i
   int splits = 1;
   if (forced_split >= 1) {
     splits = forced_split;
-  } else if (tiles * 2 <= units) {                         // under half a wave: split the contraction
+  } else if (tiles * 3 <= units) {                         // under a third of a wave: split the contraction
     splits = units / tiles;
     const int max_by_k = pl.vk_total / 4 > 0 ? pl.vk_total / 4 : 1;   // keep >= 4 k-blocks per split
     if (splits > max_by_k) splits = max_by_k;

@@ -202,6 +202,27 @@ cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, lon
     y[i] = __float2bfloat16_rn(x[i]);
 }
 
+// Up to 8 independent fp32 -> bf16 casts in one launch (blockIdx.y = tensor): the operand copies of one head forward.
+struct CastBatch {
+  const float* src[8];
+  __nv_bfloat16* dst[8];
+  long long n[8];
+};
+__global__ void __launch_bounds__(256)
+cast_bf16_batch_kernel(const CastBatch b) {
+  const float* __restrict__ x = b.src[blockIdx.y];
+  __nv_bfloat16* __restrict__ y = b.dst[blockIdx.y];
+  const long long n = b.n[blockIdx.y];
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long n4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0) ? n / 4 : 0;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    reinterpret_cast<uint2*>(y)[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+  for (long long i = n4 * 4 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    y[i] = __float2bfloat16_rn(x[i]);
+}
+
 // Column sum in two deterministic steps: [row_splits][N] partials, then a fixed-order reduction.
 // A thread owns 4 consecutive columns (one packed load per row), a block = 32 column groups x 8 row lanes.
 template <typename T>
@@ -329,6 +350,22 @@ extern "C" int dmc_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* st
   DMC_REQUIRE(x && y && n > 0, "dmc_cast_f32_to_bf16: bad arguments");
   cast_bf16_kernel<<<grid_1d(n, 1024), 256, 0, (cudaStream_t)stream>>>(x, static_cast<__nv_bfloat16*>(y), n);
   DMC_LAUNCH_CHECK("cast_bf16_kernel launch");
+  return 0;
+}
+
+extern "C" int dmc_cast_f32_to_bf16_batch(const float* const* srcs_host, void* const* dsts_host, const int64_t* ns_host,
+                                          int32_t count, void* stream) {
+  DMC_REQUIRE(srcs_host && dsts_host && ns_host && count >= 1 && count <= 8, "dmc_cast_f32_to_bf16_batch: 1..8 tensors per call");
+  CastBatch b{};
+  long long nmax = 0;
+  for (int i = 0; i < count; ++i) {
+    DMC_REQUIRE(srcs_host[i] && dsts_host[i] && ns_host[i] > 0, "dmc_cast_f32_to_bf16_batch: bad tensor %d", i);
+    b.src[i] = srcs_host[i]; b.dst[i] = static_cast<__nv_bfloat16*>(dsts_host[i]); b.n[i] = ns_host[i];
+    nmax = ns_host[i] > nmax ? ns_host[i] : nmax;
+  }
+  dim3 grid((unsigned)grid_1d(nmax, 1024), (unsigned)count);
+  cast_bf16_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(b);
+  DMC_LAUNCH_CHECK("cast_bf16_batch_kernel launch");
   return 0;
 }
 

@@ -26,6 +26,9 @@ MODES = ("bf16", "fp32", "fp32_simt")
 import weakref
 
 fused_stats_enabled = True
+fused_teacher_stats = False   # teacher row statistics + column sums from the GEMM epilogue: measured slightly slower than
+                              # the dedicated one-pass teacher kernel (the center subtraction and column sums weigh on the
+                              # epilogue), so off by default; the student's log-sum-exp partials are always fused
 _loss_ref = None          # weakref to the DINOLoss whose temperatures / center the heads should use
 last_stats = None         # stats record of the most recent NormLastLayerFn.forward (picked up by DINOHead)
 
@@ -91,13 +94,16 @@ class MlpFn(torch.autograd.Function):
         n = len(wb) // 2
         rows = x.shape[0]
         mode = resolve_mode(mode, x.shape[1], *[d for li in range(n) for d in wb[2 * li].shape])
-        acts = [prep(x.detach(), mode)]
+        pre = None
+        if mode == "bf16":       # all bf16 operand copies of this forward (features + weights) in one launch
+            pre = [Operand(t) for t in ops.cast_bf16_batch([x.detach()] + [wb[2 * li].detach() for li in range(n)])]
+        acts = [pre[0] if pre else prep(x.detach(), mode)]
         wops, zs = [], []
         sd = store_dtype(mode)
         out = None
         for li in range(n):
             W, b = wb[2 * li].detach(), wb[2 * li + 1]
-            wop = prep(W, mode)
+            wop = pre[1 + li] if pre else prep(W, mode)
             wops.append(wop)
             fo, fi = W.shape
             bias = None if b is None else b.detach().float().contiguous()
@@ -174,8 +180,10 @@ class NormLastLayerFn(torch.autograd.Function):
         loss_mod = _current_loss() if (fused_stats_enabled and mode != "fp32_simt" and K > 128) else None
         if loss_mod is not None:
             parts = ops.gemm_stats_parts(K)
-            rp = torch.empty((rows, parts, 2), dtype=torch.float32, device=z.device)
-            if who == "student":
+            rp = torch.empty((rows, parts, 2), dtype=torch.float32, device=z.device) if (who == "student" or fused_teacher_stats) else None
+            if who == "teacher" and not fused_teacher_stats:
+                stats = None
+            elif who == "student":
                 stats = dict(kind="student", scale=1.0 / loss_mod.student_temp, center=None, row_partials=rp,
                              bound=ops.last_gmax[0])
             else:

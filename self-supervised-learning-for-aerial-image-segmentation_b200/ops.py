@@ -289,6 +289,31 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def cast_bf16_batch(tensors):
+    """bf16 copies of several tensors with one launch (fp32 inputs; bf16 inputs are passed through)."""
+    lib = L.load()
+    outs = [None] * len(tensors)
+    todo = []
+    for i, t in enumerate(tensors):
+        _need_cuda(t)
+        if t.dtype == torch.bfloat16:
+            outs[i] = t
+        else:
+            t = t.float().contiguous() if t.dtype != torch.float32 else t.contiguous()
+            outs[i] = torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
+            todo.append((t, outs[i]))
+    for k in range(0, len(todo), 8):
+        grp = todo[k:k + 8]
+        n = len(grp)
+        srcs = (L.vp * n)(*[a.data_ptr() for a, _ in grp])
+        dsts = (L.vp * n)(*[b.data_ptr() for _, b in grp])
+        ns = (L.i64 * n)(*[a.numel() for a, _ in grp])
+        with _timed("cast_bf16"):
+            L.check(lib.dmc_cast_f32_to_bf16_batch(srcs, dsts, ns, n, _stream()), "dmc_cast_f32_to_bf16_batch")
+        _count()
+    return outs
+
+
 def colsum(X: torch.Tensor) -> torch.Tensor:
     lib = L.load()
     X = _rows2d(X)

@@ -263,6 +263,7 @@ def test_fused_statistics_route_matches_plain_route(mode, tol):
     res = {}
     for fused in (True, False):
         Fn.fused_stats_enabled = fused
+        Fn.fused_teacher_stats = fused                    # also cover the (default-off) teacher statistics fusion
         try:
             loss_mod = D.DINOLoss(K, C, 0.04, 0.07, 3, 10, teacher_crops_number=G).cuda()
             loss_mod.center.normal_(0, 0.2, generator=torch.Generator(device="cuda").manual_seed(5))
@@ -281,6 +282,7 @@ def test_fused_statistics_route_matches_plain_route(mode, tol):
                           loss_mod.center.clone())
         finally:
             Fn.fused_stats_enabled = True
+            Fn.fused_teacher_stats = False
     lf, lp = res[True][0], res[False][0]
     assert abs(lf - lp) / abs(lp) < tol
     for a, b in zip(res[True][1:], res[False][1:]):
