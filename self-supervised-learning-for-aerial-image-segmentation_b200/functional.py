@@ -84,71 +84,81 @@ def mm(mode, a: Operand, b: Operand, M, N, K, *, a_mn=False, b_mn=False, **kw):
     return ops.gemm(a.main, b.main, M, N, K, a_mn=a_mn, b_mn=b_mn, A_lo=a.lo, B_lo=b.lo, **kw)
 
 
-class MlpFn(torch.autograd.Function):
-    """The Linear/GELU chain of DINOHead.mlp (utils/vision_transformer.py:264-277, use_bn=False).
-    forward(mode, x, W0, b0, W1, b1, ...) -> z_last (fp32).  Bias + GELU are fused into the GEMM epilogue
-    (which also saves the pre-activation); backward fuses gelu' into the dgrad epilogue."""
+class LinearFn(torch.autograd.Function):
+    """One Linear (+ GELU) of DINOHead.mlp (utils/vision_transformer.py:264-277, use_bn=False).
+
+    forward(mode, h_in, z_in, W, b, h_op, w_op, apply_gelu) -> (h_out, z_out)
+      h_in   input activations (the features for the first layer);
+      z_in   the pre-activation h_in = gelu(z_in) came from, or None for the first layer;
+      h_op / w_op  optional ready-made GEMM operands of h_in / W (batched casts done by the caller);
+      h_out  = gelu(z_out) (store dtype) when apply_gelu, else z_out itself in fp32;  z_out is saved by the GEMM epilogue.
+
+    One autograd node per layer (rather than one for the whole MLP) so that each layer's weight gradient reaches
+    its accumulation hook -- and a data-parallel all-reduce -- as soon as that layer's wgrad has been issued.
+
+    Private gradient convention inside the chain: the gradient a layer receives for its GELU output h_out is already
+    dL/dz_out, because the consumer layer's dgrad epilogue multiplies by gelu'(z_out) (one fused pass instead of an
+    elementwise kernel).  The chain is only ever built by `mlp_forward`, which keeps both ends consistent."""
 
     @staticmethod
-    def forward(ctx, mode, x, *wb):
-        n = len(wb) // 2
-        rows = x.shape[0]
-        mode = resolve_mode(mode, x.shape[1], *[d for li in range(n) for d in wb[2 * li].shape])
-        pre = None
-        if mode == "bf16":       # all bf16 operand copies of this forward (features + weights) in one launch
-            pre = [Operand(t) for t in ops.cast_bf16_batch([x.detach()] + [wb[2 * li].detach() for li in range(n)])]
-        acts = [pre[0] if pre else prep(x.detach(), mode)]
-        wops, zs = [], []
+    def forward(ctx, mode, h_in, z_in, W, b, h_op, w_op, apply_gelu):
+        rows = h_in.shape[0]
+        fo, fi = W.shape
         sd = store_dtype(mode)
-        out = None
-        for li in range(n):
-            W, b = wb[2 * li].detach(), wb[2 * li + 1]
-            wop = pre[1 + li] if pre else prep(W, mode)
-            wops.append(wop)
-            fo, fi = W.shape
-            bias = None if b is None else b.detach().float().contiguous()
-            if li < n - 1:
-                z = torch.empty((rows, fo), dtype=sd, device=x.device)
-                h = mm(mode, acts[li], wop, rows, fo, fi, out_dtype=sd, bias=bias, act=L.ACT_GELU, aux=z, tag="gemm_mlp_fwd")
-                zs.append(z)
-                acts.append(prep(h, mode))
-            else:
-                out = mm(mode, acts[li], wop, rows, fo, fi, out_dtype=torch.float32, bias=bias, tag="gemm_mlp_fwd")
-        ctx.mode, ctx.n, ctx.rows = mode, n, rows
-        ctx.acts, ctx.wops, ctx.zs = acts, wops, zs
-        ctx.shapes = [tuple(wb[2 * li].shape) for li in range(n)]
-        ctx.has_bias = [wb[2 * li + 1] is not None for li in range(n)]
-        return out
+        if h_op is None:
+            h_op = Operand(ops._rows2d(h_in.detach())) if (mode == "bf16" and h_in.dtype == torch.bfloat16) else prep(h_in.detach(), mode)
+        if w_op is None:
+            w_op = prep(W.detach(), mode)
+        bias = None if b is None else b.detach().float().contiguous()
+        if apply_gelu:
+            z_out = torch.empty((rows, fo), dtype=sd, device=h_in.device)
+            h_out = mm(mode, h_op, w_op, rows, fo, fi, out_dtype=sd, bias=bias, act=L.ACT_GELU, aux=z_out, tag="gemm_mlp_fwd")
+        else:
+            h_out = mm(mode, h_op, w_op, rows, fo, fi, out_dtype=torch.float32, bias=bias, tag="gemm_mlp_fwd")
+            z_out = h_out.new_empty(0)
+        ctx.mode, ctx.dims = mode, (rows, fo, fi)
+        ctx.h_op, ctx.w_op, ctx.z_in = h_op, w_op, (None if z_in is None else z_in.detach())
+        ctx.has_bias = b is not None
+        ctx.mark_non_differentiable(z_out)
+        return h_out, z_out
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dz, _unused):
+        mode = ctx.mode
+        rows, fo, fi = ctx.dims
+        sd = store_dtype(mode)
+        d_full = dz.contiguous()
+        dW = db = d_in = None
         with ops.backward_cap():
-            return MlpFn._backward(ctx, dy)
-
-    @staticmethod
-    def _backward(ctx, dy):
-        mode, n, rows = ctx.mode, ctx.n, ctx.rows
-        sd = store_dtype(mode)
-        grads = [None] * (2 * n)
-        d_full = dy.contiguous()
-        d = prep(d_full, mode)
-        dx = None
-        for li in range(n - 1, -1, -1):
-            fo, fi = ctx.shapes[li]
-            # wgrad: dW[fo,fi] = d^T . act   (both operands MN-major straight from their row-major storage)
-            if ctx.needs_input_grad[2 + 2 * li]:
-                grads[2 * li] = mm(mode, d, ctx.acts[li], fo, fi, rows, a_mn=True, b_mn=True, out_dtype=torch.float32,
-                                   tag="gemm_mlp_wgrad")
-            if ctx.has_bias[li] and ctx.needs_input_grad[3 + 2 * li]:
-                grads[2 * li + 1] = ops.colsum(d_full)
-            if li > 0:
-                # dgrad with gelu'(z_{li-1}) fused: d_prev = (d . W) * gelu'(z)
-                d_full = mm(mode, d, ctx.wops[li], rows, fi, fo, b_mn=True, out_dtype=sd, act=L.ACT_GELU_BWD,
-                            aux=ctx.zs[li - 1], tag="gemm_mlp_dgrad")
-                d = prep(d_full, mode)
+            d = Operand(d_full) if (mode == "bf16" and d_full.dtype == torch.bfloat16) else prep(d_full, mode)
+            if ctx.needs_input_grad[3]:
+                # wgrad: dW[fo,fi] = dz^T . h_in   (both operands MN-major straight from their row-major storage)
+                dW = mm(mode, d, ctx.h_op, fo, fi, rows, a_mn=True, b_mn=True, out_dtype=torch.float32, tag="gemm_mlp_wgrad")
+                ops.mark_ready(dW)
+            if ctx.has_bias and ctx.needs_input_grad[4]:
+                db = ops.colsum(d_full)
+                ops.mark_ready(db)
+            if ctx.z_in is not None:
+                # dgrad with gelu'(z_in) fused: what flows upstream is already dL/dz_in
+                d_in = mm(mode, d, ctx.w_op, rows, fi, fo, b_mn=True, out_dtype=sd, act=L.ACT_GELU_BWD, aux=ctx.z_in,
+                          tag="gemm_mlp_dgrad")
             elif ctx.needs_input_grad[1]:
-                dx = mm(mode, d, ctx.wops[0], rows, fi, fo, b_mn=True, out_dtype=torch.float32, tag="gemm_mlp_dgrad")
-        return (None, dx, *grads)
+                d_in = mm(mode, d, ctx.w_op, rows, fi, fo, b_mn=True, out_dtype=torch.float32, tag="gemm_mlp_dgrad")
+        return None, d_in, None, dW, db, None, None, None
+
+
+def mlp_forward(mode, x, wb):
+    """The Linear/GELU chain: x -> z_last (fp32).  `wb` = [W0, b0, W1, b1, ...] (the nn.Linear parameters)."""
+    n = len(wb) // 2
+    mode = resolve_mode(mode, x.shape[1], *[d for li in range(n) for d in wb[2 * li].shape])
+    pre = None
+    if mode == "bf16":           # all bf16 operand copies of this forward (features + weights) in one launch
+        pre = [Operand(t) for t in ops.cast_bf16_batch([x.detach()] + [wb[2 * li].detach() for li in range(n)])]
+    h, z = x, None
+    for li in range(n):
+        h, z = LinearFn.apply(mode, h, z, wb[2 * li], wb[2 * li + 1], pre[0] if (pre and li == 0) else None,
+                              pre[1 + li] if pre else None, li < n - 1)
+    return h
 
 
 class NormLastLayerFn(torch.autograd.Function):

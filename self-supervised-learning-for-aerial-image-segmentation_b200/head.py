@@ -169,7 +169,7 @@ class DINOHead(nn.Module):
                 wb = []
                 for lin in linears:
                     wb += [lin.weight, lin.bias]
-                z = Fn.MlpFn.apply(mode, x, *wb)
+                z = Fn.mlp_forward(mode, x, wb)
             out = Fn.NormLastLayerFn.apply(mode, z, self.last_layer.weight_g, self.last_layer.weight_v)
             if Fn.last_stats is not None:       # statistics the GEMM epilogue produced for dinomc_b200.DINOLoss
                 out._dmc_stats = Fn.last_stats

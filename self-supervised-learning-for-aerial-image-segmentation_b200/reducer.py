@@ -15,13 +15,15 @@ NVSwitch) does the transport.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
 from . import ops
 
 _BIG = 32 << 20      # bytes: gradients at least this large get their own all-reduce
-_FLUSH = 16 << 20    # bytes: pending small gradients are sent as one coalesced all-reduce once they reach this
+_FLUSH = 1 << 20     # bytes: pending small gradients are sent as one coalesced all-reduce once they reach this
 
 
 class GradAllReduce:
@@ -40,7 +42,13 @@ class GradAllReduce:
     def _hook(self, p):
         g = p.grad
         self._seen += 1
-        if g.numel() * g.element_size() >= _BIG:
+        skip = os.environ.get("DMC_REDUCER_SKIP", "")       # timing experiments only: "big" / "small"
+        big = g.numel() * g.element_size() >= _BIG
+        if (skip == "big" and big) or (skip == "small" and not big):
+            if self._seen == len(self.params):
+                self._flush()
+            return
+        if big:
             ev = ops.ready_events.pop(g.data_ptr(), None)
             if ev is not None:
                 self.comm.wait_event(ev)                 # start as soon as the producing kernel is done
@@ -50,23 +58,28 @@ class GradAllReduce:
                 dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
             g.record_stream(self.comm)
         else:
-            self._pending.append(g)
+            self._pending.append((g, ops.ready_events.pop(g.data_ptr(), None)))
             self._pending_bytes += g.numel() * g.element_size()
         if self._seen == len(self.params) or self._pending_bytes >= _FLUSH:
             self._flush()
 
     def _flush(self):
         if self._pending:
-            self.comm.wait_stream(torch.cuda.current_stream())
+            if all(ev is not None for _, ev in self._pending):
+                for _, ev in self._pending:              # start as soon as the producing kernels are done
+                    self.comm.wait_event(ev)
+            else:
+                self.comm.wait_stream(torch.cuda.current_stream())
+            grads = [g for g, _ in self._pending]
             with torch.cuda.stream(self.comm):
                 try:
-                    with dist._coalescing_manager(group=self.group, device=self._pending[0].device, async_ops=False):
-                        for g in self._pending:
+                    with dist._coalescing_manager(group=self.group, device=grads[0].device, async_ops=False):
+                        for g in grads:
                             dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
                 except (AttributeError, TypeError, RuntimeError):
-                    for g in self._pending:
+                    for g in grads:
                         dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
-            for g in self._pending:
+            for g in grads:
                 g.record_stream(self.comm)
             self._pending = []
             self._pending_bytes = 0
