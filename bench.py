@@ -341,7 +341,12 @@ def main():
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        opts = None
+        try:        # NCCL kernels on a high-priority stream: they grab SMs as soon as compute CTAs retire
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        except Exception:       # noqa: BLE001
+            opts = None
+        dist.init_process_group("nccl", device_id=device, pg_options=opts)
     import dinomc_b200 as D
     D._lib.check(D._lib.load().dmc_device_check(local_rank), "dmc_device_check")
 

@@ -30,7 +30,7 @@ class GradAllReduce:
     def __init__(self, params, group=None, reserve_sms: int = 16):
         self.group = group
         self.params = [p for p in params if p.requires_grad]
-        self.comm = torch.cuda.Stream()
+        self.comm = torch.cuda.Stream(priority=-1)
         self._pending = []
         self._pending_bytes = 0
         self._seen = 0

@@ -6,7 +6,8 @@ import bench
 
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
 dev = torch.device("cuda", lr); torch.cuda.set_device(dev)
-dist.init_process_group("nccl", device_id=dev)
+opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True) if os.environ.get("HIPRI", "1") == "1" else None
+dist.init_process_group("nccl", device_id=dev, pg_options=opts)
 import dinomc_b200 as D
 D.set_teacher_overlap(True); D.set_async_center(True)
 
