@@ -409,10 +409,14 @@ def main():
     Ns, Nt, K = w["C"] * w["B"], w["G"] * w["B"], w["K"]
     alg_bytes = {   # algorithmic bytes per launch of the HBM-bound kernels
         "ce_bwd": logit_bytes * K * (2 * Ns + Nt),
+        "ce_fused": logit_bytes * K * (2 * Ns + Nt),
         "ce_fwd": logit_bytes * K * (Ns + Nt),
         "teacher_stats_colsum": logit_bytes * K * Nt,
         "ema": 12 * step.P,
         "gemm_last_fwd_student": logit_bytes * K * Ns + 2 * BN * (K + Ns),
+        "gemm_last_fwd_teacher": logit_bytes * K * Nt + 2 * BN * (K + Nt),
+        "weightnorm_fwd": 2 * (4 + logit_bytes) * K * BN,          # two launches per step (student + teacher)
+        "weightnorm_bwd": 12 * K * BN,
         "gemm_last_wgrad": logit_bytes * K * Ns + 4 * K * BN,
         "gemm_last_dgrad": logit_bytes * K * Ns + 2 * K * BN,
     }
@@ -420,7 +424,7 @@ def main():
     for name, (ms_tot, calls_tot) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
         ms, calls = ms_tot / prof_steps, calls_tot / prof_steps
         k = {"kernel": name, "ms_per_step": ms, "calls_per_step": calls}
-        if name in alg_bytes:
+        if name in alg_bytes:                 # alg_bytes[...] covers all of that op's launches in one step
             k["alg_GB"] = alg_bytes[name] / 1e9
             k["GBps"] = alg_bytes[name] / 1e9 / (ms * 1e-3)
             k["frac_of_hbm_peak"] = k["GBps"] / peaks["hbm_gbs"]
@@ -428,8 +432,13 @@ def main():
     dom = next((k for k in kernels if "GBps" in k), None)
     roofline = None
     if dom is not None:
+        # DRAM traffic of that kernel per launch from the committed `ncu --set full` capture (profiles/), if there is one
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.isfile(tpath):
+            traffic = json.load(open(tpath)).get(args.workload + ":" + args.mode, {}).get(dom["kernel"])
         roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["GBps"], "peak": peaks["hbm_gbs"],
-                    "unit": "GB/s", "frac": dom["frac_of_hbm_peak"], "traffic": None, "peak_source": peaks["source"],
+                    "unit": "GB/s", "frac": dom["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peaks["source"],
                     "step": {"t_roof_ms": t_roof_ms, "alg_GB": nbytes / 1e9, "alg_GFLOP": flops / 1e9,
                              "frac_of_step_roofline": t_roof_ms / ms_step},
                     "kernels": kernels[:12]}

@@ -22,6 +22,9 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kIters = 8;          // 4-element vectors per thread per row per CTA
 constexpr int kChunkCols = kThreads * 4 * kIters;   // 8192 columns per CTA
+#ifndef DMC_FUSED_MINBLOCKS
+#define DMC_FUSED_MINBLOCKS 2
+#endif
 constexpr int kMinBlocks = 3;      // CTAs per SM the register budget is tuned for (<= 85 registers/thread)
 
 struct CeArgs {
@@ -397,8 +400,10 @@ __device__ __forceinline__ void ce_fused_vector(const CeArgs& a, const T* s, con
   cross = fmaf(qs, a.inv_ts, cross);
 }
 
-template <typename T, int CT, int GT>
-__global__ void __launch_bounds__(kThreads, kMinBlocks)
+// ALLFAST: every vector of every row is full and aligned (K % 4 == 0, aligned pointers and strides): the ragged path is
+// not even compiled in, which keeps the hot kernel inside its register budget.
+template <typename T, int CT, int GT, bool ALLFAST>
+__global__ void __launch_bounds__(kThreads, DMC_FUSED_MINBLOCKS)
 ce_fused_kernel(const CeArgs a) {
   constexpr int MAXC = CT ? CT : 16, MAXG = GT ? GT : 4;
   const int C = CT ? CT : a.C, G = GT ? GT : a.G;
@@ -424,8 +429,12 @@ ce_fused_kernel(const CeArgs a) {
   }
   float cross = 0.f;
   for (long long col = col_begin + threadIdx.x * 4; col < col_end; col += kThreads * 4) {
-    if (a.vec_ok && (col + 4 <= a.K)) ce_fused_vector<T, MAXC, MAXG, true>(a, s, t, ds, b, col, C, G, tmc, tinv, lse2, c2, ct, scale, cross);
-    else ce_fused_vector<T, MAXC, MAXG, false>(a, s, t, ds, b, col, C, G, tmc, tinv, lse2, c2, ct, scale, cross);
+    if constexpr (ALLFAST) {
+      ce_fused_vector<T, MAXC, MAXG, true>(a, s, t, ds, b, col, C, G, tmc, tinv, lse2, c2, ct, scale, cross);
+    } else {
+      if (a.vec_ok && (col + 4 <= a.K)) ce_fused_vector<T, MAXC, MAXG, true>(a, s, t, ds, b, col, C, G, tmc, tinv, lse2, c2, ct, scale, cross);
+      else ce_fused_vector<T, MAXC, MAXG, false>(a, s, t, ds, b, col, C, G, tmc, tinv, lse2, c2, ct, scale, cross);
+    }
   }
   __shared__ float red[kThreads / 32];
   cross = warp_sum(cross);
@@ -494,9 +503,12 @@ scale_if_kernel(T* __restrict__ x, long long n, const float* __restrict__ scale,
 
 template <typename T>
 int launch_fused(const CeArgs& a, dim3 grid, cudaStream_t st) {
-  if (a.C == 8 && a.G == 2) ce_fused_kernel<T, 8, 2><<<grid, kThreads, 0, st>>>(a);
-  else if (a.C == 9 && a.G == 3) ce_fused_kernel<T, 9, 3><<<grid, kThreads, 0, st>>>(a);
-  else ce_fused_kernel<T, 0, 0><<<grid, kThreads, 0, st>>>(a);
+  const bool allfast = a.vec_ok && (a.K % 4 == 0);
+  if (a.C == 8 && a.G == 2 && allfast) ce_fused_kernel<T, 8, 2, true><<<grid, kThreads, 0, st>>>(a);
+  else if (a.C == 8 && a.G == 2) ce_fused_kernel<T, 8, 2, false><<<grid, kThreads, 0, st>>>(a);
+  else if (a.C == 9 && a.G == 3 && allfast) ce_fused_kernel<T, 9, 3, true><<<grid, kThreads, 0, st>>>(a);
+  else if (a.C == 9 && a.G == 3) ce_fused_kernel<T, 9, 3, false><<<grid, kThreads, 0, st>>>(a);
+  else ce_fused_kernel<T, 0, 0, false><<<grid, kThreads, 0, st>>>(a);
   DMC_LAUNCH_CHECK("ce_fused_kernel launch");
   return 0;
 }
