@@ -742,6 +742,7 @@ Plan make_plan(int64_t M, int64_t N, int64_t K, int in_dtype, bool three_pass, i
     while (bn > bn_min && mt * ceil_div(N, bn) < (units * 2) / 3) bn >>= 1;
   }
   if (want_stats) { bn = 256; forced_split = 1; }         // statistics parts are defined on 256-wide unsplit tiles
+  if ((debug_flags() & 128) && !want_stats && bn == 256 && K <= 512 && mt * ceil_div(N, 128) >= 4 * units) bn = 128;
   pl.block_n = bn;
   pl.n_tiles = static_cast<int>(ceil_div(N, pl.block_n));
   pl.kb_total = static_cast<int>(ceil_div(K, block_k));

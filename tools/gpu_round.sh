@@ -66,15 +66,20 @@ ncugemm)
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 3 -c 1 -f -o gpurun_out/prof_gemm_last_fwd \
       python tools/gemm_bench.py last_fwd_student > gpurun_out/ncugemm.log 2>&1
   echo "== ncu gemm rc=$?"; tail -n 5 gpurun_out/ncugemm.log; ls -la gpurun_out/*.ncu-rep ;;
+ncufull)
+  ( timeout 300 python bench.py --steps 2 --warmup 3 --graph 0 --overlap 0 --no-cpu-baseline > gpurun_out/ncufull_plain.log 2>&1 ) &&
+  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc_kernel|ce_fused_kernel|ema_kernel|teacher_pass_kernel|weightnorm_fwd_kernel|weightnorm_bwd_kernel" -s 150 -c 24 -f -o gpurun_out/prof_step_kernels \
+      python bench.py --steps 2 --warmup 3 --graph 0 --overlap 0 --no-cpu-baseline > gpurun_out/ncufull.log 2>&1
+  echo "== ncu full rc=$?"; tail -n 3 gpurun_out/ncufull.log; ls -la gpurun_out/prof_step_kernels.ncu-rep ;;
 ncuce)
   ( timeout 300 python bench.py --steps 2 --warmup 3 --graph 0 --no-cpu-baseline > gpurun_out/ncuce_plain.log 2>&1 ) &&
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"ce_fwd_kernel|ce_bwd_kernel|teacher_pass_kernel|ema_kernel|weightnorm_fwd_kernel" -s 25 -c 6 -f -o gpurun_out/prof_loss \
       python bench.py --steps 2 --warmup 3 --graph 0 --no-cpu-baseline > gpurun_out/ncuce.log 2>&1
   echo "== ncu ce rc=$?"; tail -n 5 gpurun_out/ncuce.log; ls -la gpurun_out/*.ncu-rep ;;
 ncu)
-  ( timeout 600 python bench.py --steps 2 --warmup 3 --graph 0 --no-cpu-baseline > gpurun_out/ncu_plain.log 2>&1 ) &&
+  ( timeout 600 python bench.py --steps 2 --warmup 3 --graph 0 --overlap 0 --no-cpu-baseline > gpurun_out/ncu_plain.log 2>&1 ) &&
   timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
-      python bench.py --steps 2 --warmup 3 --graph 0 --no-cpu-baseline > gpurun_out/ncu.log 2>&1
+      python bench.py --steps 2 --warmup 3 --graph 0 --overlap 0 --no-cpu-baseline > gpurun_out/ncu.log 2>&1
   echo "== ncu launches rc=$?"; tail -n 3 gpurun_out/ncu.log; wc -l gpurun_out/launches.csv ;;
 esac
 done
