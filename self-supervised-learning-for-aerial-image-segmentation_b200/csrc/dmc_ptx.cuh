@@ -8,13 +8,16 @@ namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
+// One lane of the (converged) warp.  The compiler understands elect.sync: code predicated on its result runs in exactly
+// one lane, so uniform-register instructions (UTMALDG, UTCHMMA, UTCBAR) inside need no per-lane retry loop.
 __device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
+  uint32_t pred = 0, laneid = 0;
   asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.b32 %0, 1, 0, P;\n\t}"
-      : "=r"(pred));
+      "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, %2;\n\t"
+      "@%%px mov.s32 %1, 1;\n\t"
+      "mov.s32 %0, %%rx;\n\t}"
+      : "+r"(laneid), "+r"(pred) : "r"(0xFFFFFFFFu));
   return pred != 0;
 }
 

@@ -28,6 +28,8 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include "dmc_common.cuh"
 #include "dmc_ptx.cuh"
 
@@ -65,6 +67,7 @@ struct GemmDev {
   const float* stat_bound;      // device scalar b with |D| <= b, or nullptr
   int dbg;                      // DMC_GEMM_FLAGS >> 3 (timing experiments only): 1 = no TMA store issue, 2 = no staging writes, 4 = no TMEM loads
   int tma_store;      // 1: epilogue stores D through smem staging + TMA
+  long long* trace;   // DMC_GEMM_TRACE=1 (debug): clock64() stamps of CTA 0's pipeline events, [8][512]
   // epilogue
   void* D; long long ldd; int out_dtype;
   float* partial;     // split-K partial sums [splits][M][N] (raw accumulators) or nullptr
@@ -168,6 +171,10 @@ __device__ __forceinline__ void epilogue_store_row(const Epilogue& e, float (&ac
   }
 }
 
+__device__ __forceinline__ void trace_at(const GemmDev& p, int kind, int idx) {
+  if (p.trace != nullptr && blockIdx.x == 0 && idx < 512 && (threadIdx.x & 31) == 0) p.trace[kind * 512 + idx] = clock64();
+}
+
 constexpr int kStagingBytesPerWarp = 4096;       // one 32-row x 128-byte box per epilogue warp
 constexpr int kStagingBytes = kEpiWarps * kStagingBytesPerWarp;
 
@@ -216,8 +223,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // warp-uniform for the compiler too
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) trace_at(p, 7, 0);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA0); ptx::prefetch_tensormap(&tmB0);
@@ -241,7 +249,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __syncthreads();
   if constexpr (CG2) ptx::cluster_sync();       // barrier inits and TMEM of both CTAs are in place before any remote signal
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+  if (threadIdx.x == 0) trace_at(p, 7, 1);
 
   // Work enumeration.  Work item w -> (mt = w % m_tiles, nt = (w / m_tiles) % n_tiles, split = w / (m_tiles n_tiles)).
   // round-robin: w = blockIdx.x, +gridDim.x, ...   resident: a contiguous range (same n-tile for consecutive items).
@@ -259,33 +268,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      int prev_nt = -1; uint32_t b_gen = 0;
-      for (int w = w_begin; w < w_end; w += w_step) {
-        const int mt = w % p.m_tiles;
-        const int rest = w / p.m_tiles;
-        const int nt = rest % p.n_tiles;
-        const int sp = rest / p.n_tiles;
-        const int m0 = mt * tile_m + (CG2 ? static_cast<int>(cta_rank) * kBlockM : 0);
-        const int n0 = nt * p.block_n + (CG2 ? static_cast<int>(cta_rank) * (p.block_n >> 1) : 0);
-        const int nb_rows = CG2 ? (p.block_n >> 1) : p.block_n;       // B rows (N extent) this CTA loads
-        const int vk0 = sp * p.vk_per_split;
-        const int vk1 = min(vk0 + p.vk_per_split, p.vk_total);
-        const bool load_b = p.resident && (nt != prev_nt);
-        for (int vk = vk0; vk < vk1; ++vk) {
-          const int pass = vk / p.kb_total;
-          const int k0 = (vk - pass * p.kb_total) * BLOCK_K;
-          const CUtensorMap* ta = (pass == 2) ? &tmA1 : &tmA0;   // passes: hi*hi, hi*lo, lo*hi
-          const CUtensorMap* tb = (pass == 1) ? &tmB1 : &tmB0;
-          uint8_t* sA = tiles + static_cast<size_t>(stage) * stage_bytes;
-          uint8_t* sB = p.resident ? (b_res + static_cast<size_t>(vk) * p.b_bytes) : (sA + a_stage_bytes);
-          uint64_t* bar_b = p.resident ? &bfull_bar[vk] : &full_bar[stage];
-          if (load_b) {                                           // new n-tile: refill slab vk once the MMAs
-            ptx::mbar_wait(&bempty_bar[vk], (b_gen & 1u) ^ 1u);   // that read its previous contents have retired
-            ptx::mbar_arrive_expect_tx(&bfull_bar[vk], p.b_bytes);
-          }
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+    // The WHOLE warp walks the loop (warp-uniform control flow and addresses, so the TMA operands sit in uniform
+    // registers) and one elected lane issues.  A `lane == 0` branch around the loop instead makes the compiler wrap
+    // every UTMALDG in an ELECT / R2UR.BROADCAST retry loop: measured ~800 cycles per k-block in this thread alone.
+    int stage = 0; uint32_t phase = 0;
+    int prev_nt = -1; uint32_t b_gen = 0;
+    int tr = 0;
+    for (int w = w_begin; w < w_end; w += w_step) {
+      const int mt = w % p.m_tiles;
+      const int rest = w / p.m_tiles;
+      const int nt = rest % p.n_tiles;
+      const int sp = rest / p.n_tiles;
+      const int m0 = mt * tile_m + (CG2 ? static_cast<int>(cta_rank) * kBlockM : 0);
+      const int n0 = nt * p.block_n + (CG2 ? static_cast<int>(cta_rank) * (p.block_n >> 1) : 0);
+      const int nb_rows = CG2 ? (p.block_n >> 1) : p.block_n;       // B rows (N extent) this CTA loads
+      const int vk0 = sp * p.vk_per_split;
+      const int vk1 = min(vk0 + p.vk_per_split, p.vk_total);
+      const bool load_b = p.resident && (nt != prev_nt);
+      int pass = vk0 / p.kb_total;                                   // passes: hi*hi, hi*lo, lo*hi
+      int kb = vk0 - pass * p.kb_total;
+      for (int vk = vk0; vk < vk1; ++vk) {
+        const int k0 = kb * BLOCK_K;
+        const CUtensorMap* ta = (pass == 2) ? &tmA1 : &tmA0;
+        const CUtensorMap* tb = (pass == 1) ? &tmB1 : &tmB0;
+        uint8_t* sA = tiles + static_cast<uint32_t>(stage) * stage_bytes;
+        uint8_t* sB = p.resident ? (b_res + static_cast<uint32_t>(vk) * p.b_bytes) : (sA + a_stage_bytes);
+        uint64_t* bar_b = p.resident ? &bfull_bar[vk] : &full_bar[stage];
+        if (load_b) ptx::mbar_wait(&bempty_bar[vk], (b_gen & 1u) ^ 1u);   // new n-tile: the MMAs that read slab vk retired
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+        trace_at(p, 0, tr);
+        if (ptx::elect_one()) {
+          if (load_b) ptx::mbar_arrive_expect_tx(&bfull_bar[vk], p.b_bytes);
           if constexpr (CG2) {
             // Pair: both CTAs fill their own smem but report the bytes to the LEADER's full barrier, which therefore
             // expects both CTAs' stage bytes.
@@ -305,40 +318,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 ptx::tma_load_2d_pair(sA + j * kBoxBytes, ta, lead_full, m0 + j * BOX_MN, k0);
             }
           } else {
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-          if (!p.resident || load_b) {
-            if constexpr (!B_MN) {
-              ptx::tma_load_2d(sB, tb, bar_b, k0, n0);                           // box {BLOCK_K, block_n}
-            } else {
-              for (int j = 0; j < p.block_n / BOX_MN; ++j)
-                ptx::tma_load_2d(sB + j * kBoxBytes, tb, bar_b, n0 + j * BOX_MN, k0);
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+            if (!p.resident || load_b) {
+              if constexpr (!B_MN) {
+                ptx::tma_load_2d(sB, tb, bar_b, k0, n0);                         // box {BLOCK_K, block_n}
+              } else {
+                for (int j = 0; j < p.block_n / BOX_MN; ++j)
+                  ptx::tma_load_2d(sB + j * kBoxBytes, tb, bar_b, n0 + j * BOX_MN, k0);
+              }
             }
-          }
-          for (int h = 0; h <= p.dual; ++h) {                                     // one or two 128-row A tiles
-            uint8_t* sAh = sA + h * kABytes;
-            const int mh = m0 + h * kBlockM;
-            if constexpr (!A_MN) {
-              ptx::tma_load_2d(sAh, ta, &full_bar[stage], k0, mh);              // box {BLOCK_K, 128}
-            } else {
+            for (int h = 0; h <= p.dual; ++h) {                                   // one or two 128-row A tiles
+              uint8_t* sAh = sA + h * kABytes;
+              const int mh = m0 + h * kBlockM;
+              if constexpr (!A_MN) {
+                ptx::tma_load_2d(sAh, ta, &full_bar[stage], k0, mh);            // box {BLOCK_K, 128}
+              } else {
 #pragma unroll
-              for (int j = 0; j < kBlockM / BOX_MN; ++j)                          // boxes {BOX_MN, BLOCK_K}
-                ptx::tma_load_2d(sAh + j * kBoxBytes, ta, &full_bar[stage], mh + j * BOX_MN, k0);
+                for (int j = 0; j < kBlockM / BOX_MN; ++j)                        // boxes {BOX_MN, BLOCK_K}
+                  ptx::tma_load_2d(sAh + j * kBoxBytes, ta, &full_bar[stage], mh + j * BOX_MN, k0);
+              }
             }
           }
-          }
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        if (load_b) { ++b_gen; prev_nt = nt; }
+        __syncwarp();
+        trace_at(p, 1, tr++);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        if (++kb == p.kb_total) { kb = 0; ++pass; }
       }
+      if (load_b) { ++b_gen; prev_nt = nt; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (pair: leader CTA only) =====================
-    if (lane == 0 && cta_rank == 0) {
+    // Same structure: the whole warp walks the loop and waits on the barriers, one elected lane issues the MMAs.
+    if (cta_rank == 0) {
       const uint32_t idesc = ptx::make_instr_desc(kTf32 ? 2u : 1u, A_MN, B_MN, CG2 ? 2 * kBlockM : kBlockM,
                                                   static_cast<uint32_t>(p.block_n));
+      // Shared-memory descriptors: everything but the 14-bit start address is constant; one MMA step advances the address
+      // field by a constant.  K-major: rows of 128 B, 8-row groups 1024 B apart (SBO), 32 B per MMA inside the swizzle
+      // row.  MN-major: boxes of BLOCK_K k-rows x 128 B; LBO = box stride along MN, SBO = 1024 B (8 k-rows), UMMA_K
+      // k-rows = UMMA_K * 128 B per MMA; 32-bit operands use the 32-byte-atom swizzle there (SBO = 512 B).
+      const uint64_t da_base = A_MN ? ptx::make_smem_desc_sw128(0, kBoxBytes, kMnSbo, kMnLayout) : ptx::make_smem_desc_sw128(0, 16, 1024);
+      const uint64_t db_base = B_MN ? ptx::make_smem_desc_sw128(0, kBoxBytes, kMnSbo, kMnLayout) : ptx::make_smem_desc_sw128(0, 16, 1024);
+      constexpr uint32_t kStepA = (A_MN ? UMMA_K * kRowBytes : 32) >> 4;
+      constexpr uint32_t kStepB = (B_MN ? UMMA_K * kRowBytes : 32) >> 4;
+      const uint32_t tiles_addr = ptx::smem_u32(tiles);
+      const uint32_t bres_addr = ptx::smem_u32(b_res);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       int prev_nt = -1; uint32_t b_gen = 0;
+      int tr = 0;
       for (int w = w_begin; w < w_end; w += w_step, ++it) {
         const int rest = w / p.m_tiles;
         const int nt = rest % p.n_tiles;
@@ -352,42 +380,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int acc = p.dual ? 0 : (it & 1);
         const uint32_t acc_phase = p.dual ? (it & 1u) : ((it >> 1) & 1u);
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);      // epilogue has drained this accumulator
+        trace_at(p, 4, it);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccCols);
         for (int vk = vk0; vk < vk1; ++vk) {
           if (new_b) ptx::mbar_wait(&bfull_bar[vk], b_gen & 1u);
           ptx::mbar_wait(&full_bar[stage], phase);              // TMA bytes have landed
+          trace_at(p, 2, tr);
           ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(tiles + static_cast<size_t>(stage) * stage_bytes);
-          const uint32_t b_addr = p.resident ? ptx::smem_u32(b_res + static_cast<size_t>(vk) * p.b_bytes) : (a_addr + a_stage_bytes);
+          if (ptx::elect_one()) {
+            const uint32_t a_addr = tiles_addr + static_cast<uint32_t>(stage) * stage_bytes;
+            const uint32_t b_addr = p.resident ? (bres_addr + static_cast<uint32_t>(vk) * p.b_bytes) : (a_addr + a_stage_bytes);
+            const uint64_t da0 = da_base | static_cast<uint64_t>((a_addr >> 4) & 0x3FFFu);
+            const uint64_t db0 = db_base | static_cast<uint64_t>((b_addr >> 4) & 0x3FFFu);
+            const uint32_t acc0 = (vk > vk0) ? 1u : 0u;
 #pragma unroll
-          for (int k = 0; k < kMmaPerKBlock; ++k) {
-            // K-major: rows of 128 B, 8-row groups 1024 B apart (SBO); advance 32 B per MMA inside the swizzle row.
-            // MN-major: boxes of BLOCK_K k-rows x 128 B; LBO = box stride along MN, SBO = 1024 B (8 k-rows);
-            //           advance UMMA_K k-rows = UMMA_K * 128 B per MMA.
-            //           32-bit operands must use the 32-byte-atom swizzle there (pattern repeats every 4 k-rows: SBO = 512 B).
-            const uint64_t da = A_MN ? ptx::make_smem_desc_sw128(a_addr + k * (UMMA_K * kRowBytes), kBoxBytes, kMnSbo, kMnLayout)
-                                     : ptx::make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? ptx::make_smem_desc_sw128(b_addr + k * (UMMA_K * kRowBytes), kBoxBytes, kMnSbo, kMnLayout)
-                                     : ptx::make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            if constexpr (CG2) ptx::umma_pair<kTf32>(d_tmem, da, db, idesc, (vk > vk0 || k > 0) ? 1u : 0u);
-            else ptx::umma<kTf32>(d_tmem, da, db, idesc, (vk > vk0 || k > 0) ? 1u : 0u);
-            if (p.dual) {                                       // rows 128..255 of the item: same B, second accumulator
-              const uint64_t da1 = A_MN ? ptx::make_smem_desc_sw128(a_addr + kABytes + k * (UMMA_K * kRowBytes), kBoxBytes, kMnSbo, kMnLayout)
-                                        : ptx::make_smem_desc_sw128(a_addr + kABytes + k * 32, 16, 1024);
-              ptx::umma<kTf32>(d_tmem + kAccCols, da1, db, idesc, (vk > vk0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kMmaPerKBlock; ++k) {
+              const uint64_t da = da0 + k * kStepA;
+              const uint64_t db = db0 + k * kStepB;
+              const uint32_t accum = (k > 0) ? 1u : acc0;
+              if constexpr (CG2) ptx::umma_pair<kTf32>(d_tmem, da, db, idesc, accum);
+              else ptx::umma<kTf32>(d_tmem, da, db, idesc, accum);
+              if (p.dual)                                         // rows 128..255 of the item: same B, second accumulator
+                ptx::umma<kTf32>(d_tmem + kAccCols, da + (kABytes >> 4), db, idesc, accum);
+            }
+            if constexpr (CG2) {
+              ptx::umma_commit_pair(&empty_bar[stage]);           // frees the stage in BOTH CTAs when these MMAs retire
+            } else {
+              ptx::umma_commit(&empty_bar[stage]);                // frees the smem stage when these MMAs retire
+              if (last_of_nt) ptx::umma_commit(&bempty_bar[vk]);  // ... and the resident B slab
+            }
+            if (vk + 1 == vk1) {                                  // accumulator complete -> epilogue (pair: both CTAs')
+              if constexpr (CG2) ptx::umma_commit_pair(&tmem_full[acc]);
+              else ptx::umma_commit(&tmem_full[acc]);
             }
           }
-          if constexpr (CG2) {
-            ptx::umma_commit_pair(&empty_bar[stage]);           // frees the stage in BOTH CTAs when these MMAs retire
-          } else {
-            ptx::umma_commit(&empty_bar[stage]);                // frees the smem stage when these MMAs retire
-            if (last_of_nt) ptx::umma_commit(&bempty_bar[vk]);  // ... and the resident B slab
-          }
+          __syncwarp();
+          trace_at(p, 3, tr++);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        if constexpr (CG2) ptx::umma_commit_pair(&tmem_full[acc]);   // accumulator complete -> both CTAs' epilogues
-        else ptx::umma_commit(&tmem_full[acc]);                 // accumulator complete -> epilogue
         if (new_b) { ++b_gen; prev_nt = nt; }
       }
     }
@@ -432,6 +463,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int acc = p.dual ? 0 : (it & 1);
       const uint32_t acc_phase = p.dual ? (it & 1u) : ((it >> 1) & 1u);
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      if (warp == 2) trace_at(p, 5, it);
       ptx::tc_fence_after();
       const int ncols = min(p.block_n, p.N - n0);
       for (int h = 0; h <= p.dual; ++h) {                       // dual-M: drain both accumulators of the item
@@ -618,12 +650,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
       }  // h
+      if (warp == 2) trace_at(p, 6, it);
     }
     if (p.tma_store && lane == 0) ptx::tma_store_wait_all<0>();  // all bulk stores complete before the CTA exits
   }
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) trace_at(p, 7, 2);
   if constexpr (CG2) ptx::cluster_sync();       // the peer may still signal our barriers / the leader still writes our TMEM
   if (warp == 1) {
     ptx::tc_fence_after();
@@ -889,6 +923,13 @@ extern "C" int dmc_gemm(const dmc_gemm_args* a, void* stream) {
   d.stat_row_partials = reinterpret_cast<float2*>(a->stat_row_partials); d.stat_colsum_partials = a->stat_colsum_partials;
   d.stat_bound = a->stat_bound;
   d.dbg = debug_flags() >> 3;
+  static const bool trace_on = (getenv("DMC_GEMM_TRACE") != nullptr);       // debug only: never set in production
+  static long long* trace_dev = nullptr;
+  if (trace_on) {
+    if (trace_dev == nullptr) cudaMalloc(&trace_dev, 8 * 512 * sizeof(long long));
+    cudaMemsetAsync(trace_dev, 0, 8 * 512 * sizeof(long long), st);
+    d.trace = trace_dev;
+  }
   if (a->stat_row_partials != nullptr) {
     DMC_REQUIRE(a->col_scale == nullptr && a->bias == nullptr && a->act == DMC_ACT_NONE && !a->a_mn_major && !a->b_mn_major,
                 "dmc_gemm: fused statistics need a plain epilogue and K-major operands");
@@ -925,6 +966,21 @@ const bool plain = (a->col_scale == nullptr && a->bias == nullptr && a->act == D
 #undef DMC_LAUNCH
 #undef DMC_DISPATCH
   if (rc) return rc;
+  if (trace_on) {
+    static long long h[8 * 512];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
+    const long long t0 = h[7 * 512];
+    fprintf(stderr, "TRACE M=%lld N=%lld K=%lld bn=%d stages=%d resident=%d dual=%d splits=%d grid=%d | setup=%lld end=%lld\n",
+            (long long)a->M, (long long)a->N, (long long)a->K, pl.block_n, pl.stages, pl.resident, pl.dual, pl.splits, grid,
+            h[7 * 512 + 1] - t0, h[7 * 512 + 2] - t0);
+    for (int i = 0; i < 512 && h[2 * 512 + i]; ++i)
+      fprintf(stderr, "  kb%-3d P.empty=%-7lld P.issued=%-7lld M.full=%-7lld M.commit=%-7lld\n", i, h[i] - t0, h[512 + i] - t0,
+              h[2 * 512 + i] - t0, h[3 * 512 + i] - t0);
+    for (int i = 0; i < 512 && h[5 * 512 + i]; ++i)
+      fprintf(stderr, "  tile%-3d M.tmem_empty=%-7lld E.tmem_full=%-7lld E.done=%-7lld\n", i, h[4 * 512 + i] - t0, h[5 * 512 + i] - t0,
+              h[6 * 512 + i] - t0);
+  }
 
   if (pl.splits > 1) {
     Epilogue e{a->col_scale, a->bias, a->alpha, a->act, a->aux, a->ldaux, a->aux_dtype, a->D, a->ldd, a->out_dtype,

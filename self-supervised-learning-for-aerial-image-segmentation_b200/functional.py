@@ -120,10 +120,13 @@ class LinearFn(torch.autograd.Function):
         ctx.h_op, ctx.w_op, ctx.z_in = h_op, w_op, (None if z_in is None else z_in.detach())
         ctx.has_bias = b is not None
         ctx.mark_non_differentiable(z_out)
+        ctx.set_materialize_grads(False)       # no zero-filled [rows, fo] gradient for the non-differentiable z_out
         return h_out, z_out
 
     @staticmethod
     def backward(ctx, dz, _unused):
+        if dz is None:
+            return (None,) * 8
         mode = ctx.mode
         rows, fo, fi = ctx.dims
         sd = store_dtype(mode)

@@ -52,7 +52,7 @@ multi)
   done ;;
 profstep)
   ( timeout 600 python tools/prof_step.py bf16 ) > gpurun_out/prof_step_bf16.txt 2>&1
-  echo "== prof_step rc=$?"; grep -v Warning gpurun_out/prof_step_bf16.txt | tail -45 ;;
+  echo "== prof_step rc=$?"; grep -v Warning gpurun_out/prof_step_bf16.txt | tail -30 ;;
 gemmbench)
   ( timeout 600 python tools/gemm_bench.py ) > gpurun_out/gemm_bench.log 2>&1
   echo "== gemm_bench rc=$?"; cat gpurun_out/gemm_bench.log ;;
@@ -68,9 +68,15 @@ ncugemm)
   echo "== ncu gemm rc=$?"; tail -n 5 gpurun_out/ncugemm.log; ls -la gpurun_out/*.ncu-rep ;;
 ncufull)
   ( timeout 300 python bench.py --steps 2 --warmup 3 --graph 0 --overlap 0 --no-cpu-baseline > gpurun_out/ncufull_plain.log 2>&1 ) &&
-  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc_kernel|ce_fused_kernel|ema_kernel|teacher_pass_kernel|weightnorm_fwd_kernel|weightnorm_bwd_kernel" -s 150 -c 24 -f -o gpurun_out/prof_step_kernels \
+  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc_kernel|ce_fused_kernel|ema_kernel|teacher_pass_kernel|weightnorm_fwd_kernel|weightnorm_bwd_kernel" -s 150 -c 24 -f -o /tmp/prof_step_kernels \
       python bench.py --steps 2 --warmup 3 --graph 0 --overlap 0 --no-cpu-baseline > gpurun_out/ncufull.log 2>&1
-  echo "== ncu full rc=$?"; tail -n 3 gpurun_out/ncufull.log; ls -la gpurun_out/prof_step_kernels.ncu-rep ;;
+  echo "== ncu full rc=$?"; tail -n 3 gpurun_out/ncufull.log | cut -c1-300
+  # the report is too big to travel back whole: export the raw page here, keep the report only if small
+  ncu -i /tmp/prof_step_kernels.ncu-rep --page raw --csv > gpurun_out/prof_step_kernels_raw.csv 2>/dev/null
+  ncu -i /tmp/prof_step_kernels.ncu-rep --page details --csv > gpurun_out/prof_step_kernels_details.csv 2>/dev/null
+  sz=$(stat -c %s /tmp/prof_step_kernels.ncu-rep); echo "report bytes: $sz"
+  if [ "$sz" -lt 40000000 ]; then cp /tmp/prof_step_kernels.ncu-rep gpurun_out/; fi
+  ls -la gpurun_out/ | head -30 ;;
 ncuce)
   ( timeout 300 python bench.py --steps 2 --warmup 3 --graph 0 --no-cpu-baseline > gpurun_out/ncuce_plain.log 2>&1 ) &&
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"ce_fwd_kernel|ce_bwd_kernel|teacher_pass_kernel|ema_kernel|weightnorm_fwd_kernel" -s 25 -c 6 -f -o gpurun_out/prof_loss \

@@ -29,6 +29,17 @@ for ev in prof.events():
         name = name.split("(")[0][:70]
         agg[name] += ev.device_time / N if hasattr(ev, "device_time") else ev.cuda_time / N
         cnt[name] += 1
+# launch order of the LAST profiled step (start time, duration, gap to the previous kernel's end on any stream)
+evs = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and "Memcpy" not in e.name and "Memset" not in e.name],
+             key=lambda e: e.time_range.start)
+per_step = len(evs) // N
+last = evs[-per_step:]
+t0 = last[0].time_range.start
+print(f"## launch order, last step ({per_step} kernels): start_us dur_us name")
+for e in last:
+    nm = e.name.replace("void ", "").replace("dmc::(anonymous namespace)::", "").split("(")[0][:60]
+    print(f"  {e.time_range.start - t0:9.1f} {e.time_range.end - e.time_range.start:8.1f}  {nm}")
+print(f"  step span: {last[-1].time_range.end - t0:.1f} us")
 tot = sum(agg.values())
 print(f"sum of kernel time per step: {tot:.1f} us")
 for n, v in agg.most_common(40):
