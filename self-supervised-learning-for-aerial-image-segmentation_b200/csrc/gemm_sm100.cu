@@ -105,8 +105,17 @@ __device__ __forceinline__ void epilogue_math(const Epilogue& e, float (&acc)[32
     for (int j = 0; j < 32; ++j) acc[j] *= e.alpha;
   }
   if (e.bias != nullptr) {
+    if (n == 32 && (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0) {     // col0 is a multiple of 32: 8 aligned 128-bit loads
+      const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] += __ldg(e.bias + min(col0 + j, e.N - 1));
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = __ldg(b4 + j);
+        acc[4 * j] += b.x; acc[4 * j + 1] += b.y; acc[4 * j + 2] += b.z; acc[4 * j + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] += __ldg(e.bias + min(col0 + j, e.N - 1));
+    }
   }
   if (e.act == DMC_ACT_GELU) {
     if (e.aux != nullptr) {                                  // save the pre-activation for backward
@@ -171,12 +180,127 @@ __device__ __forceinline__ void epilogue_store_row(const Epilogue& e, float (&ac
   }
 }
 
+// Pipeline trace (clock64 stamps of CTA 0): compiled in only with -DDMC_GEMM_TRACE_BUILD (tools/gemm_trace.py); the
+// production kernels carry none of it.
 __device__ __forceinline__ void trace_at(const GemmDev& p, int kind, int idx) {
+#ifdef DMC_GEMM_TRACE_BUILD
   if (p.trace != nullptr && blockIdx.x == 0 && idx < 512 && (threadIdx.x & 31) == 0) p.trace[kind * 512 + idx] = clock64();
+#endif
 }
 
 constexpr int kStagingBytesPerWarp = 4096;       // one 32-row x 128-byte box per epilogue warp
 constexpr int kStagingBytes = kEpiWarps * kStagingBytesPerWarp;
+
+// ---- lean epilogue of one finished accumulator -----------------------------------------------------------------
+// The common case: output through smem staging + TMA store, tile entirely inside N (rows >= M are clipped by the TMA
+// store), no split-K partials.  The generic chunk code below handles everything else; it spends ~9 of 10 instructions on
+// its runtime options, which is what bounded the epilogue (ncu: 745 warp-instructions per tile and warp for 84 useful).
+// A warp drains columns [c_begin, c_end) (a multiple of 64) of its 32 TMEM lanes, 64 columns per step; the TMEM loads
+// of step i+1 are issued before the statistics of step i so their latency hides behind the SFU work.
+template <int EPI, bool OUT_BF16, typename Release>
+__device__ __forceinline__ void epilogue_fast_acc(const GemmDev& p, const CUtensorMap* tmD, const Epilogue& e,
+                                                  uint32_t t_addr, int row0, int lane, int n0, int c_begin, int c_end,
+                                                  uint8_t* buf, uint32_t& n_boxes, bool release_after, Release release,
+                                                  float stat_shift, float& st_l) {
+  const long long row = static_cast<long long>(row0) + lane;
+  const bool row_ok = row < p.M;
+  uint8_t* rowp = buf + lane * 128;
+  const uint32_t sw = static_cast<uint32_t>(lane & 7);
+  uint32_t ra[32], rb[32];
+  ptx::tmem_ld_32x32(t_addr + c_begin, ra);
+  ptx::tmem_ld_32x32(t_addr + c_begin + 32, rb);
+  for (int c = c_begin; c < c_end; c += 64) {
+    const bool last = (c + 64 >= c_end);
+    ptx::tmem_ld_wait();
+    if (last && release_after) release();                     // accumulator fully read: hand it back to the MMA warp
+    float (&va)[32] = reinterpret_cast<float (&)[32]>(ra);
+    float (&vb)[32] = reinterpret_cast<float (&)[32]>(rb);
+    if constexpr (EPI == 0) {
+      if (row_ok) {
+        epilogue_math(e, va, row, n0 + c, 32, true);
+        epilogue_math(e, vb, row, n0 + c + 32, 32, true);
+      }
+    } else {
+      if (e.alpha != 1.0f) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { va[j] *= e.alpha; vb[j] *= e.alpha; }
+      }
+    }
+    if constexpr (OUT_BF16) {
+      // one box: 32 rows x 64 bf16 columns; 16-byte chunk j of row r at r*128 + ((j ^ (r & 7)) << 4)
+      uint32_t pk[32];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        pk[j] = pack_bf16(va[2 * j], va[2 * j + 1]);
+        pk[16 + j] = pack_bf16(vb[2 * j], vb[2 * j + 1]);
+      }
+      if (n_boxes != 0) {                                     // the previous TMA store must have read the buffer
+        if (lane == 0) ptx::tma_store_wait_read<0>();
+        __syncwarp();
+      }
+#pragma unroll
+      for (uint32_t j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      ptx::fence_proxy_async();                               // generic-proxy smem writes -> visible to the TMA engine
+      __syncwarp();
+      if (lane == 0) {
+        ptx::tma_store_2d(tmD, buf, n0 + c, row0);
+        ptx::tma_store_commit();
+      }
+      ++n_boxes;
+      if (!last) {
+        ptx::tmem_ld_32x32(t_addr + c + 64, ra);
+        ptx::tmem_ld_32x32(t_addr + c + 96, rb);
+      }
+      if constexpr (EPI == 2) {                               // statistics of exactly the stored (rounded) values
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          a0 += ex2(fmaf(bf16_lo(pk[j]), p.stat_sc2, -stat_shift));
+          a1 += ex2(fmaf(bf16_hi(pk[j]), p.stat_sc2, -stat_shift));
+          a2 += ex2(fmaf(bf16_lo(pk[j + 1]), p.stat_sc2, -stat_shift));
+          a3 += ex2(fmaf(bf16_hi(pk[j + 1]), p.stat_sc2, -stat_shift));
+        }
+        st_l += (a0 + a1) + (a2 + a3);
+      }
+    } else {
+      // two boxes of 32 rows x 32 fp32 columns through the same staging buffer
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float (&v)[32] = half ? vb : va;
+        if (n_boxes != 0) {
+          if (lane == 0) ptx::tma_store_wait_read<0>();
+          __syncwarp();
+        }
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(rowp + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_store_2d(tmD, buf, n0 + c + 32 * half, row0);
+          ptx::tma_store_commit();
+        }
+        ++n_boxes;
+      }
+      if constexpr (EPI == 2) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          a0 += ex2(fmaf(va[j], p.stat_sc2, -stat_shift));
+          a1 += ex2(fmaf(va[j + 1], p.stat_sc2, -stat_shift));
+          a2 += ex2(fmaf(vb[j], p.stat_sc2, -stat_shift));
+          a3 += ex2(fmaf(vb[j + 1], p.stat_sc2, -stat_shift));
+        }
+        st_l += (a0 + a1) + (a2 + a3);
+      }
+      if (!last) {
+        ptx::tmem_ld_32x32(t_addr + c + 64, ra);
+        ptx::tmem_ld_32x32(t_addr + c + 96, rb);
+      }
+    }
+  }
+}
 
 // EPI 0: full epilogue (column scale / bias / activation / aux).
 // EPI 1: "plain" -- scale by alpha, convert, store; compiled separately so the hot last-layer kernels carry none of
@@ -453,6 +577,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         stat_fixed = (stat_shift < 55.f);
       }
     }
+    // lean path (epilogue_fast_acc) for full tiles stored through TMA; everything else takes the generic chunk code
+    bool fast_ok = p.tma_store && p.partial == nullptr && p.dbg == 0 && c_begin < c_end && ((c_end - c_begin) & 63) == 0;
+    if constexpr (EPI == 0) fast_ok = fast_ok && p.col_scale == nullptr && aux_vec_ok;
+    if constexpr (EPI == 2) fast_ok = fast_ok && stat_fixed && p.stat_colsum_partials == nullptr;
+    const bool out_bf16 = (p.out_dtype == DMC_BF16);
     int it = 0;
     for (int w = w_begin; w < w_end; w += w_step, ++it) {
       const int mt = w % p.m_tiles;
@@ -465,6 +594,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       if (warp == 2) trace_at(p, 5, it);
       ptx::tc_fence_after();
+      if (fast_ok && n0 + p.block_n <= p.N) {
+        auto release = [&]() {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG2) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tmem_empty[acc]), 0));   // leader's barrier
+            else ptx::mbar_arrive(&tmem_empty[acc]);
+          }
+        };
+        for (int h = 0; h <= p.dual; ++h) {
+          const int row0 = mt * tile_m + (CG2 ? static_cast<int>(cta_rank) : h) * kBlockM + q * 32;
+          const uint32_t t_addr = tmem_base + static_cast<uint32_t>((acc + h) * kAccCols) + (static_cast<uint32_t>(q * 32) << 16);
+          float st_l = 0.f;
+          if (out_bf16)
+            epilogue_fast_acc<EPI, true>(p, &tmD, e, t_addr, row0, lane, n0, c_begin, c_end, my_staging, n_boxes, h == p.dual,
+                                         release, stat_shift, st_l);
+          else
+            epilogue_fast_acc<EPI, false>(p, &tmD, e, t_addr, row0, lane, n0, c_begin, c_end, my_staging, n_boxes, h == p.dual,
+                                          release, stat_shift, st_l);
+          if constexpr (EPI == 2) {
+            const long long row = static_cast<long long>(row0) + lane;
+            if (row < p.M) p.stat_row_partials[row * (kColGroups * p.n_tiles) + kColGroups * nt + quarter] = make_float2(stat_shift, st_l);
+          }
+        }
+        if (warp == 2) trace_at(p, 6, it);
+        continue;
+      }
       const int ncols = min(p.block_n, p.N - n0);
       for (int h = 0; h <= p.dual; ++h) {                       // dual-M: drain both accumulators of the item
       const int row0 = mt * tile_m + (CG2 ? static_cast<int>(cta_rank) : h) * kBlockM + q * 32;
