@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdinomc.so")
+LIB_PATH = os.environ.get("DMC_LIB") or os.path.join(_HERE, "libdinomc.so")   # DMC_LIB: debug builds only (tools/gemm_trace.py)
 
 DMC_F32, DMC_BF16 = 0, 1
 ACT_NONE, ACT_GELU, ACT_GELU_BWD = 0, 1, 2

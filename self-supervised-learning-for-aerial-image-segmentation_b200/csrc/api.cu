@@ -1,6 +1,7 @@
 // api.cu -- version, error reporting and device check of libdinomc.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "dmc_common.cuh"
 
@@ -20,6 +21,14 @@ int cuda_status(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return 0;
   set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
   return static_cast<int>(e);
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DMC_PDL");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return on;
 }
 }  // namespace dmc
 

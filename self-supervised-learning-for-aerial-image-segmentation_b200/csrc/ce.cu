@@ -151,6 +151,7 @@ __device__ __forceinline__ void ce_fwd_compute(const CeArgs& a, const CeVec<T, M
 template <typename T, int CT, int GT>
 __global__ void __launch_bounds__(kThreads, 2)
 ce_fwd_kernel(const CeArgs a) {
+  pdl_prologue();
   constexpr int MAXC = CT ? CT : 16, MAXG = GT ? GT : 4;
   const int C = CT ? CT : a.C, G = GT ? GT : a.G;
   const long long b = blockIdx.y;
@@ -232,6 +233,7 @@ ce_fwd_kernel(const CeArgs a) {
 __global__ void __launch_bounds__(1024)
 ce_finalize_kernel(const float2* __restrict__ ws_s, const float* __restrict__ ws_x, long long B, int C, int G, int nchunks,
                    float* __restrict__ s_lse, float* __restrict__ loss) {
+  pdl_prologue();
   __shared__ double red[32];
   double acc = 0.0;
   const long long rows = static_cast<long long>(C) * B;
@@ -315,6 +317,7 @@ __device__ __forceinline__ void ce_bwd_vector(const CeArgs& a, const T* s, const
 template <typename T, int CT, int GT>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 ce_bwd_kernel(const CeArgs a) {
+  pdl_prologue();
   constexpr int MAXC = CT ? CT : 16, MAXG = GT ? GT : 4;
   const int C = CT ? CT : a.C, G = GT ? GT : a.G;
   const long long b = blockIdx.y;
@@ -405,6 +408,7 @@ __device__ __forceinline__ void ce_fused_vector(const CeArgs& a, const T* s, con
 template <typename T, int CT, int GT, bool ALLFAST>
 __global__ void __launch_bounds__(kThreads, DMC_FUSED_MINBLOCKS)
 ce_fused_kernel(const CeArgs a) {
+  pdl_prologue();
   constexpr int MAXC = CT ? CT : 16, MAXG = GT ? GT : 4;
   const int C = CT ? CT : a.C, G = GT ? GT : a.G;
   const long long b = blockIdx.y;
@@ -452,6 +456,7 @@ ce_fused_kernel(const CeArgs a) {
 __global__ void __launch_bounds__(1024)
 ce_finalize_lse_kernel(const float* __restrict__ s_lse, const float* __restrict__ ws_x, long long B, int C, int G, int nchunks,
                        float* __restrict__ loss) {
+  pdl_prologue();
   __shared__ double red[32];
   double acc = 0.0;
   const long long rows = static_cast<long long>(C) * B;
@@ -475,6 +480,7 @@ ce_finalize_lse_kernel(const float* __restrict__ s_lse, const float* __restrict_
 // lse[m] = (max2 + log2(sum)) * ln2 from the GEMM epilogue's per-part (max2, sum) pairs.  One warp per row.
 __global__ void __launch_bounds__(256)
 lse_finalize_kernel(const float2* __restrict__ partials, long long M, int parts, float* __restrict__ lse) {
+  pdl_prologue();
   const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (r >= M) return;
   const int lane = threadIdx.x & 31;
@@ -493,6 +499,7 @@ lse_finalize_kernel(const float2* __restrict__ partials, long long M, int parts,
 template <typename T>
 __global__ void __launch_bounds__(256)
 scale_if_kernel(T* __restrict__ x, long long n, const float* __restrict__ scale, float expected) {
+  pdl_prologue();
   const float sc = __ldg(scale);
   if (sc == expected) return;
   const float f = sc / expected;
@@ -504,28 +511,28 @@ scale_if_kernel(T* __restrict__ x, long long n, const float* __restrict__ scale,
 template <typename T>
 int launch_fused(const CeArgs& a, dim3 grid, cudaStream_t st) {
   const bool allfast = a.vec_ok && (a.K % 4 == 0);
-  if (a.C == 8 && a.G == 2 && allfast) ce_fused_kernel<T, 8, 2, true><<<grid, kThreads, 0, st>>>(a);
-  else if (a.C == 8 && a.G == 2) ce_fused_kernel<T, 8, 2, false><<<grid, kThreads, 0, st>>>(a);
-  else if (a.C == 9 && a.G == 3 && allfast) ce_fused_kernel<T, 9, 3, true><<<grid, kThreads, 0, st>>>(a);
-  else if (a.C == 9 && a.G == 3) ce_fused_kernel<T, 9, 3, false><<<grid, kThreads, 0, st>>>(a);
-  else ce_fused_kernel<T, 0, 0, false><<<grid, kThreads, 0, st>>>(a);
+  if (a.C == 8 && a.G == 2 && allfast) launch_kernel(ce_fused_kernel<T, 8, 2, true>, dim3(grid), dim3(kThreads), 0, st, a);
+  else if (a.C == 8 && a.G == 2) launch_kernel(ce_fused_kernel<T, 8, 2, false>, dim3(grid), dim3(kThreads), 0, st, a);
+  else if (a.C == 9 && a.G == 3 && allfast) launch_kernel(ce_fused_kernel<T, 9, 3, true>, dim3(grid), dim3(kThreads), 0, st, a);
+  else if (a.C == 9 && a.G == 3) launch_kernel(ce_fused_kernel<T, 9, 3, false>, dim3(grid), dim3(kThreads), 0, st, a);
+  else launch_kernel(ce_fused_kernel<T, 0, 0, false>, dim3(grid), dim3(kThreads), 0, st, a);
   DMC_LAUNCH_CHECK("ce_fused_kernel launch");
   return 0;
 }
 
 template <typename T>
 int launch_fwd(const CeArgs& a, dim3 grid, cudaStream_t st) {
-  if (a.C == 8 && a.G == 2) ce_fwd_kernel<T, 8, 2><<<grid, kThreads, 0, st>>>(a);
-  else if (a.C == 9 && a.G == 3) ce_fwd_kernel<T, 9, 3><<<grid, kThreads, 0, st>>>(a);
-  else ce_fwd_kernel<T, 0, 0><<<grid, kThreads, 0, st>>>(a);
+  if (a.C == 8 && a.G == 2) launch_kernel(ce_fwd_kernel<T, 8, 2>, dim3(grid), dim3(kThreads), 0, st, a);
+  else if (a.C == 9 && a.G == 3) launch_kernel(ce_fwd_kernel<T, 9, 3>, dim3(grid), dim3(kThreads), 0, st, a);
+  else launch_kernel(ce_fwd_kernel<T, 0, 0>, dim3(grid), dim3(kThreads), 0, st, a);
   DMC_LAUNCH_CHECK("ce_fwd_kernel launch");
   return 0;
 }
 template <typename T>
 int launch_bwd(const CeArgs& a, dim3 grid, cudaStream_t st) {
-  if (a.C == 8 && a.G == 2) ce_bwd_kernel<T, 8, 2><<<grid, kThreads, 0, st>>>(a);
-  else if (a.C == 9 && a.G == 3) ce_bwd_kernel<T, 9, 3><<<grid, kThreads, 0, st>>>(a);
-  else ce_bwd_kernel<T, 0, 0><<<grid, kThreads, 0, st>>>(a);
+  if (a.C == 8 && a.G == 2) launch_kernel(ce_bwd_kernel<T, 8, 2>, dim3(grid), dim3(kThreads), 0, st, a);
+  else if (a.C == 9 && a.G == 3) launch_kernel(ce_bwd_kernel<T, 9, 3>, dim3(grid), dim3(kThreads), 0, st, a);
+  else launch_kernel(ce_bwd_kernel<T, 0, 0>, dim3(grid), dim3(kThreads), 0, st, a);
   DMC_LAUNCH_CHECK("ce_bwd_kernel launch");
   return 0;
 }
@@ -580,7 +587,7 @@ extern "C" int dmc_ce_fwd(const void* s, int32_t s_dtype, int64_t lds, const voi
   dim3 grid((unsigned)a.nchunks, (unsigned)B);
   rc = (s_dtype == DMC_BF16) ? launch_fwd<__nv_bfloat16>(a, grid, st) : launch_fwd<float>(a, grid, st);
   if (rc) return rc;
-  ce_finalize_kernel<<<1, 1024, 0, st>>>(a.ws_s, a.ws_x, B, C, G, a.nchunks, s_lse, loss);
+  launch_kernel(ce_finalize_kernel, dim3(1), dim3(1024), 0, st, a.ws_s, a.ws_x, B, C, G, a.nchunks, s_lse, loss);
   DMC_LAUNCH_CHECK("ce_finalize_kernel launch");
   return 0;
 }
@@ -613,8 +620,7 @@ extern "C" int dmc_ce_bwd(const void* s, int32_t s_dtype, int64_t lds, const voi
 
 extern "C" int dmc_lse_finalize(const float* row_partials, int64_t M, int64_t parts, float* lse, void* stream) {
   DMC_REQUIRE(row_partials && lse && M > 0 && parts > 0 && parts < (1 << 30), "dmc_lse_finalize: bad arguments");
-  lse_finalize_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const float2*>(row_partials), M, (int)parts, lse);
+  launch_kernel(lse_finalize_kernel, dim3((unsigned)ceil_div(M, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), reinterpret_cast<const float2*>(row_partials), M, (int)parts, lse);
   DMC_LAUNCH_CHECK("lse_finalize_kernel launch");
   return 0;
 }
@@ -646,7 +652,7 @@ extern "C" int dmc_ce_fused(const void* s, int32_t s_dtype, int64_t lds, const v
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   rc = (s_dtype == DMC_BF16) ? launch_fused<__nv_bfloat16>(a, grid, st) : launch_fused<float>(a, grid, st);
   if (rc) return rc;
-  ce_finalize_lse_kernel<<<1, 1024, 0, st>>>(s_lse, a.ws_x, B, C, G, a.nchunks, loss);
+  launch_kernel(ce_finalize_lse_kernel, dim3(1), dim3(1024), 0, st, s_lse, a.ws_x, B, C, G, a.nchunks, loss);
   DMC_LAUNCH_CHECK("ce_finalize_lse_kernel launch");
   return 0;
 }
@@ -656,9 +662,9 @@ extern "C" int dmc_scale_inplace_if(void* x, int32_t dtype, int64_t n, const flo
   DMC_REQUIRE(dtype == DMC_F32 || dtype == DMC_BF16, "dmc_scale_inplace_if: bad dtype");
   const int blocks = kNumSMs * 8;
   if (dtype == DMC_BF16)
-    scale_if_kernel<__nv_bfloat16><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<__nv_bfloat16*>(x), n, scale, expected);
+    launch_kernel(scale_if_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<__nv_bfloat16*>(x), n, scale, expected);
   else
-    scale_if_kernel<float><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<float*>(x), n, scale, expected);
+    launch_kernel(scale_if_kernel<float>, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<float*>(x), n, scale, expected);
   DMC_LAUNCH_CHECK("scale_if_kernel launch");
   return 0;
 }

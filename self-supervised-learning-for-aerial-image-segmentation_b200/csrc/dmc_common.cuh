@@ -30,12 +30,39 @@ int cuda_status(cudaError_t e, const char* what);     // api.cu : 0 if ok else (
     if (e__ != cudaSuccess) return ::dmc::cuda_status(e__, what);      \
   } while (0)
 
+// ---- host side: kernel launch with programmatic dependent launch (PDL) -----------------------
+// Every kernel of the library starts with pdl_prologue(): it lets the NEXT kernel in the stream be scheduled early
+// (griddepcontrol.launch_dependents) and then waits for the PREVIOUS kernel to complete and flush
+// (griddepcontrol.wait) before it touches global memory.  Launched through launch_kernel() with the programmatic
+// stream-serialization attribute, consecutive kernels overlap launch latency, block scheduling and prologues
+// (barrier init, TMEM allocation, tensor-map prefetch) with the tail of their predecessor; the data dependencies are
+// unchanged because every kernel waits before its first global access.  DMC_PDL=0 turns the attribute off (the
+// prologue instructions are then no-ops).  Works under CUDA-graph stream capture (programmatic edges).
+bool pdl_enabled();                                   // api.cu
+#ifdef __CUDACC__
+template <typename... Params, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<Params>(args)...);
+}
+#endif
+
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- device side ----------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+// See launch_kernel(): first statements of every kernel.  No global memory access may precede pdl_prologue().
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() { pdl_trigger(); pdl_wait(); }
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll

@@ -21,6 +21,7 @@ struct EmaChunk {
 
 __global__ void __launch_bounds__(256)
 ema_kernel(const EmaChunk* __restrict__ plan, float m, float omm) {
+  pdl_prologue();
   const EmaChunk c = plan[blockIdx.x];
   float* __restrict__ pk = c.teacher;
   const float* __restrict__ pq = c.student;
@@ -83,8 +84,7 @@ extern "C" int dmc_ema_build_plan(const void* const* teacher_ptrs_host, const vo
 
 extern "C" int dmc_ema_multi_tensor(const void* plan_dev, int64_t n_chunks, float m, float one_minus_m, void* stream) {
   DMC_REQUIRE(plan_dev && n_chunks > 0 && n_chunks < (1ll << 31), "dmc_ema_multi_tensor: bad plan");
-  ema_kernel<<<static_cast<unsigned>(n_chunks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const EmaChunk*>(plan_dev), m, one_minus_m);
+  launch_kernel(ema_kernel, dim3(static_cast<unsigned>(n_chunks)), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const EmaChunk*>(plan_dev), m, one_minus_m);
   DMC_LAUNCH_CHECK("ema_kernel launch");
   return 0;
 }

@@ -28,6 +28,7 @@ __device__ __forceinline__ void st_any(void* p, long long i, int dt, float v) {
 
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const SimtArgs a) {
+  pdl_prologue();
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
@@ -107,7 +108,7 @@ extern "C" int dmc_gemm_simt(const dmc_gemm_args* g, void* stream) {
   a.act = g->act; a.aux = g->aux; a.ldaux = g->ldaux; a.aux_dtype = g->aux_dtype;
   dim3 grid((unsigned)ceil_div(g->N, TN), (unsigned)ceil_div(g->M, TM));
   DMC_REQUIRE(grid.y <= 65535, "dmc_gemm_simt: M too large for this kernel (%lld)", (long long)g->M);
-  gemm_simt_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  launch_kernel(gemm_simt_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), a);
   DMC_LAUNCH_CHECK("gemm_simt_kernel launch");
   return 0;
 }

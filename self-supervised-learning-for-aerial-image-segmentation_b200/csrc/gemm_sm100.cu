@@ -374,6 +374,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if constexpr (CG2) ptx::cluster_sync();       // barrier inits and TMEM of both CTAs are in place before any remote signal
   ptx::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+  // Everything above (barrier init, TMEM allocation, tensor-map prefetch) touched no global memory: it may overlap the
+  // tail of the previous kernel in the stream.  From here on operands are read and outputs written.
+  pdl_prologue();
   if (threadIdx.x == 0) trace_at(p, 7, 1);
 
   // Work enumeration.  Work item w -> (mt = w % m_tiles, nt = (w / m_tiles) % n_tiles, split = w / (m_tiles n_tiles)).
@@ -825,6 +828,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 // Sums the split-K partials and applies the epilogue.  One thread per 4 consecutive columns.
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long M, int N, Epilogue e, const float* alpha_dev) {
+  pdl_prologue();
   const long long groups_per_row = (N + 3) / 4;
   const long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (g >= M * groups_per_row) return;
@@ -990,14 +994,16 @@ int launch_tc2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& 
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     e = cudaLaunchKernelEx(&cfg, kern, a0, a1, b0, b1, td, dev);
     if (e != cudaSuccess) return cuda_status(e, "cudaLaunchKernelEx(gemm_tc_kernel, cluster 2)");
   } else {
-    kern<<<grid, kThreads, smem_bytes, st>>>(a0, a1, b0, b1, td, dev);
+    launch_kernel(kern, dim3(grid), dim3(kThreads), smem_bytes, st, a0, a1, b0, b1, td, dev);
   }
   DMC_LAUNCH_CHECK("gemm_tc_kernel launch");
   return 0;
@@ -1143,7 +1149,7 @@ const bool plain = (a->col_scale == nullptr && a->bias == nullptr && a->act == D
                static_cast<int>(a->N)};
     const long long groups = a->M * ((a->N + 3) / 4);
     const int blocks = static_cast<int>(ceil_div(groups, 256));
-    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(static_cast<const float*>(a->workspace), pl.splits, a->M,
+    launch_kernel(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, st, static_cast<const float*>(a->workspace), pl.splits, a->M,
                                                  static_cast<int>(a->N), e, a->alpha_dev);
     DMC_LAUNCH_CHECK("splitk_reduce_kernel launch");
   }

@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 normalize_fwd_kernel(const void* __restrict__ z, int z_dtype, long long n_rows, int dim, long long ld, float eps,
                      float* __restrict__ zhat_f32, __nv_bfloat16* __restrict__ zhat_bf16, float* __restrict__ zhat_lo,
                      float* __restrict__ inv_den) {
+  pdl_prologue();
   const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= n_rows) return;
   const int lane = threadIdx.x & 31;
@@ -50,6 +51,7 @@ normalize_fwd_kernel(const void* __restrict__ z, int z_dtype, long long n_rows, 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 normalize_bwd_kernel(const float* __restrict__ dzhat, const float* __restrict__ zhat, const float* __restrict__ inv_den,
                      long long n_rows, int dim, float eps, void* __restrict__ dz, int dz_dtype) {
+  pdl_prologue();
   const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= n_rows) return;
   const int lane = threadIdx.x & 31;
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 weightnorm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, long long K, int dim,
                       float* __restrict__ w_f32, float* __restrict__ w_lo, __nv_bfloat16* __restrict__ w_bf16,
                       float* __restrict__ scale, float* __restrict__ inv_vnorm, bool vec_ok, float* __restrict__ gmax) {
+  pdl_prologue();
   const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= K) return;
   const int lane = threadIdx.x & 31;
@@ -134,6 +137,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 weightnorm_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v, const float* __restrict__ scale,
                       const float* __restrict__ inv_vnorm, long long K, int dim, float* __restrict__ dv, float* __restrict__ dg,
                       bool vec_ok) {
+  pdl_prologue();
   const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= K) return;
   const int lane = threadIdx.x & 31;
@@ -167,6 +171,7 @@ weightnorm_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v,
 // gmax = max_k |g_k| (single block; K floats are a few hundred KB at most).
 __global__ void __launch_bounds__(1024)
 absmax_kernel(const float* __restrict__ g, long long K, float* __restrict__ out) {
+  pdl_prologue();
   __shared__ float red[32];
   float m = 0.f;
   for (long long i = threadIdx.x; i < K; i += 1024) m = fmaxf(m, fabsf(g[i]));
@@ -181,6 +186,7 @@ absmax_kernel(const float* __restrict__ g, long long K, float* __restrict__ out)
 
 __global__ void __launch_bounds__(256)
 split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n) {
+  pdl_prologue();
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float v = x[i];
@@ -192,6 +198,7 @@ split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __
 
 __global__ void __launch_bounds__(256)
 cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  pdl_prologue();
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long n4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0) ? n / 4 : 0;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -210,6 +217,7 @@ struct CastBatch {
 };
 __global__ void __launch_bounds__(256)
 cast_bf16_batch_kernel(const CastBatch b) {
+  pdl_prologue();
   const float* __restrict__ x = b.src[blockIdx.y];
   __nv_bfloat16* __restrict__ y = b.dst[blockIdx.y];
   const long long n = b.n[blockIdx.y];
@@ -229,6 +237,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const T* __restrict__ X, long long M, int N, long long ld, int rows_per_split, bool vec_ok,
                       float* __restrict__ partial) {
+  pdl_prologue();
   using Q4 = Quad<T>;
   __shared__ float red[8][32][5];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
@@ -261,6 +270,7 @@ colsum_partial_kernel(const T* __restrict__ X, long long M, int N, long long ld,
 }
 __global__ void __launch_bounds__(256)
 colsum_final_kernel(const float* __restrict__ partial, int splits, int N, float* __restrict__ out) {
+  pdl_prologue();
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= N) return;
   float t = 0.f;
@@ -294,8 +304,7 @@ extern "C" int dmc_normalize_rows_fwd(const void* z, int32_t z_dtype, int64_t n_
   DMC_REQUIRE(n_rows > 0 && dim > 0 && dim < (1 << 30) && ld >= dim, "dmc_normalize_rows_fwd: bad shape n_rows=%lld dim=%lld ld=%lld", (long long)n_rows, (long long)dim, (long long)ld);
   DMC_REQUIRE(z_dtype == DMC_F32 || z_dtype == DMC_BF16, "dmc_normalize_rows_fwd: bad dtype");
   DMC_REQUIRE(zhat_f32 || zhat_bf16, "dmc_normalize_rows_fwd: no output requested");
-  normalize_fwd_kernel<<<(unsigned)ceil_div(n_rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      z, z_dtype, n_rows, (int)dim, ld, eps, zhat_f32, static_cast<__nv_bfloat16*>(zhat_bf16), zhat_lo, inv_den);
+  launch_kernel(normalize_fwd_kernel, dim3((unsigned)ceil_div(n_rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, (cudaStream_t)stream, z, z_dtype, n_rows, (int)dim, ld, eps, zhat_f32, static_cast<__nv_bfloat16*>(zhat_bf16), zhat_lo, inv_den);
   DMC_LAUNCH_CHECK("normalize_fwd_kernel launch");
   return 0;
 }
@@ -305,8 +314,7 @@ extern "C" int dmc_normalize_rows_bwd(const float* dzhat, const float* zhat, con
   DMC_REQUIRE(dzhat && zhat && inv_den && dz, "dmc_normalize_rows_bwd: null pointer");
   DMC_REQUIRE(n_rows > 0 && dim > 0 && dim < (1 << 30), "dmc_normalize_rows_bwd: bad shape");
   DMC_REQUIRE(dz_dtype == DMC_F32 || dz_dtype == DMC_BF16, "dmc_normalize_rows_bwd: bad dtype");
-  normalize_bwd_kernel<<<(unsigned)ceil_div(n_rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      dzhat, zhat, inv_den, n_rows, (int)dim, eps, dz, dz_dtype);
+  launch_kernel(normalize_bwd_kernel, dim3((unsigned)ceil_div(n_rows, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, (cudaStream_t)stream, dzhat, zhat, inv_den, n_rows, (int)dim, eps, dz, dz_dtype);
   DMC_LAUNCH_CHECK("normalize_bwd_kernel launch");
   return 0;
 }
@@ -318,11 +326,10 @@ extern "C" int dmc_weightnorm_fwd(const float* v, const float* g, int64_t K, int
   auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const bool vec_ok = (dim % 4 == 0) && al16(v) && al16(w_f32) && al16(w_lo) && al16(w_bf16);
   if (gmax != nullptr) {
-    absmax_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(g, K, gmax);
+    launch_kernel(absmax_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, g, K, gmax);
     DMC_LAUNCH_CHECK("absmax_kernel launch");
   }
-  weightnorm_fwd_kernel<<<(unsigned)ceil_div(K, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      v, g, K, (int)dim, w_f32, w_lo, static_cast<__nv_bfloat16*>(w_bf16), scale, inv_vnorm, vec_ok, gmax);
+  launch_kernel(weightnorm_fwd_kernel, dim3((unsigned)ceil_div(K, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, (cudaStream_t)stream, v, g, K, (int)dim, w_f32, w_lo, static_cast<__nv_bfloat16*>(w_bf16), scale, inv_vnorm, vec_ok, gmax);
   DMC_LAUNCH_CHECK("weightnorm_fwd_kernel launch");
   return 0;
 }
@@ -333,22 +340,21 @@ extern "C" int dmc_weightnorm_bwd(const float* dw, const float* v, const float* 
   DMC_REQUIRE(K > 0 && dim > 0 && dim < (1 << 30), "dmc_weightnorm_bwd: bad shape");
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const bool vec_ok = (dim % 4 == 0) && al16(dw) && al16(v) && al16(dv);
-  weightnorm_bwd_kernel<<<(unsigned)ceil_div(K, kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      dw, v, scale, inv_vnorm, K, (int)dim, dv, dg, vec_ok);
+  launch_kernel(weightnorm_bwd_kernel, dim3((unsigned)ceil_div(K, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, (cudaStream_t)stream, dw, v, scale, inv_vnorm, K, (int)dim, dv, dg, vec_ok);
   DMC_LAUNCH_CHECK("weightnorm_bwd_kernel launch");
   return 0;
 }
 
 extern "C" int dmc_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
   DMC_REQUIRE(x && hi && lo && n > 0, "dmc_split_tf32: bad arguments");
-  split_tf32_kernel<<<grid_1d(n, 256), 256, 0, (cudaStream_t)stream>>>(x, hi, lo, n);
+  launch_kernel(split_tf32_kernel, dim3(grid_1d(n, 256)), dim3(256), 0, (cudaStream_t)stream, x, hi, lo, n);
   DMC_LAUNCH_CHECK("split_tf32_kernel launch");
   return 0;
 }
 
 extern "C" int dmc_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream) {
   DMC_REQUIRE(x && y && n > 0, "dmc_cast_f32_to_bf16: bad arguments");
-  cast_bf16_kernel<<<grid_1d(n, 1024), 256, 0, (cudaStream_t)stream>>>(x, static_cast<__nv_bfloat16*>(y), n);
+  launch_kernel(cast_bf16_kernel, dim3(grid_1d(n, 1024)), dim3(256), 0, (cudaStream_t)stream, x, static_cast<__nv_bfloat16*>(y), n);
   DMC_LAUNCH_CHECK("cast_bf16_kernel launch");
   return 0;
 }
@@ -364,7 +370,7 @@ extern "C" int dmc_cast_f32_to_bf16_batch(const float* const* srcs_host, void* c
     nmax = ns_host[i] > nmax ? ns_host[i] : nmax;
   }
   dim3 grid((unsigned)grid_1d(nmax, 1024), (unsigned)count);
-  cast_bf16_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(b);
+  launch_kernel(cast_bf16_batch_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, b);
   DMC_LAUNCH_CHECK("cast_bf16_batch_kernel launch");
   return 0;
 }
@@ -386,13 +392,13 @@ extern "C" int dmc_colsum(const void* X, int32_t dtype, int64_t M, int64_t N, in
   const int esz = dtype == DMC_BF16 ? 2 : 4;
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(X) % (4 * esz)) == 0) && ((ld * esz) % (4 * esz) == 0);
   if (dtype == DMC_BF16)
-    colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16*>(X), M, (int)N, ld,
+    launch_kernel(colsum_partial_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, static_cast<const __nv_bfloat16*>(X), M, (int)N, ld,
                                                                                 rows_per_split, vec_ok, static_cast<float*>(workspace));
   else
-    colsum_partial_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const float*>(X), M, (int)N, ld, rows_per_split,
+    launch_kernel(colsum_partial_kernel<float>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, static_cast<const float*>(X), M, (int)N, ld, rows_per_split,
                                                                         vec_ok, static_cast<float*>(workspace));
   DMC_LAUNCH_CHECK("colsum_partial_kernel launch");
-  colsum_final_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, (cudaStream_t)stream>>>(static_cast<const float*>(workspace), splits, (int)N, out);
+  launch_kernel(colsum_final_kernel, dim3((unsigned)ceil_div(N, 256)), dim3(256), 0, (cudaStream_t)stream, static_cast<const float*>(workspace), splits, (int)N, out);
   DMC_LAUNCH_CHECK("colsum_final_kernel launch");
   return 0;
 }

@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2)
 teacher_pass_kernel(const T* __restrict__ t, long long Nt, long long K, long long ld, const float* __restrict__ center,
                     float inv_temp, float2* __restrict__ ws_stats, float* __restrict__ ws_colsum, int rows_per_block,
                     int nchunks, bool vec_ok) {
+  pdl_prologue();
   __shared__ __align__(16) float sm[kWarps][kChunk];  // 16 KiB: per-warp column sums
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.x;
@@ -126,6 +127,7 @@ teacher_pass_kernel(const T* __restrict__ t, long long Nt, long long K, long lon
 __global__ void __launch_bounds__(256)
 teacher_finalize_kernel(const float2* __restrict__ ws_stats, const float* __restrict__ ws_colsum, long long Nt, long long K,
                         int nchunks, int nrb, int row_blocks, float2* __restrict__ row_stats, float* __restrict__ colsum) {
+  pdl_prologue();
   if (static_cast<int>(blockIdx.x) < row_blocks) {
     const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
     if (r >= Nt) return;
@@ -153,6 +155,7 @@ teacher_finalize_kernel(const float2* __restrict__ ws_stats, const float* __rest
 
 __global__ void __launch_bounds__(256)
 center_update_kernel(const float* center_in, float* center_out, const float* __restrict__ colsum, long long K, float count, float mom, float omm) {
+  pdl_prologue();
   const long long k = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (k >= K) return;
   const float bc = __fdiv_rn(colsum[k], count);                        // batch_center / (len * world)
@@ -207,15 +210,15 @@ extern "C" int dmc_teacher_stats_colsum(const void* t, int32_t dtype, int64_t Nt
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid((unsigned)p.nchunks, (unsigned)p.nrb);
   if (dtype == DMC_BF16)
-    teacher_pass_kernel<__nv_bfloat16><<<grid, kWarps * 32, 0, st>>>(static_cast<const __nv_bfloat16*>(t), Nt, K, ld, center, inv_temp,
+    launch_kernel(teacher_pass_kernel<__nv_bfloat16>, dim3(grid), dim3(kWarps * 32), 0, st, static_cast<const __nv_bfloat16*>(t), Nt, K, ld, center, inv_temp,
                                                                      ws_stats, ws_colsum, p.rows_per_block, p.nchunks, vec_ok);
   else
-    teacher_pass_kernel<float><<<grid, kWarps * 32, 0, st>>>(static_cast<const float*>(t), Nt, K, ld, center, inv_temp, ws_stats,
+    launch_kernel(teacher_pass_kernel<float>, dim3(grid), dim3(kWarps * 32), 0, st, static_cast<const float*>(t), Nt, K, ld, center, inv_temp, ws_stats,
                                                              ws_colsum, p.rows_per_block, p.nchunks, vec_ok);
   DMC_LAUNCH_CHECK("teacher_pass_kernel launch");
   const int row_blocks = static_cast<int>(ceil_div(Nt, 8));
   const int col_blocks = static_cast<int>(ceil_div(K, 256));
-  teacher_finalize_kernel<<<row_blocks + col_blocks, 256, 0, st>>>(ws_stats, ws_colsum, Nt, K, p.nchunks, p.nrb, row_blocks,
+  launch_kernel(teacher_finalize_kernel, dim3(row_blocks + col_blocks), dim3(256), 0, st, ws_stats, ws_colsum, Nt, K, p.nchunks, p.nrb, row_blocks,
                                                                    reinterpret_cast<float2*>(row_stats), colsum);
   DMC_LAUNCH_CHECK("teacher_finalize_kernel launch");
   return 0;
@@ -224,7 +227,7 @@ extern "C" int dmc_teacher_stats_colsum(const void* t, int32_t dtype, int64_t Nt
 extern "C" int dmc_center_update(const float* center_in, float* center_out, const float* colsum, int64_t K, float count,
                                  float momentum, float one_minus_momentum, void* stream) {
   DMC_REQUIRE(center_in && center_out && colsum && K > 0 && count > 0.f, "dmc_center_update: bad arguments");
-  center_update_kernel<<<(unsigned)ceil_div(K, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(center_in, center_out, colsum, K, count,
+  launch_kernel(center_update_kernel, dim3((unsigned)ceil_div(K, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), center_in, center_out, colsum, K, count,
                                                                                                  momentum, one_minus_momentum);
   DMC_LAUNCH_CHECK("center_update_kernel launch");
   return 0;
@@ -237,8 +240,7 @@ extern "C" int dmc_teacher_finalize(const float* row_partials, const float* cols
               "dmc_teacher_finalize: bad shape");
   const int row_blocks = static_cast<int>(ceil_div(Nt, 8));
   const int col_blocks = static_cast<int>(ceil_div(K, 256));
-  teacher_finalize_kernel<<<row_blocks + col_blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const float2*>(row_partials), colsum_partials, Nt, K, (int)parts, (int)row_groups, row_blocks,
+  launch_kernel(teacher_finalize_kernel, dim3(row_blocks + col_blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), reinterpret_cast<const float2*>(row_partials), colsum_partials, Nt, K, (int)parts, (int)row_groups, row_blocks,
       reinterpret_cast<float2*>(row_stats), colsum);
   DMC_LAUNCH_CHECK("teacher_finalize_kernel launch");
   return 0;

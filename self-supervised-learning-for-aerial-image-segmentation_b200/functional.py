@@ -42,6 +42,73 @@ def _current_loss():
     return _loss_ref() if _loss_ref is not None else None
 
 
+# ---------------------------------------------------------------------------------------------------------
+# Auxiliary stream.  The step alternates tensor-bound kernels (the MLP GEMMs: one 320-thread CTA per SM, most
+# of the register file and shared memory, little HBM traffic) with HBM-bound streaming kernels that do not
+# depend on them: the weight-norm materialisation W = g v/||v|| of the last layer (reads 64 MiB, needed only by
+# the last GEMM) and the bias-gradient column sums of the backward pass.  Those run on a second stream, forked
+# from and joined back into the caller's stream with events, so that their 256-thread blocks (32 registers, no
+# shared memory) share the SMs with the GEMM CTAs.  Works eagerly and inside CUDA-graph capture.
+# ---------------------------------------------------------------------------------------------------------
+aux_overlap = True
+_aux_streams = {}
+
+
+def _aux_stream(device, cur):
+    key = (torch.device(device).index, cur.cuda_stream)
+    st = _aux_streams.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _aux_streams[key] = st
+    return st
+
+
+class _AuxRegion:
+    """with _AuxRegion(dev) as r: kernels launched inside run on the auxiliary stream after everything already
+    queued on the caller's stream; r.join(*tensors) makes the caller's stream wait for them."""
+
+    def __init__(self, device):
+        self.cur = torch.cuda.current_stream(device)
+        self.aux = _aux_stream(device, self.cur)
+        self.ctx = None
+        self.event = None
+
+    def __enter__(self):
+        self.aux.wait_stream(self.cur)
+        self.ctx = torch.cuda.stream(self.aux)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        self.event = torch.cuda.Event()
+        self.event.record(self.aux)
+        self.ctx.__exit__(*exc)
+        return False
+
+    def join(self, *tensors):
+        self.cur.wait_event(self.event)
+        for t in tensors:
+            if t is not None:
+                t.record_stream(self.cur)
+
+
+def last_layer_weights(mode, g, v, dim_in):
+    """The weight-normed last-layer operand W = g v/||v|| (utils/vision_transformer.py:279) in the representation
+    `mode` needs, plus scale = g/||v||, 1/||v|| and the device scalar max|g|.  With `aux_overlap` the kernel runs on
+    the auxiliary stream; the returned record carries the region to join before the first use."""
+    K = v.shape[0]
+    mode = resolve_mode(mode, dim_in, K)
+    kind = {"bf16": "bf16", "fp32": "tf32x3", "fp32_simt": "f32"}[mode]
+    region = None
+    if aux_overlap:
+        region = _AuxRegion(v.device)
+        with region:
+            w, w_lo, scale, inv_vnorm = ops.weightnorm_fwd(v.detach(), g.detach().reshape(-1), kind)
+    else:
+        w, w_lo, scale, inv_vnorm = ops.weightnorm_fwd(v.detach(), g.detach().reshape(-1), kind)
+    return dict(mode=mode, wop=Operand(w, w_lo), scale=scale, inv_vnorm=inv_vnorm, gmax=ops.last_gmax[0], region=region)
+
+
 class Operand:
     """A GEMM operand in the representation a mode needs: bf16 tensor, (hi, lo) TF32 pair, or plain fp32."""
     __slots__ = ("main", "lo")
@@ -138,15 +205,25 @@ class LinearFn(torch.autograd.Function):
                 # wgrad: dW[fo,fi] = dz^T . h_in   (both operands MN-major straight from their row-major storage)
                 dW = mm(mode, d, ctx.h_op, fo, fi, rows, a_mn=True, b_mn=True, out_dtype=torch.float32, tag="gemm_mlp_wgrad")
                 ops.mark_ready(dW)
+            region = None
             if ctx.has_bias and ctx.needs_input_grad[4]:
-                db = ops.colsum(d_full)
-                ops.mark_ready(db)
+                if aux_overlap:          # HBM-bound column sum next to the tensor-bound wgrad / dgrad of this layer
+                    region = _AuxRegion(d_full.device)
+                    with region:
+                        db = ops.colsum(d_full)
+                    d_full.record_stream(region.aux)
+                else:
+                    db = ops.colsum(d_full)
+                    ops.mark_ready(db)
             if ctx.z_in is not None:
                 # dgrad with gelu'(z_in) fused: what flows upstream is already dL/dz_in
                 d_in = mm(mode, d, ctx.w_op, rows, fi, fo, b_mn=True, out_dtype=sd, act=L.ACT_GELU_BWD, aux=ctx.z_in,
                           tag="gemm_mlp_dgrad")
             elif ctx.needs_input_grad[1]:
                 d_in = mm(mode, d, ctx.w_op, rows, fi, fo, b_mn=True, out_dtype=torch.float32, tag="gemm_mlp_dgrad")
+            if region is not None:
+                region.join(db)
+                ops.mark_ready(db)
         return None, d_in, None, dW, db, None, None, None
 
 
@@ -169,23 +246,23 @@ class NormLastLayerFn(torch.autograd.Function):
     (utils/vision_transformer.py:292-293, :279).  forward(mode, z, weight_g, weight_v) -> logits."""
 
     @staticmethod
-    def forward(ctx, mode, z, g, v):
+    def forward(ctx, mode, z, g, v, prepared=None):
         rows, dim = z.shape
         K = v.shape[0]
         mode = resolve_mode(mode, dim, K)
+        if prepared is None or prepared["mode"] != mode:
+            prepared = last_layer_weights(mode, g, v, dim)
         zhat, zhat_bf16, inv_den = ops.normalize_rows_fwd(z.detach(), want_bf16=(mode == "bf16"))
         if mode == "bf16":
             zop = Operand(zhat_bf16)
-            w, _, scale, inv_vnorm = ops.weightnorm_fwd(v.detach(), g.detach().reshape(-1), "bf16")
-            wop = Operand(w)
         elif mode == "fp32":
             zop = prep(zhat, mode)
-            w_hi, w_lo, scale, inv_vnorm = ops.weightnorm_fwd(v.detach(), g.detach().reshape(-1), "tf32x3")
-            wop = Operand(w_hi, w_lo)
         else:
             zop = Operand(zhat)
-            w, _, scale, inv_vnorm = ops.weightnorm_fwd(v.detach(), g.detach().reshape(-1), "f32")
-            wop = Operand(w)
+        wop, scale, inv_vnorm, gmax = prepared["wop"], prepared["scale"], prepared["inv_vnorm"], prepared["gmax"]
+        if prepared["region"] is not None:           # weights were materialised on the auxiliary stream: join it
+            prepared["region"].join(wop.main, wop.lo, scale, inv_vnorm, gmax)
+            prepared["region"] = None
         who = "student" if any(ctx.needs_input_grad) else "teacher"
         global last_stats
         last_stats = None
@@ -198,7 +275,7 @@ class NormLastLayerFn(torch.autograd.Function):
                 stats = None
             elif who == "student":
                 stats = dict(kind="student", scale=1.0 / loss_mod.student_temp, center=None, row_partials=rp,
-                             bound=ops.last_gmax[0])
+                             bound=gmax)
             else:
                 loss_mod.sync_center()
                 cen = loss_mod.center
@@ -236,7 +313,7 @@ class NormLastLayerFn(torch.autograd.Function):
                 # dgrad: contraction over out_dim (split-K), W read MN-major from its [K,dim] storage
                 dzhat = mm(mode, d, ctx.wop, rows, dim, K, b_mn=True, out_dtype=torch.float32, tag="gemm_last_dgrad")
                 dz = ops.normalize_rows_bwd(dzhat, zhat, inv_den)
-        return None, dz, dg, dv
+        return None, dz, dg, dv, None
 
 
 class DinoLossFn(torch.autograd.Function):

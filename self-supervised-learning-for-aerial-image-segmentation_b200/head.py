@@ -164,13 +164,17 @@ class DINOHead(nn.Module):
                 # BatchNorm1d / SyncBatchNorm stay torch modules (reference option, off by default);
                 # the weight-normed last layer below is still ours.
                 z = self.mlp(x.float())
+                prepared = None
             else:
                 linears = [self.mlp] if isinstance(self.mlp, nn.Linear) else [m for m in self.mlp if isinstance(m, nn.Linear)]
                 wb = []
                 for lin in linears:
                     wb += [lin.weight, lin.bias]
+                # the last layer's weight-norm materialisation does not depend on the MLP: start it first (auxiliary stream)
+                prepared = Fn.last_layer_weights(mode, self.last_layer.weight_g, self.last_layer.weight_v,
+                                                 self.last_layer.in_features)
                 z = Fn.mlp_forward(mode, x, wb)
-            out = Fn.NormLastLayerFn.apply(mode, z, self.last_layer.weight_g, self.last_layer.weight_v)
+            out = Fn.NormLastLayerFn.apply(mode, z, self.last_layer.weight_g, self.last_layer.weight_v, prepared)
             if Fn.last_stats is not None:       # statistics the GEMM epilogue produced for dinomc_b200.DINOLoss
                 out._dmc_stats = Fn.last_stats
                 Fn.last_stats = None

@@ -20,7 +20,11 @@ if os.environ.get("DMC_GEMM_TRACE_CHILD"):
 
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
 vals = (args + ["0"] * 7)[:7]
-env = dict(os.environ, DMC_GEMM_TRACE="1", DMC_GEMM_TRACE_CHILD="1")
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+trace_lib = os.path.join(root, "self-supervised-learning-for-aerial-image-segmentation_b200", "libdinomc_trace.so")
+if not os.path.isfile(trace_lib):
+    sys.exit("build the trace library first: DMC_TRACE=1 ./build.sh")
+env = dict(os.environ, DMC_GEMM_TRACE="1", DMC_GEMM_TRACE_CHILD="1", DMC_LIB=trace_lib)
 r = subprocess.run([sys.executable, __file__] + vals, env=env, capture_output=True, text=True)
 blocks = r.stderr.split("TRACE ")
 if len(blocks) < 3:
