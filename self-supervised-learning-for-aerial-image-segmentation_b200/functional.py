@@ -67,14 +67,21 @@ class _AuxRegion:
     """with _AuxRegion(dev) as r: kernels launched inside run on the auxiliary stream after everything already
     queued on the caller's stream; r.join(*tensors) makes the caller's stream wait for them."""
 
-    def __init__(self, device):
+    def __init__(self, device, fork_now=False):
         self.cur = torch.cuda.current_stream(device)
         self.aux = _aux_stream(device, self.cur)
         self.ctx = None
         self.event = None
+        self.fork_event = None
+        if fork_now:             # depend on what is queued on the caller's stream NOW, even if entered later
+            self.fork_event = torch.cuda.Event()
+            self.fork_event.record(self.cur)
 
     def __enter__(self):
-        self.aux.wait_stream(self.cur)
+        if self.fork_event is not None:
+            self.aux.wait_event(self.fork_event)
+        else:
+            self.aux.wait_stream(self.cur)
         self.ctx = torch.cuda.stream(self.aux)
         self.ctx.__enter__()
         return self
@@ -232,10 +239,22 @@ def mlp_forward(mode, x, wb):
     n = len(wb) // 2
     mode = resolve_mode(mode, x.shape[1], *[d for li in range(n) for d in wb[2 * li].shape])
     pre = None
-    if mode == "bf16":           # all bf16 operand copies of this forward (features + weights) in one launch
-        pre = [Operand(t) for t in ops.cast_bf16_batch([x.detach()] + [wb[2 * li].detach() for li in range(n)])]
+    region = None
+    if mode == "bf16":
+        # bf16 operand copies of this forward: features + first weight in one launch on this stream; the later
+        # layers' weights (not needed until the first GEMM has run) in a second launch on the auxiliary stream
+        if aux_overlap and n > 1:
+            first = ops.cast_bf16_batch([x.detach(), wb[0].detach()])
+            region = _AuxRegion(x.device)
+            with region:
+                rest = ops.cast_bf16_batch([wb[2 * li].detach() for li in range(1, n)])
+            pre = [Operand(t) for t in first + rest]
+        else:
+            pre = [Operand(t) for t in ops.cast_bf16_batch([x.detach()] + [wb[2 * li].detach() for li in range(n)])]
     h, z = x, None
     for li in range(n):
+        if li == 1 and region is not None:
+            region.join(*[o.main for o in pre[2:]])
         h, z = LinearFn.apply(mode, h, z, wb[2 * li], wb[2 * li + 1], pre[0] if (pre and li == 0) else None,
                               pre[1 + li] if pre else None, li < n - 1)
     return h
@@ -299,20 +318,32 @@ class NormLastLayerFn(torch.autograd.Function):
             dlogits = dlogits.to(store_dtype(mode))
         d = prep(dlogits, mode) if mode != "bf16" else Operand(ops._rows2d(dlogits))
         dz = dg = dv = None
+        region = None
         with ops.backward_cap():
             if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
                 # wgrad first: dW[K,dim] = dlogits^T . zhat (both MN-major).  dv is the largest gradient of the step
                 # (K x 256 fp32); marking it ready here lets its all-reduce overlap the dgrad and the MLP backward.
                 dw = mm(mode, d, ctx.zop, K, dim, rows, a_mn=True, b_mn=True, out_dtype=torch.float32, tag="gemm_last_wgrad")
-                dv, dg = ops.weightnorm_bwd(dw, v, scale, inv_vnorm, want_dg=ctx.needs_input_grad[2])
-                if not ctx.needs_input_grad[3]:
-                    dv = None
+                if aux_overlap:          # streaming pass on the auxiliary stream: the dgrad GEMM does not wait for it
+                    region = _AuxRegion(dw.device)
+                    with region:
+                        dv, dg = ops.weightnorm_bwd(dw, v, scale, inv_vnorm, want_dg=ctx.needs_input_grad[2])
+                        if ctx.needs_input_grad[3]:
+                            ops.mark_ready(dv)
+                    dw.record_stream(region.aux)
                 else:
-                    ops.mark_ready(dv)
+                    dv, dg = ops.weightnorm_bwd(dw, v, scale, inv_vnorm, want_dg=ctx.needs_input_grad[2])
+                    if ctx.needs_input_grad[3]:
+                        ops.mark_ready(dv)
             if ctx.needs_input_grad[1]:
                 # dgrad: contraction over out_dim (split-K), W read MN-major from its [K,dim] storage
                 dzhat = mm(mode, d, ctx.wop, rows, dim, K, b_mn=True, out_dtype=torch.float32, tag="gemm_last_dgrad")
+            if ctx.needs_input_grad[1]:
                 dz = ops.normalize_rows_bwd(dzhat, zhat, inv_den)
+            if region is not None:
+                region.join(dv, dg)
+            if not ctx.needs_input_grad[3]:
+                dv = None
         return None, dz, dg, dv, None
 
 

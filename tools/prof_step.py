@@ -13,14 +13,21 @@ import bench
 mode = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 w = dict(bench.WORKLOADS["cfg2"])
 dev = torch.device("cuda", 0)
+import dinomc_b200 as D
+D.set_teacher_overlap(True)
 step = bench.Step(w, mode, 0, 1, dev)
 for _ in range(5):
     step.run()
 torch.cuda.synchronize()
+use_graph = "--eager" not in sys.argv
+run = D.StepGraph(step.run, warmup=3).replay if use_graph else step.run
+for _ in range(3):
+    run()
+torch.cuda.synchronize()
 N = 10
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     for _ in range(N):
-        step.run()
+        run()
     torch.cuda.synchronize()
 agg, cnt = collections.Counter(), collections.Counter()
 for ev in prof.events():
@@ -38,7 +45,7 @@ t0 = last[0].time_range.start
 print(f"## launch order, last step ({per_step} kernels): start_us dur_us name")
 for e in last:
     nm = e.name.replace("void ", "").replace("dmc::(anonymous namespace)::", "").split("(")[0][:60]
-    print(f"  {e.time_range.start - t0:9.1f} {e.time_range.end - e.time_range.start:8.1f}  {nm}")
+    print(f"  {e.time_range.start - t0:9.1f} {e.time_range.end - e.time_range.start:8.1f}  s{getattr(e, 'stream', getattr(e, 'device_resource_id', '?'))}  {nm}")
 print(f"  step span: {last[-1].time_range.end - t0:.1f} us")
 tot = sum(agg.values())
 print(f"sum of kernel time per step: {tot:.1f} us")
