@@ -287,7 +287,28 @@ def cpu_baseline(w, sample_B, steps, warmup):
                 ms_per_step=med * 1e3)
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: libraries (NCCL prints its version banner on stdout) write to stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -333,7 +354,7 @@ def main():
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        _emit(line)
         return
 
     import torch.distributed as dist
@@ -456,7 +477,7 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
                 "launch_mode": "cuda_graph" if use_graph else "eager", "teacher_overlap": bool(args.overlap), "roofline": roofline, "cpu_baseline": cb,
                 "ema_params": step.P, "ema_tensors": step.n_tensors}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         # leave without tearing NCCL down: destroying communicators that CUDA graphs still reference can hang
         torch.cuda.synchronize()

@@ -46,6 +46,13 @@ int dmc_version(void);
 const char* dmc_last_error_string(void);
 /* 0 if device `device` is an sm_100 part this library can run on, else an error. */
 int dmc_device_check(int device);
+/* Programmatic dependent launch.  Every kernel of the library begins with griddepcontrol.launch_dependents +
+ * griddepcontrol.wait, and by default is launched with the programmatic-stream-serialization attribute so that
+ * its launch latency and prologue overlap the tail of the previous kernel on the stream (data dependencies are
+ * unchanged: no kernel touches global memory before the wait).  dmc_set_pdl(0) launches without the attribute,
+ * e.g. while NCCL kernels share the SMs; the environment variable DMC_PDL=0 sets the initial value.  Returns the
+ * previous setting. */
+int dmc_set_pdl(int enabled);
 
 /* ---------------------------------------------------------------------------------------------
  * GEMM:  D[M,N] = epilogue( sum_k A(m,k) * B(n,k) ),  fp32 accumulation.

@@ -42,6 +42,7 @@ SIGNATURES = {
     "dmc_version": (C.c_int, []),
     "dmc_last_error_string": (C.c_char_p, []),
     "dmc_device_check": (C.c_int, [C.c_int]),
+    "dmc_set_pdl": (C.c_int, [C.c_int]),
     "dmc_gemm_workspace_bytes": (sz, [i64, i64, i64, i32]),
     "dmc_gemm_stats_parts": (i64, [i64]),
     "dmc_gemm": (C.c_int, [C.POINTER(GemmArgs), vp]),

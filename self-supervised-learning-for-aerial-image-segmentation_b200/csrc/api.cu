@@ -23,18 +23,29 @@ int cuda_status(cudaError_t e, const char* what) {
   return static_cast<int>(e);
 }
 
-bool pdl_enabled() {
-  static const bool on = [] {
+namespace {
+int& pdl_flag() {
+  static int on = [] {
     const char* e = getenv("DMC_PDL");
-    return e == nullptr || atoi(e) != 0;
+    return (e == nullptr || atoi(e) != 0) ? 1 : 0;
   }();
   return on;
 }
+}  // namespace
+
+bool pdl_enabled() { return pdl_flag() != 0; }
 }  // namespace dmc
 
 extern "C" int dmc_version(void) { return DMC_VERSION; }
 
 extern "C" const char* dmc_last_error_string(void) { return dmc::g_err; }
+
+extern "C" int dmc_set_pdl(int enabled) {
+  int& f = dmc::pdl_flag();
+  const int prev = f;
+  f = enabled ? 1 : 0;
+  return prev;
+}
 
 extern "C" int dmc_device_check(int device) {
   cudaDeviceProp prop;

@@ -51,6 +51,8 @@ def _current_loss():
 # shared memory) share the SMs with the GEMM CTAs.  Works eagerly and inside CUDA-graph capture.
 # ---------------------------------------------------------------------------------------------------------
 aux_overlap = True
+grad_exchange_active = False     # set by GradAllReduce: the last layer's dv (64 MiB, the largest all-reduce of the step) must
+                                 # then be final as early as possible, so its weight-norm backward stays in front of the dgrad
 _aux_streams = {}
 
 
@@ -324,7 +326,7 @@ class NormLastLayerFn(torch.autograd.Function):
                 # wgrad first: dW[K,dim] = dlogits^T . zhat (both MN-major).  dv is the largest gradient of the step
                 # (K x 256 fp32); marking it ready here lets its all-reduce overlap the dgrad and the MLP backward.
                 dw = mm(mode, d, ctx.zop, K, dim, rows, a_mn=True, b_mn=True, out_dtype=torch.float32, tag="gemm_last_wgrad")
-                if aux_overlap:          # streaming pass on the auxiliary stream: the dgrad GEMM does not wait for it
+                if aux_overlap and not grad_exchange_active:   # streaming pass on the auxiliary stream: the dgrad GEMM does not wait for it
                     region = _AuxRegion(dw.device)
                     with region:
                         dv, dg = ops.weightnorm_bwd(dw, v, scale, inv_vnorm, want_dg=ctx.needs_input_grad[2])
