@@ -907,7 +907,8 @@ struct Plan {
 };
 
 // DMC_GEMM_FLAGS (debug / A-B measurements): bit 0 = no TMA-store epilogue, bit 1 = no B-resident schedule,
-// bit 2 = no dual-M work items, bits 3-5 = epilogue ablations (timing only), bit 6 = use CTA pairs (cta_group::2) where M > 128.
+// bit 2 = no dual-M work items, bits 3-5 = epilogue ablations (timing only), bit 6 = use CTA pairs (cta_group::2) where M > 128,
+// bit 8 = no CTA pairs for long contractions.
 int debug_flags() {
   static int flags = -1;
   if (flags < 0) {
@@ -927,7 +928,11 @@ Plan make_plan(int64_t M, int64_t N, int64_t K, int in_dtype, bool three_pass, i
   // CTA pairs (cta_group::2): 256-row items, half a B tile per CTA.  Correct in every layout (tests run both), but on
   // these shapes measured slower than the single-CTA schedule (8192^3: 1.11 vs 1.43 PFLOP/s), so it is opt-in:
   // DMC_GEMM_FLAGS bit 6.
-  pl.cg2 = (M > kBlockM && (debug_flags() & 64)) ? 1 : 0;
+  // Exception: very long contractions with few output tiles (the last layer's dgrad: 2048 x 256 x 65536).  There the pair
+  // halves the split-K partial traffic (9 instead of 18 splits for the same 144 CTAs) and the smem reads per MMA:
+  // measured 84 -> 76 us.  DMC_GEMM_FLAGS bit 8 disables it.
+  const bool long_k = (K >= 32768 && N <= 256 && !(debug_flags() & 256));
+  pl.cg2 = (M > kBlockM && ((debug_flags() & 64) || long_k)) ? 1 : 0;
   const int units = pl.cg2 ? kNumSMs / 2 : kNumSMs;                 // schedulable units: CTA pairs or CTAs
   const int64_t mt = ceil_div(M, pl.cg2 ? 2 * kBlockM : kBlockM);
   int bn = N > 128 ? 256 : ((N > 64 || pl.cg2) ? 128 : 64);
@@ -1084,7 +1089,7 @@ extern "C" int dmc_gemm(const dmc_gemm_args* a, void* stream) {
   d.stat_sc2 = a->stat_scale * 1.4426950408889634f; d.stat_center = a->stat_center;
   d.stat_row_partials = reinterpret_cast<float2*>(a->stat_row_partials); d.stat_colsum_partials = a->stat_colsum_partials;
   d.stat_bound = a->stat_bound;
-  d.dbg = debug_flags() >> 3;
+  d.dbg = (debug_flags() >> 3) & 7;
   static const bool trace_on = (getenv("DMC_GEMM_TRACE") != nullptr);       // debug only: never set in production
   static long long* trace_dev = nullptr;
   if (trace_on) {
