@@ -2,7 +2,9 @@
 
 Every libdinomc entry point only enqueues work on the caller's stream, never synchronises and never
 allocates (scratch comes from torch's pool through `ops.workspace`), so a step built from the drop-in
-modules -- forward, loss, backward, `ema_update_` -- is capturable as is.  Replaying the graph removes the
+modules -- forward, loss, backward, `ema_update_` -- is capturable as is.  State that the eager modules carry by
+re-binding (DINOLoss.center, main_dino_mc.py:473) is written back in place at the end of the captured step, so
+consecutive replays evolve it exactly like consecutive eager steps (tests/test_gpu_modules.py).  Replaying the graph removes the
 per-launch host cost (~50 launches per step), which is what bounds the eager path.
 
     step = dinomc_b200.StepGraph(lambda: run_one_step(static_inputs))   # warm-up + capture
@@ -29,8 +31,10 @@ class StepGraph:
         from .loss import drop_pending_events
         drop_pending_events()                   # everything has completed: no stale cross-stream events into the capture
         self.graph = torch.cuda.CUDAGraph()
+        from .loss import commit_captured_centers
         with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
             self.out = fn()
+            commit_captured_centers()           # DINOLoss.center: new value back into the buffer the step reads
         torch.cuda.synchronize()
         drop_pending_events()                   # events recorded inside the capture are not usable outside it
 

@@ -28,6 +28,30 @@ def drop_pending_events():
         m._center_event = None
 
 
+# (module, center tensor at the start of the captured step): see commit_captured_centers
+_capture_commits = []
+
+
+def commit_captured_centers():
+    """Called by StepGraph at the END of the captured step (still inside the capture).  The reference rebinds
+    `self.center` to a new tensor every step (main_dino_mc.py:473), which a replayed graph cannot express: its kernels
+    read and write fixed addresses.  So inside a capture the step's new center is copied back, after the backward pass
+    (which may still read the old values), into the buffer the step READ its center from, and the module is re-bound
+    to that buffer: every replay then sees the center the previous replay left, exactly like the eager loop."""
+    done = set()
+    for mod, persistent in _capture_commits:
+        if id(mod) in done:
+            continue
+        done.add(id(mod))
+        mod.sync_center()                       # an asynchronous exchange must have produced the new center
+        new = mod.center
+        if new.data_ptr() != persistent.data_ptr():
+            with torch.no_grad():
+                persistent.copy_(new)
+            mod.center = persistent
+    _capture_commits.clear()
+
+
 def set_async_center(enabled: bool):
     """Multi-GPU only.  When enabled, the center exchange (column-sum all-reduce + EMA, main_dino_mc.py:468-473)
     runs on a side stream and the next `DINOLoss.forward` waits for it, taking the latency-bound 256 KiB
@@ -104,6 +128,8 @@ class DINOLoss(nn.Module):
 
     @torch.no_grad()
     def _update_center_from_colsum(self, colsum, n_rows):
+        if torch.cuda.is_current_stream_capturing() and not any(m is self for m, _ in _capture_commits):
+            _capture_commits.append((self, self.center))
         world = 1
         if dist.is_available() and dist.is_initialized():
             world = dist.get_world_size()

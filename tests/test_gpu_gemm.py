@@ -224,3 +224,85 @@ print("WORST", worst)
     assert r.returncode == 0, r.stderr[-2000:]
     worst = float(r.stdout.strip().split("WORST")[-1])
     assert worst < 2e-5
+
+
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", [(256, 512, 128), (200, 320, 136), (128, 64, 64), (384, 1000, 256)])
+def test_gemm_lean_epilogue_bias_gelu(M, N, K, out_dtype):
+    """bias + GELU (+ saved pre-activation) and GELU' through the lean full-tile epilogue (TMA store, no column scale)
+    AND, for the ragged shapes, through the generic chunk code on the edge tiles of the same launch."""
+    from oracle.np_oracle import gelu, gelu_grad
+    ops, L = _ops()
+    A, B, ref = _make(M, N, K, False, False, torch.bfloat16, seed=11)
+    g = torch.Generator().manual_seed(12)
+    bias = torch.randn(N, generator=g).cuda()
+    z_ref = ref * 0.25 + bias.cpu().double().numpy()
+    tol = 2e-5 if out_dtype == torch.float32 else 1e-2
+    aux = torch.empty(M, N, dtype=out_dtype, device="cuda")
+    D = ops.gemm(A, B, M, N, K, out_dtype=out_dtype, bias=bias, alpha=0.25, act=L.ACT_GELU, aux=aux)
+    torch.cuda.synchronize()
+    assert rel_err(aux.float().cpu().numpy(), z_ref) < tol
+    assert rel_err(D.float().cpu().numpy(), gelu(z_ref)) < tol
+    Dp = ops.gemm(A, B, M, N, K, out_dtype=out_dtype, bias=bias, alpha=0.25)          # bias only
+    torch.cuda.synchronize()
+    assert rel_err(Dp.float().cpu().numpy(), z_ref) < tol
+    pre = (torch.randn(M, N, generator=g) * 2).to(out_dtype).cuda()
+    Db = ops.gemm(A, B, M, N, K, out_dtype=out_dtype, act=L.ACT_GELU_BWD, aux=pre)
+    torch.cuda.synchronize()
+    assert rel_err(Db.float().cpu().numpy(), ref * gelu_grad(pre.float().cpu().double().numpy())) < tol
+
+
+def test_gelu_device_function_accuracy():
+    """The branch-free GELU / GELU' of the epilogues (erfc by Abramowitz-Stegun 7.1.26) against fp64 erf on a dense
+    grid, through a K=1 'GEMM' whose accumulator is the grid itself (fp32 mode parity needs ~1e-6 absolute)."""
+    from oracle.np_oracle import gelu, gelu_grad
+    ops, L = _ops()
+    M, N = 256, 512
+    x = torch.linspace(-9.0, 9.0, M * N, dtype=torch.float64).reshape(M, N)
+    # D = A (M x 8) . B^T (N x 8) with A = [x_hi, x_lo, 0...] rows ... simpler: aux carries x for GELU', ones product for GELU
+    A = torch.zeros(M, 8); A[:, 0] = 1.0
+    B = torch.zeros(N, 8); B[:, 0] = 1.0
+    pre = x.float().cuda()
+    Db = ops.gemm(A.cuda(), B.cuda(), M, N, 8, out_dtype=torch.float32, act=L.ACT_GELU_BWD, aux=pre, simt=True)
+    torch.cuda.synchronize()
+    assert np.abs(Db.cpu().double().numpy() - gelu_grad(pre.cpu().double().numpy())).max() < 1e-6
+    # GELU forward: bias carries one grid row per launch (accumulator 0 + bias)
+    Az = torch.zeros(M, 8).cuda()
+    bias = torch.linspace(-9.0, 9.0, N).cuda()
+    Dg = ops.gemm(Az, B.cuda(), M, N, 8, out_dtype=torch.float32, bias=bias, act=L.ACT_GELU, simt=True)
+    torch.cuda.synchronize()
+    assert np.abs(Dg[0].cpu().double().numpy() - gelu(bias.cpu().double().numpy())).max() < 1e-6
+
+
+def test_gemm_long_contraction_uses_pairs_and_matches():
+    """K >= 32768 with N <= 256 (the last layer's dgrad shape class) runs on CTA pairs with split-K; same numbers."""
+    ops, _ = _ops()
+    M, N, K = 384, 256, 32768 + 192
+    A, B, ref = _make(M, N, K, False, True, torch.bfloat16, seed=21)
+    D = ops.gemm(A, B, M, N, K, b_mn=True, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert rel_err(D.cpu().numpy(), ref) < 2e-5
+
+
+def test_pdl_toggle_is_bit_identical():
+    """dmc_set_pdl only changes HOW kernels are launched (programmatic dependent launch), never what they compute."""
+    ops, L = _ops()
+    lib = L.load()
+    M, N, K = 512, 1024, 384
+    A, B, _ = _make(M, N, K, False, False, torch.bfloat16, seed=31)
+    bias = torch.randn(N).cuda()
+    outs = []
+    prev = lib.dmc_set_pdl(1)
+    try:
+        for on in (1, 0, 1):
+            lib.dmc_set_pdl(on)
+            h = ops.gemm(A, B, M, N, K, out_dtype=torch.bfloat16, bias=bias, act=L.ACT_GELU)
+            z, _, _ = ops.normalize_rows_fwd(h.float(), want_bf16=False)
+            cs = ops.colsum(z)
+            torch.cuda.synchronize()
+            outs.append((h.clone(), z.clone(), cs.clone()))
+    finally:
+        lib.dmc_set_pdl(prev)
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert torch.equal(a, b)

@@ -287,3 +287,68 @@ def test_fused_statistics_route_matches_plain_route(mode, tol):
     assert abs(lf - lp) / abs(lp) < tol
     for a, b in zip(res[True][1:], res[False][1:]):
         assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < tol
+
+
+def test_aux_stream_overlap_is_bit_identical(golden):
+    """functional.aux_overlap only moves independent kernels (weight-norm materialisation / backward, bias-gradient
+    column sums, later layers' operand casts) to a second stream: every result must be bit-identical."""
+    from dinomc_b200 import functional as Fn
+    results = []
+    saved = Fn.aux_overlap
+    try:
+        for flag in (True, False):
+            Fn.aux_overlap = flag
+            D, student, teacher, loss_mod = _build(golden, "bf16")
+            xs = torch.from_numpy(golden.inputs["x_student"]).cuda().requires_grad_(True)
+            xt = torch.from_numpy(golden.inputs["x_teacher"]).cuda()
+            with torch.no_grad():
+                t_out = teacher(xt)
+            loss = loss_mod(student(xs), t_out, golden.cfg["epoch"])
+            loss.backward()
+            torch.cuda.synchronize()
+            results.append([loss.detach().clone(), xs.grad.clone(), loss_mod.center.clone()] +
+                           [p.grad.clone() for p in student.parameters() if p.grad is not None])
+    finally:
+        Fn.aux_overlap = saved
+    assert len(results[0]) == len(results[1]) > 5
+    for a, b in zip(*results):
+        assert torch.equal(a, b)
+
+
+def test_step_graph_replay_matches_eager(golden):
+    """StepGraph (the whole step captured once, auxiliary streams and programmatic launches included) replays to the
+    same loss / gradients / center as the eager call sequence, step after step."""
+    import dinomc_b200 as D2
+
+    def make():
+        D, student, teacher, loss_mod = _build(golden, "bf16")
+        xs = torch.from_numpy(golden.inputs["x_student"]).cuda().requires_grad_(True)
+        xt = torch.from_numpy(golden.inputs["x_teacher"]).cuda()
+
+        def step():
+            for p in student.parameters():
+                p.grad = None
+            xs.grad = None
+            with torch.no_grad():
+                t_out = teacher(xt)
+            loss = loss_mod(student(xs), t_out, golden.cfg["epoch"])
+            loss.backward()
+            D.ema_update_(list(teacher.parameters()), list(student.parameters()), 0.99)
+            return loss
+        return step, student, teacher, loss_mod, xs
+
+    step_e, st_e, te_e, lm_e, xs_e = make()
+    step_g, st_g, te_g, lm_g, xs_g = make()
+    graph = D2.StepGraph(step_g, warmup=2)          # 2 warm-up steps + the capture pass itself executes nothing
+    n_warm = 2
+    for _ in range(n_warm):
+        step_e()
+    for _ in range(3):
+        le = step_e()
+        lg = graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(le.detach(), lg.detach())
+        assert torch.equal(xs_e.grad, xs_g.grad)
+        assert torch.equal(lm_e.center, lm_g.center)
+    for pe, pg in zip(te_e.parameters(), te_g.parameters()):
+        assert torch.equal(pe, pg)
