@@ -7,6 +7,9 @@ SRC="$PKG/csrc"
 OUT="$PKG/libdinomc.so"
 BUILD="$PKG/build"
 EXTRA=()
+if [[ -n "${DMC_VARIANT:-}" ]]; then    # experiment build: DMC_VARIANT=name DMC_VARIANT_FLAGS="-D..." -> libdinomc_<name>.so (load with DMC_LIB=)
+  OUT="$PKG/libdinomc_${DMC_VARIANT}.so"; BUILD="$PKG/build_${DMC_VARIANT}"; EXTRA=(${DMC_VARIANT_FLAGS:-})
+fi
 if [[ -n "${DMC_TRACE:-}" ]]; then      # debug build with the GEMM pipeline trace compiled in (tools/gemm_trace.py)
   OUT="$PKG/libdinomc_trace.so"; BUILD="$PKG/build_trace"; EXTRA=(-DDMC_GEMM_TRACE_BUILD)
 fi

@@ -353,12 +353,10 @@ ce_bwd_kernel(const CeArgs a) {
 // i.e. the forward statistics pass over [N_s + N_t, K] disappears.
 // ---------------------------------------------------------------------------------------------------------
 template <typename T, int MAXC, int MAXG, bool FAST>
-__device__ __forceinline__ void ce_fused_vector(const CeArgs& a, const T* s, const T* t, T* ds, long long b, long long col, int C,
-                                                int G, const float (&tmc)[MAXG], const float (&tinv)[MAXG],
-                                                const float (&lse2)[MAXC], float c2, float ct, float scale, float& cross) {
+__device__ __forceinline__ void ce_fused_compute(const CeArgs& a, const CeVec<T, MAXC, MAXG>& in, T* ds, long long b, long long col,
+                                                 int C, int G, const float (&tmc)[MAXG], const float (&tinv)[MAXG],
+                                                 const float (&lse2)[MAXC], float c2, float ct, float scale, float& cross) {
   using Q4 = Quad<T>;
-  CeVec<T, MAXC, MAXG> in;
-  ce_load<T, MAXC, MAXG, FAST>(a, s, t, b, col, C, G, in);
   float q[MAXG][4], Q[4] = {0.f, 0.f, 0.f, 0.f}, S[4] = {0.f, 0.f, 0.f, 0.f};
   float qx = 0.f;
 #pragma unroll
@@ -403,6 +401,15 @@ __device__ __forceinline__ void ce_fused_vector(const CeArgs& a, const T* s, con
   cross = fmaf(qs, a.inv_ts, cross);
 }
 
+template <typename T, int MAXC, int MAXG, bool FAST>
+__device__ __forceinline__ void ce_fused_vector(const CeArgs& a, const T* s, const T* t, T* ds, long long b, long long col, int C,
+                                                int G, const float (&tmc)[MAXG], const float (&tinv)[MAXG],
+                                                const float (&lse2)[MAXC], float c2, float ct, float scale, float& cross) {
+  CeVec<T, MAXC, MAXG> in;
+  ce_load<T, MAXC, MAXG, FAST>(a, s, t, b, col, C, G, in);
+  ce_fused_compute<T, MAXC, MAXG, FAST>(a, in, ds, b, col, C, G, tmc, tinv, lse2, c2, ct, scale, cross);
+}
+
 // ALLFAST: every vector of every row is full and aligned (K % 4 == 0, aligned pointers and strides): the ragged path is
 // not even compiled in, which keeps the hot kernel inside its register budget.
 template <typename T, int CT, int GT, bool ALLFAST>
@@ -432,12 +439,27 @@ ce_fused_kernel(const CeArgs a) {
     if (v < C) lse2[v] = -a.s_lse[v * a.B + b] * kLog2e;
   }
   float cross = 0.f;
-  for (long long col = col_begin + threadIdx.x * 4; col < col_end; col += kThreads * 4) {
-    if constexpr (ALLFAST) {
-      ce_fused_vector<T, MAXC, MAXG, true>(a, s, t, ds, b, col, C, G, tmc, tinv, lse2, c2, ct, scale, cross);
-    } else {
-      if (a.vec_ok && (col + 4 <= a.K)) ce_fused_vector<T, MAXC, MAXG, true>(a, s, t, ds, b, col, C, G, tmc, tinv, lse2, c2, ct, scale, cross);
-      else ce_fused_vector<T, MAXC, MAXG, false>(a, s, t, ds, b, col, C, G, tmc, tinv, lse2, c2, ct, scale, cross);
+  if constexpr (ALLFAST && sizeof(T) == 2) {
+    // software pipeline: the packed loads of the NEXT vector (C + G rows, 8 bytes each) are in flight while this one is
+    // computed -- twice the bytes in flight per thread at the same occupancy (the pass is bound by memory-level
+    // parallelism: 16 warps per SM x 96 bytes per thread otherwise)
+    CeVec<T, MAXC, MAXG> cur, nxt;
+    long long col = col_begin + threadIdx.x * 4;
+    if (col < col_end) ce_load<T, MAXC, MAXG, true>(a, s, t, b, col, C, G, cur);
+    for (; col < col_end; col += kThreads * 4) {
+      const long long cn = col + kThreads * 4;
+      if (cn < col_end) ce_load<T, MAXC, MAXG, true>(a, s, t, b, cn, C, G, nxt);
+      ce_fused_compute<T, MAXC, MAXG, true>(a, cur, ds, b, col, C, G, tmc, tinv, lse2, c2, ct, scale, cross);
+      cur = nxt;
+    }
+  } else {
+    for (long long col = col_begin + threadIdx.x * 4; col < col_end; col += kThreads * 4) {
+      if constexpr (ALLFAST) {
+        ce_fused_vector<T, MAXC, MAXG, true>(a, s, t, ds, b, col, C, G, tmc, tinv, lse2, c2, ct, scale, cross);
+      } else {
+        if (a.vec_ok && (col + 4 <= a.K)) ce_fused_vector<T, MAXC, MAXG, true>(a, s, t, ds, b, col, C, G, tmc, tinv, lse2, c2, ct, scale, cross);
+        else ce_fused_vector<T, MAXC, MAXG, false>(a, s, t, ds, b, col, C, G, tmc, tinv, lse2, c2, ct, scale, cross);
+      }
     }
   }
   __shared__ float red[kThreads / 32];
