@@ -19,6 +19,7 @@ __device__ __forceinline__ float ld_in(const void* p, long long i, int dt) {
 }
 
 constexpr int kWarpsPerBlock = 8;
+constexpr int kRowsPerWarp = 4;       // weightnorm_fwd, width-256 path
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 normalize_fwd_kernel(const void* __restrict__ z, int z_dtype, long long n_rows, int dim, long long ld, float eps,
@@ -76,43 +77,66 @@ weightnorm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, 
                       float* __restrict__ w_f32, float* __restrict__ w_lo, __nv_bfloat16* __restrict__ w_bf16,
                       float* __restrict__ scale, float* __restrict__ inv_vnorm, bool vec_ok, float* __restrict__ gmax) {
   pdl_prologue();
-  const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (row >= K) return;
   const int lane = threadIdx.x & 31;
-  const float* vr = v + row * dim;
   (void)gmax;
-  if (vec_ok && dim == 256) {                          // the DINO bottleneck width: whole row in registers
-    const float4* v4 = reinterpret_cast<const float4*>(vr);
-    const float4 x0 = __ldg(v4 + lane), x1 = __ldg(v4 + lane + 32);
-    float ss = x0.x * x0.x;
-    ss = fmaf(x0.y, x0.y, ss); ss = fmaf(x0.z, x0.z, ss); ss = fmaf(x0.w, x0.w, ss);
-    ss = fmaf(x1.x, x1.x, ss); ss = fmaf(x1.y, x1.y, ss); ss = fmaf(x1.z, x1.z, ss); ss = fmaf(x1.w, x1.w, ss);
-    ss = warp_sum(ss);
-    const float nrm = sqrtf(ss);
-    const float sc = g[row] / nrm;
-    if (lane == 0) { scale[row] = sc; inv_vnorm[row] = 1.0f / nrm; }
-    const float w[8] = {x0.x * sc, x0.y * sc, x0.z * sc, x0.w * sc, x1.x * sc, x1.y * sc, x1.z * sc, x1.w * sc};
-    const long long o0 = row * 256 + 4 * lane, o1 = o0 + 128;
-    if (w_lo) {
-      float hi[8], lo[8];
+  if (vec_ok && dim == 256) {                          // the DINO bottleneck width: whole rows in registers
+    // kRowsPerWarp consecutive rows per warp, all their loads issued before the first reduction: four times the bytes in
+    // flight per warp and a quarter of the blocks of the one-row-per-warp form (ncu: 52 % issue-active, 46 % DRAM before)
+    const long long row0 = (static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5)) * kRowsPerWarp;
+    if (row0 >= K) return;
+    float4 x0[kRowsPerWarp], x1[kRowsPerWarp];
+    float ss[kRowsPerWarp], gr[kRowsPerWarp];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { hi[e] = tf32_round(w[e]); lo[e] = tf32_round(w[e] - hi[e]); }
-      if (w_f32) {
-        *reinterpret_cast<float4*>(w_f32 + o0) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(w_f32 + o1) = make_float4(hi[4], hi[5], hi[6], hi[7]);
-      }
-      *reinterpret_cast<float4*>(w_lo + o0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-      *reinterpret_cast<float4*>(w_lo + o1) = make_float4(lo[4], lo[5], lo[6], lo[7]);
-    } else if (w_f32) {
-      *reinterpret_cast<float4*>(w_f32 + o0) = make_float4(w[0], w[1], w[2], w[3]);
-      *reinterpret_cast<float4*>(w_f32 + o1) = make_float4(w[4], w[5], w[6], w[7]);
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+      const long long row = min(row0 + r, K - 1);      // rows past the end repeat the last one and are not stored
+      const float4* v4 = reinterpret_cast<const float4*>(v + row * 256);
+      x0[r] = __ldg(v4 + lane); x1[r] = __ldg(v4 + lane + 32);
+      gr[r] = __ldg(g + row);
     }
-    if (w_bf16) {
-      *reinterpret_cast<uint2*>(w_bf16 + o0) = make_uint2(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]));
-      *reinterpret_cast<uint2*>(w_bf16 + o1) = make_uint2(pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+      float a = x0[r].x * x0[r].x;
+      a = fmaf(x0[r].y, x0[r].y, a); a = fmaf(x0[r].z, x0[r].z, a); a = fmaf(x0[r].w, x0[r].w, a);
+      a = fmaf(x1[r].x, x1[r].x, a); a = fmaf(x1[r].y, x1[r].y, a); a = fmaf(x1[r].z, x1[r].z, a); a = fmaf(x1[r].w, x1[r].w, a);
+      ss[r] = a;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < kRowsPerWarp; ++r) ss[r] += __shfl_xor_sync(0xffffffffu, ss[r], o);
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+      const long long row = row0 + r;
+      if (row >= K) break;                             // warp-uniform
+      const float nrm = sqrtf(ss[r]);
+      const float sc = gr[r] / nrm;                    // torch _weight_norm: v * (g / ||v||)
+      if (lane == 0) { scale[row] = sc; inv_vnorm[row] = 1.0f / nrm; }
+      const float w[8] = {x0[r].x * sc, x0[r].y * sc, x0[r].z * sc, x0[r].w * sc, x1[r].x * sc, x1[r].y * sc, x1[r].z * sc, x1[r].w * sc};
+      const long long o0 = row * 256 + 4 * lane, o1 = o0 + 128;
+      if (w_lo) {
+        float hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { hi[e] = tf32_round(w[e]); lo[e] = tf32_round(w[e] - hi[e]); }
+        if (w_f32) {
+          *reinterpret_cast<float4*>(w_f32 + o0) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(w_f32 + o1) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+        }
+        *reinterpret_cast<float4*>(w_lo + o0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<float4*>(w_lo + o1) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+      } else if (w_f32) {
+        *reinterpret_cast<float4*>(w_f32 + o0) = make_float4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<float4*>(w_f32 + o1) = make_float4(w[4], w[5], w[6], w[7]);
+      }
+      if (w_bf16) {
+        *reinterpret_cast<uint2*>(w_bf16 + o0) = make_uint2(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]));
+        *reinterpret_cast<uint2*>(w_bf16 + o1) = make_uint2(pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
+      }
     }
     return;
   }
+  const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= K) return;
+  const float* vr = v + row * dim;
   float ss = 0.f;
   for (int c = lane; c < dim; c += 32) { float x = vr[c]; ss = fmaf(x, x, ss); }
   ss = warp_sum(ss);
@@ -329,7 +353,8 @@ extern "C" int dmc_weightnorm_fwd(const float* v, const float* g, int64_t K, int
     launch_kernel(absmax_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, g, K, gmax);
     DMC_LAUNCH_CHECK("absmax_kernel launch");
   }
-  launch_kernel(weightnorm_fwd_kernel, dim3((unsigned)ceil_div(K, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, (cudaStream_t)stream, v, g, K, (int)dim, w_f32, w_lo, static_cast<__nv_bfloat16*>(w_bf16), scale, inv_vnorm, vec_ok, gmax);
+  const int64_t rows_per_block = (vec_ok && dim == 256) ? kWarpsPerBlock * kRowsPerWarp : kWarpsPerBlock;
+  launch_kernel(weightnorm_fwd_kernel, dim3((unsigned)ceil_div(K, rows_per_block)), dim3(kWarpsPerBlock * 32), 0, (cudaStream_t)stream, v, g, K, (int)dim, w_f32, w_lo, static_cast<__nv_bfloat16*>(w_bf16), scale, inv_vnorm, vec_ok, gmax);
   DMC_LAUNCH_CHECK("weightnorm_fwd_kernel launch");
   return 0;
 }
