@@ -131,7 +131,7 @@ class ClockSampler:
 class Step:
     """Owns the modules/buffers of one rank and runs one whole step on the current stream."""
 
-    def __init__(self, w, mode, rank, world, device, ddp=False, reserve_sms=16):
+    def __init__(self, w, mode, rank, world, device, ddp=False, reserve_sms=16, force_reducer=False):
         import dinomc_b200 as D
         self.D, self.w, self.world, self.device = D, w, world, device
         torch.manual_seed(0)                                          # identical weights on every rank
@@ -154,7 +154,7 @@ class Step:
         self.n_tensors = len(self.ema_student)
         self.model = self.student
         self.reducer = None
-        if world > 1:
+        if world > 1 or force_reducer:
             if ddp:
                 from torch.nn.parallel import DistributedDataParallel as DDP
                 self.model = DDP(self.student, device_ids=[device.index])  # main_dino_mc.py:260
@@ -361,6 +361,10 @@ def main():
     assert torch.cuda.is_available(), "bench.py (impl=ours) needs a CUDA device; there is no CPU fallback"
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
+    force_dp = bool(int(os.environ.get("DMC_BENCH_FORCE_DP", "0")))      # diagnostic: 1-rank NCCL group, reducer path on
+    if force_dp and world == 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29577")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=device)
     if world > 1:
         opts = None
         try:        # NCCL kernels on a high-priority stream: they grab SMs as soon as compute CTAs retire
@@ -372,9 +376,9 @@ def main():
     D._lib.check(D._lib.load().dmc_device_check(local_rank), "dmc_device_check")
 
     D.set_teacher_overlap(bool(args.overlap))
-    if world > 1 and not args.ddp:
+    if (world > 1 or force_dp) and not args.ddp:
         D.set_async_center(True)
-    step = Step(w, args.mode, rank, world, device, ddp=bool(args.ddp), reserve_sms=args.reserve_sms)
+    step = Step(w, args.mode, rank, world, device, ddp=bool(args.ddp), reserve_sms=args.reserve_sms, force_reducer=force_dp)
     ops = D.ops
     for _ in range(warmup):
         step.run()
@@ -387,7 +391,7 @@ def main():
         # the whole step is stream-ordered libdinomc launches (+ NCCL all-reduces when N > 1) on fixed buffers:
         # capture once, replay K times
         try:
-            graph = D.StepGraph(step.run, warmup=3, capture_error_mode="thread_local" if world > 1 else "global")
+            graph = D.StepGraph(step.run, warmup=3, capture_error_mode="thread_local" if (world > 1 or force_dp) else "global")
             run_value = graph.replay
         except Exception as e:          # noqa: BLE001 -- e.g. a collective that refuses capture: fall back to eager
             if world == 1:
@@ -478,10 +482,11 @@ def main():
                 "launch_mode": "cuda_graph" if use_graph else "eager", "teacher_overlap": bool(args.overlap), "roofline": roofline, "cpu_baseline": cb,
                 "ema_params": step.P, "ema_tensors": step.n_tensors}
         _emit(line)
-    if world > 1:
+    if world > 1 or force_dp:
         # leave without tearing NCCL down: destroying communicators that CUDA graphs still reference can hang
         torch.cuda.synchronize()
-        dist.barrier()
+        if world > 1:
+            dist.barrier()
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)

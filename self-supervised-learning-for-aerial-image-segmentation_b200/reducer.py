@@ -39,18 +39,19 @@ class GradAllReduce:
         if reserve_sms > 0:
             ops.backward_max_ctas = 148 - reserve_sms
         from . import functional
-        functional.grad_exchange_active = True
+        functional.grad_exchange_active = os.environ.get("DMC_REDUCER_AUXWN", "") != "1"      # env: timing experiments only
         # early-launched (PDL) GEMM CTAs hold SMs while they wait for their predecessor, which delays the NCCL kernels
         # that share the machine: measured 0.992 -> 0.969 ms per step at 2 GPUs without it
         from . import _lib
-        self._pdl_prev = _lib.load().dmc_set_pdl(0)
+        keep_pdl = os.environ.get("DMC_REDUCER_PDL", "") == "1"                               # env: timing experiments only
+        self._pdl_prev = _lib.load().dmc_set_pdl(1 if keep_pdl else 0)
 
     def _hook(self, p):
         g = p.grad
         self._seen += 1
         skip = os.environ.get("DMC_REDUCER_SKIP", "")       # timing experiments only: "big" / "small"
         big = g.numel() * g.element_size() >= _BIG
-        if (skip == "big" and big) or (skip == "small" and not big):
+        if (skip == "big" and big) or (skip == "small" and not big) or skip == "all":
             if self._seen == len(self.params):
                 self._flush()
             return

@@ -1,4 +1,5 @@
-run() { tag=$1; shift; ( env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 20 --warmup 5 --no-cpu-baseline ) > gpurun_out/n2_$tag.json 2> gpurun_out/n2_$tag.err; python - <<PY
+# A/B of the 2-GPU step (run under gpurun --gpus 2): reducer variants, same box.
+run() { tag=$1; shift; ( env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 30 --warmup 5 --no-cpu-baseline ) > gpurun_out/n2_$tag.json 2> gpurun_out/n2_$tag.err; python - <<PY
 import json
 try:
     d=[json.loads(l) for l in open("gpurun_out/n2_$tag.json") if l.startswith("{")][-1]
@@ -7,6 +8,6 @@ except Exception as e: print("$tag failed", e)
 PY
 }
 run default A=1
-run nopdl DMC_PDL=0
-run skipbig DMC_REDUCER_SKIP=big
-run skipsmall DMC_REDUCER_SKIP=small
+run pdl DMC_REDUCER_PDL=1
+run auxwn DMC_REDUCER_AUXWN=1
+run pdl_auxwn DMC_REDUCER_PDL=1 DMC_REDUCER_AUXWN=1
