@@ -15,12 +15,19 @@ w = dict(bench.WORKLOADS["cfg2"])
 dev = torch.device("cuda", 0)
 import dinomc_b200 as D
 D.set_teacher_overlap(True)
-step = bench.Step(w, mode, 0, 1, dev)
+force_dp = bool(int(os.environ.get("DMC_BENCH_FORCE_DP", "0")))     # 1-rank NCCL group: the reducer path without transfers
+if force_dp:
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29578")
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+    D.set_async_center(True)
+step = bench.Step(w, mode, 0, 1, dev, force_reducer=force_dp)
 for _ in range(5):
     step.run()
 torch.cuda.synchronize()
 use_graph = "--eager" not in sys.argv
-run = D.StepGraph(step.run, warmup=3).replay if use_graph else step.run
+run = D.StepGraph(step.run, warmup=3, capture_error_mode="thread_local" if force_dp else "global").replay if use_graph else step.run
 for _ in range(3):
     run()
 torch.cuda.synchronize()
@@ -51,3 +58,7 @@ tot = sum(agg.values())
 print(f"sum of kernel time per step: {tot:.1f} us")
 for n, v in agg.most_common(40):
     print(f"{n:72s} x{cnt[n] / N:<4.1f} {v:8.1f} us {100 * v / tot:5.1f}%")
+
+if force_dp:
+    sys.stdout.flush()
+    os._exit(0)
