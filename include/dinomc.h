@@ -216,6 +216,19 @@ int dmc_ema_build_plan(const void* const* teacher_ptrs_host, const void* const* 
                        int64_t* n_chunks_out);
 int dmc_ema_multi_tensor(const void* plan_dev, int64_t n_chunks, float m, float one_minus_m, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Per-parameter gradient clipping: utils/utils.py:145-154 `clip_gradients(model, clip)`
+ *   n = ||grad||_2 ; c = clip / (n + 1e-6) ; if c < 1: grad *= c        for every gradient tensor
+ * as two multi-tensor launches over a host-built chunk plan (cf. dmc_ema_*).  norms[n_tensors] receives the
+ * (pre-clip) norms on the device; nothing synchronises.  workspace: n_chunks floats.
+ * --------------------------------------------------------------------------------------------- */
+size_t dmc_clip_plan_bytes(const int64_t* numels_host, int64_t n_tensors);
+/* Fills plan_host (capacity from dmc_clip_plan_bytes) and *n_chunks_out.  Host-only; no CUDA calls. */
+int dmc_clip_build_plan(const void* const* grad_ptrs_host, const int64_t* numels_host, int64_t n_tensors,
+                        void* plan_host, size_t plan_bytes, int64_t* n_chunks_out);
+int dmc_clip_grads(const void* plan_dev, int64_t n_chunks, float clip, float* norms, float* workspace,
+                   size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

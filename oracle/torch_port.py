@@ -109,6 +109,20 @@ def ema_update(teacher_params, student_params, m):
         pk.data.mul_(m).add_((1 - m) * pq.detach().data)
 
 
+@torch.no_grad()
+def clip_gradients(grads, clip):
+    """utils/utils.py:145-154 on a list of gradient tensors (the reference walks `model.named_parameters()` and
+    skips parameters without a gradient).  Clips in place; returns the pre-clip norms as Python floats."""
+    norms = []
+    for g in grads:
+        param_norm = g.data.norm(2)
+        norms.append(param_norm.item())
+        clip_coef = clip / (param_norm + 1e-6)
+        if clip_coef < 1:
+            g.data.mul_(clip_coef)
+    return norms
+
+
 def step(x_student, x_teacher, student_p, teacher_p, state: LossState, epoch, ema_m, ema_extra=None):
     """One whole step of the path as SURVEY.md section 8d defines it: teacher head fwd (no grad),
     student head fwd, loss (+center), backward to head params and features, EMA over head (+extra

@@ -24,6 +24,7 @@ import torch
 from .ema import ema_update_
 from .head import DINOHead
 from .loss import DINOLoss
+from .optim import cancel_gradients_last_layer, clip_gradients
 
 
 def train_one_epoch(student, teacher, teacher_without_ddp, dino_loss, data_loader, optimizer, lr_schedule,
@@ -55,15 +56,15 @@ def train_one_epoch(student, teacher, teacher_without_ddp, dino_loss, data_loade
         if fp16_scaler is None:
             loss.backward()
             if args.clip_grad:
-                utils.clip_gradients(student, args.clip_grad)
-            utils.cancel_gradients_last_layer(epoch, student, args.freeze_last_layer)
+                clip_gradients(student, args.clip_grad)           # two multi-tensor launches, no per-parameter .item()
+            cancel_gradients_last_layer(epoch, student, args.freeze_last_layer)
             optimizer.step()
         else:
             fp16_scaler.scale(loss).backward()
             if args.clip_grad:
                 fp16_scaler.unscale_(optimizer)
-                utils.clip_gradients(student, args.clip_grad)
-            utils.cancel_gradients_last_layer(epoch, student, args.freeze_last_layer)
+                clip_gradients(student, args.clip_grad)
+            cancel_gradients_last_layer(epoch, student, args.freeze_last_layer)
             fp16_scaler.step(optimizer)
             fp16_scaler.update()
         ema_update_(teacher_params, student_params, momentum_schedule[it])      # one launch instead of 3 x #tensors

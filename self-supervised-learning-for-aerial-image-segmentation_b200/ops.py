@@ -519,3 +519,43 @@ class EmaPlan:
             L.check(lib.dmc_ema_multi_tensor(self.plan.data_ptr(), self.n_chunks, float(m), float(1.0 - float(m)), _stream()),
                     "dmc_ema_multi_tensor")
         _count()
+
+
+class ClipPlan:
+    """Device-resident chunk table over a list of gradient tensors (see dmc_clip_grads)."""
+
+    def __init__(self, grads):
+        lib = L.load()
+        grads = list(grads)
+        if not grads:
+            raise ValueError("clip: empty gradient list")
+        for g in grads:
+            _need_cuda(g)
+            if g.dtype != torch.float32:
+                raise TypeError("clip: gradients must be float32")
+            if not g.is_contiguous():
+                raise ValueError("clip: gradients must be contiguous")
+        n = len(grads)
+        self.key = tuple((g.data_ptr(), g.numel()) for g in grads)
+        numels = (L.i64 * n)(*[g.numel() for g in grads])
+        ptrs = (L.vp * n)(*[g.data_ptr() for g in grads])
+        nbytes = lib.dmc_clip_plan_bytes(numels, n)
+        host = torch.empty(max(nbytes, 8), dtype=torch.uint8).pin_memory()
+        n_chunks = L.i64(0)
+        L.check(lib.dmc_clip_build_plan(ptrs, numels, n, host.data_ptr(), host.numel(), C.byref(n_chunks)), "dmc_clip_build_plan")
+        self.n_chunks, self.n_tensors = n_chunks.value, n
+        self.device = grads[0].device
+        self.plan = host.to(self.device, non_blocking=False)
+        self.partials = torch.empty(max(self.n_chunks, 1), dtype=torch.float32, device=self.device)
+
+    def run(self, clip: float) -> torch.Tensor:
+        """Clips in place; returns the pre-clip norms [n_tensors] (device tensor, no synchronisation)."""
+        lib = L.load()
+        norms = torch.zeros(self.n_tensors, dtype=torch.float32, device=self.device)
+        if self.n_chunks == 0:
+            return norms
+        with _timed("clip_grads"):
+            L.check(lib.dmc_clip_grads(self.plan.data_ptr(), self.n_chunks, float(clip), norms.data_ptr(), self.partials.data_ptr(),
+                                       self.partials.numel() * 4, _stream()), "dmc_clip_grads")
+        _count(2)
+        return norms

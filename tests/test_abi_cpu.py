@@ -89,6 +89,32 @@ def test_ema_plan_builder_chunks_on_host():
     assert lib.dmc_ema_build_plan(tp, sp, arr, n, buf, 8, C.byref(out)) < 0      # buffer too small
 
 
+def test_clip_plan_builder_chunks_on_host():
+    import struct
+    import dinomc_b200
+    L = dinomc_b200._lib
+    lib = L.load()
+    numels = [5, 16385, 0, 40000]
+    n = len(numels)
+    arr = (L.i64 * n)(*numels)
+    nbytes = lib.dmc_clip_plan_bytes(arr, n)
+    expect_chunks = sum((x + 16383) // 16384 for x in numels)
+    assert nbytes == expect_chunks * 32
+    ptrs = (L.vp * n)(*[0x10000 * (i + 1) for i in range(n)])
+    buf = (C.c_uint8 * nbytes)()
+    out = L.i64(0)
+    assert lib.dmc_clip_build_plan(ptrs, arr, n, buf, nbytes, C.byref(out)) == 0
+    assert out.value == expect_chunks
+    entries = [struct.unpack("<qqiiii", bytes(buf[i * 32:(i + 1) * 32])) for i in range(expect_chunks)]
+    # (grad ptr, n, tensor, first chunk, chunk count, pad)
+    assert entries[0][:5] == (0x10000, 5, 0, 0, 1)
+    assert entries[1][:5] == (0x20000, 16384, 1, 1, 2) and entries[2][:5] == (0x20000 + 16384 * 4, 1, 1, 1, 2)
+    assert [e[2] for e in entries[3:]] == [3, 3, 3] and all(e[3] == 3 and e[4] == 3 for e in entries[3:])
+    assert sum(e[1] for e in entries) == sum(numels)
+    assert lib.dmc_clip_build_plan(ptrs, arr, n, buf, 8, C.byref(out)) < 0       # buffer too small
+    assert lib.dmc_clip_grads(None, 1, 1.0, None, None, 0, None) < 0             # argument validation without a device
+
+
 def test_module_surface_matches_reference_signature():
     import inspect
     import dinomc_b200 as D

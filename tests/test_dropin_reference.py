@@ -25,3 +25,23 @@ def test_install_rebinds_reference_symbols():
         assert l.center.shape == (1, 1024)
     finally:
         vits.DINOHead, main_dino_mc.DINOLoss, main_dino_mc.train_one_epoch = orig
+
+
+def test_oracle_clip_gradients_equals_reference_function():
+    """The restated clip_gradients (oracle/torch_port.py) against the reference's own utils.clip_gradients."""
+    if not reference_loader.available():
+        pytest.skip("reference not present")
+    import torch
+    from oracle import torch_port
+    _, _, utils = reference_loader.load()
+    torch.manual_seed(3)
+    model = torch.nn.Sequential(torch.nn.Linear(37, 64), torch.nn.GELU(), torch.nn.Linear(64, 5))
+    for clip in (3.0, 0.05):
+        for p in model.parameters():
+            p.grad = torch.randn_like(p) * 0.3
+        grads = [p.grad.detach().clone() for p in model.parameters()]
+        ref_norms = utils.clip_gradients(model, clip)
+        norms = torch_port.clip_gradients(grads, clip)
+        assert norms == ref_norms
+        for p, g in zip(model.parameters(), grads):
+            assert torch.equal(p.grad, g)
