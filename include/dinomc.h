@@ -229,6 +229,20 @@ int dmc_clip_build_plan(const void* const* grad_ptrs_host, const int64_t* numels
 int dmc_clip_grads(const void* plan_dev, int64_t n_chunks, float clip, float* norms, float* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * torch.optim.AdamW step (main_dino_mc.py:281-282, :391, :399) for one parameter group as one multi-tensor launch:
+ * p *= 1 - lr*wd; m.lerp_(g, 1-beta1); v = v*beta2 + (1-beta2) g g; p -= lr/(1-beta1^t) * m / (sqrt(v)/sqrt(1-beta2^t) + eps).
+ * Scalars are doubles (the Python floats of torch) and are rounded to fp32 exactly where torch's kernels round them.
+ * --------------------------------------------------------------------------------------------- */
+size_t dmc_adamw_plan_bytes(const int64_t* numels_host, int64_t n_tensors);
+/* Fills plan_host (capacity from dmc_adamw_plan_bytes) and *n_chunks_out.  Host-only; no CUDA calls. */
+int dmc_adamw_build_plan(const void* const* param_ptrs_host, const void* const* grad_ptrs_host,
+                         const void* const* exp_avg_ptrs_host, const void* const* exp_avg_sq_ptrs_host,
+                         const int64_t* numels_host, int64_t n_tensors, void* plan_host, size_t plan_bytes,
+                         int64_t* n_chunks_out);
+int dmc_adamw_multi_tensor(const void* plan_dev, int64_t n_chunks, double lr, double beta1, double beta2, double eps,
+                           double weight_decay, int64_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

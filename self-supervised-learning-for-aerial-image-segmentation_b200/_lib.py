@@ -72,6 +72,9 @@ SIGNATURES = {
     "dmc_clip_plan_bytes": (sz, [C.POINTER(i64), i64]),
     "dmc_clip_build_plan": (C.c_int, [C.POINTER(vp), C.POINTER(i64), i64, vp, sz, C.POINTER(i64)]),
     "dmc_clip_grads": (C.c_int, [vp, i64, f32, vp, vp, sz, vp]),
+    "dmc_adamw_plan_bytes": (sz, [C.POINTER(i64), i64]),
+    "dmc_adamw_build_plan": (C.c_int, [C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), i64, vp, sz, C.POINTER(i64)]),
+    "dmc_adamw_multi_tensor": (C.c_int, [vp, i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, i64, vp]),
 }
 
 _lib = None

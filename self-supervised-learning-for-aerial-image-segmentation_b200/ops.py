@@ -559,3 +559,35 @@ class ClipPlan:
                                        self.partials.numel() * 4, _stream()), "dmc_clip_grads")
         _count(2)
         return norms
+
+
+class AdamWPlan:
+    """Device-resident chunk table over (param, grad, exp_avg, exp_avg_sq) quadruples of one parameter group."""
+
+    def __init__(self, params, grads, exp_avgs, exp_avg_sqs):
+        lib = L.load()
+        n = len(params)
+        if n == 0:
+            raise ValueError("adamw: empty parameter group")
+        for t in list(params) + list(grads) + list(exp_avgs) + list(exp_avg_sqs):
+            _need_cuda(t)
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise TypeError("adamw: parameters, gradients and moments must be contiguous float32 tensors")
+        arr = lambda ts: (L.vp * n)(*[t.data_ptr() for t in ts])
+        numels = (L.i64 * n)(*[p.numel() for p in params])
+        nbytes = lib.dmc_adamw_plan_bytes(numels, n)
+        host = torch.empty(max(nbytes, 8), dtype=torch.uint8).pin_memory()
+        n_chunks = L.i64(0)
+        L.check(lib.dmc_adamw_build_plan(arr(params), arr(grads), arr(exp_avgs), arr(exp_avg_sqs), numels, n, host.data_ptr(),
+                                         host.numel(), C.byref(n_chunks)), "dmc_adamw_build_plan")
+        self.n_chunks = n_chunks.value
+        self.plan = host.to(params[0].device, non_blocking=False)
+
+    def run(self, lr, beta1, beta2, eps, weight_decay, step):
+        if self.n_chunks == 0:
+            return
+        lib = L.load()
+        with _timed("adamw"):
+            L.check(lib.dmc_adamw_multi_tensor(self.plan.data_ptr(), self.n_chunks, float(lr), float(beta1), float(beta2), float(eps),
+                                               float(weight_decay), int(step), _stream()), "dmc_adamw_multi_tensor")
+        _count()

@@ -48,3 +48,58 @@ def cancel_gradients_last_layer(epoch, model, freeze_last_layer):
     for n, p in model.named_parameters():
         if "last_layer" in n:
             p.grad = None
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    """Drop-in for `torch.optim.AdamW(params_groups)` as main_dino_mc.py:281-282 builds it (lr / weight decay rewritten
+    per iteration by the schedules at :363-367): same constructor defaults, same `param_groups` keys, same per-parameter
+    state (`step`, `exp_avg`, `exp_avg_sq`), so `state_dict()` / `load_state_dict()` interchange with the torch
+    optimizer and with the reference's checkpoints (`main_dino_mc.py:336`).  `step()` is one multi-tensor launch per
+    parameter group.  fp32 CUDA parameters only; `amsgrad` / `maximize` / `capturable` are not supported (the reference
+    uses none of them)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
+            raise ValueError("FusedAdamW: invalid hyper-parameters")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._plans = {}
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for gi, group in enumerate(self.param_groups):
+            params = [p for p in group["params"] if p.grad is not None]
+            if not params:
+                continue
+            for p in params:
+                if not p.is_cuda:
+                    raise RuntimeError("dinomc_b200 has no CPU path: FusedAdamW parameters must be CUDA tensors")
+                if p.grad.is_sparse:
+                    raise RuntimeError("FusedAdamW does not support sparse gradients")
+                st = self.state[p]
+                if len(st) == 0:
+                    st["step"] = torch.tensor(0.0, dtype=torch.float32)          # torch.optim.AdamW's layout
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            # parameters that have stepped the same number of times share a launch (normally: the whole group)
+            by_step = {}
+            for p in params:
+                st = self.state[p]
+                st["step"] += 1
+                by_step.setdefault(int(st["step"].item()), []).append(p)
+            beta1, beta2 = group["betas"]
+            for t, ps in by_step.items():
+                grads = [p.grad.data if p.grad.is_contiguous() else p.grad.data.contiguous() for p in ps]
+                key = (gi, tuple((p.data_ptr(), g.data_ptr(), self.state[p]["exp_avg"].data_ptr()) for p, g in zip(ps, grads)))
+                plan = self._plans.get(key)
+                if plan is None:
+                    if len(self._plans) > 8:
+                        self._plans.clear()
+                    plan = ops.AdamWPlan([p.data for p in ps], grads, [self.state[p]["exp_avg"] for p in ps],
+                                         [self.state[p]["exp_avg_sq"] for p in ps])
+                    self._plans[key] = plan
+                plan.run(group["lr"], beta1, beta2, group["eps"], group["weight_decay"], t)
+        return loss

@@ -115,6 +115,29 @@ def test_clip_plan_builder_chunks_on_host():
     assert lib.dmc_clip_grads(None, 1, 1.0, None, None, 0, None) < 0             # argument validation without a device
 
 
+def test_adamw_plan_builder_and_validation_on_host():
+    import struct
+    import dinomc_b200
+    L = dinomc_b200._lib
+    lib = L.load()
+    numels = [3, 20000]
+    n = len(numels)
+    arr = (L.i64 * n)(*numels)
+    nbytes = lib.dmc_adamw_plan_bytes(arr, n)
+    assert nbytes == 3 * 40
+    mk = lambda base: (L.vp * n)(*[base * (i + 1) for i in range(n)])
+    buf = (C.c_uint8 * nbytes)()
+    out = L.i64(0)
+    assert lib.dmc_adamw_build_plan(mk(0x1000), mk(0x2000), mk(0x4000), mk(0x8000), arr, n, buf, nbytes, C.byref(out)) == 0
+    assert out.value == 3
+    e = [struct.unpack("<qqqqq", bytes(buf[i * 40:(i + 1) * 40])) for i in range(3)]
+    assert e[0] == (0x1000, 0x2000, 0x4000, 0x8000, 3)
+    assert e[2] == (0x2000 + 16384 * 4, 0x4000 + 16384 * 4, 0x8000 + 16384 * 4, 0x10000 + 16384 * 4, 20000 - 16384)
+    assert lib.dmc_adamw_multi_tensor(None, 1, 1e-3, 0.9, 0.999, 1e-8, 0.01, 1, None) < 0     # null plan
+    assert lib.dmc_adamw_multi_tensor(buf, 1, 1e-3, 0.9, 0.999, 1e-8, 0.01, 0, None) < 0      # step must be >= 1
+    assert b"step" in lib.dmc_last_error_string()
+
+
 def test_module_surface_matches_reference_signature():
     import inspect
     import dinomc_b200 as D

@@ -233,3 +233,65 @@ def test_cancel_gradients_last_layer():
     D.cancel_gradients_last_layer(0, head, 1)
     for n, p in head.named_parameters():
         assert (p.grad is None) == ("last_layer" in n)
+
+
+def _two_models(seed=0):
+    torch.manual_seed(seed)
+    a = torch.nn.Sequential(torch.nn.Linear(67, 300), torch.nn.GELU(), torch.nn.Linear(300, 129), torch.nn.LayerNorm(129)).cuda()
+    import copy
+    return a, copy.deepcopy(a)
+
+
+def _groups(model):
+    """utils/utils.py:649-660 get_params_groups."""
+    reg, noreg = [], []
+    for name, p in model.named_parameters():
+        (noreg if (name.endswith(".bias") or p.dim() == 1) else reg).append(p)
+    return [{"params": reg}, {"params": noreg, "weight_decay": 0.0}]
+
+
+def test_fused_adamw_matches_torch_adamw_and_exchanges_state():
+    """FusedAdamW against torch.optim.AdamW (what main_dino_mc.py:282 constructs) under the reference's usage: two
+    parameter groups, lr / weight decay rewritten every iteration (main_dino_mc.py:363-367), then a state_dict
+    round trip in both directions."""
+    import dinomc_b200 as D
+    ma, mb = _two_models()
+    oa = torch.optim.AdamW(_groups(ma))
+    ob = D.FusedAdamW(_groups(mb))
+    g = torch.Generator().manual_seed(1)
+
+    def run(opt_a, opt_b, steps, it0):
+        for it in range(it0, it0 + steps):
+            lr, wd = 5e-4 * (1 + 0.3 * it), 0.04 + 0.01 * it
+            for opt in (opt_a, opt_b):
+                for gi, group in enumerate(opt.param_groups):
+                    group["lr"] = lr
+                    if gi == 0:
+                        group["weight_decay"] = wd
+            for pa, pb in zip(ma.parameters(), mb.parameters()):
+                gr = torch.randn(pa.shape, generator=g).cuda() * 0.1
+                pa.grad, pb.grad = gr.clone(), gr.clone()
+            opt_a.step()
+            opt_b.step()
+
+    run(oa, ob, 6, 0)
+    torch.cuda.synchronize()
+    for pa, pb in zip(ma.parameters(), mb.parameters()):
+        assert rel_err(pb.detach().cpu().numpy(), pa.detach().cpu().numpy()) < 1e-6
+    for pa, pb in zip(ma.parameters(), mb.parameters()):
+        for k in ("exp_avg", "exp_avg_sq"):
+            assert rel_err(ob.state[pb][k].cpu().numpy(), oa.state[pa][k].cpu().numpy()) < 1e-6
+        assert float(ob.state[pb]["step"]) == float(oa.state[pa]["step"]) == 6.0
+    # state exchange: torch -> fused and fused -> torch, then keep stepping
+    oc = D.FusedAdamW(_groups(mb))
+    oc.load_state_dict(oa.state_dict())
+    od = torch.optim.AdamW(_groups(ma))
+    od.load_state_dict(ob.state_dict())
+    with torch.no_grad():
+        for pa, pb in zip(ma.parameters(), mb.parameters()):
+            pb.copy_(pa)
+    run(od, oc, 3, 6)
+    torch.cuda.synchronize()
+    for pa, pb in zip(ma.parameters(), mb.parameters()):
+        assert rel_err(pb.detach().cpu().numpy(), pa.detach().cpu().numpy()) < 2e-6
+        assert float(oc.state[pb]["step"]) == 9.0
