@@ -25,6 +25,7 @@ from .head import (DINOHead, get_default_precision, set_default_precision, set_t
 from .loss import DINOLoss, set_async_center  # noqa: F401
 from .optim import FusedAdamW, cancel_gradients_last_layer, clip_gradients  # noqa: F401
 from .reducer import GradAllReduce  # noqa: F401
+from .wrapper import MultiCropWrapper  # noqa: F401
 
-__all__ = ["DINOHead", "DINOLoss", "ema_update_", "clip_gradients", "cancel_gradients_last_layer", "FusedAdamW", "StepGraph", "GradAllReduce", "set_teacher_overlap", "set_async_center", "wait_ready", "set_default_precision", "get_default_precision",
+__all__ = ["DINOHead", "DINOLoss", "ema_update_", "clip_gradients", "cancel_gradients_last_layer", "FusedAdamW", "MultiCropWrapper", "StepGraph", "GradAllReduce", "set_teacher_overlap", "set_async_center", "wait_ready", "set_default_precision", "get_default_precision",
            "ops", "functional"]

@@ -25,6 +25,7 @@ from .ema import ema_update_
 from .head import DINOHead
 from .loss import DINOLoss
 from .optim import cancel_gradients_last_layer, clip_gradients
+from .wrapper import MultiCropWrapper
 
 
 def train_one_epoch(student, teacher, teacher_without_ddp, dino_loss, data_loader, optimizer, lr_schedule,
@@ -83,6 +84,7 @@ def install(patch_train_loop: bool = True):
     import utils.vision_transformer as vits
     vits.DINOHead = DINOHead
     main_dino_mc.DINOLoss = DINOLoss
+    main_dino_mc.utils.MultiCropWrapper = MultiCropWrapper     # same contract, single feature concatenation
     if patch_train_loop:
         main_dino_mc.train_one_epoch = train_one_epoch
     return main_dino_mc

@@ -11,6 +11,7 @@ def test_install_rebinds_reference_symbols():
         pytest.skip("reference not present")
     main_dino_mc, vits, _ = reference_loader.load()
     orig = (vits.DINOHead, main_dino_mc.DINOLoss, main_dino_mc.train_one_epoch)
+    orig_wrapper = main_dino_mc.utils.MultiCropWrapper
     try:
         import dinomc_b200
         from dinomc_b200 import dropin
@@ -18,6 +19,7 @@ def test_install_rebinds_reference_symbols():
         assert vits.DINOHead is dinomc_b200.DINOHead
         assert main_dino_mc.DINOLoss is dinomc_b200.DINOLoss
         assert main_dino_mc.train_one_epoch is dropin.train_one_epoch
+        assert main_dino_mc.utils.MultiCropWrapper is dinomc_b200.MultiCropWrapper
         # the constructor calls main_dino_mc.py makes (positional teacher form at :243-246) work unchanged
         h = vits.DINOHead(384, 1024, False)
         assert h.last_layer.weight_v.shape == (1024, 256)
@@ -25,6 +27,7 @@ def test_install_rebinds_reference_symbols():
         assert l.center.shape == (1, 1024)
     finally:
         vits.DINOHead, main_dino_mc.DINOLoss, main_dino_mc.train_one_epoch = orig
+        main_dino_mc.utils.MultiCropWrapper = orig_wrapper
 
 
 def test_oracle_clip_gradients_equals_reference_function():
@@ -45,3 +48,74 @@ def test_oracle_clip_gradients_equals_reference_function():
         assert norms == ref_norms
         for p, g in zip(model.parameters(), grads):
             assert torch.equal(p.grad, g)
+
+
+def test_reference_checkpoint_layout_loads_into_dropin_modules():
+    """a checkpoint written by the reference (main_dino_mc.py:333-345: `student` / `teacher` are
+    state dicts of MultiCropWrapper(backbone, DINOHead), `dino_loss` holds the center) loads into the same wrapper built
+    around dinomc_b200.DINOHead / DINOLoss with strict=True, and back."""
+    if not reference_loader.available():
+        pytest.skip("reference not present")
+    import torch
+    import dinomc_b200
+    main_dino_mc, vits, utils = reference_loader.load()
+    reference_loader.ensure_process_group()
+    torch.manual_seed(0)
+
+    def backbone():
+        m = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * 8 * 8, 48))
+        m.fc, m.head = torch.nn.Identity(), torch.nn.Identity()
+        return m
+
+    ref_student = utils.MultiCropWrapper(backbone(), vits.DINOHead(48, 640, use_bn=False, norm_last_layer=True))
+    ref_loss = main_dino_mc.DINOLoss(640, 8, 0.04, 0.04, 0, 10, teacher_crops_number=2)
+    ref_loss.center.normal_()
+    ckpt = {"student": {"module." + k: v for k, v in ref_student.state_dict().items()},     # DDP prefix (main_dino_mc.py:260)
+            "teacher": ref_student.state_dict(), "dino_loss": ref_loss.state_dict()}
+
+    ours = utils.MultiCropWrapper(backbone(), dinomc_b200.DINOHead(48, 640, use_bn=False, norm_last_layer=True))
+    our_loss = dinomc_b200.DINOLoss(640, 8, 0.04, 0.04, 0, 10, teacher_crops_number=2)
+    missing = ours.load_state_dict({k[len("module."):]: v for k, v in ckpt["student"].items()}, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    our_loss.load_state_dict(ckpt["dino_loss"], strict=True)
+    assert torch.equal(our_loss.center, ref_loss.center)
+    for (ka, va), (kb, vb) in zip(ours.state_dict().items(), ref_student.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb)
+    # and the other way round: what we save, the reference modules load
+    ref2 = utils.MultiCropWrapper(backbone(), vits.DINOHead(48, 640, use_bn=False, norm_last_layer=True))
+    ref2.load_state_dict(ours.state_dict(), strict=True)
+    main_dino_mc.DINOLoss(640, 8, 0.04, 0.04, 0, 10, teacher_crops_number=2).load_state_dict(our_loss.state_dict(), strict=True)
+
+
+def test_multicrop_wrapper_matches_reference_wrapper():
+    """dinomc_b200.MultiCropWrapper == utils.utils.MultiCropWrapper (utils/utils.py:611-646) on DINO-MC's multi-sized crop
+    lists: same grouping, same crop-major feature order, same state_dict keys."""
+    if not reference_loader.available():
+        pytest.skip("reference not present")
+    import copy
+    import torch
+    import dinomc_b200
+    _, _, utils = reference_loader.load()
+    torch.manual_seed(0)
+
+    class Backbone(torch.nn.Module):          # resolution-agnostic toy backbone
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(3, 24, 3, padding=1)
+            self.fc, self.head = torch.nn.Linear(24, 10), torch.nn.Linear(24, 10)
+
+        def forward(self, x):
+            return self.head(self.fc(self.conv(x).mean(dim=(2, 3))))
+
+    head = torch.nn.Linear(24, 7)
+    ref = utils.MultiCropWrapper(Backbone(), copy.deepcopy(head))
+    ours = dinomc_b200.MultiCropWrapper(Backbone(), copy.deepcopy(head))
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    assert list(ours.state_dict()) == list(ref.state_dict())
+    B = 3
+    for sizes in ([32, 32, 16, 16, 16, 12, 12, 16], [32, 32], [16], [32, 32, 24, 20, 16, 12, 8, 8]):
+        crops = [torch.randn(B, 3, s, s) for s in sizes]
+        a, b = ref(list(crops)), ours(list(crops))
+        assert a.shape == (len(sizes) * B, 7)
+        assert torch.allclose(a, b, atol=1e-6)
+    assert torch.equal(ref(crops[0]), ours(crops[0]))            # a single tensor instead of a list
