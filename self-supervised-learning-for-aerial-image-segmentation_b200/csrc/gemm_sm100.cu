@@ -201,7 +201,8 @@ template <int EPI, bool OUT_BF16, typename Release>
 __device__ __forceinline__ void epilogue_fast_acc(const GemmDev& p, const CUtensorMap* tmD, const Epilogue& e,
                                                   uint32_t t_addr, int row0, int lane, int n0, int c_begin, int c_end,
                                                   uint8_t* buf, uint32_t& n_boxes, bool release_after, Release release,
-                                                  float stat_shift, float& st_l) {
+                                                  float& st_m, float& st_l) {
+  const float stat_shift = st_m;                       // EPI 2: the fixed shift (bound); EPI 3 updates st_m as it goes
   const long long row = static_cast<long long>(row0) + lane;
   const bool row_ok = row < p.M;
   uint8_t* rowp = buf + lane * 128;
@@ -251,6 +252,45 @@ __device__ __forceinline__ void epilogue_fast_acc(const GemmDev& p, const CUtens
       if (!last) {
         ptx::tmem_ld_32x32(t_addr + c + 64, ra);
         ptx::tmem_ld_32x32(t_addr + c + 96, rb);
+      }
+      if constexpr (EPI == 3) {
+        // Teacher statistics of the stored values: y2 = (t - center) * scale * log2e; online softmax pair (max, sum 2^(y2-max))
+        // of this row over the step's 64 columns, and the column sums of the warp's 32 rows read back from the staged box
+        // (lane j owns the 32-bit word j of every 128-byte row: conflict-free, 2 bf16 columns per lane).
+        if (row0 < p.M) {
+          const int nrows = min(32, p.M - row0);
+          float s0 = 0.f, s1 = 0.f;
+          for (int r = 0; r < nrows; ++r) {
+            const uint32_t wv = *reinterpret_cast<const uint32_t*>(buf + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+            s0 += bf16_lo(wv); s1 += bf16_hi(wv);
+          }
+          float* dst = p.stat_colsum_partials + static_cast<long long>(row0 >> 5) * p.N + n0 + c;
+          *reinterpret_cast<float2*>(dst + 2 * lane) = make_float2(s0, s1);
+        }
+        // pk[j] (j < 16) holds columns c+2j, c+2j+1; pk[16+j] holds c+32+2j, c+33+2j
+        const float4* cen = reinterpret_cast<const float4*>(p.stat_center + n0 + c);
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {                          // pass 1: max of (t - center) over the 64 columns
+          const float4 cc = __ldg(cen + q);
+          const uint32_t w0 = pk[2 * q], w1 = pk[2 * q + 1];
+          m0 = fmaxf(m0, fmaxf(bf16_lo(w0) - cc.x, bf16_hi(w0) - cc.y));
+          m1 = fmaxf(m1, fmaxf(bf16_lo(w1) - cc.z, bf16_hi(w1) - cc.w));
+        }
+        const float mnew = fmaxf(st_m, fmaxf(m0, m1) * p.stat_sc2);
+        st_l *= ex2(st_m - mnew);                               // 0 * 2^(-inf) = 0 on the first step
+        st_m = mnew;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {                          // pass 2: sum 2^(y2 - max)
+          const float4 cc = __ldg(cen + q);
+          const uint32_t w0 = pk[2 * q], w1 = pk[2 * q + 1];
+          a0 += ex2(fmaf(bf16_lo(w0) - cc.x, p.stat_sc2, -mnew));
+          a1 += ex2(fmaf(bf16_hi(w0) - cc.y, p.stat_sc2, -mnew));
+          a2 += ex2(fmaf(bf16_lo(w1) - cc.z, p.stat_sc2, -mnew));
+          a3 += ex2(fmaf(bf16_hi(w1) - cc.w, p.stat_sc2, -mnew));
+        }
+        st_l += (a0 + a1) + (a2 + a3);
       }
       if constexpr (EPI == 2) {                               // statistics of exactly the stored (rounded) values
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -308,6 +348,7 @@ __device__ __forceinline__ void epilogue_fast_acc(const GemmDev& p, const CUtens
 // EPI 2: plain + fused statistics of the stored (rounded) logits: per row and 128-column part the online-softmax
 //        pair (max, sum 2^(y - max)) of y = (D - center) * scale * log2e, and per 32-row group the column sums.
 //        This is what lets DINOLoss skip its separate statistics passes over the logits.
+// EPI 3: EPI 2 for the TEACHER logits (center subtracted, running maximum, 32-row column sums), lean path for bf16 output.
 // CG2: CTA pair (cluster of 2, tcgen05 cta_group::2).  One work item is 256 rows x block_n columns: each CTA of the
 //      pair owns 128 rows of A and of the accumulator and loads only HALF of the B tile; the leader CTA's single MMA
 //      thread drives both tensor cores (M = 256) reading both B halves.  A third less shared-memory fill per unit of
@@ -574,7 +615,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // y2 lies in [-shift, shift]; summing 2^(y2 - shift) directly is safe while 2*shift stays inside fp32's exponent range.
     bool stat_fixed = false;
     float stat_shift = 0.f;
-    if constexpr (EPI == 2) {
+    if constexpr (EPI >= 2) {
       if (p.stat_bound != nullptr && p.stat_center == nullptr) {
         stat_shift = fabsf(__ldg(p.stat_bound) * p.stat_sc2) * 1.01f + 0.05f;
         stat_fixed = (stat_shift < 55.f);
@@ -584,6 +625,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     bool fast_ok = p.tma_store && p.partial == nullptr && p.dbg == 0 && c_begin < c_end && ((c_end - c_begin) & 63) == 0;
     if constexpr (EPI == 0) fast_ok = fast_ok && p.col_scale == nullptr && aux_vec_ok;
     if constexpr (EPI == 2) fast_ok = fast_ok && stat_fixed && p.stat_colsum_partials == nullptr;
+    if constexpr (EPI == 3)                            // lean teacher statistics: bf16 output, center + column sums requested
+      fast_ok = fast_ok && p.stat_center != nullptr && p.stat_colsum_partials != nullptr && p.out_dtype == DMC_BF16 &&
+                (reinterpret_cast<uintptr_t>(p.stat_center) & 15) == 0;
     const bool out_bf16 = (p.out_dtype == DMC_BF16);
     int it = 0;
     for (int w = w_begin; w < w_end; w += w_step, ++it) {
@@ -610,15 +654,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const int row0 = mt * tile_m + (CG2 ? static_cast<int>(cta_rank) : h) * kBlockM + q * 32;
           const uint32_t t_addr = tmem_base + static_cast<uint32_t>((acc + h) * kAccCols) + (static_cast<uint32_t>(q * 32) << 16);
           float st_l = 0.f;
+          float st_m = (EPI == 3) ? -INFINITY : stat_shift;       // EPI 3 tracks the running maximum, EPI 2 uses the bound
           if (out_bf16)
             epilogue_fast_acc<EPI, true>(p, &tmD, e, t_addr, row0, lane, n0, c_begin, c_end, my_staging, n_boxes, h == p.dual,
-                                         release, stat_shift, st_l);
+                                         release, st_m, st_l);
           else
             epilogue_fast_acc<EPI, false>(p, &tmD, e, t_addr, row0, lane, n0, c_begin, c_end, my_staging, n_boxes, h == p.dual,
-                                          release, stat_shift, st_l);
-          if constexpr (EPI == 2) {
+                                          release, st_m, st_l);
+          if constexpr (EPI >= 2) {
             const long long row = static_cast<long long>(row0) + lane;
-            if (row < p.M) p.stat_row_partials[row * (kColGroups * p.n_tiles) + kColGroups * nt + quarter] = make_float2(stat_shift, st_l);
+            if (row < p.M) p.stat_row_partials[row * (kColGroups * p.n_tiles) + kColGroups * nt + quarter] = make_float2(st_m, st_l);
           }
         }
         if (warp == 2) trace_at(p, 6, it);
@@ -678,7 +723,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const uint4 pk = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
                                         pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
             *reinterpret_cast<uint4*>(rowp + ((((sub << 2) + j) ^ (lane & 7)) << 4)) = pk;
-            if constexpr (EPI == 2) {                           // statistics see exactly the values that are stored
+            if constexpr (EPI >= 2) {                           // statistics see exactly the values that are stored
               v[8 * j + 0] = bf16_lo(pk.x); v[8 * j + 1] = bf16_hi(pk.x); v[8 * j + 2] = bf16_lo(pk.y); v[8 * j + 3] = bf16_hi(pk.y);
               v[8 * j + 4] = bf16_lo(pk.z); v[8 * j + 5] = bf16_hi(pk.z); v[8 * j + 6] = bf16_lo(pk.w); v[8 * j + 7] = bf16_hi(pk.w);
             }
@@ -697,7 +742,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             ptx::tma_store_commit();
           }
           ++n_boxes;
-          if constexpr (EPI == 2) {
+          if constexpr (EPI >= 2) {
             if (p.stat_colsum_partials != nullptr && row0 < p.M) {
               // column sums over this warp's 32 rows, read back from the staged (swizzled) box: lane j owns the
               // 32-bit word j of every 128-byte row -> conflict-free; 2 bf16 columns or 1 fp32 column per lane.
@@ -791,12 +836,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         process(ra, c);
         process(rb, c + 32);
-        if constexpr (EPI == 2) {
+        if constexpr (EPI >= 2) {
           chunk_stats(ra, c);
           chunk_stats(rb, c + 32);
         }
       }
-      if constexpr (EPI == 2) {
+      if constexpr (EPI >= 2) {
         if (row < p.M && c_begin < c_end)
           p.stat_row_partials[row * (kColGroups * p.n_tiles) + kColGroups * nt + quarter] = make_float2(st_m, st_l);
       }
@@ -1125,8 +1170,11 @@ const bool plain = (a->col_scale == nullptr && a->bias == nullptr && a->act == D
   (amn ? (bmn ? DMC_LAUNCH(ESZ_, true, true) : DMC_LAUNCH(ESZ_, true, false))                                 \
        : (bmn ? DMC_LAUNCH(ESZ_, false, true) : DMC_LAUNCH(ESZ_, false, false)))
   if (stats) {          // last-layer forward only: K-major operands
-    rc = (esz == 2) ? launch_tc<2, false, false, 2>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st, pl.cg2)
-                    : launch_tc<4, false, false, 2>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st, pl.cg2);
+    if (a->stat_center != nullptr && esz == 2)      // teacher: center + running maximum (+ column sums), lean path in EPI 3
+      rc = launch_tc<2, false, false, 3>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st, pl.cg2);
+    else
+      rc = (esz == 2) ? launch_tc<2, false, false, 2>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st, pl.cg2)
+                      : launch_tc<4, false, false, 2>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st, pl.cg2);
   } else {
     rc = (esz == 2) ? DMC_DISPATCH(2) : DMC_DISPATCH(4);
   }
