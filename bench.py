@@ -131,7 +131,7 @@ class ClockSampler:
 class Step:
     """Owns the modules/buffers of one rank and runs one whole step on the current stream."""
 
-    def __init__(self, w, mode, rank, world, device, ddp=False, reserve_sms=16, force_reducer=False):
+    def __init__(self, w, mode, rank, world, device, ddp=False, reserve_sms=16, force_reducer=False, compress=None):
         import dinomc_b200 as D
         self.D, self.w, self.world, self.device = D, w, world, device
         torch.manual_seed(0)                                          # identical weights on every rank
@@ -160,7 +160,7 @@ class Step:
                 self.model = DDP(self.student, device_ids=[device.index])  # main_dino_mc.py:260
             else:
                 # same exchange (mean of the head gradients over ranks), graph-capturable, overlapped with bwd + EMA
-                self.reducer = D.GradAllReduce(self.student.parameters(), reserve_sms=reserve_sms)
+                self.reducer = D.GradAllReduce(self.student.parameters(), reserve_sms=reserve_sms, compress=compress)
         gs = torch.Generator(device="cpu").manual_seed(1234 + rank)
         gt = torch.Generator(device="cpu").manual_seed(4321 + rank)
         self.x_student_host = torch.randn(C * B, Din, generator=gs).pin_memory()
@@ -341,6 +341,10 @@ def main():
     ap.add_argument("--graph", type=int, default=1, help="replay the N=1 step from a CUDA graph (0 = eager launches)")
     ap.add_argument("--ddp", type=int, default=0, help="N>1: wrap the student head in torch DDP (eager) instead of GradAllReduce")
     ap.add_argument("--reserve-sms", type=int, default=16, help="N>1: SMs the backward GEMM grids leave to NCCL")
+    ap.add_argument("--grad-compress", default="none", choices=["none", "bf16"],
+                    help="N>1 gradient exchange: fp32 all-reduce (default; what DDP does in the reference), or bf16 (dW of the "
+                         "last layer averaged before its weight-norm backward + the small gradients as one flat bf16 buffer). "
+                         "bf16 measured SLOWER at 2 GPUs (1.068 vs 0.980 ms), so it stays opt-in")
     ap.add_argument("--overlap", type=int, default=1, help="teacher head forward on a side stream, overlapping the student's")
     ap.add_argument("--cpu-sample-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -355,10 +359,16 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     warmup = max(args.warmup, 3)
+    compress = None if args.grad_compress == "none" else "bf16"
+    if os.environ.get("DMC_BENCH_GRAD_COMPRESS"):                        # A/B runs under torchrun without changing the command line
+        compress = None if os.environ["DMC_BENCH_GRAD_COMPRESS"] == "none" else "bf16"
     cfg = {"workload": f"{args.workload}: {w['note']}; D={w['D']} out_dim={w['K']} batch/GPU={w['B']} "
                        f"crops={w['G']}+{w['C'] - w['G']}; EMA over {w['arch']} backbone + head",
            "global_batch": w["B"] * world, "parallelism": f"dp{world}",
-           "grad_allreduce": ("none (1 GPU)" if world == 1 else ("torch DDP" if args.ddp else "dinomc_b200.GradAllReduce (NCCL, side stream)")),
+           "grad_allreduce": ("none (1 GPU)" if world == 1 else ("torch DDP" if args.ddp else
+                                                                        "dinomc_b200.GradAllReduce (NCCL, side stream; "
+                                                                        + ("bf16 exchange: last-layer dW averaged before its weight-norm backward, small gradients in one flat bf16 buffer)"
+                                                                           if compress else "fp32)"))),
            "l2": "per-step working set (logits + gradients > 1 GiB) exceeds the 126 MB L2; no explicit flush"}
 
     if args.impl == "reference":
@@ -398,7 +408,8 @@ def main():
     D.set_teacher_overlap(bool(args.overlap))
     if (world > 1 or force_dp) and not args.ddp:
         D.set_async_center(True)
-    step = Step(w, args.mode, rank, world, device, ddp=bool(args.ddp), reserve_sms=args.reserve_sms, force_reducer=force_dp)
+    step = Step(w, args.mode, rank, world, device, ddp=bool(args.ddp), reserve_sms=args.reserve_sms, force_reducer=force_dp,
+                compress=compress)
     ops = D.ops
     for _ in range(warmup):
         step.run()

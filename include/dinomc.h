@@ -123,6 +123,10 @@ int dmc_cast_f32_to_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
  * The three arrays are HOST arrays of `count` entries. */
 int dmc_cast_f32_to_bf16_batch(const float* const* srcs_host, void* const* dsts_host, const int64_t* ns_host,
                                int32_t count, void* stream);
+/* The way back (bf16 -> fp32, exact) for up to 8 tensors in one launch: gradients after a bf16 all-reduce
+ * (the compressed form of the exchange at main_dino_mc.py:260).  HOST arrays of `count` entries. */
+int dmc_cast_bf16_to_f32_batch(const void* const* srcs_host, float* const* dsts_host, const int64_t* ns_host,
+                               int32_t count, void* stream);
 /* out[n] = sum_m X[m,n]   (bias gradients of the MLP Linears).  X is F32 or BF16. */
 size_t dmc_colsum_workspace_bytes(int64_t M, int64_t N);
 int dmc_colsum(const void* X, int32_t dtype, int64_t M, int64_t N, int64_t ld, float* out,
@@ -150,6 +154,11 @@ int dmc_weightnorm_fwd(const float* v, const float* g, int64_t K, int64_t dim,
  * utils/vision_transformer.py:281-282). */
 int dmc_weightnorm_bwd(const float* dw, const float* v, const float* scale, const float* inv_vnorm,
                        int64_t K, int64_t dim, float* dv, float* dg, void* stream);
+/* The same pass reading dW stored as BF16.  Used by the data-parallel bf16 gradient exchange (the all-reduce DDP performs
+ * at main_dino_mc.py:260): the pass is linear in dW, so the ranks average dW in bf16 (half the bytes of dv) and every
+ * rank then computes the already-averaged dv / dg from it. */
+int dmc_weightnorm_bwd_bf16(const void* dw_bf16, const float* v, const float* scale, const float* inv_vnorm,
+                            int64_t K, int64_t dim, float* dv, float* dg, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * DINOLoss (main_dino_mc.py:419-473).  Rows are crop-major: row v*B + b = crop v of sample b

@@ -50,12 +50,14 @@ SIGNATURES = {
     "dmc_split_tf32": (C.c_int, [vp, vp, vp, i64, vp]),
     "dmc_cast_f32_to_bf16": (C.c_int, [vp, vp, i64, vp]),
     "dmc_cast_f32_to_bf16_batch": (C.c_int, [C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), i32, vp]),
+    "dmc_cast_bf16_to_f32_batch": (C.c_int, [C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), i32, vp]),
     "dmc_colsum_workspace_bytes": (sz, [i64, i64]),
     "dmc_colsum": (C.c_int, [vp, i32, i64, i64, i64, vp, vp, sz, vp]),
     "dmc_normalize_rows_fwd": (C.c_int, [vp, i32, i64, i64, i64, f32, vp, vp, vp, vp, vp]),
     "dmc_normalize_rows_bwd": (C.c_int, [vp, vp, vp, i64, i64, f32, vp, i32, vp]),
     "dmc_weightnorm_fwd": (C.c_int, [vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp]),
     "dmc_weightnorm_bwd": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp, vp]),
+    "dmc_weightnorm_bwd_bf16": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp, vp]),
     "dmc_teacher_workspace_bytes": (sz, [i64, i64]),
     "dmc_teacher_stats_colsum": (C.c_int, [vp, i32, i64, i64, i64, vp, f32, vp, vp, vp, sz, vp]),
     "dmc_teacher_finalize": (C.c_int, [vp, vp, i64, i64, i64, i64, vp, vp, vp]),

@@ -157,8 +157,11 @@ weightnorm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, 
   }
 }
 
+// TD = storage type of dW: fp32 (the wgrad GEMM's default output) or bf16 (the data-parallel exchange averages dW over
+// the ranks in bf16 BEFORE this pass -- the pass is linear in dW, so mean(dv) = weightnorm_bwd(mean(dW))).
+template <typename TD>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-weightnorm_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v, const float* __restrict__ scale,
+weightnorm_bwd_kernel(const TD* __restrict__ dw, const float* __restrict__ v, const float* __restrict__ scale,
                       const float* __restrict__ inv_vnorm, long long K, int dim, float* __restrict__ dv, float* __restrict__ dg,
                       bool vec_ok) {
   pdl_prologue();
@@ -167,10 +170,15 @@ weightnorm_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v,
   const int lane = threadIdx.x & 31;
   const float iv = inv_vnorm[row], sc = scale[row];
   if (vec_ok && dim == 256) {
-    const float4* dw4 = reinterpret_cast<const float4*>(dw + row * 256);
+    using Q4 = Quad<TD>;
     const float4* v4 = reinterpret_cast<const float4*>(v + row * 256);
     float4* dv4 = reinterpret_cast<float4*>(dv + row * 256);
-    const float4 a0 = __ldg(dw4 + lane), a1 = __ldg(dw4 + lane + 32);
+    float e0[4], e1[4];
+    {
+      const typename Q4::Raw r0 = Q4::load(dw + row * 256 + lane * 4), r1 = Q4::load(dw + row * 256 + (lane + 32) * 4);
+      Q4::unpack(r0, e0); Q4::unpack(r1, e1);
+    }
+    const float4 a0 = make_float4(e0[0], e0[1], e0[2], e0[3]), a1 = make_float4(e1[0], e1[1], e1[2], e1[3]);
     float4 b0 = __ldg(v4 + lane), b1 = __ldg(v4 + lane + 32);
     b0.x *= iv; b0.y *= iv; b0.z *= iv; b0.w *= iv; b1.x *= iv; b1.y *= iv; b1.z *= iv; b1.w *= iv;   // v_hat
     float dot = a0.x * b0.x;
@@ -183,12 +191,12 @@ weightnorm_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v,
     return;
   }
   float dot = 0.f;
-  for (int c = lane; c < dim; c += 32) dot = fmaf(dw[row * dim + c], v[row * dim + c] * iv, dot);
+  for (int c = lane; c < dim; c += 32) dot = fmaf(static_cast<float>(dw[row * dim + c]), v[row * dim + c] * iv, dot);
   dot = warp_sum(dot);                                 // dW . v_hat
   if (dg && lane == 0) dg[row] = dot;
   for (int c = lane; c < dim; c += 32) {
     const long long o = row * dim + c;
-    dv[o] = sc * (dw[o] - dot * (v[o] * iv));
+    dv[o] = sc * (static_cast<float>(dw[o]) - dot * (v[o] * iv));
   }
 }
 
@@ -253,6 +261,28 @@ cast_bf16_batch_kernel(const CastBatch b) {
   }
   for (long long i = n4 * 4 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
     y[i] = __float2bfloat16_rn(x[i]);
+}
+
+// The way back: up to 8 bf16 -> fp32 widenings in one launch (gradients after a bf16 all-reduce).
+struct WidenBatch {
+  const __nv_bfloat16* src[8];
+  float* dst[8];
+  long long n[8];
+};
+__global__ void __launch_bounds__(256)
+widen_bf16_batch_kernel(const WidenBatch b) {
+  pdl_prologue();
+  const __nv_bfloat16* __restrict__ x = b.src[blockIdx.y];
+  float* __restrict__ y = b.dst[blockIdx.y];
+  const long long n = b.n[blockIdx.y];
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long n4 = ((reinterpret_cast<uintptr_t>(x) & 7) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) ? n / 4 : 0;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const uint2 r = reinterpret_cast<const uint2*>(x)[i];
+    reinterpret_cast<float4*>(y)[i] = make_float4(bf16_lo(r.x), bf16_hi(r.x), bf16_lo(r.y), bf16_hi(r.y));
+  }
+  for (long long i = n4 * 4 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    y[i] = __bfloat162float(x[i]);
 }
 
 // Column sum in two deterministic steps: [row_splits][N] partials, then a fixed-order reduction.
@@ -365,8 +395,20 @@ extern "C" int dmc_weightnorm_bwd(const float* dw, const float* v, const float* 
   DMC_REQUIRE(K > 0 && dim > 0 && dim < (1 << 30), "dmc_weightnorm_bwd: bad shape");
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const bool vec_ok = (dim % 4 == 0) && al16(dw) && al16(v) && al16(dv);
-  launch_kernel(weightnorm_bwd_kernel, dim3((unsigned)ceil_div(K, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, (cudaStream_t)stream, dw, v, scale, inv_vnorm, K, (int)dim, dv, dg, vec_ok);
+  launch_kernel(weightnorm_bwd_kernel<float>, dim3((unsigned)ceil_div(K, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, (cudaStream_t)stream, dw, v, scale, inv_vnorm, K, (int)dim, dv, dg, vec_ok);
   DMC_LAUNCH_CHECK("weightnorm_bwd_kernel launch");
+  return 0;
+}
+
+extern "C" int dmc_weightnorm_bwd_bf16(const void* dw_bf16, const float* v, const float* scale, const float* inv_vnorm,
+                                       int64_t K, int64_t dim, float* dv, float* dg, void* stream) {
+  DMC_REQUIRE(dw_bf16 && v && scale && inv_vnorm && dv, "dmc_weightnorm_bwd_bf16: null pointer");
+  DMC_REQUIRE(K > 0 && dim > 0 && dim < (1 << 30), "dmc_weightnorm_bwd_bf16: bad shape");
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool vec_ok = (dim % 4 == 0) && al16(dw_bf16) && al16(v) && al16(dv);
+  launch_kernel(weightnorm_bwd_kernel<__nv_bfloat16>, dim3((unsigned)ceil_div(K, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, (cudaStream_t)stream,
+                static_cast<const __nv_bfloat16*>(dw_bf16), v, scale, inv_vnorm, K, (int)dim, dv, dg, vec_ok);
+  DMC_LAUNCH_CHECK("weightnorm_bwd_kernel<bf16> launch");
   return 0;
 }
 
@@ -397,6 +439,22 @@ extern "C" int dmc_cast_f32_to_bf16_batch(const float* const* srcs_host, void* c
   dim3 grid((unsigned)grid_1d(nmax, 1024), (unsigned)count);
   launch_kernel(cast_bf16_batch_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, b);
   DMC_LAUNCH_CHECK("cast_bf16_batch_kernel launch");
+  return 0;
+}
+
+extern "C" int dmc_cast_bf16_to_f32_batch(const void* const* srcs_host, float* const* dsts_host, const int64_t* ns_host,
+                                          int32_t count, void* stream) {
+  DMC_REQUIRE(srcs_host && dsts_host && ns_host && count >= 1 && count <= 8, "dmc_cast_bf16_to_f32_batch: 1..8 tensors per call");
+  WidenBatch b{};
+  long long nmax = 0;
+  for (int i = 0; i < count; ++i) {
+    DMC_REQUIRE(srcs_host[i] && dsts_host[i] && ns_host[i] > 0, "dmc_cast_bf16_to_f32_batch: bad tensor %d", i);
+    b.src[i] = static_cast<const __nv_bfloat16*>(srcs_host[i]); b.dst[i] = dsts_host[i]; b.n[i] = ns_host[i];
+    nmax = ns_host[i] > nmax ? ns_host[i] : nmax;
+  }
+  dim3 grid((unsigned)grid_1d(nmax, 1024), (unsigned)count);
+  launch_kernel(widen_bf16_batch_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, b);
+  DMC_LAUNCH_CHECK("widen_bf16_batch_kernel launch");
   return 0;
 }
 

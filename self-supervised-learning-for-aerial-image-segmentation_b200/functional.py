@@ -55,6 +55,7 @@ def _current_loss():
 aux_overlap = True
 grad_exchange_active = False     # set by GradAllReduce: the last layer's dv (64 MiB, the largest all-reduce of the step) must
                                  # then be final as early as possible, so its weight-norm backward stays in front of the dgrad
+grad_exchange = None             # the active GradAllReduce (or None); with compress="bf16" the last layer hands it a bf16 dW
 _aux_streams = {}
 
 
@@ -311,6 +312,7 @@ class NormLastLayerFn(torch.autograd.Function):
         ctx.zop, ctx.wop = zop, wop
         ctx.save_for_backward(zhat, inv_den, v.detach(), scale, inv_vnorm)
         ctx.dims = (rows, dim, K)
+        ctx.g_ptr = g.data_ptr()
         return logits
 
     @staticmethod
@@ -324,7 +326,17 @@ class NormLastLayerFn(torch.autograd.Function):
         dz = dg = dv = None
         region = None
         with ops.backward_cap():
-            if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            claimed = None
+            if grad_exchange is not None and mode == "bf16" and ctx.needs_input_grad[3]:
+                claimed = grad_exchange.claim_last_layer(v.data_ptr(), ctx.g_ptr if ctx.needs_input_grad[2] else None)
+            if claimed is not None:
+                # bf16 exchange: dW leaves the GEMM in bf16, is averaged over the ranks, and the weight-norm backward runs
+                # on the averaged dW on the communication stream; weight_v.grad / weight_g.grad are set there directly
+                dw = mm(mode, d, ctx.zop, K, dim, rows, a_mn=True, b_mn=True, out_dtype=torch.bfloat16, tag="gemm_last_wgrad")
+                ops.mark_ready(dw)
+                want_dg = ctx.needs_input_grad[2]
+                grad_exchange.exchange_last_layer(dw, lambda: ops.weightnorm_bwd(dw, v, scale, inv_vnorm, want_dg=want_dg), *claimed)
+            elif ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
                 # wgrad first: dW[K,dim] = dlogits^T . zhat (both MN-major).  dv is the largest gradient of the step
                 # (K x 256 fp32); marking it ready here lets its all-reduce overlap the dgrad and the MLP backward.
                 dw = mm(mode, d, ctx.zop, K, dim, rows, a_mn=True, b_mn=True, out_dtype=torch.float32, tag="gemm_last_wgrad")

@@ -314,6 +314,44 @@ def cast_bf16_batch(tensors):
     return outs
 
 
+def widen_bf16_batch(srcs, dsts):
+    """dsts[i] (fp32, contiguous) <- srcs[i] (bf16, contiguous), eight tensors per launch (exact)."""
+    lib = L.load()
+    pairs = list(zip(srcs, dsts))
+    for a, b in pairs:
+        _need_cuda(a, b)
+        if a.dtype != torch.bfloat16 or b.dtype != torch.float32 or a.numel() != b.numel() or not (a.is_contiguous() and b.is_contiguous()):
+            raise ValueError("widen_bf16_batch: expects contiguous bf16 sources and fp32 destinations of equal size")
+    for k in range(0, len(pairs), 8):
+        grp = pairs[k:k + 8]
+        n = len(grp)
+        sp = (L.vp * n)(*[a.data_ptr() for a, _ in grp])
+        dp = (L.vp * n)(*[b.data_ptr() for _, b in grp])
+        ns = (L.i64 * n)(*[a.numel() for a, _ in grp])
+        with _timed("widen_bf16"):
+            L.check(lib.dmc_cast_bf16_to_f32_batch(sp, dp, ns, n, _stream()), "dmc_cast_bf16_to_f32_batch")
+        _count()
+
+
+def narrow_bf16_into(srcs, dsts):
+    """dsts[i] (bf16 views, e.g. slices of one flat exchange buffer) <- srcs[i] (fp32), eight tensors per launch."""
+    lib = L.load()
+    pairs = list(zip(srcs, dsts))
+    for a, b in pairs:
+        _need_cuda(a, b)
+        if a.dtype != torch.float32 or b.dtype != torch.bfloat16 or a.numel() != b.numel() or not (a.is_contiguous() and b.is_contiguous()):
+            raise ValueError("narrow_bf16_into: expects contiguous fp32 sources and bf16 destinations of equal size")
+    for k in range(0, len(pairs), 8):
+        grp = pairs[k:k + 8]
+        n = len(grp)
+        sp = (L.vp * n)(*[a.data_ptr() for a, _ in grp])
+        dp = (L.vp * n)(*[b.data_ptr() for _, b in grp])
+        ns = (L.i64 * n)(*[a.numel() for a, _ in grp])
+        with _timed("cast_bf16"):
+            L.check(lib.dmc_cast_f32_to_bf16_batch(sp, dp, ns, n, _stream()), "dmc_cast_f32_to_bf16_batch")
+        _count()
+
+
 def colsum(X: torch.Tensor) -> torch.Tensor:
     lib = L.load()
     X = _rows2d(X)
@@ -398,13 +436,15 @@ def weightnorm_bwd(dw, v, scale, inv_vnorm, want_dg: bool):
     lib = L.load()
     _need_cuda(dw, v)
     dw, v = dw.contiguous(), v.contiguous()
-    assert dw.dtype == torch.float32
+    if dw.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError(f"weightnorm_bwd: dW must be float32 or bfloat16, got {dw.dtype}")
     K, dim = v.shape
     dv = torch.empty_like(v)
     dg = torch.empty((K, 1), dtype=torch.float32, device=v.device) if want_dg else None
+    fn, name = ((lib.dmc_weightnorm_bwd, "dmc_weightnorm_bwd") if dw.dtype == torch.float32
+                else (lib.dmc_weightnorm_bwd_bf16, "dmc_weightnorm_bwd_bf16"))
     with _timed("weightnorm_bwd"):
-        L.check(lib.dmc_weightnorm_bwd(dw.data_ptr(), v.data_ptr(), scale.data_ptr(), inv_vnorm.data_ptr(), K, dim, dv.data_ptr(),
-                                       _p(dg), _stream()), "dmc_weightnorm_bwd")
+        L.check(fn(dw.data_ptr(), v.data_ptr(), scale.data_ptr(), inv_vnorm.data_ptr(), K, dim, dv.data_ptr(), _p(dg), _stream()), name)
     _count()
     return dv, dg
 

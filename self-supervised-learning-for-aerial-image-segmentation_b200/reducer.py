@@ -9,6 +9,15 @@ NCCL transfers (89 MB of head gradients at K = 65536) overlap the rest of the ba
   * while a reducer is active the persistent GEMM grids of the backward pass leave `reserve_sms` SMs free, so the
     NCCL kernel neither queues behind a one-CTA-per-SM GEMM nor starves its tail CTAs.
 
+`compress="bf16"` (the bf16-GEMM mode's exchange; same idea as torch's `bf16_compress_hook` for DDP) halves the bytes:
+
+  * the weight-normed last layer is exchanged BEFORE its weight-norm backward: the wgrad GEMM writes dW in bf16, the
+    ranks average dW (32 MB instead of the 64 MB fp32 dv) and every rank then runs the weight-norm backward on the
+    averaged dW on the communication stream -- that pass is linear in dW, so the result is the averaged dv (and dg).
+    No extra pass over memory: the GEMM writes half the bytes and the weight-norm backward reads half the bytes;
+  * the small gradients are narrowed into ONE flat bf16 buffer (one launch), averaged with one all-reduce, and widened
+    back into their fp32 `.grad` tensors (one launch).
+
 Unlike `DistributedDataParallel` it keeps no Python-side reducer state between steps, which makes the whole step
 (collectives included) capturable in one CUDA graph (`StepGraph`).  `torch.distributed` (NCCL over NVLink /
 NVSwitch) does the transport.
@@ -27,19 +36,24 @@ _FLUSH = 1 << 20     # bytes: pending small gradients are sent as one coalesced 
 
 
 class GradAllReduce:
-    def __init__(self, params, group=None, reserve_sms: int = 16):
+    def __init__(self, params, group=None, reserve_sms: int = 16, compress=None):
+        if compress not in (None, "bf16"):
+            raise ValueError(f"GradAllReduce: compress must be None or 'bf16', got {compress!r}")
         self.group = group
+        self.compress = compress
         self.params = [p for p in params if p.requires_grad]
+        self._by_ptr = {p.data_ptr(): p for p in self.params}
         self.comm = torch.cuda.Stream(priority=-1)
         self._pending = []
         self._pending_bytes = 0
         self._seen = 0
         self._handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
-        self.bytes_per_step = sum(p.numel() * p.element_size() for p in self.params)
+        self.bytes_per_step = sum(p.numel() * (2 if compress == "bf16" else p.element_size()) for p in self.params)
         if reserve_sms > 0:
             ops.backward_max_ctas = 148 - reserve_sms
         from . import functional
         functional.grad_exchange_active = os.environ.get("DMC_REDUCER_AUXWN", "") != "1"      # env: timing experiments only
+        functional.grad_exchange = self
         # early-launched (PDL) GEMM CTAs hold SMs while they wait for their predecessor, which delays the NCCL kernels
         # that share the machine: measured 0.992 -> 0.969 ms per step at 2 GPUs without it
         from . import _lib
@@ -62,7 +76,10 @@ class GradAllReduce:
             else:
                 self.comm.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm):
-                dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
+                if self._compressible(g):
+                    self._exchange_bf16([g])
+                else:
+                    dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
             g.record_stream(self.comm)
         else:
             self._pending.append((g, ops.ready_events.pop(g.data_ptr(), None)))
@@ -78,11 +95,19 @@ class GradAllReduce:
             else:
                 self.comm.wait_stream(torch.cuda.current_stream())
             grads = [g for g, _ in self._pending]
+            narrow = [g for g in grads if self._compressible(g)]
+            grads = [g for g in grads if not self._compressible(g)]
+            with torch.cuda.stream(self.comm):
+                if narrow:
+                    self._exchange_bf16(narrow)
+            for g in narrow:
+                g.record_stream(self.comm)
             with torch.cuda.stream(self.comm):
                 try:
-                    with dist._coalescing_manager(group=self.group, device=grads[0].device, async_ops=False):
-                        for g in grads:
-                            dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
+                    if grads:
+                        with dist._coalescing_manager(group=self.group, device=grads[0].device, async_ops=False):
+                            for g in grads:
+                                dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
                 except (AttributeError, TypeError, RuntimeError):
                     for g in grads:
                         dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
@@ -92,6 +117,63 @@ class GradAllReduce:
             self._pending_bytes = 0
         if self._seen >= len(self.params):
             self._seen = 0
+
+    # ---- bf16 exchange --------------------------------------------------------------------------------------
+    def _compressible(self, g):
+        return self.compress == "bf16" and g.dtype == torch.float32 and g.is_contiguous()
+
+    def _exchange_bf16(self, grads):
+        """On the current (communication) stream: fp32 gradients -> one flat bf16 buffer -> all-reduce(AVG) -> back."""
+        offs, total = [], 0
+        for g in grads:
+            offs.append(total)
+            total += (g.numel() + 7) & ~7                      # keep every slice 16-byte aligned
+        flat = torch.empty(total, dtype=torch.bfloat16, device=grads[0].device)
+        views = [flat[o:o + g.numel()] for o, g in zip(offs, grads)]
+        if total != sum(g.numel() for g in grads):
+            flat.zero_()                                       # padding travels through the all-reduce: keep it finite
+        ops.narrow_bf16_into([g.view(-1) for g in grads], views)
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+        ops.widen_bf16_batch(views, [g.view(-1) for g in grads])
+
+    def claim_last_layer(self, v_ptr, g_ptr=None):
+        """For NormLastLayerFn.backward: the parameters (weight_v[, weight_g]) whose gradients may be produced from an
+        averaged dW, or None when that route does not apply (no compression, foreign parameters, or a gradient already
+        accumulated in `.grad` -- then the regular route through autograd runs)."""
+        if self.compress != "bf16":
+            return None
+        pv = self._by_ptr.get(v_ptr)
+        if pv is None or pv.grad is not None:
+            return None
+        pg = None
+        if g_ptr is not None:
+            pg = self._by_ptr.get(g_ptr)
+            if pg is None or pg.grad is not None:
+                return None
+        return pv, pg
+
+    def exchange_last_layer(self, dw, weightnorm_bwd, pv, pg):
+        """Average the bf16 dW over the ranks, then run `weightnorm_bwd()` (-> dv, dg) on the averaged dW, all on the
+        communication stream; the results become `pv.grad` / `pg.grad` directly (they are complete after `wait()`)."""
+        cur = torch.cuda.current_stream()
+        ev = ops.ready_events.pop(dw.data_ptr(), None)
+        if ev is not None:
+            self.comm.wait_event(ev)
+        else:
+            self.comm.wait_stream(cur)
+        with torch.cuda.stream(self.comm):
+            dist.all_reduce(dw, op=dist.ReduceOp.AVG, group=self.group)
+            dv, dg = weightnorm_bwd()
+        dw.record_stream(self.comm)
+        dv.record_stream(cur)
+        pv.grad = dv.view_as(pv)
+        self._seen += 1
+        if pg is not None:
+            dg.record_stream(cur)
+            pg.grad = dg.view_as(pg)
+            self._seen += 1
+        if self._seen == len(self.params):
+            self._flush()
 
     def wait(self):
         """Join: later work on the current stream sees the averaged gradients."""
@@ -106,4 +188,6 @@ class GradAllReduce:
         ops.backward_max_ctas = 0
         from . import functional, _lib
         functional.grad_exchange_active = False
+        if functional.grad_exchange is self:
+            functional.grad_exchange = None
         _lib.load().dmc_set_pdl(self._pdl_prev)

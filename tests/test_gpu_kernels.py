@@ -64,6 +64,14 @@ def test_weightnorm(K, dim):
     assert rel_err(dv.cpu().numpy(), (gn / nrm) * (dw.double().numpy() - dot * vhat)) < 2e-6
     dv2, dg2 = ops.weightnorm_bwd(dw.cuda(), v.cuda(), scale, inv_vnorm, want_dg=False)
     assert dg2 is None and torch.equal(dv, dv2)
+    # dW stored as bf16 (the bf16 gradient exchange averages dW before this pass): exact on the bf16 values
+    dwb = dw.bfloat16()
+    dv3, dg3 = ops.weightnorm_bwd(dwb.cuda(), v.cuda(), scale, inv_vnorm, want_dg=True)
+    dot3 = (dwb.double().numpy() * vhat).sum(-1, keepdims=True)
+    assert rel_err(dg3.cpu().numpy(), dot3) < 2e-6
+    assert rel_err(dv3.cpu().numpy(), (gn / nrm) * (dwb.double().numpy() - dot3 * vhat)) < 2e-6
+    dv4, _ = ops.weightnorm_bwd(dwb.float().cuda(), v.cuda(), scale, inv_vnorm, want_dg=False)
+    assert torch.equal(dv3, dv4)                                      # same arithmetic as the fp32 instantiation
 
 
 @pytest.mark.parametrize("M,N", [(2048, 256), (100, 70), (7, 2048)])
@@ -83,6 +91,18 @@ def test_split_and_cast():
     assert rel_err((hi.double() + lo.double()).cpu().numpy(), x.double().numpy()) < 3e-7
     y = ops.cast_bf16(x.cuda())
     assert torch.equal(y.cpu(), x.bfloat16())                         # round-to-nearest-even, like torch
+    # flat bf16 exchange buffer and back (narrow_bf16_into / widen_bf16_batch, 8 tensors per launch, odd sizes and offsets)
+    srcs = [_rand(n, 1, seed=20 + i).reshape(-1).cuda() for i, n in enumerate([5, 4096, 33, 1, 777, 8, 1000, 64, 3, 129])]
+    offs = np.cumsum([0] + [(t.numel() + 7) & ~7 for t in srcs])
+    flat = torch.zeros(int(offs[-1]), dtype=torch.bfloat16, device="cuda")
+    views = [flat[int(o):int(o) + t.numel()] for o, t in zip(offs, srcs)]
+    ops.narrow_bf16_into(srcs, views)
+    back = [torch.empty_like(t) for t in srcs]
+    ops.widen_bf16_batch(views, back)
+    for t, v_, b in zip(srcs, views, back):
+        assert torch.equal(v_, t.bfloat16()) and torch.equal(b, t.bfloat16().float())
+    with pytest.raises(ValueError):
+        ops.widen_bf16_batch([srcs[0]], [back[0]])                    # fp32 source is rejected
 
 
 @pytest.mark.parametrize("Nt,K", [(64, 512), (16, 384), (6, 1000), (512, 4096), (40, 65536)])

@@ -165,6 +165,86 @@ def test_ddp_wrapping_single_rank(golden):
             dist.destroy_process_group()
 
 
+def test_bf16_gradient_exchange_single_rank(golden):
+    """GradAllReduce(compress="bf16") on a 1-rank NCCL group: the last layer's dW leaves the wgrad GEMM in bf16, is
+    'averaged', and the weight-norm backward runs on the communication stream and sets weight_v.grad (and weight_g.grad
+    when the gain is trainable, golden tp_small) directly; the small gradients travel through one flat bf16 buffer.
+    Everything must still meet the bf16-GEMM tolerance against the reference's gradients, eagerly and from a CUDA graph."""
+    if golden.name not in ("mc_small", "tp_small"):
+        pytest.skip("two cases are enough")
+    import os
+    import torch.distributed as dist
+    created = False
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29577")
+        dist.init_process_group("nccl", rank=0, world_size=1)
+        created = True
+    D, student, teacher, loss_mod = _build(golden, "bf16")
+    red = None
+    try:
+        c, ref, tol = golden.cfg, golden.ref64, 2e-2
+        red = D.GradAllReduce(student.parameters(), compress="bf16")
+        xs = torch.from_numpy(golden.inputs["x_student"]).cuda().requires_grad_(True)
+        xt = torch.from_numpy(golden.inputs["x_teacher"]).cuda()
+        center0 = loss_mod.center.clone()
+
+        def step():
+            for p in student.parameters():
+                p.grad = None
+            xs.grad = None
+            with torch.no_grad():
+                t_out = teacher(xt)
+            loss = loss_mod(student(xs), t_out, c["epoch"])
+            loss.backward()
+            red.wait()
+            return loss
+
+        def check(loss):
+            torch.cuda.synchronize()
+            assert abs(float(loss) - float(ref["loss1"])) / abs(float(ref["loss1"])) < tol
+            assert rel_err(xs.grad.cpu().numpy(), ref["grad.x"]) < tol
+            n = 0
+            for name, p in student.named_parameters():
+                key = "grad." + name
+                if key in ref:
+                    assert p.grad is not None and p.grad.dtype == torch.float32 and p.grad.shape == p.shape, name
+                    assert rel_err(p.grad.cpu().numpy().reshape(ref[key].shape), ref[key]) < tol, name
+                    n += 1
+                else:
+                    assert p.grad is None, name
+            assert n >= 3
+
+        def reset_center():
+            loss_mod.center.copy_(center0)                         # in place: also the buffer a captured step reads
+
+        check(step())
+        eager_v = student.last_layer.weight_v.grad.clone()
+        reset_center()
+        check(step())                                              # a second step claims the route again (.grad was reset)
+        assert torch.equal(student.last_layer.weight_v.grad, eager_v)
+        g = D.StepGraph(step, warmup=2, capture_error_mode="thread_local")
+        reset_center()
+        check(g.replay())
+        assert torch.equal(student.last_layer.weight_v.grad, eager_v)
+        reset_center()
+        # a gradient already sitting in .grad (accumulation) sends the last layer through the regular autograd route
+        for p in student.parameters():
+            p.grad = None
+        student.last_layer.weight_v.grad = torch.zeros_like(student.last_layer.weight_v)
+        with torch.no_grad():
+            t_out = teacher(xt)
+        loss_mod(student(xs), t_out, c["epoch"]).backward()
+        red.wait()
+        torch.cuda.synchronize()
+        assert rel_err(student.last_layer.weight_v.grad.cpu().numpy(), ref["grad.last_layer.weight_v"]) < tol
+    finally:
+        if red is not None:
+            red.remove()
+        if created:
+            dist.destroy_process_group()
+
+
 @pytest.mark.parametrize("mode", ["bf16", "fp32"])
 def test_headline_size_properties(mode):
     """ViT-S/8 head at BASELINE cfg2 size (D=384, K=65536, B=256/4 to bound memory in fp32, 2+6 crops):
