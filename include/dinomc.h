@@ -252,6 +252,20 @@ int dmc_adamw_build_plan(const void* const* param_ptrs_host, const void* const* 
 int dmc_adamw_multi_tensor(const void* plan_dev, int64_t n_chunks, double lr, double beta1, double beta2, double eps,
                            double weight_decay, int64_t step, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The reference's LARS step (utils/utils.py:570-608; `--optimizer lars`, main_dino_mc.py:285-286) for one parameter group
+ * as two multi-tensor launches.  Per parameter: adapt = (ndim != 1); d = adapt ? g + wd*p : g;
+ * q = adapt && ||p|| > 0 && ||d|| > 0 ? eta*||p||/||d|| : 1; mu = mu*momentum + d*q; p -= lr*mu.
+ * adapt_host[i] != 0 marks the tensors with ndim != 1.  workspace: 2 floats per chunk.
+ * --------------------------------------------------------------------------------------------- */
+size_t dmc_lars_plan_bytes(const int64_t* numels_host, int64_t n_tensors);
+/* Fills plan_host (capacity from dmc_lars_plan_bytes) and *n_chunks_out.  Host-only; no CUDA calls. */
+int dmc_lars_build_plan(const void* const* param_ptrs_host, const void* const* grad_ptrs_host,
+                        const void* const* mu_ptrs_host, const int64_t* numels_host, const int32_t* adapt_host,
+                        int64_t n_tensors, void* plan_host, size_t plan_bytes, int64_t* n_chunks_out);
+int dmc_lars_multi_tensor(const void* plan_dev, int64_t n_chunks, double lr, double weight_decay, double momentum,
+                          double eta, float* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

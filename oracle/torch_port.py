@@ -123,6 +123,24 @@ def clip_gradients(grads, clip):
     return norms
 
 
+@torch.no_grad()
+def lars_step(params, grads, mus, lr, weight_decay, momentum=0.9, eta=0.001):
+    """utils/utils.py:584-608 (`LARS.step`) for one parameter group, on plain tensor lists: `params` and the momentum
+    buffers `mus` are updated in place.  Parameters with ndim == 1 get neither weight decay nor the trust ratio."""
+    for p, dp, mu in zip(params, grads, mus):
+        if dp is None:
+            continue
+        if p.ndim != 1:
+            dp = dp.add(p, alpha=weight_decay)
+            param_norm = torch.norm(p)
+            update_norm = torch.norm(dp)
+            one = torch.ones_like(param_norm)
+            q = torch.where(param_norm > 0., torch.where(update_norm > 0, (eta * param_norm / update_norm), one), one)
+            dp = dp.mul(q)
+        mu.mul_(momentum).add_(dp)
+        p.add_(mu, alpha=-lr)
+
+
 def step(x_student, x_teacher, student_p, teacher_p, state: LossState, epoch, ema_m, ema_extra=None):
     """One whole step of the path as SURVEY.md section 8d defines it: teacher head fwd (no grad),
     student head fwd, loss (+center), backward to head params and features, EMA over head (+extra

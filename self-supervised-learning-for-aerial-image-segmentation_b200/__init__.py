@@ -10,6 +10,7 @@ Python identifier).  Public surface mirrors the reference:
     ema_update_(teacher_params, student_params, m)
     clip_gradients(model, clip), cancel_gradients_last_layer(epoch, model, freeze_last_layer)   # utils/utils.py:145-162
     FusedAdamW(params_groups)                                 # torch.optim.AdamW of main_dino_mc.py:282, one launch per group
+    FusedLARS(params_groups)                                  # utils.LARS of main_dino_mc.py:286, two launches per group
     StepGraph(fn)      # capture a whole step into a CUDA graph and replay it
     dropin.install()   # patch the reference's modules in place
 
@@ -23,9 +24,9 @@ from .graph import StepGraph  # noqa: F401
 from .head import (DINOHead, get_default_precision, set_default_precision, set_teacher_overlap,  # noqa: F401
                    wait_ready)
 from .loss import DINOLoss, set_async_center  # noqa: F401
-from .optim import FusedAdamW, cancel_gradients_last_layer, clip_gradients  # noqa: F401
+from .optim import FusedAdamW, FusedLARS, cancel_gradients_last_layer, clip_gradients  # noqa: F401
 from .reducer import GradAllReduce  # noqa: F401
 from .wrapper import MultiCropWrapper  # noqa: F401
 
-__all__ = ["DINOHead", "DINOLoss", "ema_update_", "clip_gradients", "cancel_gradients_last_layer", "FusedAdamW", "MultiCropWrapper", "StepGraph", "GradAllReduce", "set_teacher_overlap", "set_async_center", "wait_ready", "set_default_precision", "get_default_precision",
+__all__ = ["DINOHead", "DINOLoss", "ema_update_", "clip_gradients", "cancel_gradients_last_layer", "FusedAdamW", "FusedLARS", "MultiCropWrapper", "StepGraph", "GradAllReduce", "set_teacher_overlap", "set_async_center", "wait_ready", "set_default_precision", "get_default_precision",
            "ops", "functional"]

@@ -77,6 +77,9 @@ SIGNATURES = {
     "dmc_adamw_plan_bytes": (sz, [C.POINTER(i64), i64]),
     "dmc_adamw_build_plan": (C.c_int, [C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), i64, vp, sz, C.POINTER(i64)]),
     "dmc_adamw_multi_tensor": (C.c_int, [vp, i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, i64, vp]),
+    "dmc_lars_plan_bytes": (sz, [C.POINTER(i64), i64]),
+    "dmc_lars_build_plan": (C.c_int, [C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(i32), i64, vp, sz, C.POINTER(i64)]),
+    "dmc_lars_multi_tensor": (C.c_int, [vp, i64, C.c_double, C.c_double, C.c_double, C.c_double, vp, sz, vp]),
 }
 
 _lib = None

@@ -631,3 +631,38 @@ class AdamWPlan:
             L.check(lib.dmc_adamw_multi_tensor(self.plan.data_ptr(), self.n_chunks, float(lr), float(beta1), float(beta2), float(eps),
                                                float(weight_decay), int(step), _stream()), "dmc_adamw_multi_tensor")
         _count()
+
+
+class LarsPlan:
+    """Device-resident chunk table over (param, grad, mu) triples of one parameter group (see dmc_lars_multi_tensor)."""
+
+    def __init__(self, params, grads, mus):
+        lib = L.load()
+        n = len(params)
+        if n == 0:
+            raise ValueError("lars: empty parameter group")
+        for t in list(params) + list(grads) + list(mus):
+            _need_cuda(t)
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise TypeError("lars: parameters, gradients and momentum buffers must be contiguous float32 tensors")
+        arr = lambda ts: (L.vp * n)(*[t.data_ptr() for t in ts])
+        numels = (L.i64 * n)(*[p.numel() for p in params])
+        adapt = (L.i32 * n)(*[int(p.dim() != 1) for p in params])
+        nbytes = lib.dmc_lars_plan_bytes(numels, n)
+        host = torch.empty(max(nbytes, 8), dtype=torch.uint8).pin_memory()
+        n_chunks = L.i64(0)
+        L.check(lib.dmc_lars_build_plan(arr(params), arr(grads), arr(mus), numels, adapt, n, host.data_ptr(), host.numel(),
+                                        C.byref(n_chunks)), "dmc_lars_build_plan")
+        self.n_chunks = n_chunks.value
+        self.plan = host.to(params[0].device, non_blocking=False)
+        self.partials = torch.empty(max(2 * self.n_chunks, 2), dtype=torch.float32, device=params[0].device)
+
+    def run(self, lr, weight_decay, momentum, eta):
+        if self.n_chunks == 0:
+            return
+        lib = L.load()
+        with _timed("lars"):
+            L.check(lib.dmc_lars_multi_tensor(self.plan.data_ptr(), self.n_chunks, float(lr), float(weight_decay), float(momentum),
+                                              float(eta), self.partials.data_ptr(), self.partials.numel() * 4, _stream()),
+                    "dmc_lars_multi_tensor")
+        _count(2)

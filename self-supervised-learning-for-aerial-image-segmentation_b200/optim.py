@@ -103,3 +103,44 @@ class FusedAdamW(torch.optim.Optimizer):
                     self._plans[key] = plan
                 plan.run(group["lr"], beta1, beta2, group["eps"], group["weight_decay"], t)
         return loss
+
+
+class FusedLARS(torch.optim.Optimizer):
+    """Drop-in for the reference's `utils.LARS(params_groups)` (utils/utils.py:570-608, main_dino_mc.py:285-286): same
+    constructor and defaults, same `param_groups` keys (lr / weight_decay rewritten per iteration by the schedules at
+    main_dino_mc.py:363-367), same per-parameter state (`mu`), so `state_dict()` / `load_state_dict()` interchange with
+    the reference optimizer and its checkpoints.  `step()` is two multi-tensor launches per parameter group (norms, then
+    update) with the trust ratio formed on the device: no per-parameter norm kernels, `where`s or temporaries.  Like the
+    reference, parameters with `ndim == 1` (biases, norm scales) get neither weight decay nor the LARS adaptation, and
+    the two filter arguments are accepted and ignored.  fp32 CUDA parameters only."""
+
+    def __init__(self, params, lr=0, weight_decay=0, momentum=0.9, eta=0.001, weight_decay_filter=None,
+                 lars_adaptation_filter=None):
+        defaults = dict(lr=lr, weight_decay=weight_decay, momentum=momentum, eta=eta, weight_decay_filter=weight_decay_filter,
+                        lars_adaptation_filter=lars_adaptation_filter)
+        super().__init__(params, defaults)
+        self._plans = {}
+
+    @torch.no_grad()
+    def step(self):
+        for gi, group in enumerate(self.param_groups):
+            params = [p for p in group["params"] if p.grad is not None]
+            if not params:
+                continue
+            for p in params:
+                if not p.is_cuda:
+                    raise RuntimeError("dinomc_b200 has no CPU path: FusedLARS parameters must be CUDA tensors")
+                if p.grad.is_sparse:
+                    raise RuntimeError("FusedLARS does not support sparse gradients")
+                st = self.state[p]
+                if "mu" not in st:
+                    st["mu"] = torch.zeros_like(p)
+            grads = [p.grad.data if p.grad.is_contiguous() else p.grad.data.contiguous() for p in params]
+            key = (gi, tuple((p.data_ptr(), g.data_ptr(), self.state[p]["mu"].data_ptr()) for p, g in zip(params, grads)))
+            plan = self._plans.get(key)
+            if plan is None:
+                if len(self._plans) > 8:
+                    self._plans.clear()
+                plan = ops.LarsPlan([p.data for p in params], grads, [self.state[p]["mu"] for p in params])
+                self._plans[key] = plan
+            plan.run(group["lr"], group["weight_decay"], group["momentum"], group["eta"])

@@ -138,6 +138,36 @@ def test_adamw_plan_builder_and_validation_on_host():
     assert b"step" in lib.dmc_last_error_string()
 
 
+def test_lars_plan_builder_and_validation_on_host():
+    import struct
+    import dinomc_b200
+    L = dinomc_b200._lib
+    lib = L.load()
+    numels = [3, 20000]
+    n = len(numels)
+    arr = (L.i64 * n)(*numels)
+    adapt = (L.i32 * n)(0, 1)
+    nbytes = lib.dmc_lars_plan_bytes(arr, n)
+    assert nbytes == 3 * 48
+    mk = lambda base: (L.vp * n)(*[base * (i + 1) for i in range(n)])
+    buf = (C.c_uint8 * nbytes)()
+    out = L.i64(0)
+    assert lib.dmc_lars_build_plan(mk(0x1000), mk(0x2000), mk(0x4000), arr, adapt, n, buf, nbytes, C.byref(out)) == 0
+    assert out.value == 3
+    e = [struct.unpack("<qqqqiiii", bytes(buf[i * 48:(i + 1) * 48])) for i in range(3)]
+    assert e[0] == (0x1000, 0x2000, 0x4000, 3, 0, 1, 0, 0)                       # 1-D tensor: no adaptation, own chunk range
+    assert e[1] == (0x2000, 0x4000, 0x8000, 16384, 1, 2, 1, 0)
+    assert e[2] == (0x2000 + 16384 * 4, 0x4000 + 16384 * 4, 0x8000 + 16384 * 4, 20000 - 16384, 1, 2, 1, 0)
+    assert lib.dmc_lars_build_plan(mk(0x1000), mk(0x2000), mk(0x4000), arr, adapt, n, buf, nbytes - 1, C.byref(out)) < 0
+    assert lib.dmc_lars_multi_tensor(None, 1, 0.1, 0.0, 0.9, 0.001, None, 0, None) < 0      # null plan
+    ws = (C.c_float * 2)()
+    assert lib.dmc_lars_multi_tensor(buf, 3, 0.1, 0.0, 0.9, 0.001, ws, 8, None) < 0         # workspace too small for 3 chunks
+    assert b"workspace" in lib.dmc_last_error_string()
+    import inspect
+    assert list(inspect.signature(dinomc_b200.FusedLARS.__init__).parameters)[1:] == [
+        "params", "lr", "weight_decay", "momentum", "eta", "weight_decay_filter", "lars_adaptation_filter"]
+
+
 def test_module_surface_matches_reference_signature():
     import inspect
     import dinomc_b200 as D

@@ -50,6 +50,37 @@ def test_oracle_clip_gradients_equals_reference_function():
             assert torch.equal(p.grad, g)
 
 
+def test_oracle_lars_equals_reference_optimizer():
+    """The restated LARS step (oracle/torch_port.py) against the reference's own utils.LARS (utils/utils.py:570-608) under
+    the reference's usage: two parameter groups, lr / weight decay rewritten per iteration; bit-identical on CPU."""
+    if not reference_loader.available():
+        pytest.skip("reference not present")
+    import copy
+    import torch
+    from oracle import torch_port
+    _, _, utils = reference_loader.load()
+    torch.manual_seed(5)
+    ma = torch.nn.Sequential(torch.nn.Linear(37, 64), torch.nn.GELU(), torch.nn.Linear(64, 5), torch.nn.LayerNorm(5))
+    mb = copy.deepcopy(ma)
+    opt = utils.LARS(utils.get_params_groups(ma))
+    mus = [torch.zeros_like(p) for p in mb.parameters()]
+    for it in range(4):
+        lr, wd = 0.3 * (1 + it), 1e-4 * (1 + it)
+        for gi, group in enumerate(opt.param_groups):
+            group["lr"] = lr
+            if gi == 0:
+                group["weight_decay"] = wd
+        grads = []
+        for pa in ma.parameters():
+            pa.grad = torch.randn_like(pa) * 0.2
+            grads.append(pa.grad.clone())
+        opt.step()
+        torch_port.lars_step([p.data for p in mb.parameters()], grads, mus, lr, wd)
+        for pa, pb, mu in zip(ma.parameters(), mb.parameters(), mus):
+            assert torch.equal(pa, pb)
+            assert torch.equal(opt.state[pa]["mu"], mu)
+
+
 def test_reference_checkpoint_layout_loads_into_dropin_modules():
     """a checkpoint written by the reference (main_dino_mc.py:333-345: `student` / `teacher` are
     state dicts of MultiCropWrapper(backbone, DINOHead), `dino_loss` holds the center) loads into the same wrapper built

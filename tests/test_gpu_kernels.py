@@ -315,3 +315,59 @@ def test_fused_adamw_matches_torch_adamw_and_exchanges_state():
     for pa, pb in zip(ma.parameters(), mb.parameters()):
         assert rel_err(pb.detach().cpu().numpy(), pa.detach().cpu().numpy()) < 2e-6
         assert float(oc.state[pb]["step"]) == 9.0
+
+
+def test_fused_lars_matches_reference_lars_and_exchanges_state():
+    """FusedLARS against the restated reference LARS (oracle/torch_port.lars_step, pinned bit-for-bit to utils.LARS in
+    tests/test_dropin_reference.py) under the reference's usage (main_dino_mc.py:285-286, :363-367): two parameter groups,
+    scheduled lr / weight decay; includes an all-zero weight (trust ratio falls back to 1) and a state_dict round trip."""
+    import dinomc_b200 as D
+    from oracle import torch_port
+    ma, mb = _two_models(seed=2)
+    with torch.no_grad():
+        ma[2].weight.zero_(); mb[2].weight.zero_()            # ||p|| = 0 -> q = 1
+    ref_p = [p.detach().cpu().clone() for p in ma.parameters()]
+    ref_mu = [torch.zeros_like(p) for p in ref_p]
+    names = [n for n, _ in mb.named_parameters()]
+    reg = [i for i, (n, p) in enumerate(mb.named_parameters()) if not (n.endswith(".bias") or p.dim() == 1)]
+    noreg = [i for i in range(len(names)) if i not in reg]
+    opt = D.FusedLARS(_groups(mb))
+    assert set(opt.param_groups[0]) >= {"lr", "weight_decay", "momentum", "eta", "weight_decay_filter", "lars_adaptation_filter"}
+    g = torch.Generator().manual_seed(7)
+
+    def run(o, steps, it0):
+        for it in range(it0, it0 + steps):
+            lr, wd = 0.2 * (1 + 0.5 * it), 1e-4 * (1 + it)
+            for gi, group in enumerate(o.param_groups):
+                group["lr"] = lr
+                if gi == 0:
+                    group["weight_decay"] = wd
+            grads = [torch.randn(p.shape, generator=g) * 0.1 for p in ref_p]
+            for p, gr in zip(mb.parameters(), grads):
+                p.grad = gr.cuda()
+            o.step()
+            torch_port.lars_step([ref_p[i] for i in reg], [grads[i] for i in reg], [ref_mu[i] for i in reg], lr, wd)
+            torch_port.lars_step([ref_p[i] for i in noreg], [grads[i] for i in noreg], [ref_mu[i] for i in noreg], lr, 0.0)
+
+    run(opt, 5, 0)
+    torch.cuda.synchronize()
+    for p, rp, rmu, n in zip(mb.parameters(), ref_p, ref_mu, names):
+        assert rel_err(p.detach().cpu().numpy(), rp.numpy()) < 1e-6, n
+        assert rel_err(opt.state[p]["mu"].cpu().numpy(), rmu.numpy()) < 1e-6, n
+    # state_dict round trip into a fresh optimizer (same layout as the reference's: state[p] = {"mu"}), keep stepping
+    opt2 = D.FusedLARS(_groups(mb))
+    opt2.load_state_dict(opt.state_dict())
+    run(opt2, 3, 5)
+    torch.cuda.synchronize()
+    for p, rp, n in zip(mb.parameters(), ref_p, names):
+        assert rel_err(p.detach().cpu().numpy(), rp.numpy()) < 2e-6, n
+    # a parameter without a gradient is skipped, CPU parameters are rejected
+    for p in mb.parameters():
+        p.grad = None
+    before = [p.detach().clone() for p in mb.parameters()]
+    opt2.step()
+    assert all(torch.equal(a, b) for a, b in zip(before, mb.parameters()))
+    cpu = torch.nn.Linear(4, 4)
+    cpu.weight.grad = torch.zeros_like(cpu.weight)
+    with pytest.raises(RuntimeError):
+        D.FusedLARS([cpu.weight]).step()

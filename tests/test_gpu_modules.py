@@ -165,6 +165,46 @@ def test_ddp_wrapping_single_rank(golden):
             dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-5), ("bf16", 2e-2)])
+def test_use_bn_head_matches_torch_restatement(mode, tol):
+    """`use_bn_in_head` (utils/vision_transformer.py:268-274).  The BatchNorm1d MLP stays torch
+    modules; F.normalize and the weight-normed last layer (forward and backward) run on our kernels.  Checked against the
+    same head evaluated in float64 on the CPU (train-mode batch statistics), including the running statistics."""
+    import copy
+    import torch.nn.functional as F
+    import dinomc_b200 as D
+    torch.manual_seed(11)
+    head = D.DINOHead(64, 1024, use_bn=True, norm_last_layer=False, hidden_dim=128, bottleneck_dim=64).cuda()
+    assert [type(m).__name__ for m in head.mlp] == ["Linear", "BatchNorm1d", "GELU", "Linear", "BatchNorm1d", "GELU", "Linear"]
+    head.precision = mode
+    with torch.no_grad():
+        head.last_layer.weight_g.uniform_(0.5, 1.5)
+    ref_mlp = copy.deepcopy(head.mlp).cpu().double()
+    g64 = head.last_layer.weight_g.detach().cpu().double().requires_grad_(True)
+    v64 = head.last_layer.weight_v.detach().cpu().double().requires_grad_(True)
+    x = torch.randn(48, 64, generator=torch.Generator().manual_seed(12))
+    up = torch.randn(48, 1024, generator=torch.Generator().manual_seed(13))
+    xg = x.cuda().requires_grad_(True)
+    out = head(xg)
+    (out.float() * up.cuda()).sum().backward()
+    x64 = x.double().requires_grad_(True)
+    z = F.normalize(ref_mlp(x64), dim=-1, p=2)
+    ref = z @ (v64 * (g64 / v64.norm(dim=1, keepdim=True))).t()
+    (ref * up.double()).sum().backward()
+    assert rel_err(out.detach().float().cpu().numpy(), ref.detach().numpy()) < tol
+    assert rel_err(xg.grad.cpu().numpy(), x64.grad.numpy()) < tol
+    assert rel_err(head.last_layer.weight_v.grad.cpu().numpy(), v64.grad.numpy()) < tol
+    assert rel_err(head.last_layer.weight_g.grad.cpu().numpy(), g64.grad.numpy()) < tol
+    wmax = max(float(q.grad.abs().max()) for q in ref_mlp.parameters())
+    for (n, p), q in zip(head.mlp.named_parameters(), ref_mlp.parameters()):
+        if n in ("0.bias", "3.bias"):          # a bias in front of a BatchNorm has an exactly-zero gradient: only rounding noise
+            assert float(p.grad.abs().max()) < 1e-4 * wmax and float(q.grad.abs().max()) < 1e-10, n
+        else:
+            assert rel_err(p.grad.cpu().numpy(), q.grad.numpy()) < tol, n
+    assert rel_err(head.mlp[1].running_var.cpu().numpy(), ref_mlp[1].running_var.numpy()) < 1e-5
+    assert "mlp.1.running_mean" in head.state_dict()          # buffers: in checkpoints, excluded from the EMA zip (parameters only)
+
+
 def test_bf16_gradient_exchange_single_rank(golden):
     """GradAllReduce(compress="bf16") on a 1-rank NCCL group: the last layer's dW leaves the wgrad GEMM in bf16, is
     'averaged', and the weight-norm backward runs on the communication stream and sets weight_v.grad (and weight_g.grad
