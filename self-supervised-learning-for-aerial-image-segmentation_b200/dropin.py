@@ -3,13 +3,16 @@
     import dinomc_b200.dropin as dropin
     dropin.install()                      # before main_dino_mc.train_dino(args)
 
-`install()` rebinds three names inside the reference's modules:
+`install()` rebinds these names inside the reference's modules:
 
   utils.vision_transformer.DINOHead  -> dinomc_b200.DINOHead   (constructed at main_dino_mc.py:236-246)
   main_dino_mc.DINOLoss              -> dinomc_b200.DINOLoss   (constructed at main_dino_mc.py:269-277)
   main_dino_mc.train_one_epoch       -> train_one_epoch below  (the EMA loop at :403-406 is inline in the
                                          reference and has no seam of its own; this is the same step with the
                                          per-parameter loop replaced by one ema_update_ call)
+
+  utils.MultiCropWrapper             -> dinomc_b200.MultiCropWrapper   (utils/utils.py:611-646; one feature concatenation)
+  utils.LARS                         -> dinomc_b200.FusedLARS  (constructed at main_dino_mc.py:286 for `--optimizer lars`)
 
 Everything else -- argument parsing, data loading, backbones, MultiCropWrapper, DDP, the optimizer, gradient
 clipping, checkpointing, logging -- stays the reference's code, looked up at run time.
@@ -24,7 +27,7 @@ import torch
 from .ema import ema_update_
 from .head import DINOHead
 from .loss import DINOLoss
-from .optim import cancel_gradients_last_layer, clip_gradients
+from .optim import FusedLARS, cancel_gradients_last_layer, clip_gradients
 from .wrapper import MultiCropWrapper
 
 
@@ -85,6 +88,7 @@ def install(patch_train_loop: bool = True):
     vits.DINOHead = DINOHead
     main_dino_mc.DINOLoss = DINOLoss
     main_dino_mc.utils.MultiCropWrapper = MultiCropWrapper     # same contract, single feature concatenation
+    main_dino_mc.utils.LARS = FusedLARS                        # `--optimizer lars` (main_dino_mc.py:285-286): same signature / state
     if patch_train_loop:
         main_dino_mc.train_one_epoch = train_one_epoch
     return main_dino_mc

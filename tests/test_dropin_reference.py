@@ -12,10 +12,12 @@ def test_install_rebinds_reference_symbols():
     main_dino_mc, vits, _ = reference_loader.load()
     orig = (vits.DINOHead, main_dino_mc.DINOLoss, main_dino_mc.train_one_epoch)
     orig_wrapper = main_dino_mc.utils.MultiCropWrapper
+    orig_lars = main_dino_mc.utils.LARS
     try:
         import dinomc_b200
         from dinomc_b200 import dropin
         dropin.install()
+        assert main_dino_mc.utils.LARS is dinomc_b200.FusedLARS
         assert vits.DINOHead is dinomc_b200.DINOHead
         assert main_dino_mc.DINOLoss is dinomc_b200.DINOLoss
         assert main_dino_mc.train_one_epoch is dropin.train_one_epoch
@@ -28,6 +30,7 @@ def test_install_rebinds_reference_symbols():
     finally:
         vits.DINOHead, main_dino_mc.DINOLoss, main_dino_mc.train_one_epoch = orig
         main_dino_mc.utils.MultiCropWrapper = orig_wrapper
+        main_dino_mc.utils.LARS = orig_lars
 
 
 def test_oracle_clip_gradients_equals_reference_function():
