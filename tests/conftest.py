@@ -60,3 +60,38 @@ def rel_err(a, b):
     b = np.asarray(b, np.float64)
     denom = max(float(np.abs(b).max()), 1e-30)
     return float(np.abs(a - b).max()) / denom
+
+
+class OptimGolden:
+    """tests/golden/optim_small.npz: the reference's own utils.LARS / utils.clip_gradients on a small model
+    (oracle/gen_golden_optim.py)."""
+
+    def __init__(self):
+        import torch
+        z = np.load(os.path.join(GOLDEN_DIR, "optim_small.npz"))
+        self.z = z
+        self.names = z["names"].tolist()
+        self.steps = int(z["steps"])
+        self.model = torch.nn.Sequential(torch.nn.Linear(130, 150), torch.nn.GELU(), torch.nn.Linear(150, 9), torch.nn.LayerNorm(9))
+        assert [n for n, _ in self.model.named_parameters()] == self.names
+        with torch.no_grad():
+            for n, p in self.model.named_parameters():
+                p.copy_(torch.from_numpy(z["p0." + n]))
+
+    @staticmethod
+    def schedule(it):
+        return 0.3 * (1 + 0.5 * it), 1e-4 * (1 + it)
+
+    def grads(self, it):
+        import torch
+        return [torch.from_numpy(self.z[f"g{it}." + n].copy()) for n in self.names]
+
+    def groups(self, model):
+        """utils/utils.py:649-660 get_params_groups -> index lists (regularized, not regularized)."""
+        reg = [i for i, (n, p) in enumerate(model.named_parameters()) if not (n.endswith(".bias") or len(p.shape) == 1)]
+        return reg, [i for i in range(len(self.names)) if i not in reg]
+
+
+@pytest.fixture
+def optim_golden():
+    return OptimGolden()

@@ -371,3 +371,34 @@ def test_fused_lars_matches_reference_lars_and_exchanges_state():
     cpu.weight.grad = torch.zeros_like(cpu.weight)
     with pytest.raises(RuntimeError):
         D.FusedLARS([cpu.weight]).step()
+
+
+def test_fused_lars_and_clip_against_reference_outputs(optim_golden):
+    """FusedLARS and clip_gradients against outputs of the REFERENCE's own utils.LARS / utils.clip_gradients
+    (tests/golden/optim_small.npz, generated in the build container by oracle/gen_golden_optim.py)."""
+    import dinomc_b200 as D
+    G = optim_golden
+    model = G.model.cuda()
+    ps = list(model.parameters())
+    reg, noreg = G.groups(model)
+    opt = D.FusedLARS([{"params": [ps[i] for i in reg]}, {"params": [ps[i] for i in noreg], "weight_decay": 0.0}])
+    for it in range(G.steps):
+        lr, wd = G.schedule(it)
+        for gi, group in enumerate(opt.param_groups):
+            group["lr"] = lr
+            if gi == 0:
+                group["weight_decay"] = wd
+        for p, g in zip(ps, G.grads(it)):
+            p.grad = g.cuda()
+        opt.step()
+    torch.cuda.synchronize()
+    for n, p in zip(G.names, ps):
+        assert rel_err(p.detach().cpu().numpy(), G.z["lars.p." + n]) < 1e-6, n
+        assert rel_err(opt.state[p]["mu"].cpu().numpy(), G.z["lars.mu." + n]) < 1e-6, n
+    for clip in (3.0, 0.05):
+        for p, g in zip(ps, G.grads(0)):
+            p.grad = g.cuda()
+        norms = D.clip_gradients(model, clip)
+        assert rel_err(norms.cpu().numpy(), G.z[f"clip{clip}.norms"]) < 1e-6
+        for n, p in zip(G.names, ps):
+            assert rel_err(p.grad.cpu().numpy(), G.z[f"clip{clip}.g." + n]) < 1e-6, n

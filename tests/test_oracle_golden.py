@@ -96,3 +96,31 @@ def test_torch_port_step(golden, dtype, tol):
         for k, ref in golden.ref32.items():
             if k.startswith("ema."):
                 assert np.array_equal(tp[k[4:]].detach().numpy(), ref), k
+
+
+def test_torch_port_lars_and_clip_against_reference_outputs(optim_golden):
+    """oracle/torch_port.lars_step / clip_gradients against outputs of the reference's own utils.LARS / utils.clip_gradients
+    (tests/golden/optim_small.npz).  Same torch ops in the same order: 1e-6 leaves room for a different CPU vector width
+    in torch.norm on another host (bit-identical in the build container, tests/test_dropin_reference.py)."""
+    import torch
+    from oracle import torch_port
+    G = optim_golden
+    params = [p.detach().clone() for p in G.model.parameters()]
+    mus = [torch.zeros_like(p) for p in params]
+    reg, noreg = G.groups(G.model)
+    for it in range(G.steps):
+        lr, wd = G.schedule(it)
+        gr = G.grads(it)
+        torch_port.lars_step([params[i] for i in reg], [gr[i] for i in reg], [mus[i] for i in reg], lr, wd)
+        torch_port.lars_step([params[i] for i in noreg], [gr[i] for i in noreg], [mus[i] for i in noreg], lr, 0.0)
+    for n, p, mu in zip(G.names, params, mus):
+        assert rel_err(p.numpy(), G.z["lars.p." + n]) < 1e-6, n
+        assert rel_err(mu.numpy(), G.z["lars.mu." + n]) < 1e-6, n
+    for clip in (3.0, 0.05):
+        gr = G.grads(0)
+        norms = torch_port.clip_gradients(gr, clip)
+        assert rel_err(np.array(norms), G.z[f"clip{clip}.norms"]) < 1e-6
+        for n, g in zip(G.names, gr):
+            assert rel_err(g.numpy(), G.z[f"clip{clip}.g." + n]) < 1e-6, n
+    n3 = G.z["clip3.0.norms"]
+    assert (G.z["clip0.05.norms"] > 0.05).all() and (n3 > 3.0).any() and (n3 < 3.0).any()     # one case clips everything, one some
