@@ -56,6 +56,10 @@ aux_overlap = True
 grad_exchange_active = False     # set by GradAllReduce: the last layer's dv (64 MiB, the largest all-reduce of the step) must
                                  # then be final as early as possible, so its weight-norm backward stays in front of the dgrad
 grad_exchange = None             # the active GradAllReduce (or None); with compress="bf16" the last layer hands it a bf16 dW
+import os as _os
+wgrad_bf16 = _os.environ.get("DMC_WGRAD_BF16", "") == "1"   # EXPERIMENT (off; not yet measured): in the bf16-GEMM mode the last layer's
+                                 # wgrad stores dW in bf16 and the weight-norm backward reads it (-64 MB of traffic per step at
+                                 # K = 65536; same kernels as the bf16 gradient exchange, gradients stay within the 2e-2 tolerance)
 _aux_streams = {}
 
 
@@ -339,7 +343,8 @@ class NormLastLayerFn(torch.autograd.Function):
             elif ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
                 # wgrad first: dW[K,dim] = dlogits^T . zhat (both MN-major).  dv is the largest gradient of the step
                 # (K x 256 fp32); marking it ready here lets its all-reduce overlap the dgrad and the MLP backward.
-                dw = mm(mode, d, ctx.zop, K, dim, rows, a_mn=True, b_mn=True, out_dtype=torch.float32, tag="gemm_last_wgrad")
+                dw = mm(mode, d, ctx.zop, K, dim, rows, a_mn=True, b_mn=True,
+                        out_dtype=torch.bfloat16 if (wgrad_bf16 and mode == "bf16") else torch.float32, tag="gemm_last_wgrad")
                 if aux_overlap and not grad_exchange_active:   # streaming pass on the auxiliary stream: the dgrad GEMM does not wait for it
                     region = _AuxRegion(dw.device)
                     with region:

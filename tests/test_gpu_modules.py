@@ -205,6 +205,22 @@ def test_use_bn_head_matches_torch_restatement(mode, tol):
     assert "mlp.1.running_mean" in head.state_dict()          # buffers: in checkpoints, excluded from the EMA zip (parameters only)
 
 
+@pytest.mark.skipif(not __import__("os").environ.get("DMC_TEST_EXPERIMENTAL"), reason="experimental switch, not part of the default path")
+def test_experimental_bf16_wgrad_storage(golden, monkeypatch):
+    """functional.wgrad_bf16: dW of the last layer stored in bf16 between the wgrad GEMM and the weight-norm backward."""
+    import dinomc_b200.functional as Fn
+    monkeypatch.setattr(Fn, "wgrad_bf16", True)
+    D, student, teacher, loss_mod = _build(golden, "bf16")
+    c, ref = golden.cfg, golden.ref64
+    xs = torch.from_numpy(golden.inputs["x_student"]).cuda().requires_grad_(True)
+    with torch.no_grad():
+        t_out = teacher(torch.from_numpy(golden.inputs["x_teacher"]).cuda())
+    loss_mod(student(xs), t_out, c["epoch"]).backward()
+    for name, p in student.named_parameters():
+        if "grad." + name in ref:
+            assert rel_err(p.grad.cpu().numpy().reshape(ref["grad." + name].shape), ref["grad." + name]) < 2e-2, name
+
+
 def test_bf16_gradient_exchange_single_rank(golden):
     """GradAllReduce(compress="bf16") on a 1-rank NCCL group: the last layer's dW leaves the wgrad GEMM in bf16, is
     'averaged', and the weight-norm backward runs on the communication stream and sets weight_v.grad (and weight_g.grad
