@@ -11,6 +11,7 @@
 // small workspace and are merged in a fixed order (deterministic, no atomics).
 // HBM-bound: algorithmic bytes = Nt*K*sizeof(logit) read; everything else is O(Nt + K).
 #include <math.h>
+#include <stdlib.h>
 
 #include "dmc_common.cuh"
 
@@ -168,7 +169,14 @@ TeacherPlan teacher_plan(int64_t Nt, int64_t K) {
   TeacherPlan p{};
   p.nchunks = static_cast<int>(ceil_div(K, kChunk));
   const int64_t rows_unit = kWarps * kRowsInFlight;
-  int64_t nrb = ceil_div(8 * kNumSMs, p.nchunks);
+  // grid size target: 8 CTAs per SM's worth of (chunk, row block) pairs.  DMC_TEACHER_TARGET_CTAS (read once) overrides it
+  // for timing experiments: fewer, longer-lived CTAs amortise the per-CTA prologue (center loads, smem merge).
+  static const int64_t target_ctas = [] {
+    const char* e = getenv("DMC_TEACHER_TARGET_CTAS");
+    const long v = e ? strtol(e, nullptr, 10) : 0;
+    return static_cast<int64_t>(v > 0 ? v : 8 * kNumSMs);
+  }();
+  int64_t nrb = ceil_div(target_ctas, p.nchunks);
   const int64_t max_rb = ceil_div(Nt, rows_unit);
   if (nrb > max_rb) nrb = max_rb;
   if (nrb < 1) nrb = 1;

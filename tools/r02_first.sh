@@ -21,5 +21,8 @@ PY
 run default DMC_NOP=1
 run wgrad_bf16 DMC_WGRAD_BF16=1          # dW stored bf16 between wgrad and weight-norm backward (-64 MB / step)
 run default2 DMC_NOP=1                   # run-to-run spread
+for n in 296 592 2368; do                # teacher statistics pass: CTA count (default 1184 = 8 per SM); it is latency-bound (26 % DRAM)
+  run teacher_ctas_$n DMC_TEACHER_TARGET_CTAS=$n
+done
 # where the MLP backward goes: one ncu full capture of the layer-2 dgrad (GELU' epilogue) and the layer-3 shapes
 tools/ncu_src.sh mlp_dgrad2 3 python tools/gemm_bench.py mlp_dgrad2
