@@ -73,6 +73,37 @@ def roofline_model(w, P, logit_bytes):
     return flops, nbytes
 
 
+def op_models(w, P, e):
+    """{op tag: (algorithmic bytes, algorithmic flops)} of ALL launches of that op in one step (DESIGN.md section 4);
+    e = bytes per stored logit.  Tags are the ones ops.py times its C-ABI calls under."""
+    D, K, B, C, G = w["D"], w["K"], w["B"], w["C"], w["G"]
+    Ns, Nt = C * B, G * B
+    mlp_w = D * H + H * H + H * BN                      # MLP weights of one head
+    f_mlp = lambda n: 2 * n * mlp_w
+    f_last = lambda n: 2 * n * BN * K
+    act = lambda n: n * (D + 2 * H + BN)                # activation elements of one head forward
+    return {
+        # loss
+        "ce_fused": (e * K * (2 * Ns + Nt), 0), "ce_bwd": (e * K * (2 * Ns + Nt), 0), "ce_fwd": (e * K * (Ns + Nt), 0),
+        "teacher_stats_colsum": (e * K * Nt, 0),
+        # EMA (+ the teacher's operand shadows it emits)
+        "ema": (12 * P, 0),
+        # last layer
+        "gemm_last_fwd_student": (e * K * Ns + 2 * BN * (K + Ns), f_last(Ns)),
+        "gemm_last_fwd_teacher": (e * K * Nt + 2 * BN * (K + Nt), f_last(Nt)),
+        "gemm_last_wgrad": (e * K * Ns + 2 * BN * Ns + 4 * K * BN, f_last(Ns)),
+        "gemm_last_dgrad": (e * K * Ns + 2 * K * BN + 4 * BN * Ns, f_last(Ns)),
+        "weightnorm_fwd": ((4 + e) * K * BN, 0), "weightnorm_bwd": (12 * K * BN, 0),
+        # MLP (bf16 operands / activations, fp32 weight gradients)
+        "gemm_mlp_fwd": (2 * (act(Ns) + act(Nt)) + 2 * 2 * mlp_w, f_mlp(Ns) + f_mlp(Nt)),
+        "gemm_mlp_dgrad": (2 * 2 * act(Ns) + 2 * mlp_w, f_mlp(Ns)),
+        "gemm_mlp_wgrad": (2 * 2 * act(Ns) + 4 * mlp_w, f_mlp(Ns)),
+        "cast_bf16": (6 * (Ns * D + Nt * D + mlp_w), 0),
+        "colsum": (2 * Ns * (2 * H + BN), 0),
+        "normalize_fwd": (10 * BN * (Ns + Nt), 0), "normalize_bwd": (12 * BN * Ns, 0),
+    }
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -191,11 +222,52 @@ class Step:
         s_out = self.model(xs)
         loss = self.loss_mod(s_out, t_out, 0)
         loss.backward()
-        self.D.ema_update_(self.ema_teacher, self.ema_student, self.m)
         if self.reducer is not None:
-            self.reducer.wait()             # averaged gradients are complete at the end of the step ...
-        self.loss_mod.sync_center()         # ... and so is the all-reduced center (no-op unless it ran asynchronously)
+            # main_dino_mc.py:383-406: the optimizer consumes the averaged gradients BEFORE the EMA reads the student, so
+            # the EMA must not be used to hide the gradient exchange: join the exchange first
+            self.reducer.wait()
+        self.D.ema_update_(self.ema_teacher, self.ema_student, self.m)
+        self.loss_mod.sync_center()         # the all-reduced center is complete too (no-op unless it ran asynchronously)
         return loss
+
+    def verify_exchange(self):
+        """N > 1, after the timed region: numbers evidence for the gradient exchange.  One eager step WITH the reducer,
+        one WITHOUT (local gradients, averaged here by a plain fp32 NCCL all-reduce); reports whether every rank holds
+        bit-identical exchanged gradients and how far they are from the plain mean of the local gradients."""
+        import torch.distributed as dist
+        params = [p for p in self.student.parameters() if p.requires_grad]
+        state = (self.loss_mod.center.detach().clone(), [t.detach().clone() for t in self.ema_teacher])
+        self.run()
+        torch.cuda.synchronize()
+        got = [p.grad.detach().clone() for p in params]
+        with torch.no_grad():                                   # same inputs and state for the second pass
+            self.loss_mod.sync_center()
+            self.loss_mod.center.copy_(state[0])
+            for t, q in zip(self.ema_teacher, state[1]):
+                t.copy_(q)
+        red, self.reducer = self.reducer, None
+        red.remove()
+        try:
+            self.run()
+            torch.cuda.synchronize()
+            ref = [p.grad.detach().clone() for p in params]
+        finally:
+            self.reducer = red
+        worst, scale = 0.0, 0.0
+        for g, r in zip(got, ref):
+            dist.all_reduce(r, op=dist.ReduceOp.AVG)
+            worst = max(worst, float((g.double() - r.double()).abs().max()) / max(float(r.double().abs().max()), 1e-30))
+        # bit-identity across ranks: every rank's byte-level checksum of the exchanged gradients must agree
+        acc = torch.zeros((), dtype=torch.int64, device=self.device)
+        for g in got:
+            acc += g.contiguous().view(torch.int32).to(torch.int64).sum()
+        lo, hi = acc.clone(), acc.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        w_t = torch.tensor([worst], device=self.device, dtype=torch.float64)
+        dist.all_reduce(w_t, op=dist.ReduceOp.MAX)
+        return {"grads_bit_identical_across_ranks": bool(int(lo) == int(hi)), "checksum": int(acc),
+                "max_rel_diff_vs_mean_of_local_grads": float(w_t), "tensors": len(got)}
 
     def _prefetch(self, idx):
         if self.stage_consumed[idx] is not None:             # do not overwrite a stage its consumer has not copied out yet
@@ -280,7 +352,8 @@ def per_kernel_times(step, steps):
 
 
 def cpu_baseline(w, sample_B, steps, warmup):
-    """oracle/torch_port.py (the reference's eager path restated) on the host cores, bounded sample."""
+    """oracle/torch_port.py (the reference's eager path restated op for op) on the host cores.  `sample_B` = samples
+    per step; by default the workload's own per-GPU batch, i.e. the same step the GPU arm runs."""
     from oracle import torch_port as T
     torch.set_num_threads(os.cpu_count() or 1)
     Din, K, C, G = w["D"], w["K"], w["C"], w["G"]
@@ -300,11 +373,12 @@ def cpu_baseline(w, sample_B, steps, warmup):
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     med = float(np.median(times))
+    full = (sample_B == w["B"])
     return dict(value=sample_B / med, unit="samples/s", cores=torch.get_num_threads(), kind="port",
-                sample=f"B={sample_B} of {w['B']} samples per step (same D={Din}, K={K}, {C} crops, full "
-                       f"{sum(t.numel() for t in bb_s) / 1e6 + sum(v.numel() for v in sp.values()) / 1e6:.1f}M-param EMA), "
-                       f"{warmup} warm-up + {steps} steps, torch CPU fp32, median",
-                ms_per_step=med * 1e3)
+                sample=(f"{'the full step' if full else 'REDUCED batch'}: B={sample_B} samples per step (workload B={w['B']}; D={Din}, K={K}, "
+                        f"{C} crops, {sum(t.numel() for t in bb_s) / 1e6 + sum(v.numel() for v in sp.values()) / 1e6:.1f}M-param EMA), "
+                        f"{warmup} warm-up + {steps} timed steps, oracle/torch_port.py on torch CPU fp32, median"),
+                ms_per_step=med * 1e3, sample_batch=sample_B)
 
 
 _JSON_FD = None
@@ -346,7 +420,10 @@ def main():
                          "last layer averaged before its weight-norm backward + the small gradients as one flat bf16 buffer). "
                          "bf16 measured SLOWER at 2 GPUs (1.068 vs 0.980 ms), so it stays opt-in")
     ap.add_argument("--overlap", type=int, default=1, help="teacher head forward on a side stream, overlapping the student's")
-    ap.add_argument("--cpu-sample-batch", type=int, default=32)
+    ap.add_argument("--cpu-sample-batch", type=int, default=0,
+                    help="samples per CPU step for cpu_baseline / --impl reference (0 = the workload's own per-GPU batch)")
+    ap.add_argument("--verify", type=int, default=1, help="N>1: after timing, check the exchanged gradients (bit-identical across "
+                                                          "ranks, equal to the mean of the ranks' local gradients)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -371,19 +448,28 @@ def main():
                                                                            if compress else "fp32)"))),
            "l2": "per-step working set (logits + gradients > 1 GiB) exceeds the 126 MB L2; no explicit flush"}
 
+    cpu_B = args.cpu_sample_batch or w["B"]
     if args.impl == "reference":
-        # The reference's own (eager PyTorch) path on this box's host cores; rank 0 only.
+        # The reference's own (eager PyTorch) path on this box's host cores: ONE host process with every core, at the
+        # workload's per-GPU batch, whatever N the launch names (the other ranks exit without work) -- so the line says
+        # n_gpus = 1 and global_batch = B: it is the same number at every N and must not be scaled by N.
         if rank != 0:
             return
-        steps = min(args.steps, 10)
-        cb = cpu_baseline(w, args.cpu_sample_batch, steps, min(warmup, 3))
+        ref_warm = min(warmup, 3)
+        cb = cpu_baseline(w, cpu_B, args.steps, ref_warm)
+        cfg_ref = dict(cfg)
+        cfg_ref.update({"global_batch": cpu_B, "parallelism": "host cores, one process",
+                        "grad_allreduce": "none (one host process)", "launched_with_gpus": args.gpus})
+        if cpu_B != w["B"]:
+            cfg_ref["workload"] += f"; CPU arm runs a reduced batch of {cpu_B}"
         line = {"impl": "reference", "metric": "DINO head+loss+center+EMA step samples/sec", "value": cb["value"],
-                "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(warmup, 3),
+                "unit": "samples/s", "n_gpus": 1, "steps": args.steps, "warmup": ref_warm,
                 "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "config": cfg,
+                "dtype": "f32", "data": "synthetic", "config": cfg_ref,
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
+                "gpu_launches": 0,
+                "note": "CPU arm (a GPU-over-CPU ratio against it says nothing about kernel quality; see roofline)"}
         _emit(line)
         return
 
@@ -455,53 +541,59 @@ def main():
                     "stream during the previous step) and D2H of its loss; the host reads the loss of step i-1 while step i runs") if use_graph
                    else "eager module calls + per-step H2D/D2H"}
 
-    # live per-kernel timing for the roofline object
+    # per-op device time for the roofline object: CUPTI kernel durations attributed to the libdinomc op that launched them
+    # (ops.profile_kernels); CUDA-event pairs around the ops only if the profiler attributes nothing
     peaks = load_peaks()
-    prof = per_kernel_times(step, min(args.steps, 20))     # {op: (total ms, total calls)} over those steps
+    prof_steps = min(args.steps, 10)
+    prof_us, timing = {}, "cupti"
+    try:
+        prof_us = ops.profile_kernels(step.run, prof_steps)                      # {op: (us per step, kernels per step)}
+    except Exception as e:              # noqa: BLE001
+        print(f"[rank {rank}] profile_kernels failed ({type(e).__name__}: {e}); using CUDA events", file=sys.stderr)
+    if not prof_us:
+        timing = "cuda_events"
+        ev = per_kernel_times(step, prof_steps)
+        prof_us = {k: (ms * 1e3 / prof_steps, n / prof_steps) for k, (ms, n) in ev.items()}
     logit_bytes = 2 if args.mode == "bf16" else 4
     flops, nbytes = roofline_model(w, step.P, logit_bytes)
     t_roof_ms = max(flops / (peaks["bf16_tflops"] * 1e12), nbytes / (peaks["hbm_gbs"] * 1e9)) * 1e3
+    models = op_models(w, step.P, logit_bytes)
+    traffic_db = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.isfile(tpath):
+        traffic_db = json.load(open(tpath)).get(args.workload + ":" + args.mode, {})
     kernels = []
-    Ns, Nt, K = w["C"] * w["B"], w["G"] * w["B"], w["K"]
-    alg_bytes = {   # algorithmic bytes per launch of the HBM-bound kernels
-        "ce_bwd": logit_bytes * K * (2 * Ns + Nt),
-        "ce_fused": logit_bytes * K * (2 * Ns + Nt),
-        "ce_fwd": logit_bytes * K * (Ns + Nt),
-        "teacher_stats_colsum": logit_bytes * K * Nt,
-        "ema": 12 * step.P,
-        "gemm_last_fwd_student": logit_bytes * K * Ns + 2 * BN * (K + Ns),
-        "gemm_last_fwd_teacher": logit_bytes * K * Nt + 2 * BN * (K + Nt),
-        "weightnorm_fwd": 2 * (4 + logit_bytes) * K * BN,          # two launches per step (student + teacher)
-        "weightnorm_bwd": 12 * K * BN,
-        "gemm_last_wgrad": logit_bytes * K * Ns + 4 * K * BN,
-        "gemm_last_dgrad": logit_bytes * K * Ns + 2 * K * BN,
-    }
-    prof_steps = min(args.steps, 20)
-    for name, (ms_tot, calls_tot) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
-        ms, calls = ms_tot / prof_steps, calls_tot / prof_steps
-        k = {"kernel": name, "ms_per_step": ms, "calls_per_step": calls}
-        if name in alg_bytes:                 # alg_bytes[...] covers all of that op's launches in one step
-            k["alg_GB"] = alg_bytes[name] / 1e9
-            k["GBps"] = alg_bytes[name] / 1e9 / (ms * 1e-3)
-            k["frac_of_hbm_peak"] = k["GBps"] / peaks["hbm_gbs"]
+    for name, (us, calls) in sorted(prof_us.items(), key=lambda kv: -kv[1][0]):
+        k = {"kernel": name, "us_per_step": us, "launches_per_step": calls}
+        if name in models:                    # algorithmic bytes / flops of ALL of that op's launches in one step
+            b, f = models[name]
+            t_hbm, t_tc = b / (peaks["hbm_gbs"] * 1e9), f / (peaks["bf16_tflops"] * 1e12)
+            k["bound"] = "tensor" if t_tc > t_hbm else "hbm"
+            k["alg_GB"], k["alg_GFLOP"] = b / 1e9, f / 1e9
+            if k["bound"] == "hbm":
+                k["achieved"], k["peak"], k["unit"] = b / 1e9 / (us * 1e-6), peaks["hbm_gbs"], "GB/s"
+            else:
+                k["achieved"], k["peak"], k["unit"] = f / 1e12 / (us * 1e-6), peaks["bf16_tflops"], "TFLOP/s"
+            k["frac"] = k["achieved"] / k["peak"]
+            k["traffic"] = traffic_db.get(name)
         kernels.append(k)
-    dom = next((k for k in kernels if "GBps" in k), None)
+    dom = next((k for k in kernels if "frac" in k), None)           # largest time share
     roofline = None
     if dom is not None:
-        # DRAM traffic of that kernel per launch from the committed `ncu --set full` capture (profiles/), if there is one
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.isfile(tpath):
-            traffic = json.load(open(tpath)).get(args.workload + ":" + args.mode, {}).get(dom["kernel"])
-        roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["GBps"], "peak": peaks["hbm_gbs"],
-                    "unit": "GB/s", "frac": dom["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peaks["source"],
+        roofline = {"bound": dom["bound"], "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": dom["peak"],
+                    "unit": dom["unit"], "frac": dom["frac"], "traffic": dom["traffic"], "peak_source": peaks["source"],
+                    "timing": timing + " kernel durations over eager steps, all launches of the op per step",
                     "step": {"t_roof_ms": t_roof_ms, "alg_GB": nbytes / 1e9, "alg_GFLOP": flops / 1e9,
                              "frac_of_step_roofline": t_roof_ms / ms_step},
-                    "kernels": kernels[:12]}
+                    "kernels": kernels}
+
+    verify = None
+    if world > 1 and args.verify and step.reducer is not None:
+        verify = step.verify_exchange()
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        c = cpu_baseline(w, args.cpu_sample_batch, 5, 2)
+        c = cpu_baseline(w, cpu_B, 3, 1)
         cb = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
@@ -512,6 +604,8 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
                 "launch_mode": "cuda_graph" if use_graph else "eager", "teacher_overlap": bool(args.overlap), "roofline": roofline, "cpu_baseline": cb,
                 "ema_params": step.P, "ema_tensors": step.n_tensors}
+        if verify is not None:
+            line["exchange_check"] = verify
         _emit(line)
     if world > 1 or force_dp:
         # leave without tearing NCCL down: destroying communicators that CUDA graphs still reference can hang

@@ -80,23 +80,60 @@ def profile_end():
     return out
 
 
+_annotate = False       # profile_kernels(): wrap every op in a torch.profiler range so CUPTI kernels are attributed to it
+
+
 class _timed:
-    __slots__ = ("name", "e0")
+    __slots__ = ("name", "e0", "rf")
 
     def __init__(self, name):
         self.name = name
+        self.rf = None
 
     def __enter__(self):
         if _prof_events is not None:
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e0.record()
+        if _annotate:
+            self.rf = torch.profiler.record_function("dmc:" + self.name)
+            self.rf.__enter__()
 
     def __exit__(self, *exc):
+        if self.rf is not None:
+            self.rf.__exit__(*exc)
+            self.rf = None
         if _prof_events is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
             _prof_events.append((self.name, self.e0, e1))
         return False
+
+
+def profile_kernels(fn, steps: int):
+    """Run `fn` `steps` times under torch.profiler (CUPTI activity records) with every libdinomc op wrapped in a
+    profiler range, and return {op tag: (kernel microseconds per step, kernels per step)} -- pure kernel durations
+    (no launch gaps, no event overhead), each kernel attributed to the op whose C-ABI call launched it.  Returns {}
+    when the profiler delivered no attributed kernels (the caller then falls back to event timing)."""
+    global _annotate
+    from torch.profiler import ProfilerActivity, profile
+    _annotate = True
+    try:
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for _ in range(steps):
+                fn()
+            torch.cuda.synchronize()
+    finally:
+        _annotate = False
+    out = {}
+    for ev in prof.events():
+        if not ev.name.startswith("dmc:"):
+            continue
+        ks = getattr(ev, "kernels", None) or []
+        if not ks:
+            continue
+        us, n = out.get(ev.name[4:], (0.0, 0))
+        out[ev.name[4:]] = (us + sum(float(k.duration) for k in ks), n + len(ks))
+    return {k: (us / steps, n / steps) for k, (us, n) in out.items()}
 
 
 def _dt(t: torch.Tensor) -> int:
