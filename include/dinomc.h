@@ -225,6 +225,22 @@ int dmc_ema_build_plan(const void* const* teacher_ptrs_host, const void* const* 
                        int64_t* n_chunks_out);
 int dmc_ema_multi_tensor(const void* plan_dev, int64_t n_chunks, float m, float one_minus_m, void* stream);
 
+/* Plan v2: the same update (main_dino_mc.py:403-406, bit-exact), with
+ *   - (m, 1-m) read from DEVICE memory (scalars_dev[0..1], fp32): a captured CUDA graph then follows the momentum
+ *     schedule (main_dino_mc.py:404 `m = momentum_schedule[it]`) instead of freezing the captured value;
+ *   - optional bf16 "shadow" copies of the NEW teacher values (shadow_bf16_ptrs_host[i], may be NULL per tensor or
+ *     as a whole): the teacher head's MLP GEMM operands for the next step (utils/vision_transformer.py:291);
+ *   - optionally the weight-normed last layer (utils/vision_transformer.py:279) handled row-wise: tensor wn_v_index is
+ *     weight_v [rows, wn_dim], tensor wn_g_index is weight_g [rows]; besides both EMA updates the kernel writes
+ *     wn_w_bf16[rows, wn_dim] = g v/||v|| (bf16), wn_scale[rows] = g/||v||, wn_inv_norm[rows] = 1/||v|| of the NEW
+ *     values -- what dmc_weightnorm_fwd would compute next step.  wn_v_index = -1 disables it. */
+size_t dmc_ema_plan2_bytes(const int64_t* numels_host, int64_t n_tensors, int64_t wn_v_index, int64_t wn_dim);
+int dmc_ema_build_plan2(const void* const* teacher_ptrs_host, const void* const* student_ptrs_host,
+                        const int64_t* numels_host, void* const* shadow_bf16_ptrs_host, int64_t n_tensors,
+                        int64_t wn_v_index, int64_t wn_g_index, int64_t wn_dim, void* wn_w_bf16, float* wn_scale,
+                        float* wn_inv_norm, void* plan_host, size_t plan_bytes, int64_t* n_chunks_out);
+int dmc_ema_multi_tensor2(const void* plan_dev, int64_t n_chunks, const float* scalars_dev, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Per-parameter gradient clipping: utils/utils.py:145-154 `clip_gradients(model, clip)`
  *   n = ||grad||_2 ; c = clip / (n + 1e-6) ; if c < 1: grad *= c        for every gradient tensor

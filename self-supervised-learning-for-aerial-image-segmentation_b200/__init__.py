@@ -21,12 +21,12 @@ kernels raises.
 from . import _lib, functional, ops  # noqa: F401
 from .ema import ema_update_  # noqa: F401
 from .graph import StepGraph  # noqa: F401
-from .head import (DINOHead, get_default_precision, set_default_precision, set_teacher_overlap,  # noqa: F401
-                   wait_ready)
+from .head import (DINOHead, get_default_precision, set_default_precision, set_operand_shadows,  # noqa: F401
+                   set_teacher_overlap, wait_ready)
 from .loss import DINOLoss, set_async_center  # noqa: F401
 from .optim import FusedAdamW, FusedLARS, cancel_gradients_last_layer, clip_gradients  # noqa: F401
 from .reducer import GradAllReduce  # noqa: F401
 from .wrapper import MultiCropWrapper  # noqa: F401
 
-__all__ = ["DINOHead", "DINOLoss", "ema_update_", "clip_gradients", "cancel_gradients_last_layer", "FusedAdamW", "FusedLARS", "MultiCropWrapper", "StepGraph", "GradAllReduce", "set_teacher_overlap", "set_async_center", "wait_ready", "set_default_precision", "get_default_precision",
+__all__ = ["DINOHead", "DINOLoss", "ema_update_", "clip_gradients", "cancel_gradients_last_layer", "FusedAdamW", "FusedLARS", "MultiCropWrapper", "StepGraph", "GradAllReduce", "set_teacher_overlap", "set_operand_shadows", "set_async_center", "wait_ready", "set_default_precision", "get_default_precision",
            "ops", "functional"]

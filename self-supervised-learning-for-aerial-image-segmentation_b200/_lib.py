@@ -71,6 +71,10 @@ SIGNATURES = {
     "dmc_ema_plan_bytes": (sz, [C.POINTER(i64), i64]),
     "dmc_ema_build_plan": (C.c_int, [C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), i64, vp, sz, C.POINTER(i64)]),
     "dmc_ema_multi_tensor": (C.c_int, [vp, i64, f32, f32, vp]),
+    "dmc_ema_plan2_bytes": (sz, [C.POINTER(i64), i64, i64, i64]),
+    "dmc_ema_build_plan2": (C.c_int, [C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), i64, i64, i64, i64, vp, vp, vp,
+                                      vp, sz, C.POINTER(i64)]),
+    "dmc_ema_multi_tensor2": (C.c_int, [vp, i64, vp, vp]),
     "dmc_clip_plan_bytes": (sz, [C.POINTER(i64), i64]),
     "dmc_clip_build_plan": (C.c_int, [C.POINTER(vp), C.POINTER(i64), i64, vp, sz, C.POINTER(i64)]),
     "dmc_clip_grads": (C.c_int, [vp, i64, f32, vp, vp, sz, vp]),

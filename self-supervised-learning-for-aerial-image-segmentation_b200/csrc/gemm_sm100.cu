@@ -1015,7 +1015,10 @@ Plan make_plan(int64_t M, int64_t N, int64_t K, int in_dtype, bool three_pass, i
   const size_t b_bytes = static_cast<size_t>(pl.block_n) * kRowBytes;
   pl.tma_store = (store_ok && pl.splits == 1 && !(debug_flags() & 1)) ? 1 : 0;
   const size_t kBarrierBytes = 512;
-  size_t budget = 227 * 1024 - 1024 /*alignment slack*/ - kBarrierBytes - (pl.tma_store ? kStagingBytes : 0);
+  // DMC_GEMM_SMEM_RESERVE_KB (timing experiments): shared memory left unused so that small CTAs of other kernels
+  // (1 KiB reserved each) can be co-resident with the one-CTA-per-SM GEMM
+  static const size_t smem_reserve = [] { const char* e = getenv("DMC_GEMM_SMEM_RESERVE_KB"); return e ? static_cast<size_t>(atoi(e)) * 1024 : size_t(0); }();
+  size_t budget = 227 * 1024 - 1024 /*alignment slack*/ - kBarrierBytes - (pl.tma_store ? kStagingBytes : 0) - smem_reserve;
   // B-resident schedule: the whole contraction's worth of B for one n-tile stays in smem (<= 8 slabs, <= 128 KiB),
   // leaving >= 4 A-only stages.  Pays off when several m-tiles share an n-tile.
   const size_t res_bytes = static_cast<size_t>(pl.vk_total) * b_bytes;

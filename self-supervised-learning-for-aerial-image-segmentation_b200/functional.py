@@ -23,7 +23,10 @@ MODES = ("bf16", "fp32", "fp32_simt")
 # DINOLoss -- so the most recently used DINOLoss registers itself here (weak reference) and the head asks it.
 # Everything is validated again inside DINOLoss.forward; on any mismatch the separate passes run instead.
 # ---------------------------------------------------------------------------------------------------------
+import os as _os0
 import weakref
+
+_os_environ_get = _os0.environ.get
 
 fused_stats_enabled = True
 fused_teacher_stats = False   # teacher row statistics + column sums from the GEMM epilogue (EPI 3, lean path for bf16 logits):
@@ -53,6 +56,7 @@ def _current_loss():
 # shared memory) share the SMs with the GEMM CTAs.  Works eagerly and inside CUDA-graph capture.
 # ---------------------------------------------------------------------------------------------------------
 aux_overlap = True
+defer_joins = _os_environ_get("DMC_DEFER_JOINS", "1") != "0"       # see _AuxRegion.join_at_end_of_backward
 grad_exchange_active = False     # set by GradAllReduce: the last layer's dv (64 MiB, the largest all-reduce of the step) must
                                  # then be final as early as possible, so its weight-norm backward stays in front of the dgrad
 grad_exchange = None             # the active GradAllReduce (or None); with compress="bf16" the last layer hands it a bf16 dW
@@ -107,8 +111,16 @@ class _AuxRegion:
             if t is not None:
                 t.record_stream(self.cur)
 
+    def join_at_end_of_backward(self, *tensors):
+        """Inside an autograd backward: join when the whole backward pass has been queued (engine callback) instead of
+        now.  For results nothing later in the backward pass reads (parameter gradients): the caller's stream then does
+        not stall on the auxiliary kernel in the middle of the pass, and everything is joined before `backward()` returns."""
+        if not defer_joins:
+            return self.join(*tensors)
+        torch.autograd.Variable._execution_engine.queue_callback(lambda: self.join(*tensors))
 
-def last_layer_weights(mode, g, v, dim_in):
+
+def last_layer_weights(mode, g, v, dim_in, after_current=True):
     """The weight-normed last-layer operand W = g v/||v|| (utils/vision_transformer.py:279) in the representation
     `mode` needs, plus scale = g/||v||, 1/||v|| and the device scalar max|g|.  With `aux_overlap` the kernel runs on
     the auxiliary stream; the returned record carries the region to join before the first use."""
@@ -202,6 +214,7 @@ class LinearFn(torch.autograd.Function):
         ctx.mode, ctx.dims = mode, (rows, fo, fi)
         ctx.h_op, ctx.w_op, ctx.z_in = h_op, w_op, (None if z_in is None else z_in.detach())
         ctx.has_bias = b is not None
+        ctx.bias_param = b
         ctx.mark_non_differentiable(z_out)
         ctx.set_materialize_grads(False)       # no zero-filled [rows, fo] gradient for the non-differentiable z_out
         return h_out, z_out
@@ -215,6 +228,7 @@ class LinearFn(torch.autograd.Function):
         sd = store_dtype(mode)
         d_full = dz.contiguous()
         dW = db = d_in = None
+        ctx.bias_grad_empty = ctx.bias_param is not None and ctx.bias_param.grad is None
         with ops.backward_cap():
             d = Operand(d_full) if (mode == "bf16" and d_full.dtype == torch.bfloat16) else prep(d_full, mode)
             if ctx.needs_input_grad[3]:
@@ -238,18 +252,26 @@ class LinearFn(torch.autograd.Function):
             elif ctx.needs_input_grad[1]:
                 d_in = mm(mode, d, ctx.w_op, rows, fi, fo, b_mn=True, out_dtype=torch.float32, tag="gemm_mlp_dgrad")
             if region is not None:
-                region.join(db)
-                ops.mark_ready(db)
+                if ctx.bias_grad_empty:              # only AccumulateGrad consumes db, and only to store it
+                    with torch.cuda.stream(region.aux):
+                        ops.mark_ready(db)
+                    region.join_at_end_of_backward(db)
+                else:
+                    region.join(db)
+                    ops.mark_ready(db)
         return None, d_in, None, dW, db, None, None, None
 
 
-def mlp_forward(mode, x, wb):
-    """The Linear/GELU chain: x -> z_last (fp32).  `wb` = [W0, b0, W1, b1, ...] (the nn.Linear parameters)."""
+def mlp_forward(mode, x, wb, w_ops=None, after_first_gemm=None):
+    """The Linear/GELU chain: x -> z_last (fp32).  `wb` = [W0, b0, W1, b1, ...] (the nn.Linear parameters);
+    `w_ops` = ready-made bf16 operands of the weights (a teacher's EMA-refreshed shadows), or None."""
     n = len(wb) // 2
     mode = resolve_mode(mode, x.shape[1], *[d for li in range(n) for d in wb[2 * li].shape])
     pre = None
     region = None
-    if mode == "bf16":
+    if mode == "bf16" and w_ops is not None:
+        pre = [Operand(ops.cast_bf16(x.detach()))] + list(w_ops)
+    elif mode == "bf16":
         # bf16 operand copies of this forward: features + first weight in one launch on this stream; the later
         # layers' weights (not needed until the first GEMM has run) in a second launch on the auxiliary stream
         if aux_overlap and n > 1:
@@ -266,6 +288,9 @@ def mlp_forward(mode, x, wb):
             region.join(*[o.main for o in pre[2:]])
         h, z = LinearFn.apply(mode, h, z, wb[2 * li], wb[2 * li + 1], pre[0] if (pre and li == 0) else None,
                               pre[1 + li] if pre else None, li < n - 1)
+        if li == 0 and after_first_gemm is not None:
+            after_first_gemm()          # e.g. fork the last layer's weight-norm pass here: it then shares the machine with the
+                                        # remaining (tensor-bound) GEMMs instead of delaying the first one
     return h
 
 
@@ -317,6 +342,7 @@ class NormLastLayerFn(torch.autograd.Function):
         ctx.save_for_backward(zhat, inv_den, v.detach(), scale, inv_vnorm)
         ctx.dims = (rows, dim, K)
         ctx.g_ptr = g.data_ptr()
+        ctx.v_param, ctx.g_param = v, g
         return logits
 
     @staticmethod
@@ -362,7 +388,10 @@ class NormLastLayerFn(torch.autograd.Function):
             if ctx.needs_input_grad[1]:
                 dz = ops.normalize_rows_bwd(dzhat, zhat, inv_den)
             if region is not None:
-                region.join(dv, dg)
+                if ctx.v_param.grad is None and (ctx.g_param.grad is None or not ctx.needs_input_grad[2]):
+                    region.join_at_end_of_backward(dv, dg)       # dv / dg are only stored by AccumulateGrad
+                else:
+                    region.join(dv, dg)
             if not ctx.needs_input_grad[3]:
                 dv = None
         return None, dz, dg, dv, None
@@ -383,7 +412,9 @@ class DinoLossFn(torch.autograd.Function):
         s_d, t_d = s.detach(), t.detach()
         center = center.detach().reshape(-1)
         K = s_d.shape[1]
-        if t_pre is not None:
+        if t_pre is not None and t_pre["kind"] == "teacher_final":
+            t_stats, colsum = t_pre["t_stats"], t_pre["colsum"]
+        elif t_pre is not None:
             t_stats, colsum = ops.teacher_finalize(t_pre["row_partials"], t_pre["colsum_partials"], t_d.shape[0], K)
         else:
             t_stats, colsum = ops.teacher_stats_colsum(t_d, center, inv_tt)

@@ -33,6 +33,31 @@ def get_default_precision() -> str:
 # ---------------------------------------------------------------------------------------------
 _teacher_overlap = False
 _side_streams = {}
+_operand_shadows = os.environ.get("DMC_TEACHER_SHADOWS", "1") != "0"
+
+
+def set_operand_shadows(enabled: bool):
+    """When enabled (default), a DINOHead that runs under torch.no_grad() with all parameters frozen (the EMA teacher,
+    main_dino_mc.py:264-265) in the bf16-GEMM mode keeps bf16 copies of its GEMM operands -- the MLP weights and the
+    weight-normed W = g v/||v|| -- which `ema_update_` refreshes in the same pass that updates the parameters.  The
+    teacher forward then skips its cast launches and its weight-norm pass.  The copies are used only while every
+    parameter is exactly what that EMA pass wrote (`_version` and storage checks); otherwise the regular path runs."""
+    global _operand_shadows
+    _operand_shadows = bool(enabled)
+
+
+_wn_after_first_gemm = os.environ.get("DMC_WN_AFTER_FIRST_GEMM", "1") != "0"       # env: timing experiments
+_early_teacher_stats = os.environ.get("DMC_EARLY_TEACHER_STATS", "1") != "0"
+
+
+def set_early_teacher_stats(enabled: bool):
+    """When enabled (default), a frozen no-grad head (the teacher) whose logits will go to a registered DINOLoss launches
+    that loss's teacher statistics pass (row softmax statistics + column sums, main_dino_mc.py:446,468) itself, on a side
+    stream, right after its last GEMM -- the HBM-bound pass then runs next to the student head's tensor-bound MLP GEMMs
+    instead of after them.  DINOLoss re-validates the result (temperature, center identity and version, row count) and
+    runs the pass itself on any mismatch."""
+    global _early_teacher_stats
+    _early_teacher_stats = bool(enabled)
 
 
 def set_teacher_overlap(enabled: bool):
@@ -52,6 +77,18 @@ def wait_ready(t):
         torch.cuda.current_stream(t.device).wait_event(ev)
         t._dmc_ready_event = None
     return t
+
+
+_stats_streams = {}
+
+
+def _stats_stream(device, cur):
+    key = (torch.device(device).index, cur.cuda_stream)
+    st = _stats_streams.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _stats_streams[key] = st
+    return st
 
 
 def _side_stream(device):
@@ -127,6 +164,7 @@ class DINOHead(nn.Module):
             self.last_layer.weight_g.requires_grad = False
         self.use_bn = use_bn
         self.precision = None                   # None -> module default (set_default_precision / autocast)
+        self._shadow = None                     # operand shadows of a frozen (teacher) head, see set_operand_shadows
 
     def _init_weights(self, m):
         if isinstance(m, nn.Linear):
@@ -157,6 +195,40 @@ class DINOHead(nn.Module):
             return out
         return self._forward(x)
 
+    # ---- operand shadows (teacher) ----------------------------------------------------------------------------
+    def _linears(self):
+        return [self.mlp] if isinstance(self.mlp, nn.Linear) else [m for m in self.mlp if isinstance(m, nn.Linear)]
+
+    def _shadow_state(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _mark_shadow_fresh(self):
+        if self._shadow is not None:
+            self._shadow["state"] = self._shadow_state()
+
+    def _fresh_shadow(self, mode, x):
+        """The shadow record if it may be used for this forward, else None (allocating it on first sight of a teacher)."""
+        if not _operand_shadows or mode != "bf16" or self.use_bn or torch.is_grad_enabled():
+            return None
+        if any(p.requires_grad for p in self.parameters()):
+            return None
+        lins = self._linears()
+        K, dim = self.last_layer.weight_v.shape
+        if Fn.resolve_mode(mode, x.shape[1], dim, K, *[d for lin in lins for d in lin.weight.shape]) != "bf16":
+            return None
+        sh = self._shadow
+        if sh is None or sh["device"] != x.device:
+            dev = x.device
+            sh = dict(device=dev, state=None, weights=[lin.weight for lin in lins],
+                      mlp=[torch.empty(lin.weight.shape, dtype=torch.bfloat16, device=dev) for lin in lins],
+                      what=torch.empty((K, dim), dtype=torch.bfloat16, device=dev),
+                      scale=torch.empty(K, dtype=torch.float32, device=dev),
+                      inv_norm=torch.empty(K, dtype=torch.float32, device=dev))
+            self._shadow = sh
+            from . import ema
+            ema.register_shadow_head(self)
+        return sh if (sh["state"] is not None and sh["state"] == self._shadow_state()) else None
+
     def _forward(self, x):
         mode = self._mode()
         with torch.autocast("cuda", enabled=False):
@@ -166,16 +238,58 @@ class DINOHead(nn.Module):
                 z = self.mlp(x.float())
                 prepared = None
             else:
-                linears = [self.mlp] if isinstance(self.mlp, nn.Linear) else [m for m in self.mlp if isinstance(m, nn.Linear)]
+                linears = self._linears()
                 wb = []
                 for lin in linears:
                     wb += [lin.weight, lin.bias]
-                # the last layer's weight-norm materialisation does not depend on the MLP: start it first (auxiliary stream)
-                prepared = Fn.last_layer_weights(mode, self.last_layer.weight_g, self.last_layer.weight_v,
-                                                 self.last_layer.in_features)
-                z = Fn.mlp_forward(mode, x, wb)
+                sh = self._fresh_shadow(mode, x)
+                if sh is not None:
+                    # operands written by the last EMA pass: no casts, no weight-norm pass
+                    prepared = dict(mode="bf16", wop=Fn.Operand(sh["what"]), scale=sh["scale"], inv_vnorm=sh["inv_norm"],
+                                    gmax=None, region=None)
+                    z = Fn.mlp_forward(mode, x, wb, w_ops=[Fn.Operand(t) for t in sh["mlp"]])
+                elif _wn_after_first_gemm:
+                    # the last layer's weight-norm materialisation (HBM-bound, 64 MiB read at out_dim 65536) does not depend
+                    # on the MLP: fork it onto the auxiliary stream once the first GEMM is queued, so that it runs next to
+                    # the remaining tensor-bound GEMMs (forked before them it takes the whole machine and delays the chain)
+                    box = {}
+
+                    def fork():
+                        box["p"] = Fn.last_layer_weights(mode, self.last_layer.weight_g, self.last_layer.weight_v,
+                                                         self.last_layer.in_features)
+                    z = Fn.mlp_forward(mode, x, wb, after_first_gemm=fork)
+                    prepared = box["p"]
+                else:
+                    prepared = Fn.last_layer_weights(mode, self.last_layer.weight_g, self.last_layer.weight_v,
+                                                     self.last_layer.in_features)
+                    z = Fn.mlp_forward(mode, x, wb)
             out = Fn.NormLastLayerFn.apply(mode, z, self.last_layer.weight_g, self.last_layer.weight_v, prepared)
             if Fn.last_stats is not None:       # statistics the GEMM epilogue produced for dinomc_b200.DINOLoss
                 out._dmc_stats = Fn.last_stats
                 Fn.last_stats = None
+            elif (_early_teacher_stats and not torch.is_grad_enabled() and out.dtype in (torch.bfloat16, torch.float32)
+                  and not any(p.requires_grad for p in self.parameters())):
+                self._launch_teacher_stats(out)
             return out
+
+    def _launch_teacher_stats(self, out):
+        """The registered DINOLoss's teacher pass over `out`, on a side stream (see set_early_teacher_stats)."""
+        from . import ops
+        loss_mod = Fn._current_loss()
+        if loss_mod is None or loss_mod.center.shape[-1] != out.shape[1] or loss_mod.center.device != out.device:
+            return
+        if out.shape[0] % loss_mod.teacher_crops_number:
+            return
+        loss_mod.sync_center()
+        cen = loss_mod.center
+        cur = torch.cuda.current_stream(out.device)
+        side = _stats_stream(out.device, cur)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            t_stats, colsum = ops.teacher_stats_colsum(out, cen.reshape(-1), loss_mod._last_inv_tt)
+        ev = torch.cuda.Event()
+        ev.record(side)
+        out.record_stream(side)
+        cen.record_stream(side)
+        out._dmc_stats = dict(kind="teacher_final", scale=loss_mod._last_inv_tt, t_stats=t_stats, colsum=colsum, event=ev,
+                              stream=side, center_ptr=cen.data_ptr(), center_version=cen._version, rows=out.shape[0])

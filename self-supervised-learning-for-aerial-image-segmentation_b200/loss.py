@@ -99,6 +99,8 @@ class DINOLoss(nn.Module):
         if teacher_output.shape[0] // G != B:
             raise ValueError("student and teacher batches differ")
         temp = float(self.teacher_temp_schedule[epoch])
+        if ops.capture_notes is not None and torch.cuda.is_current_stream_capturing():
+            ops.capture_notes.append(("loss", self, epoch, temp))       # StepGraph re-captures when the temperature changes
         self.sync_center()
         wait_ready(teacher_output)              # no-op unless the teacher head ran on the overlap side stream
         s, t = self._common(student_output, teacher_output.detach())
@@ -109,11 +111,17 @@ class DINOLoss(nn.Module):
                                       and s_pre["row_partials"].shape[0] == s.shape[0]):
             s_pre = None
         t_pre = getattr(teacher_output, "_dmc_stats", None) if t.data_ptr() == teacher_output.data_ptr() else None
-        if t_pre is not None and not (t_pre.get("kind") == "teacher" and t_pre["scale"] == inv_tt
+        if t_pre is not None and not (t_pre.get("kind") in ("teacher", "teacher_final") and t_pre["scale"] == inv_tt
                                       and t_pre["center_ptr"] == self.center.data_ptr()
                                       and t_pre["center_version"] == self.center._version
-                                      and t_pre["row_partials"].shape[0] == t.shape[0]):
+                                      and (t_pre["row_partials"].shape[0] if t_pre["kind"] == "teacher" else t_pre["rows"]) == t.shape[0]):
             t_pre = None
+        if t_pre is not None and t_pre["kind"] == "teacher_final":
+            # the teacher head already ran this loss's statistics pass on a side stream: wait for it here
+            cur = torch.cuda.current_stream()
+            cur.wait_event(t_pre["event"])
+            t_pre["t_stats"].record_stream(cur)
+            t_pre["colsum"].record_stream(cur)
         self._last_inv_tt = inv_tt
         Fn.register_loss(self)
         loss, colsum = Fn.DinoLossFn.apply(s, t, self.center, inv_ts, inv_tt, B, C, G, s_pre, t_pre)
@@ -128,6 +136,17 @@ class DINOLoss(nn.Module):
 
     @torch.no_grad()
     def _update_center_from_colsum(self, colsum, n_rows):
+        if ops.preserve_state:
+            # StepGraph warm-up: run the same kernels (and collectives) but keep the center as it is
+            keep = self.center
+            try:
+                ops.preserve_state = False
+                self._update_center_from_colsum(colsum, n_rows)
+                self.sync_center()
+            finally:
+                ops.preserve_state = True
+                self.center = keep
+            return
         if torch.cuda.is_current_stream_capturing() and not any(m is self for m, _ in _capture_commits):
             _capture_commits.append((self, self.center))
         world = 1

@@ -124,15 +124,30 @@ def profile_kernels(fn, steps: int):
             torch.cuda.synchronize()
     finally:
         _annotate = False
+    # Attribute every kernel to the op range whose C-ABI call launched it: kernel -> (correlation id) -> the CUDA runtime
+    # launch call on the host -> the "dmc:<tag>" range that contains that call's start time.
+    import bisect
+    evs = list(prof.events())
+    cuda_t = torch.autograd.DeviceType.CUDA
+    ranges = sorted((e.time_range.start, e.time_range.end, e.name[4:]) for e in evs
+                    if e.device_type != cuda_t and e.name.startswith("dmc:"))
+    starts = [r[0] for r in ranges]
+    launches = {}
+    for e in evs:
+        if e.device_type != cuda_t and e.name.startswith("cudaLaunch"):
+            launches[e.id] = e.time_range.start
     out = {}
-    for ev in prof.events():
-        if not ev.name.startswith("dmc:"):
+    for e in evs:
+        if e.device_type != cuda_t or "memcpy" in e.name.lower() or "memset" in e.name.lower():
             continue
-        ks = getattr(ev, "kernels", None) or []
-        if not ks:
+        t = launches.get(e.id)
+        if t is None:
             continue
-        us, n = out.get(ev.name[4:], (0.0, 0))
-        out[ev.name[4:]] = (us + sum(float(k.duration) for k in ks), n + len(ks))
+        i = bisect.bisect_right(starts, t) - 1
+        if i < 0 or t > ranges[i][1]:
+            continue
+        us, n = out.get(ranges[i][2], (0.0, 0))
+        out[ranges[i][2]] = (us + float(e.time_range.end - e.time_range.start), n + 1)
     return {k: (us / steps, n / steps) for k, (us, n) in out.items()}
 
 
@@ -557,10 +572,25 @@ def ce_bwd(s, t, center, t_stats, s_lse, grad_out, B, C, G, inv_ts, inv_tt):
 # ---------------------------------------------------------------------------------------------
 # EMA
 # ---------------------------------------------------------------------------------------------
-class EmaPlan:
-    """Device-resident chunk table for one (teacher, student) parameter-list pair."""
+# StepGraph runs its warm-up steps with this set: every kernel of the step runs (allocator pools, plans and workspaces get
+# their final shape) but persistent training state is left exactly as it was -- the EMA runs with m = 1 (an exact identity),
+# DINOLoss keeps its center, optimizers refuse to step.
+preserve_state = False
+# filled while a StepGraph captures: ("ema", plan, m) / ("loss", module, epoch, temperature)
+capture_notes = None
 
-    def __init__(self, teacher_params, student_params):
+
+class EmaPlan:
+    """Device-resident chunk table for one (teacher, student) parameter-list pair (plan v2, see dmc_ema_build_plan2).
+
+    `shadows`: {index in the zipped lists: bf16 tensor} -- bf16 copies of the new teacher values written by the same pass;
+    `wn`: (v_index, g_index, dim, w_bf16, scale, inv_norm) -- the weight-normed last layer handled row-wise.
+    The momentum lives in a 2-float device buffer refilled from a ring of pinned host slots, so a captured graph reads
+    the value of the CURRENT iteration (StepGraph.replay(momentum=...))."""
+
+    _RING = 64
+
+    def __init__(self, teacher_params, student_params, shadows=None, wn=None):
         lib = L.load()
         teacher_params, student_params = list(teacher_params), list(student_params)
         n = min(len(teacher_params), len(student_params))      # zip() semantics of main_dino_mc.py:405
@@ -575,26 +605,62 @@ class EmaPlan:
                 raise ValueError(f"ema: shape mismatch {tuple(pk.shape)} vs {tuple(pq.shape)}")
             if not pk.is_contiguous() or not pq.is_contiguous():
                 raise ValueError("ema: parameters must be contiguous")
-        self.key = tuple((pk.data_ptr(), pq.data_ptr(), pk.numel()) for pk, pq in zip(tp, sp))
+        shadows = dict(shadows or {})
+        for i, sh in shadows.items():
+            _need_cuda(sh)
+            if sh.dtype != torch.bfloat16 or not sh.is_contiguous() or sh.numel() != tp[i].numel():
+                raise ValueError("ema: a shadow must be a contiguous bfloat16 tensor of the parameter's size")
         numels = (L.i64 * n)(*[pk.numel() for pk in tp])
         tptr = (L.vp * n)(*[pk.data_ptr() for pk in tp])
         sptr = (L.vp * n)(*[pq.data_ptr() for pq in sp])
-        nbytes = lib.dmc_ema_plan_bytes(numels, n)
+        shp = (L.vp * n)(*[(shadows[i].data_ptr() if i in shadows else None) for i in range(n)])
+        wv, wg, wdim, ww, wscale, winv = (-1, -1, 0, None, None, None) if wn is None else wn
+        if wn is not None:
+            _need_cuda(ww, wscale, winv)
+        nbytes = lib.dmc_ema_plan2_bytes(numels, n, wv, wdim)
         host = torch.empty(max(nbytes, 8), dtype=torch.uint8).pin_memory()
         n_chunks = L.i64(0)
-        L.check(lib.dmc_ema_build_plan(tptr, sptr, numels, n, host.data_ptr(), host.numel(), C.byref(n_chunks)),
-                "dmc_ema_build_plan")
+        L.check(lib.dmc_ema_build_plan2(tptr, sptr, numels, shp, n, wv, wg, wdim, _p(ww), _p(wscale), _p(winv), host.data_ptr(),
+                                        host.numel(), C.byref(n_chunks)), "dmc_ema_build_plan2")
         self.n_chunks = n_chunks.value
         self.n_params = sum(pk.numel() for pk in tp)
         self.device = tp[0].device
         self.plan = host.to(self.device, non_blocking=False)
+        self.keep = (list(shadows.values()), ww, wscale, winv)          # outputs the plan's raw pointers refer to
+        self.scalars = torch.zeros(2, dtype=torch.float32, device=self.device)
+        self._ring = torch.zeros((self._RING, 2), dtype=torch.float32).pin_memory()
+        self._ring_np = self._ring.numpy()
+        self._ring_ev = [None] * self._RING
+        self._ring_i = 0
+        self.m_on_device = None
+
+    def set_momentum(self, m: float):
+        """Refill the device scalars (m, 1-m) on the current stream.  (1 - m) is formed in float64 like the reference
+        (`(1 - m) * param_q`, m = np.float64 from cosine_scheduler), then both are rounded to fp32."""
+        i = self._ring_i
+        self._ring_i = (i + 1) % self._RING
+        if self._ring_ev[i] is not None:
+            self._ring_ev[i].synchronize()                      # the copy that last read this slot has completed (normally long ago)
+        self._ring_np[i, 0] = float(m)
+        self._ring_np[i, 1] = 1.0 - float(m)
+        self.scalars.copy_(self._ring[i], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._ring_ev[i] = ev
+        self.m_on_device = float(m)
 
     def run(self, m: float):
         lib = L.load()
-        # m is float64 (momentum_schedule[it]); (1 - m) is formed in float64 like the reference, then both -> fp32
+        m = 1.0 if preserve_state else float(m)
+        if torch.cuda.is_current_stream_capturing():
+            # the refill is not captured: StepGraph issues it before each replay (the graph must not freeze m)
+            if capture_notes is not None:
+                capture_notes.append(("ema", self, m))
+        elif m != self.m_on_device:
+            self.set_momentum(m)
         with _timed("ema"):
-            L.check(lib.dmc_ema_multi_tensor(self.plan.data_ptr(), self.n_chunks, float(m), float(1.0 - float(m)), _stream()),
-                    "dmc_ema_multi_tensor")
+            L.check(lib.dmc_ema_multi_tensor2(self.plan.data_ptr(), self.n_chunks, self.scalars.data_ptr(), _stream()),
+                    "dmc_ema_multi_tensor2")
         _count()
 
 

@@ -26,11 +26,19 @@ def clip_gradients(model, clip) -> torch.Tensor:
     grads = [p.grad.data for p in params if p.grad is not None]
     if not grads:
         return torch.zeros(0)
+    copies = []                       # (original, contiguous fp32 stand-in): e.g. channels_last conv gradients of a ResNet
     for i, g in enumerate(grads):
         if not g.is_cuda:
             raise RuntimeError("dinomc_b200 has no CPU path: gradients must be CUDA tensors")
         if g.dtype != torch.float32 or not g.is_contiguous():
-            raise TypeError("clip_gradients: gradients must be contiguous float32 tensors")
+            c = g.to(dtype=torch.float32, memory_format=torch.contiguous_format, copy=True)
+            copies.append((g, c))
+            grads[i] = c
+    if copies:                        # stand-ins move every call: no plan caching, clip, copy back
+        norms = ops.ClipPlan(grads).run(float(clip))
+        for g, c in copies:
+            g.copy_(c)
+        return norms
     key = tuple((g.data_ptr(), g.numel()) for g in grads)
     plan = _plans.get(key)
     if plan is None:
@@ -50,6 +58,12 @@ def cancel_gradients_last_layer(epoch, model, freeze_last_layer):
             p.grad = None
 
 
+def _refuse_inside_graph(name):
+    if ops.preserve_state or torch.cuda.is_current_stream_capturing():
+        raise RuntimeError(f"{name}.step() cannot be part of a StepGraph: its update depends on host-side state (step count, "
+                           "scheduled lr / weight decay) that a captured graph would freeze.  Call it outside the captured step.")
+
+
 class FusedAdamW(torch.optim.Optimizer):
     """Drop-in for `torch.optim.AdamW(params_groups)` as main_dino_mc.py:281-282 builds it (lr / weight decay rewritten
     per iteration by the schedules at :363-367): same constructor defaults, same `param_groups` keys, same per-parameter
@@ -66,6 +80,7 @@ class FusedAdamW(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self, closure=None):
+        _refuse_inside_graph("FusedAdamW")
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -90,6 +105,8 @@ class FusedAdamW(torch.optim.Optimizer):
                 st = self.state[p]
                 st["step"] += 1
                 by_step.setdefault(int(st["step"].item()), []).append(p)
+            if group.get("amsgrad") or group.get("maximize"):
+                raise RuntimeError("FusedAdamW does not implement amsgrad / maximize (the reference uses neither)")
             beta1, beta2 = group["betas"]
             for t, ps in by_step.items():
                 grads = [p.grad.data if p.grad.is_contiguous() else p.grad.data.contiguous() for p in ps]
@@ -123,6 +140,7 @@ class FusedLARS(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self):
+        _refuse_inside_graph("FusedLARS")
         for gi, group in enumerate(self.param_groups):
             params = [p for p in group["params"] if p.grad is not None]
             if not params:

@@ -475,10 +475,7 @@ def test_step_graph_replay_matches_eager(golden):
 
     step_e, st_e, te_e, lm_e, xs_e = make()
     step_g, st_g, te_g, lm_g, xs_g = make()
-    graph = D2.StepGraph(step_g, warmup=2)          # 2 warm-up steps + the capture pass itself executes nothing
-    n_warm = 2
-    for _ in range(n_warm):
-        step_e()
+    graph = D2.StepGraph(step_g, warmup=2)          # the warm-up steps preserve teacher / center; the capture pass executes nothing
     for _ in range(3):
         le = step_e()
         lg = graph.replay()
@@ -488,3 +485,125 @@ def test_step_graph_replay_matches_eager(golden):
         assert torch.equal(lm_e.center, lm_g.center)
     for pe, pg in zip(te_e.parameters(), te_g.parameters()):
         assert torch.equal(pe, pg)
+
+
+def test_step_graph_follows_schedules(golden):
+    """A captured step must not freeze host scalars the reference changes while training (main_dino_mc.py:404, :445):
+    replay(momentum=...) follows the EMA momentum schedule through device-resident scalars, replay(epoch=...) re-captures
+    when the teacher temperature of that epoch differs.  Checked against eager steps with the same schedule."""
+    if golden.name != "tp_small":
+        pytest.skip("the case with a warm-up temperature schedule")
+    import dinomc_b200 as D2
+    c = golden.cfg
+    moms = [0.99, 0.9925, 0.995, 0.9975]
+    epochs = [0, 0, 1, min(2, c["nepochs"] - 1)]
+
+    def make():
+        D, student, teacher, loss_mod = _build(golden, "bf16")
+        xs = torch.from_numpy(golden.inputs["x_student"]).cuda().requires_grad_(True)
+        xt = torch.from_numpy(golden.inputs["x_teacher"]).cuda()
+
+        def step(epoch=0, m=moms[0]):
+            for p in student.parameters():
+                p.grad = None
+            xs.grad = None
+            with torch.no_grad():
+                t_out = teacher(xt)
+            loss = loss_mod(student(xs), t_out, epoch)
+            loss.backward()
+            D.ema_update_(list(teacher.parameters()), list(student.parameters()), m)
+            return loss
+        return step, teacher, loss_mod, xs
+
+    step_e, te_e, lm_e, xs_e = make()
+    step_g, te_g, lm_g, xs_g = make()
+    assert len(set(float(lm_e.teacher_temp_schedule[e]) for e in epochs)) > 1, "the case must exercise a temperature change"
+    t0 = [p.detach().clone() for p in te_g.parameters()]
+    c0 = lm_g.center.detach().clone()
+    graph = D2.StepGraph(step_g, warmup=2)
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(t0, te_g.parameters())), "warm-up must not advance the EMA teacher"
+    assert torch.equal(c0, lm_g.center), "warm-up must not advance the center"
+    for m, e in zip(moms, epochs):
+        le = step_e(epoch=e, m=m)
+        lg = graph.replay(momentum=m, epoch=e)
+        torch.cuda.synchronize()
+        assert torch.equal(le.detach(), lg.detach()), (m, e)
+        assert torch.equal(xs_e.grad, xs_g.grad)
+        assert torch.equal(lm_e.center, lm_g.center)
+        for pe, pg in zip(te_e.parameters(), te_g.parameters()):
+            assert torch.equal(pe, pg)
+
+
+def test_step_graph_refuses_optimizer_and_fixed_epoch(golden):
+    if golden.name != "tp_small":
+        pytest.skip("one case is enough")
+    import dinomc_b200 as D2
+    D, student, teacher, loss_mod = _build(golden, "bf16")
+    xs = torch.from_numpy(golden.inputs["x_student"]).cuda().requires_grad_(True)
+    xt = torch.from_numpy(golden.inputs["x_teacher"]).cuda()
+    opt = D2.FusedAdamW([p for p in student.parameters() if p.requires_grad], lr=1e-3)
+
+    def step_with_opt():
+        with torch.no_grad():
+            t_out = teacher(xt)
+        loss_mod(student(xs), t_out, 0).backward()
+        opt.step()
+
+    with pytest.raises(RuntimeError, match="StepGraph"):
+        D2.StepGraph(step_with_opt, warmup=1)
+
+    def step_fixed():
+        for p in student.parameters():
+            p.grad = None
+        with torch.no_grad():
+            t_out = teacher(xt)
+        loss = loss_mod(student(xs), t_out, 0)
+        loss.backward()
+        return loss
+
+    g = D2.StepGraph(step_fixed, warmup=1)
+    g.replay()
+    late = golden.cfg["nepochs"] - 1
+    if float(loss_mod.teacher_temp_schedule[late]) != float(loss_mod.teacher_temp_schedule[0]):
+        with pytest.raises(RuntimeError, match="epoch"):
+            g.replay(epoch=late)
+
+
+def test_teacher_operand_shadows_match_regular_path(golden):
+    """The EMA pass refreshes the frozen teacher's bf16 GEMM operands (MLP weights, W = g v/||v||); a teacher forward
+    from those shadows must equal the regular path (casts + weight-norm pass) bit for bit, and any other write to the
+    teacher's parameters must switch the shadows off until the next EMA pass."""
+    import dinomc_b200 as D2
+    D, student, teacher, loss_mod = _build(golden, "bf16")
+    xt = torch.from_numpy(golden.inputs["x_teacher"]).cuda()
+    tp, sp = list(teacher.parameters()), list(student.parameters())
+    with torch.no_grad():
+        teacher(xt)                                             # first sight of a frozen no-grad head: allocates the shadows
+    assert teacher._shadow is not None and teacher._shadow["state"] is None
+    D2.ema_update_(tp, sp, 0.9)
+    with torch.no_grad():
+        assert teacher._fresh_shadow("bf16", xt) is not None
+        out_shadow = teacher(xt).clone()
+        D2.head.set_operand_shadows(False)
+        try:
+            out_regular = teacher(xt).clone()
+        finally:
+            D2.head.set_operand_shadows(True)
+    assert torch.equal(out_shadow, out_regular)
+    # the shadow of the last layer equals the weight-norm kernel's own output on the updated parameters
+    w, _, scale, inv = D2.ops.weightnorm_fwd(teacher.last_layer.weight_v.detach(), teacher.last_layer.weight_g.detach().reshape(-1), "bf16")
+    assert torch.equal(w, teacher._shadow["what"]) and torch.equal(scale, teacher._shadow["scale"])
+    assert torch.equal(inv, teacher._shadow["inv_norm"])
+    # EMA stays bit-exact with the reference's op sequence (including weight_g, which travels with the rows)
+    ref_t = [p.detach().clone() for p in tp]
+    D2.ema_update_(tp, sp, 0.75)
+    for r, q in zip(ref_t, sp):
+        r.mul_(0.75).add_((1 - 0.75) * q.detach())
+    assert all(torch.equal(a, b) for a, b in zip(ref_t, tp))
+    # a foreign write invalidates
+    with torch.no_grad():
+        teacher.last_layer.weight_v.mul_(1.5)
+        assert teacher._fresh_shadow("bf16", xt) is None
+        out2 = teacher(xt)
+    assert torch.isfinite(out2.float()).all()

@@ -14,7 +14,7 @@ mode = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 w = dict(bench.WORKLOADS["cfg2"])
 dev = torch.device("cuda", 0)
 import dinomc_b200 as D
-D.set_teacher_overlap(True)
+D.set_teacher_overlap(os.environ.get('DMC_BENCH_OVERLAP', '1') != '0')
 force_dp = bool(int(os.environ.get("DMC_BENCH_FORCE_DP", "0")))     # 1-rank NCCL group: the reducer path without transfers
 if force_dp:
     import torch.distributed as dist
