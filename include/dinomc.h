@@ -53,6 +53,13 @@ int dmc_device_check(int device);
  * e.g. while NCCL kernels share the SMs; the environment variable DMC_PDL=0 sets the initial value.  Returns the
  * previous setting. */
 int dmc_set_pdl(int enabled);
+/* Grid cap for the row-streaming kernels (dmc_weightnorm_fwd, dmc_weightnorm_bwd[_bf16]) launched from the CALLING
+ * THREAD until changed again; 0 = no cap (default).  These kernels are HBM-bound and normally launch thousands of CTAs,
+ * which keep every SM full: a one-CTA-per-SM tcgen05 GEMM queued behind them cannot start before they drain.  Capped at
+ * one CTA per SM (148) they walk their rows with a grid-stride loop and leave registers and shared memory for a GEMM CTA
+ * on every SM, so an auxiliary-stream weight-norm pass (utils/vision_transformer.py:279) runs NEXT TO the MLP GEMMs.
+ * Returns the previous cap. */
+int dmc_set_streaming_ctas(int n);
 
 /* ---------------------------------------------------------------------------------------------
  * GEMM:  D[M,N] = epilogue( sum_k A(m,k) * B(n,k) ),  fp32 accumulation.
@@ -173,9 +180,15 @@ int dmc_teacher_stats_colsum(const void* t, int32_t dtype, int64_t Nt, int64_t K
                              const float* center, float inv_temp, float* row_stats, float* colsum,
                              void* workspace, size_t workspace_bytes, void* stream);
 /* Same outputs as dmc_teacher_stats_colsum, but from the partials the last-layer GEMM's epilogue already wrote
- * (dmc_gemm_args.stat_row_partials [Nt][parts] and stat_colsum_partials [row_groups][K]): no pass over the logits. */
+ * (dmc_gemm_args.stat_row_partials [Nt][parts] and stat_colsum_partials [row_groups][K]): no pass over the logits.
+ * colsum_partials may be NULL (then colsum is not written: row statistics only, see dmc_rowdot for the column sums). */
 int dmc_teacher_finalize(const float* row_partials, const float* colsum_partials, int64_t Nt, int64_t K, int64_t parts,
                          int64_t row_groups, float* row_stats, float* colsum, void* stream);
+/* out[k] = sum_j W[k, j] * x[j] (W row-major [K, dim], F32 or BF16; x, out fp32).  With W = the weight-normed last layer's
+ * operand g v/||v|| and x = the column sum of the teacher's normalised bottleneck rows, this IS torch.sum(teacher_output,
+ * dim=0) of main_dino_mc.py:468 (sum_rows zhat_r . W_k = (sum_rows zhat_r) . W_k), from 2*K*dim bytes instead of a pass
+ * over the [Nt, K] logits.  Honours dmc_set_streaming_ctas. */
+int dmc_rowdot(const void* W, int32_t dtype, int64_t K, int64_t dim, const float* x, float* out, void* stream);
 
 /* center_out = center_in * momentum + (colsum / count) * one_minus_momentum  (main_dino_mc.py:470-473)
  * with the reference's fp32 roundings: true division by count (= Nt * world_size), separate multiplies and

@@ -43,6 +43,7 @@ SIGNATURES = {
     "dmc_last_error_string": (C.c_char_p, []),
     "dmc_device_check": (C.c_int, [C.c_int]),
     "dmc_set_pdl": (C.c_int, [C.c_int]),
+    "dmc_set_streaming_ctas": (C.c_int, [C.c_int]),
     "dmc_gemm_workspace_bytes": (sz, [i64, i64, i64, i32]),
     "dmc_gemm_stats_parts": (i64, [i64]),
     "dmc_gemm": (C.c_int, [C.POINTER(GemmArgs), vp]),
@@ -61,6 +62,7 @@ SIGNATURES = {
     "dmc_teacher_workspace_bytes": (sz, [i64, i64]),
     "dmc_teacher_stats_colsum": (C.c_int, [vp, i32, i64, i64, i64, vp, f32, vp, vp, vp, sz, vp]),
     "dmc_teacher_finalize": (C.c_int, [vp, vp, i64, i64, i64, i64, vp, vp, vp]),
+    "dmc_rowdot": (C.c_int, [vp, i32, i64, i64, vp, vp, vp]),
     "dmc_lse_finalize": (C.c_int, [vp, i64, i64, vp, vp]),
     "dmc_ce_fused": (C.c_int, [vp, i32, i64, vp, i32, i64, vp, vp, vp, i64, i32, i32, i64, f32, f32, vp, i32, i64, vp, vp, sz, vp]),
     "dmc_scale_inplace_if": (C.c_int, [vp, i32, i64, vp, f32, vp]),

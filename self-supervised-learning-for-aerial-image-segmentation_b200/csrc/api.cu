@@ -34,7 +34,18 @@ int& pdl_flag() {
 }  // namespace
 
 bool pdl_enabled() { return pdl_flag() != 0; }
+
+namespace {
+thread_local int g_streaming_ctas = 0;
+}
+int streaming_ctas() { return g_streaming_ctas; }
 }  // namespace dmc
+
+extern "C" int dmc_set_streaming_ctas(int n) {
+  const int prev = dmc::g_streaming_ctas;
+  dmc::g_streaming_ctas = n > 0 ? n : 0;
+  return prev;
+}
 
 extern "C" int dmc_version(void) { return DMC_VERSION; }
 

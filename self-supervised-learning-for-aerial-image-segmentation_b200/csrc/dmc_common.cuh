@@ -39,6 +39,14 @@ int cuda_status(cudaError_t e, const char* what);     // api.cu : 0 if ok else (
 // unchanged because every kernel waits before its first global access.  DMC_PDL=0 turns the attribute off (the
 // prologue instructions are then no-ops).  Works under CUDA-graph stream capture (programmatic edges).
 bool pdl_enabled();                                   // api.cu
+// Grid cap for the row-streaming kernels (weight-norm forward / backward), calling-thread local, 0 = none.  With a cap of
+// one CTA per SM (148) such a kernel leaves registers and shared memory for a one-CTA-per-SM GEMM on every SM, so the two
+// run side by side; uncapped, its thousands of CTAs keep every SM full and a GEMM queued behind it cannot start.
+int streaming_ctas();                                 // api.cu
+inline unsigned streaming_grid(int64_t blocks) {
+  const int cap = streaming_ctas();
+  return static_cast<unsigned>((cap > 0 && blocks > cap) ? cap : blocks);
+}
 #ifdef __CUDACC__
 template <typename... Params, typename... Args>
 inline cudaError_t launch_kernel(void (*kern)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

@@ -59,6 +59,10 @@ struct GemmDev {
   uint32_t b_bytes;   // block_n * 128
   int resident;       // 1: B-resident schedule (contiguous tile ranges, B slabs loaded once per n-tile)
   int dual;           // 1: "dual-M": a work item is 256 rows = two accumulators that share every B k-block
+  int banks;          // > 1 (3xTF32 only): the contraction is spread over `banks` TMEM accumulators of block_n columns that the
+                      // epilogue adds in fp32 registers.  tcgen05 accumulation TRUNCATES (measured: results shrink towards zero
+                      // by ~4e-8 per MMA of a chain), so fp32-grade results need short chains: hi*hi k-blocks rotate over
+                      // banks 0..banks-2, the small hi*lo / lo*hi terms share the last bank
   // fused output statistics (EPI == 2): softmax row partials and 32-row column sums of the stored values
   float stat_sc2;               // stat_scale * log2(e)
   const float* stat_center;     // [N] or nullptr
@@ -257,7 +261,7 @@ __device__ __forceinline__ void epilogue_fast_acc(const GemmDev& p, const CUtens
         // Teacher statistics of the stored values: y2 = (t - center) * scale * log2e; online softmax pair (max, sum 2^(y2-max))
         // of this row over the step's 64 columns, and the column sums of the warp's 32 rows read back from the staged box
         // (lane j owns the 32-bit word j of every 128-byte row: conflict-free, 2 bf16 columns per lane).
-        if (row0 < p.M) {
+        if (p.stat_colsum_partials != nullptr && row0 < p.M) {          // optional: the caller may get the column sums elsewhere
           const int nrows = min(32, p.M - row0);
           float s0 = 0.f, s1 = 0.f;
           for (int r = 0; r < nrows; ++r) {
@@ -545,13 +549,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // last tile of this CTA that uses the resident B of this n-tile -> release the slabs afterwards
         const bool last_of_nt = p.resident && ((w + 1 >= w_end) || (((w + 1) / p.m_tiles) % p.n_tiles != nt));
         // single-M: two accumulators ping-pong between MMA and epilogue; dual-M: both belong to this work item
-        const int acc = p.dual ? 0 : (it & 1);
-        const uint32_t acc_phase = p.dual ? (it & 1u) : ((it >> 1) & 1u);
+        const bool one_set = p.dual || p.banks > 1;            // the work item owns all of TMEM: no ping-pong
+        const int acc = one_set ? 0 : (it & 1);
+        const uint32_t acc_phase = one_set ? (it & 1u) : ((it >> 1) & 1u);
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);      // epilogue has drained this accumulator
         trace_at(p, 4, it);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccCols);
+        const uint32_t d_tmem0 = tmem_base + static_cast<uint32_t>(acc * kAccCols);
+        uint32_t banks_used = 0;
+        int bpass = vk0 / p.kb_total;
+        int bkb = vk0 - bpass * p.kb_total;
         for (int vk = vk0; vk < vk1; ++vk) {
+          uint32_t d_tmem = d_tmem0;
+          uint32_t bank_started = (vk > vk0) ? 1u : 0u;
+          if (p.banks > 1) {
+            const int bank = (bpass == 0) ? (bkb % (p.banks - 1)) : (p.banks - 1);
+            d_tmem = tmem_base + static_cast<uint32_t>(bank * p.block_n);
+            bank_started = (banks_used >> bank) & 1u;
+            banks_used |= 1u << bank;
+            if (++bkb == p.kb_total) { bkb = 0; ++bpass; }
+          }
           if (new_b) ptx::mbar_wait(&bfull_bar[vk], b_gen & 1u);
           ptx::mbar_wait(&full_bar[stage], phase);              // TMA bytes have landed
           trace_at(p, 2, tr);
@@ -561,7 +578,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const uint32_t b_addr = p.resident ? (bres_addr + static_cast<uint32_t>(vk) * p.b_bytes) : (a_addr + a_stage_bytes);
             const uint64_t da0 = da_base | static_cast<uint64_t>((a_addr >> 4) & 0x3FFFu);
             const uint64_t db0 = db_base | static_cast<uint64_t>((b_addr >> 4) & 0x3FFFu);
-            const uint32_t acc0 = (vk > vk0) ? 1u : 0u;
+            const uint32_t acc0 = bank_started;
 #pragma unroll
             for (int k = 0; k < kMmaPerKBlock; ++k) {
               const uint64_t da = da0 + k * kStepA;
@@ -622,11 +639,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
     }
     // lean path (epilogue_fast_acc) for full tiles stored through TMA; everything else takes the generic chunk code
-    bool fast_ok = p.tma_store && p.partial == nullptr && p.dbg == 0 && c_begin < c_end && ((c_end - c_begin) & 63) == 0;
+    bool fast_ok = p.tma_store && p.partial == nullptr && p.dbg == 0 && c_begin < c_end && ((c_end - c_begin) & 63) == 0 &&
+                   p.banks <= 1;
     if constexpr (EPI == 0) fast_ok = fast_ok && p.col_scale == nullptr && aux_vec_ok;
     if constexpr (EPI == 2) fast_ok = fast_ok && stat_fixed && p.stat_colsum_partials == nullptr;
     if constexpr (EPI == 3)                            // lean teacher statistics: bf16 output, center + column sums requested
-      fast_ok = fast_ok && p.stat_center != nullptr && p.stat_colsum_partials != nullptr && p.out_dtype == DMC_BF16 &&
+      fast_ok = fast_ok && p.stat_center != nullptr && p.out_dtype == DMC_BF16 &&
                 (reinterpret_cast<uintptr_t>(p.stat_center) & 15) == 0;
     const bool out_bf16 = (p.out_dtype == DMC_BF16);
     int it = 0;
@@ -636,8 +654,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int nt = rest % p.n_tiles;
       const int sp = rest / p.n_tiles;
       const int n0 = nt * p.block_n;
-      const int acc = p.dual ? 0 : (it & 1);
-      const uint32_t acc_phase = p.dual ? (it & 1u) : ((it >> 1) & 1u);
+      const bool one_set = p.dual || p.banks > 1;
+      const int acc = one_set ? 0 : (it & 1);
+      const uint32_t acc_phase = one_set ? (it & 1u) : ((it >> 1) & 1u);
+      uint32_t banks_used = 0;                                  // which accumulator banks this work item's MMAs wrote
+      if (p.banks > 1) {
+        const int vk0 = sp * p.vk_per_split;
+        const int vk1 = min(vk0 + p.vk_per_split, p.vk_total);
+        const int n_hh = max(0, min(vk1, p.kb_total) - vk0);    // hi*hi k-blocks of this split: consecutive from k-block vk0
+        for (int i = 0; i < min(n_hh, p.banks - 1); ++i) banks_used |= 1u << ((vk0 + i) % (p.banks - 1));
+        if (vk1 > p.kb_total) banks_used |= 1u << (p.banks - 1);
+      }
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       if (warp == 2) trace_at(p, 5, it);
       ptx::tc_fence_after();
@@ -819,6 +846,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           st_l += (a0 + a1) + (a2 + a3);
         }
       };
+      if (p.banks > 1) {
+        // 3xTF32 with accumulator banks: sum the banks in fp32 registers (exact IEEE adds), 32 columns at a time
+        for (int c = c_begin; c < c_end; c += 32) {
+          uint32_t ra[32], rt[32];
+          float (&va)[32] = reinterpret_cast<float (&)[32]>(ra);
+          float (&vt)[32] = reinterpret_cast<float (&)[32]>(rt);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) va[j] = 0.f;
+          for (int b = 0; b < p.banks; ++b) {
+            if (!((banks_used >> b) & 1u)) continue;            // warp-uniform
+            ptx::tmem_ld_32x32(tmem_base + static_cast<uint32_t>(b * p.block_n + c) + (static_cast<uint32_t>(q * 32) << 16), rt);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) va[j] += vt[j];
+          }
+          if (c + 32 >= c_end) {                                // this warp's last read of the accumulators: hand back
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+          }
+          process(ra, c);
+          if constexpr (EPI >= 2) chunk_stats(ra, c);
+        }
+      } else
       for (int c = c_begin; c < c_end; c += 64) {               // this warp's column range, 64 columns at a time
         uint32_t ra[32], rb[32];
         if (!(p.dbg & 4)) {
@@ -947,7 +998,7 @@ int make_tmap(CUtensorMap* tm, const void* base, int esz, int64_t rows, int64_t 
 }
 
 struct Plan {
-  int block_n, m_tiles, n_tiles, kb_total, passes, vk_total, splits, vk_per_split, stages, resident, tma_store, dual, cg2;
+  int block_n, m_tiles, n_tiles, kb_total, passes, vk_total, splits, vk_per_split, stages, resident, tma_store, dual, cg2, banks;
   size_t smem_bytes, workspace_bytes;
 };
 
@@ -976,8 +1027,13 @@ Plan make_plan(int64_t M, int64_t N, int64_t K, int in_dtype, bool three_pass, i
   // Exception: very long contractions with few output tiles (the last layer's dgrad: 2048 x 256 x 65536).  There the pair
   // halves the split-K partial traffic (9 instead of 18 splits for the same 144 CTAs) and the smem reads per MMA:
   // measured 84 -> 76 us.  DMC_GEMM_FLAGS bit 8 disables it.
-  const bool long_k = (K >= 32768 && N <= 256 && !(debug_flags() & 256));
-  pl.cg2 = (M > kBlockM && ((debug_flags() & 64) || long_k)) ? 1 : 0;
+  // 3xTF32 (fp32 parity mode): accumulator banks keep every tcgen05 accumulation chain short (see GemmDev::banks).  At most
+  // kMaxChainKb hi*hi k-blocks (x4 MMAs) per bank: the widest tile whose banks reach that without splitting the contraction,
+  // else 64-wide tiles (8 banks) plus split-K.  DMC_GEMM_FLAGS bit 9 turns the banks off (A/B measurements of the error).
+  constexpr int kMaxChainKb = 22;
+  const bool use_banks = three_pass && !(debug_flags() & 512);
+  const bool long_k = (K >= 32768 && N <= 256 && !(debug_flags() & 256)) && !use_banks;
+  pl.cg2 = (M > kBlockM && !use_banks && ((debug_flags() & 64) || long_k)) ? 1 : 0;
   const int units = pl.cg2 ? kNumSMs / 2 : kNumSMs;                 // schedulable units: CTA pairs or CTAs
   const int64_t mt = ceil_div(M, pl.cg2 ? 2 * kBlockM : kBlockM);
   int bn = N > 128 ? 256 : ((N > 64 || pl.cg2) ? 128 : 64);
@@ -986,6 +1042,23 @@ Plan make_plan(int64_t M, int64_t N, int64_t K, int in_dtype, bool three_pass, i
     while (bn > bn_min && mt * ceil_div(N, bn) < (units * 2) / 3) bn >>= 1;
   }
   if (want_stats) { bn = 256; forced_split = 1; }         // statistics parts are defined on 256-wide unsplit tiles
+  pl.banks = 1;
+  if (use_banks) {
+    const int kb = static_cast<int>(ceil_div(K, block_k));
+    if (!want_stats) {
+      bn = 64;
+      for (int cand = 256; cand >= 64; cand >>= 1) {
+        if (cand > 64 && cand / 2 >= N) continue;             // no wider than the output needs
+        if (ceil_div(kb, kTmemCols / cand - 1) <= kMaxChainKb) { bn = cand; break; }
+      }
+    }
+    pl.banks = kTmemCols / bn;
+    if (forced_split == 0) {
+      const int64_t per_split = static_cast<int64_t>(kMaxChainKb) * (pl.banks - 1);   // virtual k-blocks per split
+      forced_split = static_cast<int>(ceil_div(3 * static_cast<int64_t>(kb), per_split));
+      if (ceil_div(kb, pl.banks - 1) <= kMaxChainKb) forced_split = 1;
+    }
+  }
   if ((debug_flags() & 128) && !want_stats && bn == 256 && K <= 512 && mt * ceil_div(N, 128) >= 4 * units) bn = 128;
   pl.block_n = bn;
   pl.n_tiles = static_cast<int>(ceil_div(N, pl.block_n));
@@ -994,7 +1067,7 @@ Plan make_plan(int64_t M, int64_t N, int64_t K, int in_dtype, bool three_pass, i
   pl.vk_total = pl.kb_total * pl.passes;
   // dual-M (single-CTA kernels only): 256-row work items whose two accumulators share every B k-block from smem.
   pl.dual = 0;
-  if (!pl.cg2 && !(debug_flags() & 4) && M > kBlockM && pl.vk_total >= 16 && !want_stats) {
+  if (!pl.cg2 && !(debug_flags() & 4) && M > kBlockM && pl.vk_total >= 16 && !want_stats && pl.banks == 1) {
     const int64_t items = ceil_div(M, 2 * kBlockM) * pl.n_tiles;
     if (K >= 8192 || items >= kNumSMs) pl.dual = 1;
   }
@@ -1133,7 +1206,7 @@ extern "C" int dmc_gemm(const dmc_gemm_args* a, void* stream) {
   d.block_n = pl.block_n; d.m_tiles = pl.m_tiles; d.n_tiles = pl.n_tiles;
   d.kb_total = pl.kb_total; d.vk_total = pl.vk_total; d.splits = pl.splits; d.vk_per_split = pl.vk_per_split;
   d.stages = pl.stages; d.b_bytes = static_cast<uint32_t>(pl.block_n) * kRowBytes;
-  d.resident = pl.resident; d.tma_store = pl.tma_store; d.dual = pl.dual;
+  d.resident = pl.resident; d.tma_store = pl.tma_store; d.dual = pl.dual; d.banks = pl.banks;
   d.stat_sc2 = a->stat_scale * 1.4426950408889634f; d.stat_center = a->stat_center;
   d.stat_row_partials = reinterpret_cast<float2*>(a->stat_row_partials); d.stat_colsum_partials = a->stat_colsum_partials;
   d.stat_bound = a->stat_bound;

@@ -19,7 +19,7 @@ __device__ __forceinline__ float ld_in(const void* p, long long i, int dt) {
 }
 
 constexpr int kWarpsPerBlock = 8;
-constexpr int kRowsPerWarp = 4;       // weightnorm_fwd, width-256 path
+constexpr int kRowsPerWarp = 3;       // weightnorm_fwd, width-256 path: 3 rows x 2 x 128 bits in flight per lane within 40 registers
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 normalize_fwd_kernel(const void* __restrict__ z, int z_dtype, long long n_rows, int dim, long long ld, float eps,
@@ -72,7 +72,8 @@ normalize_bwd_kernel(const float* __restrict__ dzhat, const float* __restrict__ 
 
 // Vector path (dim % 4 == 0, 16-byte aligned rows): each lane owns float4 #lane, #lane+32, ... of its row; the
 // usual bottleneck width (256) keeps the whole row in registers between the two passes.
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+// <= 40 registers (6 CTAs / SM bound): one 256-thread CTA then fits next to a resident GEMM CTA (168 regs x 320 threads)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 6)
 weightnorm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, long long K, int dim,
                       float* __restrict__ w_f32, float* __restrict__ w_lo, __nv_bfloat16* __restrict__ w_bf16,
                       float* __restrict__ scale, float* __restrict__ inv_vnorm, bool vec_ok, float* __restrict__ gmax) {
@@ -82,8 +83,10 @@ weightnorm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, 
   if (vec_ok && dim == 256) {                          // the DINO bottleneck width: whole rows in registers
     // kRowsPerWarp consecutive rows per warp, all their loads issued before the first reduction: four times the bytes in
     // flight per warp and a quarter of the blocks of the one-row-per-warp form (ncu: 52 % issue-active, 46 % DRAM before)
-    const long long row0 = (static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5)) * kRowsPerWarp;
-    if (row0 >= K) return;
+    const long long nblk = (K + kWarpsPerBlock * kRowsPerWarp - 1) / (kWarpsPerBlock * kRowsPerWarp);
+    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {     // grid-stride over row groups (see streaming_grid)
+    const long long row0 = (blk * kWarpsPerBlock + (threadIdx.x >> 5)) * kRowsPerWarp;
+    if (row0 >= K) continue;
     float4 x0[kRowsPerWarp], x1[kRowsPerWarp];
     float ss[kRowsPerWarp], gr[kRowsPerWarp];
 #pragma unroll
@@ -132,10 +135,11 @@ weightnorm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, 
         *reinterpret_cast<uint2*>(w_bf16 + o1) = make_uint2(pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
       }
     }
+    }
     return;
   }
-  const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (row >= K) return;
+  for (long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5); row < K;
+       row += static_cast<long long>(gridDim.x) * kWarpsPerBlock) {
   const float* vr = v + row * dim;
   float ss = 0.f;
   for (int c = lane; c < dim; c += 32) { float x = vr[c]; ss = fmaf(x, x, ss); }
@@ -155,6 +159,7 @@ weightnorm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, 
     }
     if (w_bf16) w_bf16[o] = __float2bfloat16_rn(w);
   }
+  }
 }
 
 // TD = storage type of dW: fp32 (the wgrad GEMM's default output) or bf16 (the data-parallel exchange averages dW over
@@ -165,9 +170,9 @@ weightnorm_bwd_kernel(const TD* __restrict__ dw, const float* __restrict__ v, co
                       const float* __restrict__ inv_vnorm, long long K, int dim, float* __restrict__ dv, float* __restrict__ dg,
                       bool vec_ok) {
   pdl_prologue();
-  const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (row >= K) return;
   const int lane = threadIdx.x & 31;
+  for (long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5); row < K;
+       row += static_cast<long long>(gridDim.x) * kWarpsPerBlock) {          // grid-stride (see streaming_grid)
   const float iv = inv_vnorm[row], sc = scale[row];
   if (vec_ok && dim == 256) {
     using Q4 = Quad<TD>;
@@ -188,7 +193,7 @@ weightnorm_bwd_kernel(const TD* __restrict__ dw, const float* __restrict__ v, co
     if (dg && lane == 0) dg[row] = dot;
     dv4[lane] = make_float4(sc * (a0.x - dot * b0.x), sc * (a0.y - dot * b0.y), sc * (a0.z - dot * b0.z), sc * (a0.w - dot * b0.w));
     dv4[lane + 32] = make_float4(sc * (a1.x - dot * b1.x), sc * (a1.y - dot * b1.y), sc * (a1.z - dot * b1.z), sc * (a1.w - dot * b1.w));
-    return;
+    continue;
   }
   float dot = 0.f;
   for (int c = lane; c < dim; c += 32) dot = fmaf(static_cast<float>(dw[row * dim + c]), v[row * dim + c] * iv, dot);
@@ -197,6 +202,7 @@ weightnorm_bwd_kernel(const TD* __restrict__ dw, const float* __restrict__ v, co
   for (int c = lane; c < dim; c += 32) {
     const long long o = row * dim + c;
     dv[o] = sc * (static_cast<float>(dw[o]) - dot * (v[o] * iv));
+  }
   }
 }
 
@@ -384,7 +390,7 @@ extern "C" int dmc_weightnorm_fwd(const float* v, const float* g, int64_t K, int
     DMC_LAUNCH_CHECK("absmax_kernel launch");
   }
   const int64_t rows_per_block = (vec_ok && dim == 256) ? kWarpsPerBlock * kRowsPerWarp : kWarpsPerBlock;
-  launch_kernel(weightnorm_fwd_kernel, dim3((unsigned)ceil_div(K, rows_per_block)), dim3(kWarpsPerBlock * 32), 0, (cudaStream_t)stream, v, g, K, (int)dim, w_f32, w_lo, static_cast<__nv_bfloat16*>(w_bf16), scale, inv_vnorm, vec_ok, gmax);
+  launch_kernel(weightnorm_fwd_kernel, dim3(streaming_grid(ceil_div(K, rows_per_block))), dim3(kWarpsPerBlock * 32), 0, (cudaStream_t)stream, v, g, K, (int)dim, w_f32, w_lo, static_cast<__nv_bfloat16*>(w_bf16), scale, inv_vnorm, vec_ok, gmax);
   DMC_LAUNCH_CHECK("weightnorm_fwd_kernel launch");
   return 0;
 }
@@ -395,7 +401,7 @@ extern "C" int dmc_weightnorm_bwd(const float* dw, const float* v, const float* 
   DMC_REQUIRE(K > 0 && dim > 0 && dim < (1 << 30), "dmc_weightnorm_bwd: bad shape");
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const bool vec_ok = (dim % 4 == 0) && al16(dw) && al16(v) && al16(dv);
-  launch_kernel(weightnorm_bwd_kernel<float>, dim3((unsigned)ceil_div(K, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, (cudaStream_t)stream, dw, v, scale, inv_vnorm, K, (int)dim, dv, dg, vec_ok);
+  launch_kernel(weightnorm_bwd_kernel<float>, dim3(streaming_grid(ceil_div(K, kWarpsPerBlock))), dim3(kWarpsPerBlock * 32), 0, (cudaStream_t)stream, dw, v, scale, inv_vnorm, K, (int)dim, dv, dg, vec_ok);
   DMC_LAUNCH_CHECK("weightnorm_bwd_kernel launch");
   return 0;
 }
@@ -406,7 +412,7 @@ extern "C" int dmc_weightnorm_bwd_bf16(const void* dw_bf16, const float* v, cons
   DMC_REQUIRE(K > 0 && dim > 0 && dim < (1 << 30), "dmc_weightnorm_bwd_bf16: bad shape");
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const bool vec_ok = (dim % 4 == 0) && al16(dw_bf16) && al16(v) && al16(dv);
-  launch_kernel(weightnorm_bwd_kernel<__nv_bfloat16>, dim3((unsigned)ceil_div(K, kWarpsPerBlock)), dim3(kWarpsPerBlock * 32), 0, (cudaStream_t)stream,
+  launch_kernel(weightnorm_bwd_kernel<__nv_bfloat16>, dim3(streaming_grid(ceil_div(K, kWarpsPerBlock))), dim3(kWarpsPerBlock * 32), 0, (cudaStream_t)stream,
                 static_cast<const __nv_bfloat16*>(dw_bf16), v, scale, inv_vnorm, K, (int)dim, dv, dg, vec_ok);
   DMC_LAUNCH_CHECK("weightnorm_bwd_kernel<bf16> launch");
   return 0;

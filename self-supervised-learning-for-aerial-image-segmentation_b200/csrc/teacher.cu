@@ -163,6 +163,33 @@ center_update_kernel(const float* center_in, float* center_out, const float* __r
   center_out[k] = __fadd_rn(__fmul_rn(center_in[k], mom), __fmul_rn(bc, omm));  // center * m + bc * (1 - m), no FMA
 }
 
+// out[k] = sum_j W[k, j] * x[j]  (W row-major [K, dim] bf16 or fp32, x fp32 [dim]); one warp per row, grid-stride.
+// With x = the column sum of the teacher's normalised bottleneck rows this is the per-GPU batch column sum of the teacher
+// logits (main_dino_mc.py:468: sum_rows (zhat_r . W_k) = (sum_rows zhat_r) . W_k) without a pass over the [Nt, K] logits.
+template <typename T>
+__global__ void __launch_bounds__(256)
+rowdot_kernel(const T* __restrict__ W, const float* __restrict__ x, long long K, int dim, float* __restrict__ out, bool vec_ok) {
+  pdl_prologue();
+  const int lane = threadIdx.x & 31;
+  for (long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5); row < K; row += static_cast<long long>(gridDim.x) * 8) {
+    const T* wr = W + row * dim;
+    float acc = 0.f;
+    if (vec_ok) {
+      constexpr int N = Vec<T>::N;
+      for (int c = lane * N; c < dim; c += 32 * N) {
+        float w[N];
+        Vec<T>::load(wr + c, w);
+#pragma unroll
+        for (int e = 0; e < N; ++e) acc = fmaf(w[e], __ldg(x + c + e), acc);
+      }
+    } else {
+      for (int c = lane; c < dim; c += 32) acc = fmaf(Vec<T>::load1(wr + c), __ldg(x + c), acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[row] = acc;
+  }
+}
+
 struct TeacherPlan { int nchunks, nrb, rows_per_block; size_t stats_bytes, colsum_bytes; };
 
 TeacherPlan teacher_plan(int64_t Nt, int64_t K) {
@@ -243,13 +270,29 @@ extern "C" int dmc_center_update(const float* center_in, float* center_out, cons
 
 extern "C" int dmc_teacher_finalize(const float* row_partials, const float* colsum_partials, int64_t Nt, int64_t K, int64_t parts,
                                     int64_t row_groups, float* row_stats, float* colsum, void* stream) {
-  DMC_REQUIRE(row_partials && colsum_partials && row_stats && colsum, "dmc_teacher_finalize: null pointer");
-  DMC_REQUIRE(Nt > 0 && K > 0 && parts > 0 && row_groups > 0 && parts < (1 << 30) && row_groups < (1 << 30),
+  DMC_REQUIRE(row_partials && row_stats, "dmc_teacher_finalize: null pointer");
+  DMC_REQUIRE((colsum_partials == nullptr) || colsum, "dmc_teacher_finalize: colsum_partials given without colsum");
+  DMC_REQUIRE(Nt > 0 && K > 0 && parts > 0 && parts < (1 << 30) && row_groups < (1 << 30) && (colsum_partials == nullptr || row_groups > 0),
               "dmc_teacher_finalize: bad shape");
   const int row_blocks = static_cast<int>(ceil_div(Nt, 8));
-  const int col_blocks = static_cast<int>(ceil_div(K, 256));
+  const int col_blocks = colsum_partials ? static_cast<int>(ceil_div(K, 256)) : 0;      // no column partials: row statistics only
   launch_kernel(teacher_finalize_kernel, dim3(row_blocks + col_blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), reinterpret_cast<const float2*>(row_partials), colsum_partials, Nt, K, (int)parts, (int)row_groups, row_blocks,
       reinterpret_cast<float2*>(row_stats), colsum);
   DMC_LAUNCH_CHECK("teacher_finalize_kernel launch");
+  return 0;
+}
+
+extern "C" int dmc_rowdot(const void* W, int32_t dtype, int64_t K, int64_t dim, const float* x, float* out, void* stream) {
+  DMC_REQUIRE(W && x && out, "dmc_rowdot: null pointer");
+  DMC_REQUIRE(K > 0 && dim > 0 && dim < (1 << 30), "dmc_rowdot: bad shape");
+  DMC_REQUIRE(dtype == DMC_F32 || dtype == DMC_BF16, "dmc_rowdot: bad dtype %d", dtype);
+  const int n = (dtype == DMC_BF16) ? 8 : 4;
+  const bool vec_ok = (dim % n == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  const unsigned grid = streaming_grid(ceil_div(K, 8));
+  if (dtype == DMC_BF16)
+    launch_kernel(rowdot_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(W), x, K, (int)dim, out, vec_ok);
+  else
+    launch_kernel(rowdot_kernel<float>, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const float*>(W), x, K, (int)dim, out, vec_ok);
+  DMC_LAUNCH_CHECK("rowdot_kernel launch");
   return 0;
 }

@@ -57,11 +57,13 @@ def _current_loss():
 # ---------------------------------------------------------------------------------------------------------
 aux_overlap = True
 defer_joins = _os_environ_get("DMC_DEFER_JOINS", "1") != "0"       # see _AuxRegion.join_at_end_of_backward
+polite_ctas = int(_os_environ_get("DMC_POLITE_CTAS", "148"))       # grid cap of auxiliary-stream weight-norm passes (0 = none)
+teacher_epilogue_stats = _os_environ_get("DMC_TEACHER_EPILOGUE_STATS", "1") != "0"
 grad_exchange_active = False     # set by GradAllReduce: the last layer's dv (64 MiB, the largest all-reduce of the step) must
                                  # then be final as early as possible, so its weight-norm backward stays in front of the dgrad
 grad_exchange = None             # the active GradAllReduce (or None); with compress="bf16" the last layer hands it a bf16 dW
 import os as _os
-wgrad_bf16 = _os.environ.get("DMC_WGRAD_BF16", "") == "1"   # EXPERIMENT (off; not yet measured): in the bf16-GEMM mode the last layer's
+wgrad_bf16 = _os.environ.get("DMC_WGRAD_BF16", "1") == "1"   # (measured: step 0.797 -> 0.785 ms) in the bf16-GEMM mode the last layer's
                                  # wgrad stores dW in bf16 and the weight-norm backward reads it (-64 MB of traffic per step at
                                  # K = 65536; same kernels as the bf16 gradient exchange, gradients stay within the 2e-2 tolerance)
 _aux_streams = {}
@@ -117,7 +119,11 @@ class _AuxRegion:
         not stall on the auxiliary kernel in the middle of the pass, and everything is joined before `backward()` returns."""
         if not defer_joins:
             return self.join(*tensors)
-        torch.autograd.Variable._execution_engine.queue_callback(lambda: self.join(*tensors))
+        for t in tensors:                   # allocator bookkeeping now; the callback must not keep the tensors alive
+            if t is not None:               # (a second reference would make AccumulateGrad CLONE the gradient instead of taking it)
+                t.record_stream(self.cur)
+        cur, event = self.cur, self.event
+        torch.autograd.Variable._execution_engine.queue_callback(lambda: cur.wait_event(event))
 
 
 def last_layer_weights(mode, g, v, dim_in, after_current=True):
@@ -130,7 +136,7 @@ def last_layer_weights(mode, g, v, dim_in, after_current=True):
     region = None
     if aux_overlap:
         region = _AuxRegion(v.device)
-        with region:
+        with region, ops.polite(polite_ctas):          # one CTA per SM: runs NEXT TO the MLP GEMMs instead of in front of them
             w, w_lo, scale, inv_vnorm = ops.weightnorm_fwd(v.detach(), g.detach().reshape(-1), kind)
     else:
         w, w_lo, scale, inv_vnorm = ops.weightnorm_fwd(v.detach(), g.detach().reshape(-1), kind)
@@ -324,7 +330,22 @@ class NormLastLayerFn(torch.autograd.Function):
         if loss_mod is not None:
             parts = ops.gemm_stats_parts(K)
             rp = torch.empty((rows, parts, 2), dtype=torch.float32, device=z.device) if (who == "student" or fused_teacher_stats) else None
-            if who == "teacher" and not fused_teacher_stats:
+            if who == "teacher" and teacher_epilogue_stats and mode == "bf16" and not fused_teacher_stats:
+                # Teacher: row softmax statistics from the GEMM epilogue (EPI 3, no column sums); the per-GPU batch column sum
+                # of the logits (main_dino_mc.py:468) by linearity, sum_rows(zhat_r . W_k) = (sum_rows zhat_r) . W_k: a
+                # [K, dim] x [dim] product on a side stream next to the GEMM -- the [Nt, K] logits are never read back.
+                loss_mod.sync_center()
+                cen = loss_mod.center
+                rp = torch.empty((rows, parts, 2), dtype=torch.float32, device=z.device)
+                stats = dict(kind="teacher", scale=loss_mod._last_inv_tt, center=cen.reshape(-1), row_partials=rp,
+                             colsum_partials=None, center_ptr=cen.data_ptr(), center_version=cen._version)
+                side = _AuxRegion(z.device)
+                with side, ops.polite(polite_ctas):
+                    zbar = ops.colsum(zhat_bf16)
+                    side_colsum = ops.rowdot(wop.main, zbar)
+                zhat_bf16.record_stream(side.aux)
+                wop.main.record_stream(side.aux)
+            elif who == "teacher" and not fused_teacher_stats:
                 stats = None
             elif who == "student":
                 stats = dict(kind="student", scale=1.0 / loss_mod.student_temp, center=None, row_partials=rp,
@@ -336,6 +357,10 @@ class NormLastLayerFn(torch.autograd.Function):
                              colsum_partials=torch.empty(((rows + 31) // 32, K), dtype=torch.float32, device=z.device),
                              center_ptr=cen.data_ptr(), center_version=cen._version)
         logits = mm(mode, zop, wop, rows, K, dim, out_dtype=store_dtype(mode), tag="gemm_last_fwd_" + who, stats=stats)
+        if stats is not None and stats["kind"] == "teacher" and stats["colsum_partials"] is None:
+            t_stats, _ = ops.teacher_finalize(stats["row_partials"], None, rows, K)
+            stats = dict(kind="teacher_final", scale=stats["scale"], t_stats=t_stats, colsum=side_colsum, event=side.event,
+                         center_ptr=stats["center_ptr"], center_version=stats["center_version"], rows=rows)
         last_stats = stats
         ctx.mode = mode
         ctx.zop, ctx.wop = zop, wop
@@ -373,7 +398,7 @@ class NormLastLayerFn(torch.autograd.Function):
                         out_dtype=torch.bfloat16 if (wgrad_bf16 and mode == "bf16") else torch.float32, tag="gemm_last_wgrad")
                 if aux_overlap and not grad_exchange_active:   # streaming pass on the auxiliary stream: the dgrad GEMM does not wait for it
                     region = _AuxRegion(dw.device)
-                    with region:
+                    with region, ops.polite(polite_ctas):
                         dv, dg = ops.weightnorm_bwd(dw, v, scale, inv_vnorm, want_dg=ctx.needs_input_grad[2])
                         if ctx.needs_input_grad[3]:
                             ops.mark_ready(dv)

@@ -265,16 +265,46 @@ def gemm_stats_parts(N: int) -> int:
 
 
 def teacher_finalize(row_partials, colsum_partials, Nt, K):
-    """(row_stats [Nt,2], colsum [K]) from the partials the last-layer GEMM epilogue wrote."""
+    """(row_stats [Nt,2], colsum [K] or None) from the partials the last-layer GEMM epilogue wrote.  With
+    `colsum_partials` None only the row statistics are merged (the column sums then come from `rowdot`)."""
     lib = L.load()
     row_stats = torch.empty((Nt, 2), dtype=torch.float32, device=row_partials.device)
-    colsum_ = torch.empty(K, dtype=torch.float32, device=row_partials.device)
+    colsum_ = torch.empty(K, dtype=torch.float32, device=row_partials.device) if colsum_partials is not None else None
     with _timed("teacher_finalize"):
-        L.check(lib.dmc_teacher_finalize(row_partials.data_ptr(), colsum_partials.data_ptr(), Nt, K, row_partials.shape[1],
-                                         colsum_partials.shape[0], row_stats.data_ptr(), colsum_.data_ptr(), _stream()),
+        L.check(lib.dmc_teacher_finalize(row_partials.data_ptr(), _p(colsum_partials), Nt, K, row_partials.shape[1],
+                                         colsum_partials.shape[0] if colsum_partials is not None else 0,
+                                         row_stats.data_ptr(), _p(colsum_), _stream()),
                 "dmc_teacher_finalize")
     _count()
     return row_stats, colsum_
+
+
+def rowdot(W: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """out[k] = sum_j W[k, j] * x[j]  (W [K, dim] fp32 / bf16 contiguous, x fp32 [dim])."""
+    lib = L.load()
+    _need_cuda(W, x)
+    if not W.is_contiguous() or W.dim() != 2 or x.dtype != torch.float32 or x.numel() != W.shape[1] or not x.is_contiguous():
+        raise ValueError("rowdot: W must be a contiguous [K, dim] matrix and x a contiguous fp32 vector of dim entries")
+    out = torch.empty(W.shape[0], dtype=torch.float32, device=W.device)
+    with _timed("rowdot"):
+        L.check(lib.dmc_rowdot(W.data_ptr(), _dt(W), W.shape[0], W.shape[1], x.data_ptr(), out.data_ptr(), _stream()), "dmc_rowdot")
+    _count()
+    return out
+
+
+class polite:
+    """Context manager: row-streaming kernels launched inside (weight-norm forward / backward, rowdot) use at most `n`
+    CTAs (default one per SM) and so leave room for a one-CTA-per-SM GEMM on every SM (dmc_set_streaming_ctas)."""
+
+    def __init__(self, n: int = 148):
+        self.n = n
+
+    def __enter__(self):
+        self.prev = L.load().dmc_set_streaming_ctas(int(self.n))
+
+    def __exit__(self, *exc):
+        L.load().dmc_set_streaming_ctas(self.prev)
+        return False
 
 
 def lse_finalize(row_partials):
