@@ -162,7 +162,7 @@ class ClockSampler:
 class Step:
     """Owns the modules/buffers of one rank and runs one whole step on the current stream."""
 
-    def __init__(self, w, mode, rank, world, device, ddp=False, reserve_sms=16, force_reducer=False, compress=None):
+    def __init__(self, w, mode, rank, world, device, ddp=False, reserve_sms=16, force_reducer=False, compress=None, transport="nccl"):
         import dinomc_b200 as D
         self.D, self.w, self.world, self.device = D, w, world, device
         torch.manual_seed(0)                                          # identical weights on every rank
@@ -191,7 +191,7 @@ class Step:
                 self.model = DDP(self.student, device_ids=[device.index])  # main_dino_mc.py:260
             else:
                 # same exchange (mean of the head gradients over ranks), graph-capturable, overlapped with bwd + EMA
-                self.reducer = D.GradAllReduce(self.student.parameters(), reserve_sms=reserve_sms, compress=compress)
+                self.reducer = D.GradAllReduce(self.student.parameters(), reserve_sms=reserve_sms, compress=compress, transport=transport)
         gs = torch.Generator(device="cpu").manual_seed(1234 + rank)
         gt = torch.Generator(device="cpu").manual_seed(4321 + rank)
         self.x_student_host = torch.randn(C * B, Din, generator=gs).pin_memory()
@@ -419,6 +419,9 @@ def main():
                     help="N>1 gradient exchange: fp32 all-reduce (default; what DDP does in the reference), or bf16 (dW of the "
                          "last layer averaged before its weight-norm backward + the small gradients as one flat bf16 buffer). "
                          "bf16 measured SLOWER at 2 GPUs (1.068 vs 0.980 ms), so it stays opt-in")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1 gradient exchange transport: 'peer' = libdinomc's own all-reduce kernel over NVLink/NVSwitch symmetric "
+                         "memory (bf16 exchange; falls back to 'nccl' if symmetric memory is unavailable), 'nccl' = torch.distributed")
     ap.add_argument("--overlap", type=int, default=1, help="teacher head forward on a side stream, overlapping the student's")
     ap.add_argument("--cpu-sample-batch", type=int, default=0,
                     help="samples per CPU step for cpu_baseline / --impl reference (0 = the workload's own per-GPU batch)")
@@ -437,6 +440,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     warmup = max(args.warmup, 3)
     compress = None if args.grad_compress == "none" else "bf16"
+    if args.exchange == "peer" and args.mode == "bf16" and "--grad-compress" not in sys.argv:
+        compress = "bf16"               # the peer transport exchanges bf16 buffers (gradients stay within the bf16-mode tolerance)
     if os.environ.get("DMC_BENCH_GRAD_COMPRESS"):                        # A/B runs under torchrun without changing the command line
         compress = None if os.environ["DMC_BENCH_GRAD_COMPRESS"] == "none" else "bf16"
     cfg = {"workload": f"{args.workload}: {w['note']}; D={w['D']} out_dim={w['K']} batch/GPU={w['B']} "
@@ -490,12 +495,37 @@ def main():
         dist.init_process_group("nccl", device_id=device, pg_options=opts)
     import dinomc_b200 as D
     D._lib.check(D._lib.load().dmc_device_check(local_rank), "dmc_device_check")
+    transport = "nccl"
+    if world > 1 and args.exchange == "peer" and compress == "bf16" and not args.ddp:
+        # probe symmetric memory + the exchange kernel on every rank; all ranks must agree before relying on it
+        ok = 1
+        try:
+            from dinomc_b200.xrank import SymmetricBuffer
+            probe = SymmetricBuffer(4096, torch.bfloat16)
+            probe.tensor.fill_(1.0)
+            probe.allreduce_(1.0 / world)
+            torch.cuda.synchronize()
+            ok = int(bool((probe.tensor.float() == 1.0).all()))
+            multicast = probe.multicast
+            del probe
+        except Exception as e:          # noqa: BLE001
+            print(f"[rank {rank}] symmetric-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
+            ok, multicast = 0, False
+        flag = torch.tensor([ok], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag) == 1:
+            transport = "peer"
+            cfg["grad_allreduce"] = ("dinomc_b200.GradAllReduce over libdinomc's own all-reduce kernel (dmc_xrank_allreduce: symmetric memory, "
+                                     + ("multimem.ld_reduce / multimem.st through NVSwitch" if multicast else "peer loads / stores")
+                                     + "; bf16 exchange: last-layer dW averaged before its weight-norm backward, small gradients in one flat bf16 buffer)")
+        elif "--grad-compress" not in sys.argv:
+            compress = None
 
     D.set_teacher_overlap(bool(args.overlap))
     if (world > 1 or force_dp) and not args.ddp:
         D.set_async_center(True)
     step = Step(w, args.mode, rank, world, device, ddp=bool(args.ddp), reserve_sms=args.reserve_sms, force_reducer=force_dp,
-                compress=compress)
+                compress=compress, transport=transport)
     ops = D.ops
     for _ in range(warmup):
         step.run()

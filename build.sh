@@ -19,7 +19,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
 mkdir -p "$BUILD"
 objs=()
 pids=()
-for f in api gemm_sm100 gemm_simt rowops teacher ce ema clip adamw lars; do
+for f in api gemm_sm100 gemm_simt rowops teacher ce ema clip adamw lars xrank; do
   o="$BUILD/$f.o"
   objs+=("$o")
   if [[ ! -f "$o" || "$SRC/$f.cu" -nt "$o" || "$SRC/dmc_common.cuh" -nt "$o" || "$SRC/dmc_ptx.cuh" -nt "$o" || "$ROOT/include/dinomc.h" -nt "$o" ]]; then

@@ -77,6 +77,9 @@ SIGNATURES = {
     "dmc_ema_build_plan2": (C.c_int, [C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), i64, i64, i64, i64, vp, vp, vp,
                                       vp, sz, C.POINTER(i64)]),
     "dmc_ema_multi_tensor2": (C.c_int, [vp, i64, vp, vp]),
+    "dmc_xrank_signal_bytes": (sz, [i32, i32]),
+    "dmc_xrank_allreduce": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), i64, i32, i32, i32, f32, i32, i32, C.POINTER(vp),
+                                      C.POINTER(i64), C.POINTER(i64), vp]),
     "dmc_clip_plan_bytes": (sz, [C.POINTER(i64), i64]),
     "dmc_clip_build_plan": (C.c_int, [C.POINTER(vp), C.POINTER(i64), i64, vp, sz, C.POINTER(i64)]),
     "dmc_clip_grads": (C.c_int, [vp, i64, f32, vp, vp, sz, vp]),

@@ -57,8 +57,13 @@ def _current_loss():
 # ---------------------------------------------------------------------------------------------------------
 aux_overlap = True
 defer_joins = _os_environ_get("DMC_DEFER_JOINS", "1") != "0"       # see _AuxRegion.join_at_end_of_backward
-polite_ctas = int(_os_environ_get("DMC_POLITE_CTAS", "148"))       # grid cap of auxiliary-stream weight-norm passes (0 = none)
-teacher_epilogue_stats = _os_environ_get("DMC_TEACHER_EPILOGUE_STATS", "1") != "0"
+# Grid cap of the auxiliary-stream weight-norm passes (0 = none, the default).  MEASURED (profiles/r02_scheduling_ab.md): capped
+# at one CTA per SM these passes do run next to the GEMMs, but at 0.6 TB/s (8 warps per SM cannot keep enough loads in
+# flight): weight-norm forward 22 -> 143 us, backward 28 -> 176 us, step 0.80 -> 0.97 ms.  Kept as a switch, off.
+polite_ctas = int(_os_environ_get("DMC_POLITE_CTAS", "0"))
+# Teacher row statistics from the GEMM epilogue (EPI 3) + column sums by linearity (rowdot).  MEASURED: step 0.873 -> 0.971 ms
+# with it (the running-maximum epilogue more than doubles the teacher's last GEMM); kept as a switch, off.
+teacher_epilogue_stats = _os_environ_get("DMC_TEACHER_EPILOGUE_STATS", "0") != "0"
 grad_exchange_active = False     # set by GradAllReduce: the last layer's dv (64 MiB, the largest all-reduce of the step) must
                                  # then be final as early as possible, so its weight-norm backward stays in front of the dgrad
 grad_exchange = None             # the active GradAllReduce (or None); with compress="bf16" the last layer hands it a bf16 dW
@@ -387,7 +392,8 @@ class NormLastLayerFn(torch.autograd.Function):
             if claimed is not None:
                 # bf16 exchange: dW leaves the GEMM in bf16, is averaged over the ranks, and the weight-norm backward runs
                 # on the averaged dW on the communication stream; weight_v.grad / weight_g.grad are set there directly
-                dw = mm(mode, d, ctx.zop, K, dim, rows, a_mn=True, b_mn=True, out_dtype=torch.bfloat16, tag="gemm_last_wgrad")
+                dw = mm(mode, d, ctx.zop, K, dim, rows, a_mn=True, b_mn=True, out_dtype=torch.bfloat16, tag="gemm_last_wgrad",
+                        out=grad_exchange.last_layer_buffer(K, dim))       # peer transport: straight into symmetric memory
                 ops.mark_ready(dw)
                 want_dg = ctx.needs_input_grad[2]
                 grad_exchange.exchange_last_layer(dw, lambda: ops.weightnorm_bwd(dw, v, scale, inv_vnorm, want_dg=want_dg), *claimed)

@@ -110,16 +110,19 @@ class DINOLoss(nn.Module):
         if s_pre is not None and not (s_pre.get("kind") == "student" and s_pre["scale"] == inv_ts
                                       and s_pre["row_partials"].shape[0] == s.shape[0]):
             s_pre = None
-        t_pre = getattr(teacher_output, "_dmc_stats", None) if t.data_ptr() == teacher_output.data_ptr() else None
+        raw_pre = getattr(teacher_output, "_dmc_stats", None)
+        if raw_pre is not None and raw_pre.get("event") is not None:
+            # statistics a teacher head launched on a side stream: ALWAYS join that stream here, used or not (inside a CUDA
+            # graph capture an unjoined side stream is an error; outside it keeps the allocator's stream bookkeeping simple)
+            torch.cuda.current_stream().wait_event(raw_pre["event"])
+        t_pre = raw_pre if t.data_ptr() == teacher_output.data_ptr() else None
         if t_pre is not None and not (t_pre.get("kind") in ("teacher", "teacher_final") and t_pre["scale"] == inv_tt
                                       and t_pre["center_ptr"] == self.center.data_ptr()
                                       and t_pre["center_version"] == self.center._version
                                       and (t_pre["row_partials"].shape[0] if t_pre["kind"] == "teacher" else t_pre["rows"]) == t.shape[0]):
             t_pre = None
         if t_pre is not None and t_pre["kind"] == "teacher_final":
-            # the teacher head already ran this loss's statistics pass on a side stream: wait for it here
             cur = torch.cuda.current_stream()
-            cur.wait_event(t_pre["event"])
             t_pre["t_stats"].record_stream(cur)
             t_pre["colsum"].record_stream(cur)
         self._last_inv_tt = inv_tt

@@ -39,11 +39,28 @@ if os.environ.get("DMC_REDUCER_FLUSH_MB"):      # env: timing experiments only
 
 
 class GradAllReduce:
-    def __init__(self, params, group=None, reserve_sms: int = 16, compress=None):
+    def __init__(self, params, group=None, reserve_sms: int = 16, compress=None, transport="nccl"):
+        """transport = "nccl": torch.distributed all-reduces (fp32, or bf16 with compress="bf16").
+        transport = "peer": the bf16 exchange runs on libdinomc's own NVLink / NVSwitch all-reduce kernel over symmetric
+        memory (xrank.SymmetricBuffer; needs compress="bf16"): the last layer's wgrad GEMM writes dW straight into a
+        symmetric buffer, ONE kernel averages it over the ranks (multimem.ld_reduce / multimem.st through the switch),
+        the weight-norm backward runs on the average; the small gradients travel as one flat bf16 buffer whose all-reduce
+        kernel also widens the result back into the fp32 .grad tensors.  The kernel is one 256-thread, <= 40-register
+        CTA per SM: it is co-resident with the backward GEMMs, so no SMs are reserved."""
         if compress not in (None, "bf16"):
             raise ValueError(f"GradAllReduce: compress must be None or 'bf16', got {compress!r}")
+        if transport not in ("nccl", "peer"):
+            raise ValueError(f"GradAllReduce: transport must be 'nccl' or 'peer', got {transport!r}")
+        if transport == "peer" and compress != "bf16":
+            raise ValueError("GradAllReduce: transport='peer' exchanges bf16 buffers; pass compress='bf16'")
         self.group = group
         self.compress = compress
+        self.transport = transport
+        self._dw_buf = None             # peer transport: symmetric bf16 buffer of the last layer's dW
+        self._small_buf = None          # peer transport: flat symmetric bf16 buffer of the small gradients
+        self._small_key = None
+        if transport == "peer":
+            reserve_sms = 0             # the exchange kernel shares SMs with the GEMMs
         self.params = [p for p in params if p.requires_grad]
         self._by_ptr = {p.data_ptr(): p for p in self.params}
         self.comm = torch.cuda.Stream(priority=-1)
@@ -60,7 +77,7 @@ class GradAllReduce:
         # early-launched (PDL) GEMM CTAs hold SMs while they wait for their predecessor, which delays the NCCL kernels
         # that share the machine: measured 0.992 -> 0.969 ms per step at 2 GPUs without it
         from . import _lib
-        keep_pdl = os.environ.get("DMC_REDUCER_PDL", "") == "1"                               # env: timing experiments only
+        keep_pdl = os.environ.get("DMC_REDUCER_PDL", "1" if transport == "peer" else "") == "1"   # env: timing experiments only
         self._pdl_prev = _lib.load().dmc_set_pdl(1 if keep_pdl else 0)
 
     def _hook(self, p):
@@ -125,8 +142,42 @@ class GradAllReduce:
     def _compressible(self, g):
         return self.compress == "bf16" and g.dtype == torch.float32 and g.is_contiguous()
 
+    def last_layer_buffer(self, K, dim):
+        """peer transport: the [K, dim] bf16 view of the symmetric buffer the last layer's wgrad GEMM writes dW into
+        (None for the NCCL transport).  Allocated (collectively) on first use -- outside any graph capture."""
+        if self.transport != "peer":
+            return None
+        if self._dw_buf is None or self._dw_buf.numel != K * dim:
+            from .xrank import SymmetricBuffer
+            self._dw_buf = SymmetricBuffer(K * dim, torch.bfloat16, group=self.group)
+        return self._dw_buf.tensor.view(K, dim)
+
+    def _exchange_bf16_peer(self, grads):
+        """peer transport, on the communication stream: fp32 gradients -> flat symmetric bf16 buffer (one launch) -> ONE
+        all-reduce kernel that also widens the averaged values back into the fp32 gradients."""
+        offs, total = [], 0
+        for g in grads:
+            offs.append(total)
+            total += (g.numel() + 7) & ~7
+        key = tuple((g.numel()) for g in grads)
+        if self._small_buf is None or self._small_key != key:
+            from .xrank import SymmetricBuffer
+            self._small_buf = SymmetricBuffer(total, torch.bfloat16, group=self.group)
+            self._small_key = key
+        flat = self._small_buf.tensor
+        views = [flat[o:o + g.numel()] for o, g in zip(offs, grads)]
+        ops.narrow_bf16_into([g.view(-1) for g in grads], views)
+        world = dist.get_world_size(self.group)
+        if len(grads) <= 8:             # the head has 6: the exchange kernel widens the result into the fp32 gradients itself
+            self._small_buf.allreduce_(1.0 / world, widen_to=[g.view(-1) for g in grads], widen_offsets=offs)
+        else:
+            self._small_buf.allreduce_(1.0 / world)
+            ops.widen_bf16_batch(views, [g.view(-1) for g in grads])
+
     def _exchange_bf16(self, grads):
         """On the current (communication) stream: fp32 gradients -> one flat bf16 buffer -> all-reduce(AVG) -> back."""
+        if self.transport == "peer":
+            return self._exchange_bf16_peer(grads)
         offs, total = [], 0
         for g in grads:
             offs.append(total)
@@ -165,7 +216,10 @@ class GradAllReduce:
         else:
             self.comm.wait_stream(cur)
         with torch.cuda.stream(self.comm):
-            dist.all_reduce(dw, op=dist.ReduceOp.AVG, group=self.group)
+            if self.transport == "peer" and self._dw_buf is not None and dw.data_ptr() == self._dw_buf.tensor.data_ptr():
+                self._dw_buf.allreduce_(1.0 / dist.get_world_size(self.group))      # in place, in the symmetric buffer
+            else:
+                dist.all_reduce(dw, op=dist.ReduceOp.AVG, group=self.group)
             dv, dg = weightnorm_bwd()
         dw.record_stream(self.comm)
         dv.record_stream(cur)
