@@ -217,11 +217,16 @@ class Step:
         for p in self.student.parameters():
             p.grad = None
         xs.grad = None
+        dbg = os.environ.get("DMC_XRANK_DEBUG") and not torch.cuda.is_current_stream_capturing()
+        t0 = time.perf_counter()
         with torch.no_grad():
             t_out = self.teacher(xt)
         s_out = self.model(xs)
         loss = self.loss_mod(s_out, t_out, 0)
+        t1 = time.perf_counter()
         loss.backward()
+        if dbg:
+            print(f"[step host ms] forward+loss {1e3 * (t1 - t0):.1f}  backward {1e3 * (time.perf_counter() - t1):.1f}", file=sys.stderr, flush=True)
         if self.reducer is not None:
             # main_dino_mc.py:383-406: the optimizer consumes the averaged gradients BEFORE the EMA reads the student, so
             # the EMA must not be used to hide the gradient exchange: join the exchange first
@@ -253,10 +258,13 @@ class Step:
             ref = [p.grad.detach().clone() for p in params]
         finally:
             self.reducer = red
-        worst, scale = 0.0, 0.0
-        for g, r in zip(got, ref):
+        worst, per = 0.0, {}
+        names = [n for n, p in self.student.named_parameters() if p.requires_grad]
+        for n, g, r in zip(names, got, ref):
             dist.all_reduce(r, op=dist.ReduceOp.AVG)
-            worst = max(worst, float((g.double() - r.double()).abs().max()) / max(float(r.double().abs().max()), 1e-30))
+            e = float((g.double() - r.double()).abs().max()) / max(float(r.double().abs().max()), 1e-30)
+            per[n] = e
+            worst = max(worst, e)
         # bit-identity across ranks: every rank's byte-level checksum of the exchanged gradients must agree
         acc = torch.zeros((), dtype=torch.int64, device=self.device)
         for g in got:
@@ -267,7 +275,8 @@ class Step:
         w_t = torch.tensor([worst], device=self.device, dtype=torch.float64)
         dist.all_reduce(w_t, op=dist.ReduceOp.MAX)
         return {"grads_bit_identical_across_ranks": bool(int(lo) == int(hi)), "checksum": int(acc),
-                "max_rel_diff_vs_mean_of_local_grads": float(w_t), "tensors": len(got)}
+                "max_rel_diff_vs_mean_of_local_grads": float(w_t), "tensors": len(got),
+                "rel_diff_per_tensor_rank0": {k: float("%.3g" % v) for k, v in per.items()}}
 
     def _prefetch(self, idx):
         if self.stage_consumed[idx] is not None:             # do not overwrite a stage its consumer has not copied out yet
@@ -543,9 +552,13 @@ def main():
         except Exception as e:          # noqa: BLE001 -- e.g. a collective that refuses capture: fall back to eager
             if world == 1:
                 raise
-            print(f"[rank {rank}] CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
+            import traceback
+            print(f"[rank {rank}] CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly\n"
+                  + "".join(traceback.format_exception(type(e), e, e.__traceback__))[-6000:], file=sys.stderr)
             use_graph, graph = False, None
             torch.cuda.synchronize()
+            from dinomc_b200.loss import drop_pending_events
+            drop_pending_events()        # events recorded inside the failed capture are unusable
 
     l0 = ops.launch_count
     step.run()

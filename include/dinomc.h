@@ -38,7 +38,11 @@ enum { DMC_F32 = 0, DMC_BF16 = 1 };
 enum {
   DMC_ACT_NONE = 0,
   DMC_ACT_GELU = 1,     /* D = gelu(z); if aux != NULL also aux = z (pre-activation, saved for backward) */
-  DMC_ACT_GELU_BWD = 2  /* D = z * gelu'(aux)   (aux = the saved pre-activation)                        */
+  DMC_ACT_GELU_BWD = 2, /* D = z * gelu'(aux)   (aux = the saved pre-activation)                        */
+  DMC_ACT_NORMALIZE_BWD = 3 /* backward of F.normalize (utils/vision_transformer.py:292) fused into the split-K reduction of
+                               the last layer's dgrad: D[m,:] = (z[m,:] - (z[m,:] . aux[m,:]) aux[m,:]) * row_scale[m], with
+                               aux = the normalised rows (fp32) and row_scale = 1/max(||row||, eps); rows clamped by eps
+                               (row_scale * row_eps >= 1) get no projection term.  N <= 1024; the contraction is always split. */
 };
 
 int dmc_version(void);
@@ -109,6 +113,8 @@ typedef struct dmc_gemm_args {
   float stat_scale; const float* stat_center; float* stat_row_partials; float* stat_colsum_partials;
   const float* stat_bound; /* optional device scalar b >= max |D| (e.g. the largest weight-norm gain when the rows of A
                               are unit vectors): lets the epilogue skip the running max (used only without a center) */
+  const float* row_scale;  /* DMC_ACT_NORMALIZE_BWD: [M] */
+  float row_eps;           /* DMC_ACT_NORMALIZE_BWD: the eps of F.normalize */
 } dmc_gemm_args;
 
 /* Number of 128-column parts per row that the fused statistics produce for an N-column output. */

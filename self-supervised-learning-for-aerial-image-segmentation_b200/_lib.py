@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DMC_LIB") or os.path.join(_HERE, "libdinomc.so")   # DMC_LIB: debug builds only (tools/gemm_trace.py)
 
 DMC_F32, DMC_BF16 = 0, 1
-ACT_NONE, ACT_GELU, ACT_GELU_BWD = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_GELU_BWD, ACT_NORMALIZE_BWD = 0, 1, 2, 3
 
 i32, i64, f32, vp, sz = C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_size_t
 
@@ -34,6 +34,7 @@ class GemmArgs(C.Structure):
         ("max_ctas", i32),
         ("stat_scale", f32), ("stat_center", vp), ("stat_row_partials", vp), ("stat_colsum_partials", vp),
         ("stat_bound", vp),
+        ("row_scale", vp), ("row_eps", f32),
     ]
 
 

@@ -958,6 +958,61 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long M,
   }
 }
 
+// Split-K reduction fused with the backward of F.normalize (DMC_ACT_NORMALIZE_BWD): one warp per output row (N <= 1024).
+// Sums the partials in fixed order (deterministic), then dz = (dzhat - (dzhat . zhat) zhat) / ||z|| and the store in the
+// output dtype -- replaces splitk_reduce + normalize_bwd (+ the bf16 cast of dz in the bf16-GEMM mode): three launches on the
+// critical path between the last layer's dgrad and the MLP backward.
+__global__ void __launch_bounds__(256)
+splitk_normalize_bwd_kernel(const float* __restrict__ partial, int splits, long long M, int N, float alpha, const float* alpha_dev,
+                            const float* __restrict__ zhat, long long ldz, const float* __restrict__ row_scale, float eps,
+                            void* __restrict__ D, long long ldd, int out_dtype) {
+  pdl_prologue();
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  if (alpha_dev) alpha *= __ldg(alpha_dev);
+  const float inv = row_scale[row];
+  const bool clamped = (inv * eps >= 1.0f);
+  constexpr int kMaxPerLane = 8;                       // N <= 1024: up to 8 float4 per lane
+  float4 acc[kMaxPerLane];
+  const int nv = N >> 2;                               // N % 4 == 0 (checked on the host)
+  float proj = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nv) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < splits; ++s) {
+        const float4 t = *reinterpret_cast<const float4*>(partial + (static_cast<long long>(s) * M + row) * N + 4 * v);
+        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+      }
+      a.x *= alpha; a.y *= alpha; a.z *= alpha; a.w *= alpha;
+      acc[i] = a;
+      if (!clamped) {
+        const float4 z = *reinterpret_cast<const float4*>(zhat + row * ldz + 4 * v);
+        proj = fmaf(a.x, z.x, proj); proj = fmaf(a.y, z.y, proj); proj = fmaf(a.z, z.z, proj); proj = fmaf(a.w, z.w, proj);
+      }
+    }
+  }
+  proj = warp_sum(proj);
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nv) {
+      float4 a = acc[i];
+      if (!clamped) {
+        const float4 z = *reinterpret_cast<const float4*>(zhat + row * ldz + 4 * v);
+        a.x -= proj * z.x; a.y -= proj * z.y; a.z -= proj * z.z; a.w -= proj * z.w;
+      }
+      a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
+      if (out_dtype == DMC_BF16)
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(D) + row * ldd + 4 * v) = make_uint2(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w));
+      else
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(D) + row * ldd + 4 * v) = a;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -1163,7 +1218,14 @@ extern "C" int dmc_gemm(const dmc_gemm_args* a, void* stream) {
   DMC_REQUIRE(a->A && a->B && a->D, "dmc_gemm: null operand");
   DMC_REQUIRE(a->in_dtype == DMC_BF16 || a->in_dtype == DMC_F32, "dmc_gemm: bad in_dtype %d", a->in_dtype);
   DMC_REQUIRE(a->out_dtype == DMC_BF16 || a->out_dtype == DMC_F32, "dmc_gemm: bad out_dtype %d", a->out_dtype);
-  DMC_REQUIRE(a->act >= DMC_ACT_NONE && a->act <= DMC_ACT_GELU_BWD, "dmc_gemm: bad act %d", a->act);
+  DMC_REQUIRE(a->act >= DMC_ACT_NONE && a->act <= DMC_ACT_NORMALIZE_BWD, "dmc_gemm: bad act %d", a->act);
+  const bool norm_bwd = (a->act == DMC_ACT_NORMALIZE_BWD);
+  if (norm_bwd) {
+    DMC_REQUIRE(a->aux != nullptr && a->aux_dtype == DMC_F32 && a->row_scale != nullptr, "dmc_gemm: DMC_ACT_NORMALIZE_BWD needs aux (fp32 rows) and row_scale");
+    DMC_REQUIRE(a->N % 4 == 0 && a->N <= 1024 && a->col_scale == nullptr && a->bias == nullptr, "dmc_gemm: DMC_ACT_NORMALIZE_BWD needs N %% 4 == 0, N <= 1024 and no column scale / bias");
+    DMC_REQUIRE((reinterpret_cast<uintptr_t>(a->aux) & 15) == 0 && (a->ldaux % 4) == 0 && (reinterpret_cast<uintptr_t>(a->D) & 15) == 0 &&
+                (a->ldd * ((a->out_dtype == DMC_BF16) ? 2 : 4)) % 16 == 0, "dmc_gemm: DMC_ACT_NORMALIZE_BWD needs 16-byte aligned rows");
+  }
   DMC_REQUIRE(a->act != DMC_ACT_GELU_BWD || a->aux != nullptr, "dmc_gemm: DMC_ACT_GELU_BWD needs aux");
   DMC_REQUIRE((a->A_lo == nullptr) == (a->B_lo == nullptr), "dmc_gemm: A_lo and B_lo must be given together");
   const bool three = (a->A_lo != nullptr);
@@ -1175,6 +1237,9 @@ extern "C" int dmc_gemm(const dmc_gemm_args* a, void* stream) {
   const int out_esz = (a->out_dtype == DMC_BF16) ? 2 : 4;
   const bool store_ok = ((reinterpret_cast<uintptr_t>(a->D) & 15) == 0) && ((a->ldd * out_esz) % 16 == 0);
   Plan pl = make_plan(a->M, a->N, a->K, a->in_dtype, three, a->split_k, store_ok, a->stat_row_partials != nullptr);
+  if (norm_bwd && pl.splits < 2 && a->K >= 2 * block_k)        // the row operation lives in the split-K reducer
+    pl = make_plan(a->M, a->N, a->K, a->in_dtype, three, 2, store_ok, false);
+  DMC_REQUIRE(!norm_bwd || pl.splits >= 2, "dmc_gemm: DMC_ACT_NORMALIZE_BWD needs a contraction of at least two k-blocks");
   if (pl.splits > 1) {
     DMC_REQUIRE(a->workspace != nullptr && a->workspace_bytes >= pl.workspace_bytes,
                 "dmc_gemm: split-K needs a workspace of %zu bytes (got %zu)", pl.workspace_bytes, a->workspace_bytes);
@@ -1237,7 +1302,7 @@ extern "C" int dmc_gemm(const dmc_gemm_args* a, void* stream) {
     grid = 2 * (num_work < pairs_cap ? num_work : pairs_cap);
   }
   const bool amn = a->a_mn_major != 0, bmn = a->b_mn_major != 0;
-const bool plain = (a->col_scale == nullptr && a->bias == nullptr && a->act == DMC_ACT_NONE);
+const bool plain = (a->col_scale == nullptr && a->bias == nullptr && (a->act == DMC_ACT_NONE || norm_bwd));
   const bool stats = (a->stat_row_partials != nullptr);
 #define DMC_LAUNCH(ESZ_, AMN_, BMN_)                                                                          \
   (plain ? launch_tc<ESZ_, AMN_, BMN_, 1>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st, pl.cg2)                 \
@@ -1273,7 +1338,12 @@ const bool plain = (a->col_scale == nullptr && a->bias == nullptr && a->act == D
               h[6 * 512 + i] - t0);
   }
 
-  if (pl.splits > 1) {
+  if (pl.splits > 1 && norm_bwd) {
+    launch_kernel(splitk_normalize_bwd_kernel, dim3(static_cast<unsigned>(ceil_div(a->M, 8))), dim3(256), 0, st,
+                  static_cast<const float*>(a->workspace), pl.splits, a->M, static_cast<int>(a->N), a->alpha, a->alpha_dev,
+                  static_cast<const float*>(a->aux), a->ldaux, a->row_scale, a->row_eps, a->D, a->ldd, a->out_dtype);
+    DMC_LAUNCH_CHECK("splitk_normalize_bwd_kernel launch");
+  } else if (pl.splits > 1) {
     Epilogue e{a->col_scale, a->bias, a->alpha, a->act, a->aux, a->ldaux, a->aux_dtype, a->D, a->ldd, a->out_dtype,
                static_cast<int>(a->N)};
     const long long groups = a->M * ((a->N + 3) / 4);

@@ -64,6 +64,7 @@ polite_ctas = int(_os_environ_get("DMC_POLITE_CTAS", "0"))
 # Teacher row statistics from the GEMM epilogue (EPI 3) + column sums by linearity (rowdot).  MEASURED: step 0.873 -> 0.971 ms
 # with it (the running-maximum epilogue more than doubles the teacher's last GEMM); kept as a switch, off.
 teacher_epilogue_stats = _os_environ_get("DMC_TEACHER_EPILOGUE_STATS", "0") != "0"
+fuse_normalize_bwd = _os_environ_get("DMC_FUSE_NORMALIZE_BWD", "1") != "0"
 grad_exchange_active = False     # set by GradAllReduce: the last layer's dv (64 MiB, the largest all-reduce of the step) must
                                  # then be final as early as possible, so its weight-norm backward stays in front of the dgrad
 grad_exchange = None             # the active GradAllReduce (or None); with compress="bf16" the last layer hands it a bf16 dW
@@ -414,10 +415,15 @@ class NormLastLayerFn(torch.autograd.Function):
                     if ctx.needs_input_grad[3]:
                         ops.mark_ready(dv)
             if ctx.needs_input_grad[1]:
-                # dgrad: contraction over out_dim (split-K), W read MN-major from its [K,dim] storage
-                dzhat = mm(mode, d, ctx.wop, rows, dim, K, b_mn=True, out_dtype=torch.float32, tag="gemm_last_dgrad")
-            if ctx.needs_input_grad[1]:
-                dz = ops.normalize_rows_bwd(dzhat, zhat, inv_den)
+                # dgrad: contraction over out_dim (split-K), W read MN-major from its [K,dim] storage.  The backward of
+                # F.normalize rides in the split-K reduction (one launch instead of reduce + normalize_bwd).
+                per_kb = 64 if mode == "bf16" else 32
+                if fuse_normalize_bwd and mode != "fp32_simt" and dim % 4 == 0 and dim <= 1024 and K >= 2 * per_kb:
+                    dz = mm(mode, d, ctx.wop, rows, dim, K, b_mn=True, out_dtype=torch.float32, act=L.ACT_NORMALIZE_BWD, aux=zhat,
+                            row_scale=inv_den, row_eps=1e-12, tag="gemm_last_dgrad")
+                else:
+                    dzhat = mm(mode, d, ctx.wop, rows, dim, K, b_mn=True, out_dtype=torch.float32, tag="gemm_last_dgrad")
+                    dz = ops.normalize_rows_bwd(dzhat, zhat, inv_den)
             if region is not None:
                 if ctx.v_param.grad is None and (ctx.g_param.grad is None or not ctx.needs_input_grad[2]):
                     region.join_at_end_of_backward(dv, dg)       # dv / dg are only stored by AccumulateGrad

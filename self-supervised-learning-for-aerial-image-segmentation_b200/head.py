@@ -178,10 +178,17 @@ class DINOHead(nn.Module):
             mode = "bf16" if torch.is_autocast_enabled() else "fp32"
         return mode
 
+    def _is_inference(self, x):
+        """True for a forward that builds no autograd graph: no gradient mode or an input without gradient, and every
+        parameter frozen -- the EMA teacher as main_dino_mc.py:264-265,373 runs it (NOT under no_grad there)."""
+        if torch.is_grad_enabled() and x.requires_grad:
+            return False
+        return not any(p.requires_grad for p in self.parameters())
+
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError("dinomc_b200.DINOHead runs on CUDA (sm_100a) only; there is no CPU fallback")
-        if _teacher_overlap and not torch.is_grad_enabled():
+        if _teacher_overlap and self._is_inference(x):
             cur = torch.cuda.current_stream(x.device)
             side = _side_stream(x.device)
             side.wait_stream(cur)                       # inputs (features, EMA'd weights) are ready on `cur`
@@ -208,9 +215,7 @@ class DINOHead(nn.Module):
 
     def _fresh_shadow(self, mode, x):
         """The shadow record if it may be used for this forward, else None (allocating it on first sight of a teacher)."""
-        if not _operand_shadows or mode != "bf16" or self.use_bn or torch.is_grad_enabled():
-            return None
-        if any(p.requires_grad for p in self.parameters()):
+        if not _operand_shadows or mode != "bf16" or self.use_bn or not self._is_inference(x):
             return None
         lins = self._linears()
         K, dim = self.last_layer.weight_v.shape
@@ -233,9 +238,18 @@ class DINOHead(nn.Module):
         mode = self._mode()
         with torch.autocast("cuda", enabled=False):
             if self.use_bn:
-                # BatchNorm1d / SyncBatchNorm stay torch modules (reference option, off by default);
-                # the weight-normed last layer below is still ours.
-                z = self.mlp(x.float())
+                # use_bn_in_head (utils/vision_transformer.py:268-274): every Linear runs on the tcgen05 GEMM (bias in the
+                # epilogue, own wgrad / dgrad); BatchNorm1d -- or SyncBatchNorm after the reference's convert_sync_batchnorm
+                # (main_dino_mc.py:250-252), with its cross-rank statistics -- and GELU stay torch modules between them.
+                lins = self._linears()
+                mode_r = Fn.resolve_mode(mode, x.shape[1], *[d for lin in lins for d in lin.weight.shape])
+                h = x if x.dtype in (torch.float32, torch.bfloat16) else x.float()
+                for m in (self.mlp if isinstance(self.mlp, nn.Sequential) else [self.mlp]):
+                    if isinstance(m, nn.Linear):
+                        h, _ = Fn.LinearFn.apply(mode_r, h, None, m.weight, m.bias, None, None, False)
+                    else:
+                        h = m(h)
+                z = h
                 prepared = None
             else:
                 linears = self._linears()
@@ -267,8 +281,7 @@ class DINOHead(nn.Module):
             if Fn.last_stats is not None:       # statistics the GEMM epilogue produced for dinomc_b200.DINOLoss
                 out._dmc_stats = Fn.last_stats
                 Fn.last_stats = None
-            elif (_early_teacher_stats and not torch.is_grad_enabled() and out.dtype in (torch.bfloat16, torch.float32)
-                  and not any(p.requires_grad for p in self.parameters())):
+            elif _early_teacher_stats and out.dtype in (torch.bfloat16, torch.float32) and self._is_inference(x):
                 self._launch_teacher_stats(out)
             return out
 

@@ -208,7 +208,7 @@ def tma_ok(t: torch.Tensor) -> bool:
 
 def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, A_lo=None, B_lo=None, out=None, out_dtype=torch.float32,
          col_scale=None, bias=None, alpha=1.0, alpha_dev=None, act=L.ACT_NONE, aux=None, simt=False, split_k=0,
-         tag="gemm", stats=None):
+         tag="gemm", stats=None, row_scale=None, row_eps=0.0):
     """D[M,N] = epilogue(sum_k A(m,k) B(n,k)).  A is stored [M,K] (a_mn=False) or [K,M] (a_mn=True);
     B is stored [N,K] (b_mn=False) or [K,N] (b_mn=True).  See dmc_gemm in include/dinomc.h."""
     lib = L.load()
@@ -239,6 +239,9 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, A_lo=None, B_lo=None, out=Non
         g.aux, g.ldaux, g.aux_dtype = aux.data_ptr(), aux.stride(0), _dt(aux)
     g.split_k = split_k
     g.max_ctas = gemm_max_ctas
+    if row_scale is not None:
+        _need_cuda(row_scale)
+        g.row_scale, g.row_eps = row_scale.data_ptr(), float(row_eps)
     if stats is not None:        # fused softmax / column-sum statistics of the stored output (see dmc_gemm_args)
         g.stat_scale = float(stats["scale"])
         g.stat_center = _p(stats.get("center"))
@@ -251,6 +254,8 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, A_lo=None, B_lo=None, out=Non
         _count()
         return out
     nbytes = lib.dmc_gemm_workspace_bytes(M, N, K, g.in_dtype) if split_k == 0 else split_k * M * N * 4
+    if act == L.ACT_NORMALIZE_BWD:
+        nbytes = max(nbytes, 2 * M * N * 4)         # this epilogue lives in the split-K reducer: the contraction is always split
     if nbytes:
         ws = workspace(nbytes, A.device)
         g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel()

@@ -31,6 +31,7 @@ import torch.distributed as dist
 
 from . import ops
 
+_DEBUG = bool(os.environ.get("DMC_XRANK_DEBUG"))
 _BIG = 32 << 20      # bytes: gradients at least this large get their own all-reduce
 _FLUSH = 64 << 20    # bytes: pending small gradients are sent as one coalesced all-reduce once they reach this, i.e. normally ONE
                      # launch after the last wgrad, overlapping the EMA (2 GPUs: 0.9715 ms with a 1 MB threshold = 4 launches, 0.9463 ms with one)
@@ -164,9 +165,13 @@ class GradAllReduce:
             from .xrank import SymmetricBuffer
             self._small_buf = SymmetricBuffer(total, torch.bfloat16, group=self.group)
             self._small_key = key
+        import time
+        t0 = time.perf_counter()
         flat = self._small_buf.tensor
         views = [flat[o:o + g.numel()] for o, g in zip(offs, grads)]
         ops.narrow_bf16_into([g.view(-1) for g in grads], views)
+        if _DEBUG:
+            self._dbg("narrow launch", t0)
         world = dist.get_world_size(self.group)
         if len(grads) <= 8:             # the head has 6: the exchange kernel widens the result into the fp32 gradients itself
             self._small_buf.allreduce_(1.0 / world, widen_to=[g.view(-1) for g in grads], widen_offsets=offs)
@@ -206,6 +211,13 @@ class GradAllReduce:
                 return None
         return pv, pg
 
+    def _dbg(self, what, t0):
+        import sys
+        import time
+        dt = time.perf_counter() - t0
+        if dt > 2e-3:
+            print(f"[reducer] {what} took {dt * 1e3:.1f} ms on the host", file=sys.stderr, flush=True)
+
     def exchange_last_layer(self, dw, weightnorm_bwd, pv, pg):
         """Average the bf16 dW over the ranks, then run `weightnorm_bwd()` (-> dv, dg) on the averaged dW, all on the
         communication stream; the results become `pv.grad` / `pg.grad` directly (they are complete after `wait()`)."""
@@ -215,13 +227,22 @@ class GradAllReduce:
             self.comm.wait_event(ev)
         else:
             self.comm.wait_stream(cur)
+        import time
+        t0 = time.perf_counter()
+        peer = self.transport == "peer" and self._dw_buf is not None and dw.data_ptr() == self._dw_buf.tensor.data_ptr()
         with torch.cuda.stream(self.comm):
-            if self.transport == "peer" and self._dw_buf is not None and dw.data_ptr() == self._dw_buf.tensor.data_ptr():
+            if peer:
                 self._dw_buf.allreduce_(1.0 / dist.get_world_size(self.group))      # in place, in the symmetric buffer
             else:
                 dist.all_reduce(dw, op=dist.ReduceOp.AVG, group=self.group)
+            if _DEBUG:
+                self._dbg("last-layer all-reduce launch", t0)
+                t0 = time.perf_counter()
             dv, dg = weightnorm_bwd()
-        dw.record_stream(self.comm)
+        if _DEBUG:
+            self._dbg("weight-norm backward launch", t0)
+        if not peer:                     # symmetric buffers are persistent: nothing for the caching allocator to track
+            dw.record_stream(self.comm)
         dv.record_stream(cur)
         pv.grad = dv.view_as(pv)
         self._seen += 1

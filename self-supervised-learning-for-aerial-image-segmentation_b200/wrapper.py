@@ -14,12 +14,18 @@ from torch import nn
 
 
 class MultiCropWrapper(nn.Module):
-    def __init__(self, backbone, head):
+    def __init__(self, backbone, head, *, stage_features: bool = True):
+        """`stage_features` (plumbing only): when no autograd graph is being built (the frozen teacher, main_dino_mc.py:373) the per-group backbone
+        outputs are written straight into ONE persistent `[n_crops * B, D]` buffer (`torch.cat(..., out=buffer)`) that the
+        head reads -- no per-step allocation and a fixed address (what a captured step needs).  With autograd (the student)
+        the single concatenation stays, because its backward scatters the feature gradient back to the groups."""
         super().__init__()
         # disable layers dedicated to ImageNet labels classification (utils/utils.py:622-623)
         backbone.fc, backbone.head = nn.Identity(), nn.Identity()
         self.backbone = backbone
         self.head = head
+        self.stage_features = stage_features
+        self._stage = None
 
     @staticmethod
     def _groups(x):
@@ -41,5 +47,14 @@ class MultiCropWrapper(nn.Module):
             if isinstance(out, tuple):          # XCiT returns a tuple (:639-640)
                 out = out[0]
             outs.append(out)
-        feats = outs[0] if len(outs) == 1 else torch.cat(outs)
+        if len(outs) == 1:
+            feats = outs[0]
+        elif self.stage_features and all(o.dim() == 2 for o in outs) and not (torch.is_grad_enabled() and any(o.requires_grad for o in outs)):
+            rows, dim = sum(o.shape[0] for o in outs), outs[0].shape[1]
+            st = self._stage
+            if st is None or st.shape != (rows, dim) or st.dtype != outs[0].dtype or st.device != outs[0].device:
+                st = self._stage = torch.empty((rows, dim), dtype=outs[0].dtype, device=outs[0].device)
+            feats = torch.cat(outs, out=st)
+        else:
+            feats = torch.cat(outs)
         return self.head(feats)

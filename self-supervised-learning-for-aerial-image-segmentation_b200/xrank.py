@@ -32,7 +32,11 @@ class SymmetricBuffer:
     """A flat buffer that exists on every rank of `group` in symmetric memory, with an in-place all-reduce."""
 
     def __init__(self, numel: int, dtype: torch.dtype, group=None, ctas: int = 148):
+        import os
+        import sys
         import torch.distributed._symmetric_memory as symm
+        if os.environ.get("DMC_XRANK_DEBUG"):
+            print(f"[xrank] allocating SymmetricBuffer({numel}, {dtype}) capturing={torch.cuda.is_current_stream_capturing()}", file=sys.stderr, flush=True)
         if dtype not in (torch.bfloat16, torch.float32):
             raise TypeError("SymmetricBuffer: float32 or bfloat16")
         group = group if group is not None else dist.group.WORLD

@@ -153,3 +153,84 @@ def test_multicrop_wrapper_matches_reference_wrapper():
         assert a.shape == (len(sizes) * B, 7)
         assert torch.allclose(a, b, atol=1e-6)
     assert torch.equal(ref(crops[0]), ours(crops[0]))            # a single tensor instead of a list
+
+
+def test_restart_from_checkpoint_restores_dropin_modules(tmp_path):
+    """The reference's own resume path (utils/utils.py:165-197, called at main_dino_mc.py:310-319) against a checkpoint with
+    the reference's layout (main_dino_mc.py:333-343, incl. the `fp16_scaler` entry :341-342 and a DDP-prefixed student):
+    the drop-in MultiCropWrapper / DINOHead / DINOLoss / FusedAdamW objects are restored through `restart_from_checkpoint`
+    exactly like the reference's own objects."""
+    if not reference_loader.available():
+        pytest.skip("reference not present")
+    import argparse
+    import torch
+    import dinomc_b200
+    main_dino_mc, vits, utils = reference_loader.load()
+    torch.manual_seed(1)
+
+    def backbone():
+        m = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(12, 48))
+        m.fc, m.head = torch.nn.Identity(), torch.nn.Identity()
+        return m
+
+    # a checkpoint written by the REFERENCE's objects (student saved under DDP's `module.` prefix, like :334)
+    ref_student = utils.MultiCropWrapper(backbone(), vits.DINOHead(48, 640, use_bn=False, norm_last_layer=True))
+    ref_teacher = utils.MultiCropWrapper(backbone(), vits.DINOHead(48, 640, False))
+    ref_loss = main_dino_mc.DINOLoss(640, 8, 0.04, 0.04, 0, 10, teacher_crops_number=2)
+    ref_loss.center.normal_()
+    ref_opt = torch.optim.AdamW(utils.get_params_groups(ref_student))
+    for p in ref_student.parameters():
+        if p.requires_grad:
+            p.grad = torch.randn_like(p) * 0.01
+    ref_opt.step()
+    scaler_sd = {"scale": 4096.0, "growth_factor": 2.0, "backoff_factor": 0.5, "growth_interval": 2000, "_growth_tracker": 7}
+    ckpt = {"student": {"module." + k: v for k, v in ref_student.state_dict().items()},
+            "teacher": ref_teacher.state_dict(), "optimizer": ref_opt.state_dict(), "epoch": 3,
+            "args": argparse.Namespace(arch="vit_small"), "dino_loss": ref_loss.state_dict(), "fp16_scaler": scaler_sd}
+    path = tmp_path / "checkpoint.pth"
+    torch.save(ckpt, path)
+
+    class DDPLike(torch.nn.Module):             # what `student` is at :260 -- parameters live under `module.`
+        def __init__(self, m):
+            super().__init__()
+            self.module = m
+
+    student = DDPLike(dinomc_b200.MultiCropWrapper(backbone(), dinomc_b200.DINOHead(48, 640, use_bn=False, norm_last_layer=True)))
+    teacher = dinomc_b200.MultiCropWrapper(backbone(), dinomc_b200.DINOHead(48, 640, False))
+    loss = dinomc_b200.DINOLoss(640, 8, 0.04, 0.04, 0, 10, teacher_crops_number=2)
+    opt = dinomc_b200.FusedAdamW(utils.get_params_groups(student))
+
+    class ScalerLike:                            # torch's GradScaler.load_state_dict refuses when CUDA is absent (disabled scaler)
+        def __init__(self):
+            self.sd = None
+
+        def load_state_dict(self, sd):
+            self.sd = dict(sd)
+
+    fp16 = ScalerLike()
+    to_restore = {"epoch": 0}
+    orig_load = torch.load
+    torch.load = lambda *a, **k: orig_load(*a, **{**k, "weights_only": False})     # the reference's torch 2.5 default
+    try:
+        utils.restart_from_checkpoint(str(path), run_variables=to_restore, student=student, teacher=teacher, optimizer=opt,
+                                      fp16_scaler=fp16, dino_loss=loss)
+    finally:
+        torch.load = orig_load
+    assert to_restore["epoch"] == 3
+    for k, v in ref_student.state_dict().items():
+        assert torch.equal(student.module.state_dict()[k], v), k
+    for k, v in ref_teacher.state_dict().items():
+        assert torch.equal(teacher.state_dict()[k], v), k
+    assert torch.equal(loss.center, ref_loss.center)
+    assert fp16.sd == scaler_sd
+    # optimizer state: same per-parameter moments as torch.optim.AdamW saved
+    ref_state = ref_opt.state_dict()["state"]
+    got_state = opt.state_dict()["state"]
+    assert set(ref_state) == set(got_state)
+    for i in ref_state:
+        assert torch.equal(ref_state[i]["exp_avg"], got_state[i]["exp_avg"])
+        assert torch.equal(ref_state[i]["exp_avg_sq"], got_state[i]["exp_avg_sq"])
+        assert float(ref_state[i]["step"]) == float(got_state[i]["step"])
+    # and back: a checkpoint written from the drop-in objects loads into the reference's
+    ref2 = utils.MultiCropWrapper(backbone(), vits.DINOHead(48, 640, use_bn=False, norm_last_layer=True))
+    ref2.load_state_dict(student.module.state_dict(), strict=True)

@@ -582,8 +582,8 @@ def test_teacher_operand_shadows_match_regular_path(golden):
         teacher(xt)                                             # first sight of a frozen no-grad head: allocates the shadows
     assert teacher._shadow is not None and teacher._shadow["state"] is None
     D2.ema_update_(tp, sp, 0.9)
+    assert teacher._fresh_shadow("bf16", xt) is not None      # frozen parameters + an input without gradient: no no_grad needed
     with torch.no_grad():
-        assert teacher._fresh_shadow("bf16", xt) is not None
         out_shadow = teacher(xt).clone()
         D2.head.set_operand_shadows(False)
         try:
