@@ -68,6 +68,7 @@ class GradAllReduce:
         self._pending = []
         self._pending_bytes = 0
         self._seen = 0
+        self._claimed = set()
         self._handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
         self.bytes_per_step = sum(p.numel() * (2 if compress == "bf16" else p.element_size()) for p in self.params)
         if reserve_sms > 0:
@@ -82,6 +83,12 @@ class GradAllReduce:
         self._pdl_prev = _lib.load().dmc_set_pdl(1 if keep_pdl else 0)
 
     def _hook(self, p):
+        if id(p) in self._claimed:
+            # exchange_last_layer already produced this parameter's averaged gradient.  torch calls the post-accumulate
+            # hook of a parameter even when the backward returned None for it (measured on torch 2.11), so without this the
+            # last layer was exchanged a second time as a "big" gradient.
+            self._claimed.discard(id(p))
+            return
         g = p.grad
         self._seen += 1
         skip = os.environ.get("DMC_REDUCER_SKIP", "")       # timing experiments only: "big" / "small"
@@ -245,10 +252,12 @@ class GradAllReduce:
             dw.record_stream(self.comm)
         dv.record_stream(cur)
         pv.grad = dv.view_as(pv)
+        self._claimed.add(id(pv))
         self._seen += 1
         if pg is not None:
             dg.record_stream(cur)
             pg.grad = dg.view_as(pg)
+            self._claimed.add(id(pg))
             self._seen += 1
         if self._seen == len(self.params):
             self._flush()
