@@ -432,6 +432,8 @@ def main():
                     help="N>1 gradient exchange transport: 'peer' = libdinomc's own all-reduce kernel over NVLink/NVSwitch symmetric "
                          "memory (bf16 exchange; falls back to 'nccl' if symmetric memory is unavailable), 'nccl' = torch.distributed")
     ap.add_argument("--overlap", type=int, default=1, help="teacher head forward on a side stream, overlapping the student's")
+    ap.add_argument("--hiprio", type=int, default=0, help="run (and capture) the step on a high-priority stream: its kernels get SM "
+                                                         "slots before the auxiliary-stream streaming kernels (experiment)")
     ap.add_argument("--cpu-sample-batch", type=int, default=0,
                     help="samples per CPU step for cpu_baseline / --impl reference (0 = the workload's own per-GPU batch)")
     ap.add_argument("--verify", type=int, default=1, help="N>1: after timing, check the exchanged gradients (bit-identical across "
@@ -535,6 +537,10 @@ def main():
         D.set_async_center(True)
     step = Step(w, args.mode, rank, world, device, ddp=bool(args.ddp), reserve_sms=args.reserve_sms, force_reducer=force_dp,
                 compress=compress, transport=transport)
+    if transport == "peer":
+        from dinomc_b200.xrank import SymmetricBuffer
+        step.loss_mod.center_exchange = SymmetricBuffer(w["K"], torch.float32, ctas=16)      # the center exchange leaves NCCL too
+        cfg["center_allreduce"] = "dmc_xrank_allreduce (fp32, 16 CTAs), asynchronous: consumed by the next step"
     ops = D.ops
     for _ in range(warmup):
         step.run()
@@ -547,7 +553,8 @@ def main():
         # the whole step is stream-ordered libdinomc launches (+ NCCL all-reduces when N > 1) on fixed buffers:
         # capture once, replay K times
         try:
-            graph = D.StepGraph(step.run, warmup=3, capture_error_mode="thread_local" if (world > 1 or force_dp) else "global")
+            graph = D.StepGraph(step.run, warmup=3, capture_error_mode="thread_local" if (world > 1 or force_dp) else "global",
+                                stream=torch.cuda.Stream(priority=-1) if args.hiprio else None)
             run_value = graph.replay
         except Exception as e:          # noqa: BLE001 -- e.g. a collective that refuses capture: fall back to eager
             if world == 1:

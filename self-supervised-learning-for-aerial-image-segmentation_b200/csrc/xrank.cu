@@ -48,17 +48,25 @@ struct XrankArgs {
 // put: CAS 0 -> 1 at the PEER's slot (spins while the previous signal has not been consumed); wait: CAS 1 -> 0 at OWN slot.
 __device__ __forceinline__ void put_signal(uint32_t* addr) {
   uint32_t old;
-  do {
+  for (;;) {
     asm volatile("atom.global.release.sys.cas.b32 %0, [%1], 0, 1;" : "=r"(old) : "l"(addr) : "memory");
-  } while (old != 0u);
+    if (old == 0u) break;
+    __nanosleep(128);                               // the previous signal has not been consumed yet: back off, do not hammer NVLink
+  }
 }
 __device__ __forceinline__ void wait_signal(uint32_t* addr) {
-  uint32_t old;
+  // Poll with a plain acquire LOAD and back off between polls: 148 CTAs x `world` threads spinning on system-scope
+  // atomics measurably slowed the GEMM sharing the SMs (dgrad 66 -> 240 us at 2 GPUs).  Only this thread consumes the
+  // slot, so once the signal is seen a plain store resets it.
   long long spins = 0;
-  do {
-    asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], 1, 0;" : "=r"(old) : "l"(addr) : "memory");
-    if (++spins > (1ll << 31)) __trap();          // a peer never arrived: fail loudly instead of hanging the box
-  } while (old != 1u);
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.global.acquire.sys.b32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+    if (v == 1u) break;
+    __nanosleep(256);
+    if (++spins > (1ll << 26)) __trap();            // ~20 s: a peer never arrived -- fail loudly instead of hanging the box
+  }
+  asm volatile("st.global.relaxed.sys.b32 [%0], %1;" :: "l"(addr), "r"(0u) : "memory");
 }
 
 // All CTAs with the same blockIdx on every rank meet.  Slot layout of a pad: [channel][block][sender rank].

@@ -466,10 +466,13 @@ class DinoLossFn(torch.autograd.Function):
         ctx.save_for_backward(s_d, t_d, center, t_stats, s_lse)
         ctx.cfg = (B, C, G, inv_ts, inv_tt)
         ctx.mark_non_differentiable(colsum)
+        ctx.set_materialize_grads(False)         # no zero-filled [K] gradient for the non-differentiable column sum
         return loss, colsum
 
     @staticmethod
     def backward(ctx, gloss, _gcolsum):
+        if gloss is None:
+            return (None,) * 10
         s, t, center, t_stats, s_lse = ctx.saved_tensors
         B, C, G, inv_ts, inv_tt = ctx.cfg
         if ctx.fused and not ctx.used:

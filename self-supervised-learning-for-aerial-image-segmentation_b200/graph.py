@@ -34,17 +34,18 @@ from . import ops
 
 
 class StepGraph:
-    def __init__(self, fn, warmup: int = 3, capture_error_mode: str = "global", epoch=None):
+    def __init__(self, fn, warmup: int = 3, capture_error_mode: str = "global", epoch=None, stream=None):
         """`fn()` (or `fn(epoch=...)`) must read its inputs from fixed (static) device tensors; its return value
         (tensor or tuple of tensors) is kept as the static output of the graph."""
         self.fn = fn
         self.capture_error_mode = capture_error_mode
+        self.stream = stream                    # capture stream (e.g. a high-priority one); None = torch's default side stream
         try:
             self._takes_epoch = "epoch" in inspect.signature(fn).parameters
         except (TypeError, ValueError):
             self._takes_epoch = False
         self.epoch = epoch if epoch is not None else (0 if self._takes_epoch else None)
-        side = torch.cuda.Stream()
+        side = stream if stream is not None else torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         ops.preserve_state = True
         try:
@@ -66,7 +67,7 @@ class StepGraph:
         self.graph = torch.cuda.CUDAGraph()
         ops.capture_notes = []
         try:
-            with torch.cuda.graph(self.graph, capture_error_mode=self.capture_error_mode):
+            with torch.cuda.graph(self.graph, stream=self.stream, capture_error_mode=self.capture_error_mode):
                 self.out = self._call()
                 commit_captured_centers()       # DINOLoss.center: new value back into the buffer the step reads
             notes = ops.capture_notes

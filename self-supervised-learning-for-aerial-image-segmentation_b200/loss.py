@@ -72,6 +72,8 @@ class DINOLoss(nn.Module):
         self.register_buffer("center", torch.zeros(1, out_dim))
         self._center_event = None
         self._comm_stream = None
+        self.center_exchange = None     # optional xrank.SymmetricBuffer (fp32, >= out_dim): the column-sum all-reduce (:469) then
+                                        # runs on libdinomc's own NVLink / NVSwitch kernel instead of NCCL
         _instances.add(self)
         # same schedule construction as main_dino_mc.py:431-435
         self.teacher_temp_schedule = np.concatenate((
@@ -131,6 +133,18 @@ class DINOLoss(nn.Module):
         self._update_center_from_colsum(colsum, teacher_output.shape[0])
         return loss
 
+    def _allreduce_colsum(self, colsum):
+        """SUM of the per-GPU column sums over the ranks (main_dino_mc.py:469), on the current stream."""
+        buf = self.center_exchange
+        if buf is None:
+            dist.all_reduce(colsum)
+            return colsum
+        k = colsum.numel()
+        view = buf.tensor[:k]
+        view.copy_(colsum.reshape(-1))
+        buf.allreduce_(1.0)
+        return view
+
     def sync_center(self):
         """Make the current stream wait for an in-flight asynchronous center exchange (no-op otherwise)."""
         if self._center_event is not None:
@@ -162,7 +176,7 @@ class DINOLoss(nn.Module):
             comm = self._comm_stream
             comm.wait_stream(cur)                       # colsum and the old center were produced on `cur`
             with torch.cuda.stream(comm):
-                dist.all_reduce(colsum)                 # main_dino_mc.py:469
+                colsum = self._allreduce_colsum(colsum)     # main_dino_mc.py:469
                 new_center = ops.center_update(self.center, colsum, n_rows * world, self.center_momentum)
             colsum.record_stream(comm)
             self.center.record_stream(comm)
@@ -173,7 +187,7 @@ class DINOLoss(nn.Module):
             self.center = new_center
             return
         if world > 1:
-            dist.all_reduce(colsum)                     # main_dino_mc.py:469 (65536 fp32 = 256 KiB over NCCL)
+            colsum = self._allreduce_colsum(colsum)     # main_dino_mc.py:469 (65536 fp32 = 256 KiB)
         # rebinding the buffer (like the reference, :473) keeps the old tensor alive for backward
         self.center = ops.center_update(self.center, colsum, n_rows * world, self.center_momentum)
 

@@ -58,10 +58,15 @@ class GradAllReduce:
         self.compress = compress
         self.transport = transport
         self._dw_buf = None             # peer transport: symmetric bf16 buffer of the last layer's dW
-        self._small_buf = None          # peer transport: flat symmetric bf16 buffer of the small gradients
-        self._small_key = None
+        self._small_bufs = {}           # peer transport: flat symmetric bf16 buffers of the small gradients, one per flush shape
+        self._keep = []                 # tensors produced on the caller's stream and read on the communication stream: kept
+                                        # alive until wait() (inside a graph capture record_stream() does not defer reuse)
+        self._flush_bytes = _FLUSH
         if transport == "peer":
             reserve_sms = 0             # the exchange kernel shares SMs with the GEMMs
+            # flush the small gradients in two batches: the later MLP layers' (19 of 25 MB) leave while the first layer's
+            # backward still runs, only the first layer's 3 MB are exchanged after the last wgrad
+            self._flush_bytes = int(float(os.environ.get("DMC_PEER_FLUSH_MB", "8")) * (1 << 20))
         self.params = [p for p in params if p.requires_grad]
         self._by_ptr = {p.data_ptr(): p for p in self.params}
         self.comm = torch.cuda.Stream(priority=-1)
@@ -112,7 +117,7 @@ class GradAllReduce:
         else:
             self._pending.append((g, ops.ready_events.pop(g.data_ptr(), None)))
             self._pending_bytes += g.numel() * g.element_size()
-        if self._seen == len(self.params) or self._pending_bytes >= _FLUSH:
+        if self._seen == len(self.params) or self._pending_bytes >= self._flush_bytes:
             self._flush()
 
     def _flush(self):
@@ -168,22 +173,22 @@ class GradAllReduce:
             offs.append(total)
             total += (g.numel() + 7) & ~7
         key = tuple((g.numel()) for g in grads)
-        if self._small_buf is None or self._small_key != key:
+        buf = self._small_bufs.get(key)
+        if buf is None:
             from .xrank import SymmetricBuffer
-            self._small_buf = SymmetricBuffer(total, torch.bfloat16, group=self.group)
-            self._small_key = key
+            buf = self._small_bufs[key] = SymmetricBuffer(total, torch.bfloat16, group=self.group)
         import time
         t0 = time.perf_counter()
-        flat = self._small_buf.tensor
+        flat = buf.tensor
         views = [flat[o:o + g.numel()] for o, g in zip(offs, grads)]
         ops.narrow_bf16_into([g.view(-1) for g in grads], views)
         if _DEBUG:
             self._dbg("narrow launch", t0)
         world = dist.get_world_size(self.group)
         if len(grads) <= 8:             # the head has 6: the exchange kernel widens the result into the fp32 gradients itself
-            self._small_buf.allreduce_(1.0 / world, widen_to=[g.view(-1) for g in grads], widen_offsets=offs)
+            buf.allreduce_(1.0 / world, widen_to=[g.view(-1) for g in grads], widen_offsets=offs)
         else:
-            self._small_buf.allreduce_(1.0 / world)
+            buf.allreduce_(1.0 / world)
             ops.widen_bf16_batch(views, [g.view(-1) for g in grads])
 
     def _exchange_bf16(self, grads):
@@ -250,6 +255,7 @@ class GradAllReduce:
             self._dbg("weight-norm backward launch", t0)
         if not peer:                     # symmetric buffers are persistent: nothing for the caching allocator to track
             dw.record_stream(self.comm)
+            self._keep.append(dw)        # ... and inside a graph capture only a live reference keeps the block from being reused
         dv.record_stream(cur)
         pv.grad = dv.view_as(pv)
         self._claimed.add(id(pv))
@@ -267,6 +273,7 @@ class GradAllReduce:
         self._flush()
         self._seen = 0
         torch.cuda.current_stream().wait_stream(self.comm)
+        self._keep.clear()
 
     def remove(self):
         for h in self._handles:

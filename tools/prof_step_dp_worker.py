@@ -19,6 +19,9 @@ D.set_teacher_overlap(True)
 D.set_async_center(True)
 w = dict(bench.WORKLOADS[os.environ.get("DMC_PROF_WORKLOAD", "cfg2")])
 step = bench.Step(w, "bf16", rank, world, dev, compress=compress, transport=transport)
+if transport == "peer":
+    from dinomc_b200.xrank import SymmetricBuffer
+    step.loss_mod.center_exchange = SymmetricBuffer(w["K"], torch.float32, ctas=16)
 for _ in range(5):
     step.run()
 torch.cuda.synchronize()
