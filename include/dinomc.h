@@ -39,6 +39,8 @@ enum {
   DMC_ACT_NONE = 0,
   DMC_ACT_GELU = 1,     /* D = gelu(z); if aux != NULL also aux = z (pre-activation, saved for backward) */
   DMC_ACT_GELU_BWD = 2, /* D = z * gelu'(aux)   (aux = the saved pre-activation)                        */
+  DMC_ACT_GELU_DG = 4,  /* D = gelu(z) and aux = gelu'(z) (one evaluation; aux required): the layer's backward then uses    */
+  DMC_ACT_MUL_AUX = 5,  /* D = z * aux            -- a plain multiply in the dgrad epilogue instead of a GELU' evaluation */
   DMC_ACT_NORMALIZE_BWD = 3 /* backward of F.normalize (utils/vision_transformer.py:292) fused into the split-K reduction of
                                the last layer's dgrad: D[m,:] = (z[m,:] - (z[m,:] . aux[m,:]) aux[m,:]) * row_scale[m], with
                                aux = the normalised rows (fp32) and row_scale = 1/max(||row||, eps); rows clamped by eps
@@ -185,6 +187,16 @@ size_t dmc_teacher_workspace_bytes(int64_t Nt, int64_t K);
 int dmc_teacher_stats_colsum(const void* t, int32_t dtype, int64_t Nt, int64_t K, int64_t ld,
                              const float* center, float inv_temp, float* row_stats, float* colsum,
                              void* workspace, size_t workspace_bytes, void* stream);
+/* Same pass with caller-supplied bounds: bounds_dev[0] >= max |t| (for logits of unit rows against weight-normed rows: the
+ * largest gain, utils/vision_transformer.py:279,292), bounds_dev[1] >= max |center| (device scalars, e.g. from dmc_absmax).
+ * While (b0 + b1) * inv_temp * log2(e) stays below 55 the row sums use that fixed shift instead of the row maximum -- one
+ * pass over the registers, about half the instructions of the general form (the pass is instruction-bound) -- and the
+ * reported "maximum" of a row is the shift; otherwise identical to dmc_teacher_stats_colsum. */
+int dmc_teacher_stats_colsum_bounded(const void* t, int32_t dtype, int64_t Nt, int64_t K, int64_t ld,
+                                     const float* center, float inv_temp, const float* bounds_dev, float* row_stats,
+                                     float* colsum, void* workspace, size_t workspace_bytes, void* stream);
+/* out[0] = max_i |x[i]| (fp32, single CTA: for vectors of at most a few hundred thousand entries). */
+int dmc_absmax(const float* x, int64_t n, float* out, void* stream);
 /* Same outputs as dmc_teacher_stats_colsum, but from the partials the last-layer GEMM's epilogue already wrote
  * (dmc_gemm_args.stat_row_partials [Nt][parts] and stat_colsum_partials [row_groups][K]): no pass over the logits.
  * colsum_partials may be NULL (then colsum is not written: row statistics only, see dmc_rowdot for the column sums). */

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DMC_LIB") or os.path.join(_HERE, "libdinomc.so")   # DMC_LIB: debug builds only (tools/gemm_trace.py)
 
 DMC_F32, DMC_BF16 = 0, 1
-ACT_NONE, ACT_GELU, ACT_GELU_BWD, ACT_NORMALIZE_BWD = 0, 1, 2, 3
+ACT_NONE, ACT_GELU, ACT_GELU_BWD, ACT_NORMALIZE_BWD, ACT_GELU_DG, ACT_MUL_AUX = 0, 1, 2, 3, 4, 5
 
 i32, i64, f32, vp, sz = C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_size_t
 
@@ -62,6 +62,8 @@ SIGNATURES = {
     "dmc_weightnorm_bwd_bf16": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp, vp]),
     "dmc_teacher_workspace_bytes": (sz, [i64, i64]),
     "dmc_teacher_stats_colsum": (C.c_int, [vp, i32, i64, i64, i64, vp, f32, vp, vp, vp, sz, vp]),
+    "dmc_teacher_stats_colsum_bounded": (C.c_int, [vp, i32, i64, i64, i64, vp, f32, vp, vp, vp, vp, sz, vp]),
+    "dmc_absmax": (C.c_int, [vp, i64, vp, vp]),
     "dmc_teacher_finalize": (C.c_int, [vp, vp, i64, i64, i64, i64, vp, vp, vp]),
     "dmc_rowdot": (C.c_int, [vp, i32, i64, i64, vp, vp, vp]),
     "dmc_lse_finalize": (C.c_int, [vp, i64, i64, vp, vp]),

@@ -80,6 +80,11 @@ gemm_simt_kernel(const SimtArgs a) {
         v = gelu_f(v);
       } else if (a.act == DMC_ACT_GELU_BWD) {
         v *= gelu_grad_f(ld_any(a.aux, row * a.ldaux + col, a.aux_dtype));
+      } else if (a.act == DMC_ACT_GELU_DG) {
+        st_any(a.aux, row * a.ldaux + col, a.aux_dtype, gelu_grad_f(v));
+        v = gelu_f(v);
+      } else if (a.act == DMC_ACT_MUL_AUX) {
+        v *= ld_any(a.aux, row * a.ldaux + col, a.aux_dtype);
       }
       st_any(a.D, row * a.ldd + col, a.out_dtype, v);
     }

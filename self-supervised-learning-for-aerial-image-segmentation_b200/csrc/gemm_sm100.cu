@@ -143,6 +143,48 @@ __device__ __forceinline__ void epilogue_math(const Epilogue& e, float (&acc)[32
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] = gelu_f(acc[j]);
+  } else if (e.act == DMC_ACT_GELU_DG) {
+    // D = gelu(z) and aux = gelu'(z) from ONE evaluation (they share exp(-z^2/2)): the backward epilogue is then a plain
+    // multiply (DMC_ACT_MUL_AUX) instead of a second, exposed GELU' evaluation per element
+    float dg[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float phi, dens;
+      gelu_parts(acc[j], phi, dens);
+      dg[j] = fmaf(acc[j] * dens, 0.39894228040143268f, phi);
+      acc[j] *= phi;
+    }
+    if (aux_vec_ok && n == 32) {
+      if (e.aux_dtype == DMC_BF16) {
+        uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.aux) + row * e.ldaux + col0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          p[j] = make_uint4(pack_bf16(dg[8 * j], dg[8 * j + 1]), pack_bf16(dg[8 * j + 2], dg[8 * j + 3]),
+                            pack_bf16(dg[8 * j + 4], dg[8 * j + 5]), pack_bf16(dg[8 * j + 6], dg[8 * j + 7]));
+      } else {
+        float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.aux) + row * e.ldaux + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) p[j] = make_float4(dg[4 * j], dg[4 * j + 1], dg[4 * j + 2], dg[4 * j + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < n) store_elem(e.aux, row * e.ldaux + col0 + j, e.aux_dtype, dg[j]);
+    }
+  } else if (e.act == DMC_ACT_MUL_AUX) {
+    if (aux_vec_ok && n == 32 && e.aux_dtype == DMC_BF16) {
+      const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.aux) + row * e.ldaux + col0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 w = p[j];
+        acc[8 * j + 0] *= bf16_lo(w.x); acc[8 * j + 1] *= bf16_hi(w.x); acc[8 * j + 2] *= bf16_lo(w.y); acc[8 * j + 3] *= bf16_hi(w.y);
+        acc[8 * j + 4] *= bf16_lo(w.z); acc[8 * j + 5] *= bf16_hi(w.z); acc[8 * j + 6] *= bf16_lo(w.w); acc[8 * j + 7] *= bf16_hi(w.w);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < n) acc[j] *= load_elem(e.aux, row * e.ldaux + col0 + j, e.aux_dtype);
+    }
   } else if (e.act == DMC_ACT_GELU_BWD) {
     if (aux_vec_ok && n == 32 && e.aux_dtype == DMC_BF16) {
       const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.aux) + row * e.ldaux + col0);
@@ -953,6 +995,11 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long M,
       v = gelu_f(v);
     } else if (e.act == DMC_ACT_GELU_BWD) {
       v *= gelu_grad_f(load_elem(e.aux, row * e.ldaux + col, e.aux_dtype));
+    } else if (e.act == DMC_ACT_GELU_DG) {
+      store_elem(e.aux, row * e.ldaux + col, e.aux_dtype, gelu_grad_f(v));
+      v = gelu_f(v);
+    } else if (e.act == DMC_ACT_MUL_AUX) {
+      v *= load_elem(e.aux, row * e.ldaux + col, e.aux_dtype);
     }
     store_elem(e.D, row * e.ldd + col, e.out_dtype, v);
   }
@@ -1218,7 +1265,8 @@ extern "C" int dmc_gemm(const dmc_gemm_args* a, void* stream) {
   DMC_REQUIRE(a->A && a->B && a->D, "dmc_gemm: null operand");
   DMC_REQUIRE(a->in_dtype == DMC_BF16 || a->in_dtype == DMC_F32, "dmc_gemm: bad in_dtype %d", a->in_dtype);
   DMC_REQUIRE(a->out_dtype == DMC_BF16 || a->out_dtype == DMC_F32, "dmc_gemm: bad out_dtype %d", a->out_dtype);
-  DMC_REQUIRE(a->act >= DMC_ACT_NONE && a->act <= DMC_ACT_NORMALIZE_BWD, "dmc_gemm: bad act %d", a->act);
+  DMC_REQUIRE(a->act >= DMC_ACT_NONE && a->act <= DMC_ACT_MUL_AUX, "dmc_gemm: bad act %d", a->act);
+  DMC_REQUIRE((a->act != DMC_ACT_GELU_DG && a->act != DMC_ACT_MUL_AUX) || a->aux != nullptr, "dmc_gemm: DMC_ACT_GELU_DG / DMC_ACT_MUL_AUX need aux");
   const bool norm_bwd = (a->act == DMC_ACT_NORMALIZE_BWD);
   if (norm_bwd) {
     DMC_REQUIRE(a->aux != nullptr && a->aux_dtype == DMC_F32 && a->row_scale != nullptr, "dmc_gemm: DMC_ACT_NORMALIZE_BWD needs aux (fp32 rows) and row_scale");

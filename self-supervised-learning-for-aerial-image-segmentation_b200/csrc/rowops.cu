@@ -491,3 +491,10 @@ extern "C" int dmc_colsum(const void* X, int32_t dtype, int64_t M, int64_t N, in
   DMC_LAUNCH_CHECK("colsum_final_kernel launch");
   return 0;
 }
+
+extern "C" int dmc_absmax(const float* x, int64_t n, float* out, void* stream) {
+  DMC_REQUIRE(x && out && n > 0, "dmc_absmax: bad arguments");
+  launch_kernel(absmax_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, x, n, out);
+  DMC_LAUNCH_CHECK("absmax_kernel launch");
+  return 0;
+}

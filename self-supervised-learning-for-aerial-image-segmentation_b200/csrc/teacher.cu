@@ -26,10 +26,13 @@ constexpr int kNV = kChunk / (32 * 4);
 // FULL: the whole 512-column chunk lies inside K and is aligned (packed loads, no per-element guards).
 template <typename T> struct RowsInFlight { static constexpr int value = 16 / sizeof(T) / 2; };   // 4 (bf16) / 2 (fp32)
 
-template <typename T, bool FULL>
+// FIXED: every y2 = (t - center) * ct is known to lie below `shift` (caller-supplied bounds on |t| and |center|): the sum
+// 2^(y2 - shift) needs no running maximum -- ONE pass over the registers, no warp max reduction, half the instructions
+// (the pass is instruction-bound).  `cb` then already holds -center * ct - shift and the reported maximum is `shift`.
+template <typename T, bool FULL, bool FIXED>
 __device__ __forceinline__ void teacher_rows(const T* __restrict__ t, long long K, long long ld, long long col0, int lane,
                                              long long r0, long long r_end, const float (&cb)[kNV][4], float ct,
-                                             float (&cs)[kNV][4], float2* __restrict__ ws_stats, int nchunks, int chunk) {
+                                             float (&cs)[kNV][4], float2* __restrict__ ws_stats, int nchunks, int chunk, float shift) {
   using Q4 = Quad<T>;
   constexpr int RIF = RowsInFlight<T>::value;
   typename Q4::Raw raw[RIF][kNV];
@@ -48,7 +51,23 @@ __device__ __forceinline__ void teacher_rows(const T* __restrict__ t, long long 
 #pragma unroll
   for (int j = 0; j < RIF; ++j) {
     const long long r = r0 + j;
-    if (r < r_end) {                                     // warp-uniform
+    if (FIXED && r < r_end) {                            // warp-uniform
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < kNV; ++i) {
+        float x[4];
+        Q4::unpack(raw[j][i], x);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          cs[i][e] += x[e];
+          float v = fmaf(x[e], ct, cb[i][e]);            // (t - center) / temp * log2(e) - shift
+          if (!FULL && (col0 + (i * 32 + lane) * 4 + e >= K)) v = -INFINITY;
+          if (e & 1) l1 += ex2(v); else l0 += ex2(v);
+        }
+      }
+      const float l = warp_sum(l0 + l1);
+      if (lane == 0) ws_stats[r * nchunks + chunk] = make_float2(shift, l);
+    } else if (r < r_end) {                              // warp-uniform
       float m = -INFINITY;
 #pragma unroll
       for (int i = 0; i < kNV; ++i) {
@@ -85,7 +104,7 @@ template <typename T>
 __global__ void __launch_bounds__(kWarps * 32, 2)
 teacher_pass_kernel(const T* __restrict__ t, long long Nt, long long K, long long ld, const float* __restrict__ center,
                     float inv_temp, float2* __restrict__ ws_stats, float* __restrict__ ws_colsum, int rows_per_block,
-                    int nchunks, bool vec_ok) {
+                    int nchunks, bool vec_ok, const float* __restrict__ bounds) {
   pdl_prologue();
   __shared__ __align__(16) float sm[kWarps][kChunk];  // 16 KiB: per-warp column sums
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -93,6 +112,12 @@ teacher_pass_kernel(const T* __restrict__ t, long long Nt, long long K, long lon
   const long long col0 = static_cast<long long>(chunk) * kChunk;
   const bool full = vec_ok && (col0 + kChunk <= K);
   const float ct = inv_temp * kLog2e;
+  float shift = 0.f;
+  bool fixed = false;
+  if (bounds != nullptr) {                             // {max |t|, max |center|}: fixed shift while 2^(-2 shift) stays a normal fp32
+    shift = (__ldg(bounds) + __ldg(bounds + 1)) * fabsf(ct) * 1.01f + 0.05f;
+    fixed = shift < 55.f;
+  }
 
   float cb[kNV][4], cs[kNV][4];                        // cb = -center * ct (folded into one FFMA per logit)
 #pragma unroll
@@ -100,7 +125,7 @@ teacher_pass_kernel(const T* __restrict__ t, long long Nt, long long K, long lon
     const long long c = col0 + (i * 32 + lane) * 4;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      cb[i][e] = (c + e < K) ? -__ldg(center + c + e) * ct : 0.f;
+      cb[i][e] = ((c + e < K) ? -__ldg(center + c + e) * ct : 0.f) - (fixed ? shift : 0.f);
       cs[i][e] = 0.f;
     }
   }
@@ -108,8 +133,10 @@ teacher_pass_kernel(const T* __restrict__ t, long long Nt, long long K, long lon
   const long long r_end = min(r_begin + rows_per_block, Nt);
   constexpr int RIF = RowsInFlight<T>::value;
   for (long long r0 = r_begin + warp * RIF; r0 < r_end; r0 += kWarps * RIF) {
-    if (full) teacher_rows<T, true>(t, K, ld, col0, lane, r0, r_end, cb, ct, cs, ws_stats, nchunks, chunk);
-    else teacher_rows<T, false>(t, K, ld, col0, lane, r0, r_end, cb, ct, cs, ws_stats, nchunks, chunk);
+    if (full && fixed) teacher_rows<T, true, true>(t, K, ld, col0, lane, r0, r_end, cb, ct, cs, ws_stats, nchunks, chunk, shift);
+    else if (full) teacher_rows<T, true, false>(t, K, ld, col0, lane, r0, r_end, cb, ct, cs, ws_stats, nchunks, chunk, shift);
+    else if (fixed) teacher_rows<T, false, true>(t, K, ld, col0, lane, r0, r_end, cb, ct, cs, ws_stats, nchunks, chunk, shift);
+    else teacher_rows<T, false, false>(t, K, ld, col0, lane, r0, r_end, cb, ct, cs, ws_stats, nchunks, chunk, shift);
   }
 #pragma unroll
   for (int i = 0; i < kNV; ++i)
@@ -227,9 +254,9 @@ extern "C" size_t dmc_teacher_workspace_bytes(int64_t Nt, int64_t K) {
   return p.stats_bytes + p.colsum_bytes;
 }
 
-extern "C" int dmc_teacher_stats_colsum(const void* t, int32_t dtype, int64_t Nt, int64_t K, int64_t ld, const float* center,
-                                        float inv_temp, float* row_stats, float* colsum, void* workspace,
-                                        size_t workspace_bytes, void* stream) {
+static int teacher_stats_impl(const void* t, int32_t dtype, int64_t Nt, int64_t K, int64_t ld, const float* center,
+                              float inv_temp, const float* bounds, float* row_stats, float* colsum, void* workspace,
+                              size_t workspace_bytes, void* stream) {
   DMC_REQUIRE(t && center && row_stats && colsum && workspace, "dmc_teacher_stats_colsum: null pointer");
   DMC_REQUIRE(Nt > 0 && K > 0 && ld >= K, "dmc_teacher_stats_colsum: bad shape Nt=%lld K=%lld ld=%lld", (long long)Nt, (long long)K, (long long)ld);
   DMC_REQUIRE(dtype == DMC_F32 || dtype == DMC_BF16, "dmc_teacher_stats_colsum: bad dtype %d", dtype);
@@ -246,10 +273,10 @@ extern "C" int dmc_teacher_stats_colsum(const void* t, int32_t dtype, int64_t Nt
   dim3 grid((unsigned)p.nchunks, (unsigned)p.nrb);
   if (dtype == DMC_BF16)
     launch_kernel(teacher_pass_kernel<__nv_bfloat16>, dim3(grid), dim3(kWarps * 32), 0, st, static_cast<const __nv_bfloat16*>(t), Nt, K, ld, center, inv_temp,
-                                                                     ws_stats, ws_colsum, p.rows_per_block, p.nchunks, vec_ok);
+                                                                     ws_stats, ws_colsum, p.rows_per_block, p.nchunks, vec_ok, bounds);
   else
     launch_kernel(teacher_pass_kernel<float>, dim3(grid), dim3(kWarps * 32), 0, st, static_cast<const float*>(t), Nt, K, ld, center, inv_temp, ws_stats,
-                                                             ws_colsum, p.rows_per_block, p.nchunks, vec_ok);
+                                                             ws_colsum, p.rows_per_block, p.nchunks, vec_ok, bounds);
   DMC_LAUNCH_CHECK("teacher_pass_kernel launch");
   const int row_blocks = static_cast<int>(ceil_div(Nt, 8));
   const int col_blocks = static_cast<int>(ceil_div(K, 256));
@@ -257,6 +284,19 @@ extern "C" int dmc_teacher_stats_colsum(const void* t, int32_t dtype, int64_t Nt
                                                                    reinterpret_cast<float2*>(row_stats), colsum);
   DMC_LAUNCH_CHECK("teacher_finalize_kernel launch");
   return 0;
+}
+
+extern "C" int dmc_teacher_stats_colsum(const void* t, int32_t dtype, int64_t Nt, int64_t K, int64_t ld, const float* center,
+                                        float inv_temp, float* row_stats, float* colsum, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  return teacher_stats_impl(t, dtype, Nt, K, ld, center, inv_temp, nullptr, row_stats, colsum, workspace, workspace_bytes, stream);
+}
+
+extern "C" int dmc_teacher_stats_colsum_bounded(const void* t, int32_t dtype, int64_t Nt, int64_t K, int64_t ld, const float* center,
+                                                float inv_temp, const float* bounds_dev, float* row_stats, float* colsum,
+                                                void* workspace, size_t workspace_bytes, void* stream) {
+  DMC_REQUIRE(bounds_dev != nullptr, "dmc_teacher_stats_colsum_bounded: null bounds");
+  return teacher_stats_impl(t, dtype, Nt, K, ld, center, inv_temp, bounds_dev, row_stats, colsum, workspace, workspace_bytes, stream);
 }
 
 extern "C" int dmc_center_update(const float* center_in, float* center_out, const float* colsum, int64_t K, float count,

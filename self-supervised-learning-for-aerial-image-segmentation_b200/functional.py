@@ -65,6 +65,7 @@ polite_ctas = int(_os_environ_get("DMC_POLITE_CTAS", "0"))
 # with it (the running-maximum epilogue more than doubles the teacher's last GEMM); kept as a switch, off.
 teacher_epilogue_stats = _os_environ_get("DMC_TEACHER_EPILOGUE_STATS", "0") != "0"
 fuse_normalize_bwd = _os_environ_get("DMC_FUSE_NORMALIZE_BWD", "1") != "0"
+gelu_dg = _os_environ_get("DMC_GELU_DG", "1") != "0"      # MLP forward saves gelu'(z) for the backward instead of z
 grad_exchange_active = False     # set by GradAllReduce: the last layer's dv (64 MiB, the largest all-reduce of the step) must
                                  # then be final as early as possible, so its weight-norm backward stays in front of the dgrad
 grad_exchange = None             # the active GradAllReduce (or None); with compress="bf16" the last layer hands it a bf16 dW
@@ -219,11 +220,14 @@ class LinearFn(torch.autograd.Function):
         bias = None if b is None else b.detach().float().contiguous()
         if apply_gelu:
             z_out = torch.empty((rows, fo), dtype=sd, device=h_in.device)
-            h_out = mm(mode, h_op, w_op, rows, fo, fi, out_dtype=sd, bias=bias, act=L.ACT_GELU, aux=z_out, tag="gemm_mlp_fwd")
+            # with `gelu_dg` the epilogue saves gelu'(z) instead of z (same bytes): the backward epilogue becomes a multiply
+            h_out = mm(mode, h_op, w_op, rows, fo, fi, out_dtype=sd, bias=bias, act=L.ACT_GELU_DG if gelu_dg else L.ACT_GELU,
+                       aux=z_out, tag="gemm_mlp_fwd")
         else:
             h_out = mm(mode, h_op, w_op, rows, fo, fi, out_dtype=torch.float32, bias=bias, tag="gemm_mlp_fwd")
             z_out = h_out.new_empty(0)
         ctx.mode, ctx.dims = mode, (rows, fo, fi)
+        ctx.gelu_dg = gelu_dg               # what THIS layer's z_out holds; the consumer layer reads it from its own ctx.z_in_is_dg
         ctx.h_op, ctx.w_op, ctx.z_in = h_op, w_op, (None if z_in is None else z_in.detach())
         ctx.has_bias = b is not None
         ctx.bias_param = b
@@ -259,7 +263,7 @@ class LinearFn(torch.autograd.Function):
                     ops.mark_ready(db)
             if ctx.z_in is not None:
                 # dgrad with gelu'(z_in) fused: what flows upstream is already dL/dz_in
-                d_in = mm(mode, d, ctx.w_op, rows, fi, fo, b_mn=True, out_dtype=sd, act=L.ACT_GELU_BWD, aux=ctx.z_in,
+                d_in = mm(mode, d, ctx.w_op, rows, fi, fo, b_mn=True, out_dtype=sd, act=L.ACT_MUL_AUX if ctx.gelu_dg else L.ACT_GELU_BWD, aux=ctx.z_in,
                           tag="gemm_mlp_dgrad")
             elif ctx.needs_input_grad[1]:
                 d_in = mm(mode, d, ctx.w_op, rows, fi, fo, b_mn=True, out_dtype=torch.float32, tag="gemm_mlp_dgrad")

@@ -539,8 +539,21 @@ def weightnorm_bwd(dw, v, scale, inv_vnorm, want_dg: bool):
 # ---------------------------------------------------------------------------------------------
 # loss kernels
 # ---------------------------------------------------------------------------------------------
-def teacher_stats_colsum(t: torch.Tensor, center: torch.Tensor, inv_temp: float):
-    """One pass over teacher logits: (row_stats [Nt,2] = (max, 1/sum), colsum [K])."""
+def absmax_into(x: torch.Tensor, out: torch.Tensor):
+    """out[0] <- max |x| (fp32 device scalar slot; no synchronisation)."""
+    lib = L.load()
+    _need_cuda(x, out)
+    x = x.reshape(-1)
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise TypeError("absmax_into: contiguous float32 input")
+    with _timed("absmax"):
+        L.check(lib.dmc_absmax(x.data_ptr(), x.numel(), out.data_ptr(), _stream()), "dmc_absmax")
+    _count()
+
+
+def teacher_stats_colsum(t: torch.Tensor, center: torch.Tensor, inv_temp: float, bounds=None):
+    """One pass over teacher logits: (row_stats [Nt,2] = (max, 1/sum), colsum [K]).  `bounds`: optional device tensor
+    {>= max|t|, >= max|center|} enabling the fixed-shift fast path (see dmc_teacher_stats_colsum_bounded)."""
     lib = L.load()
     t = _rows2d(t)
     _need_cuda(t, center)
@@ -552,9 +565,15 @@ def teacher_stats_colsum(t: torch.Tensor, center: torch.Tensor, inv_temp: float)
     nbytes = lib.dmc_teacher_workspace_bytes(Nt, K)
     ws = workspace(nbytes, t.device)
     with _timed("teacher_stats_colsum"):
-        L.check(lib.dmc_teacher_stats_colsum(t.data_ptr(), _dt(t), Nt, K, t.stride(0), center.data_ptr(), inv_temp,
-                                             row_stats.data_ptr(), colsum_.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
-                "dmc_teacher_stats_colsum")
+        if bounds is not None:
+            _need_cuda(bounds)
+            L.check(lib.dmc_teacher_stats_colsum_bounded(t.data_ptr(), _dt(t), Nt, K, t.stride(0), center.data_ptr(), inv_temp,
+                                                         bounds.data_ptr(), row_stats.data_ptr(), colsum_.data_ptr(), ws.data_ptr(),
+                                                         ws.numel(), _stream()), "dmc_teacher_stats_colsum_bounded")
+        else:
+            L.check(lib.dmc_teacher_stats_colsum(t.data_ptr(), _dt(t), Nt, K, t.stride(0), center.data_ptr(), inv_temp,
+                                                 row_stats.data_ptr(), colsum_.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+                    "dmc_teacher_stats_colsum")
     _count(2)
     return row_stats, colsum_
 
