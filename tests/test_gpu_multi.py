@@ -19,7 +19,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_dir, compress=None):
+def _worker(rank, world, port, out_dir, compress=None, transport="nccl"):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -46,7 +46,10 @@ def _worker(rank, world, port, out_dir, compress=None):
         for p in head.parameters():
             p.grad = None
         # the same step with the reducer: gradients become the mean over ranks
-        red = D.GradAllReduce(head.parameters(), compress=compress)
+        red = D.GradAllReduce(head.parameters(), compress=compress, transport=transport)
+        if transport == "peer":
+            from dinomc_b200.xrank import SymmetricBuffer
+            loss_mod.center_exchange = SymmetricBuffer(K, torch.float32, ctas=4)     # the center all-reduce on the same kernel
         loss_mod.center.zero_()
         loss2 = loss_mod(head(xs), t_out, 0)
         loss2.backward()
@@ -100,3 +103,76 @@ def test_bf16_gradient_exchange_two_gpus(tmp_path):
             err = (r[i]["reduced"][name].double() - mean).abs().max() / mean.abs().max()
             assert err < 2e-2, (name, float(err))
         assert torch.equal(r[0]["reduced"][name], r[1]["reduced"][name])
+
+
+def test_peer_memory_exchange_two_gpus(tmp_path):
+    """transport="peer": the same bf16 exchange and the center all-reduce on libdinomc's own NVLink / NVSwitch all-reduce
+    kernel (dmc_xrank_allreduce over symmetric memory) instead of NCCL: mean of the ranks' local gradients within the
+    bf16-GEMM tolerance, bit-identical replicas, center equal to the reference's all-reduced update."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from oracle import np_oracle as O
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path), "bf16", "peer"), nprocs=2, join=True)
+    r = [torch.load(os.path.join(tmp_path, f"rank{i}.pt")) for i in range(2)]
+    assert set(r[0]["reduced"]) == set(r[0]["local"])
+    for name in r[0]["local"]:
+        mean = (r[0]["local"][name].double() + r[1]["local"][name].double()) / 2
+        for i in range(2):
+            err = (r[i]["reduced"][name].double() - mean).abs().max() / mean.abs().max()
+            assert err < 2e-2, (name, float(err))
+        assert torch.equal(r[0]["reduced"][name], r[1]["reduced"][name])
+
+
+def _xrank_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from dinomc_b200.xrank import SymmetricBuffer
+        res = {}
+        for name, numel, dtype, ctas in (("bf16", 1 << 20, torch.bfloat16, 148), ("f32", 65536, torch.float32, 8), ("ragged", 8 * 1001, torch.bfloat16, 3)):
+            buf = SymmetricBuffer(numel, dtype, ctas=ctas)
+            g = torch.Generator().manual_seed(7 + rank)
+            x = (torch.randn(buf.numel, generator=g) * 0.1).to(dtype).cuda()
+            for rep in range(3):                                   # the signal pads must be reusable launch after launch
+                buf.tensor.copy_(x)
+                buf.allreduce_(1.0 / world)
+            torch.cuda.synchronize()
+            res[name] = (x.cpu(), buf.tensor.cpu(), buf.multicast)
+        # widening epilogue
+        buf = SymmetricBuffer(4096 + 16, torch.bfloat16, ctas=5)
+        a, b = torch.zeros(4096, device="cuda"), torch.zeros(11, device="cuda")
+        src = (torch.arange(buf.numel).float() * 1e-3 * (rank + 1)).bfloat16().cuda()
+        buf.tensor.copy_(src)
+        buf.allreduce_(1.0 / world, widen_to=[a, b], widen_offsets=[0, 4096])
+        torch.cuda.synchronize()
+        res["widen"] = (src.cpu(), a.cpu(), b.cpu())
+        torch.save(res, os.path.join(out_dir, f"x{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_xrank_allreduce_kernel_two_gpus(tmp_path):
+    """dmc_xrank_allreduce through the C ABI on 2 GPUs: sums equal the fp32 sum of the ranks' inputs (bf16: rounded once),
+    every rank ends with the same bits, repeated launches reuse the signal pads, the widening epilogue fills fp32 tensors."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_xrank_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r = [torch.load(os.path.join(tmp_path, f"x{i}.pt")) for i in range(2)]
+    for name in ("bf16", "f32", "ragged"):
+        ref = (r[0][name][0].double() + r[1][name][0].double()) / 2
+        for i in range(2):
+            got = r[i][name][1].double()
+            tol = 5e-3 if name != "f32" else 1e-6
+            assert float((got - ref).abs().max()) <= tol * float(ref.abs().max()), name
+        assert torch.equal(r[0][name][1], r[1][name][1])
+    ref = (r[0]["widen"][0].double() + r[1]["widen"][0].double()) / 2
+    for i in range(2):
+        assert float((r[i]["widen"][1].double() - ref[:4096]).abs().max()) <= 5e-3 * float(ref.abs().max())
+        assert float((r[i]["widen"][2].double() - ref[4096:4107]).abs().max()) <= 5e-3 * float(ref.abs().max())
