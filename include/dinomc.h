@@ -115,6 +115,9 @@ typedef struct dmc_gemm_args {
   float stat_scale; const float* stat_center; float* stat_row_partials; float* stat_colsum_partials;
   const float* stat_bound; /* optional device scalar b >= max |D| (e.g. the largest weight-norm gain when the rows of A
                               are unit vectors): lets the epilogue skip the running max (used only without a center) */
+  const float* stat_bound2; /* optional second device scalar ADDED to stat_bound; with stat_center set, stat_bound + stat_bound2 must
+                               bound |D| + |center| (e.g. max gain + max |center|): the TEACHER statistics then use the same
+                               fixed-shift form (bf16 output; while the shift stays below 55, else the running-maximum form) */
   const float* row_scale;  /* DMC_ACT_NORMALIZE_BWD: [M] */
   float row_eps;           /* DMC_ACT_NORMALIZE_BWD: the eps of F.normalize */
 } dmc_gemm_args;

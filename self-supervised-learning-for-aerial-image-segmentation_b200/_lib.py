@@ -34,6 +34,7 @@ class GemmArgs(C.Structure):
         ("max_ctas", i32),
         ("stat_scale", f32), ("stat_center", vp), ("stat_row_partials", vp), ("stat_colsum_partials", vp),
         ("stat_bound", vp),
+        ("stat_bound2", vp),
         ("row_scale", vp), ("row_eps", f32),
     ]
 

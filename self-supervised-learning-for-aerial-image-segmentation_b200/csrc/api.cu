@@ -35,6 +35,23 @@ int& pdl_flag() {
 
 bool pdl_enabled() { return pdl_flag() != 0; }
 
+void prefer_max_smem_carveout(const void* func) {
+  // tiny open-addressed set of kernels already configured (benign races: at worst the attribute is set twice)
+  static const void* seen[256] = {nullptr};
+  static const bool enabled = [] { const char* e = getenv("DMC_MAX_SMEM_CARVEOUT"); return e == nullptr || atoi(e) != 0; }();
+  if (!enabled) return;
+  size_t h = (reinterpret_cast<uintptr_t>(func) >> 4) & 255;
+  for (int probe = 0; probe < 256; ++probe, h = (h + 1) & 255) {
+    if (seen[h] == func) return;
+    if (seen[h] == nullptr) {
+      seen[h] = func;
+      cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaGetLastError();                   // a hint: never fail a launch because of it
+      return;
+    }
+  }
+}
+
 namespace {
 thread_local int g_streaming_ctas = 0;
 }

@@ -69,6 +69,7 @@ struct GemmDev {
   float2* stat_row_partials;    // [M][kColGroups * n_tiles]
   float* stat_colsum_partials;  // [ceil(M/32)][N] or nullptr
   const float* stat_bound;      // device scalar b with |D| <= b, or nullptr
+  const float* stat_bound2;     // optional second device scalar added to it (e.g. max |center|)
   int dbg;                      // DMC_GEMM_FLAGS >> 3 (timing experiments only): 1 = no TMA store issue, 2 = no staging writes, 4 = no TMEM loads
   int tma_store;      // 1: epilogue stores D through smem staging + TMA
   long long* trace;   // DMC_GEMM_TRACE=1 (debug): clock64() stamps of CTA 0's pipeline events, [8][512]
@@ -340,12 +341,27 @@ __device__ __forceinline__ void epilogue_fast_acc(const GemmDev& p, const CUtens
       }
       if constexpr (EPI == 2) {                               // statistics of exactly the stored (rounded) values
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (p.stat_center != nullptr) {
+          // teacher form, fixed shift: sum 2^((t - center) * sc2 - shift).  pk[2q], pk[2q+1] hold columns c+4q .. c+4q+3 (q < 8)
+          // and c+32+4(q-8) .. (q >= 8); the center values are the same for every lane (row) of the warp: broadcast loads
+          const float4* cen = reinterpret_cast<const float4*>(p.stat_center + n0 + c);
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          a0 += ex2(fmaf(bf16_lo(pk[j]), p.stat_sc2, -stat_shift));
-          a1 += ex2(fmaf(bf16_hi(pk[j]), p.stat_sc2, -stat_shift));
-          a2 += ex2(fmaf(bf16_lo(pk[j + 1]), p.stat_sc2, -stat_shift));
-          a3 += ex2(fmaf(bf16_hi(pk[j + 1]), p.stat_sc2, -stat_shift));
+          for (int q = 0; q < 16; ++q) {
+            const float4 cc = __ldg(cen + q);
+            const uint32_t w0 = pk[2 * q], w1 = pk[2 * q + 1];
+            a0 += ex2(fmaf(bf16_lo(w0) - cc.x, p.stat_sc2, -stat_shift));
+            a1 += ex2(fmaf(bf16_hi(w0) - cc.y, p.stat_sc2, -stat_shift));
+            a2 += ex2(fmaf(bf16_lo(w1) - cc.z, p.stat_sc2, -stat_shift));
+            a3 += ex2(fmaf(bf16_hi(w1) - cc.w, p.stat_sc2, -stat_shift));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            a0 += ex2(fmaf(bf16_lo(pk[j]), p.stat_sc2, -stat_shift));
+            a1 += ex2(fmaf(bf16_hi(pk[j]), p.stat_sc2, -stat_shift));
+            a2 += ex2(fmaf(bf16_lo(pk[j + 1]), p.stat_sc2, -stat_shift));
+            a3 += ex2(fmaf(bf16_hi(pk[j + 1]), p.stat_sc2, -stat_shift));
+          }
         }
         st_l += (a0 + a1) + (a2 + a3);
       }
@@ -672,19 +688,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     uint32_t n_boxes = 0;                                            // boxes this warp has stored so far
     // EPI 2, bounded logits: with |D| <= bound (device scalar: max gain of the weight-normed rows) and no center, every
     // y2 lies in [-shift, shift]; summing 2^(y2 - shift) directly is safe while 2*shift stays inside fp32's exponent range.
-    bool stat_fixed = false;
+    bool stat_fixed = false;                    // fixed shift, no center: lean and generic paths
+    bool stat_fixed_center = false;             // fixed shift WITH a center (teacher, bound = max |t| + max |center|): lean bf16 path only
     float stat_shift = 0.f;
     if constexpr (EPI >= 2) {
-      if (p.stat_bound != nullptr && p.stat_center == nullptr) {
-        stat_shift = fabsf(__ldg(p.stat_bound) * p.stat_sc2) * 1.01f + 0.05f;
-        stat_fixed = (stat_shift < 55.f);
+      if (p.stat_bound != nullptr) {
+        const float b = __ldg(p.stat_bound) + (p.stat_bound2 != nullptr ? __ldg(p.stat_bound2) : 0.f);
+        stat_shift = fabsf(b * p.stat_sc2) * 1.01f + 0.05f;
+        if (p.stat_center == nullptr) stat_fixed = (stat_shift < 55.f);
+        else stat_fixed_center = (stat_shift < 55.f) && p.out_dtype == DMC_BF16 && (reinterpret_cast<uintptr_t>(p.stat_center) & 15) == 0;
+        if (!stat_fixed && !stat_fixed_center) stat_shift = 0.f;
       }
     }
     // lean path (epilogue_fast_acc) for full tiles stored through TMA; everything else takes the generic chunk code
     bool fast_ok = p.tma_store && p.partial == nullptr && p.dbg == 0 && c_begin < c_end && ((c_end - c_begin) & 63) == 0 &&
                    p.banks <= 1;
     if constexpr (EPI == 0) fast_ok = fast_ok && p.col_scale == nullptr && aux_vec_ok;
-    if constexpr (EPI == 2) fast_ok = fast_ok && stat_fixed && p.stat_colsum_partials == nullptr;
+    if constexpr (EPI == 2) fast_ok = fast_ok && (stat_fixed || stat_fixed_center) && p.stat_colsum_partials == nullptr;
     if constexpr (EPI == 3)                            // lean teacher statistics: bf16 output, center + column sums requested
       fast_ok = fast_ok && p.stat_center != nullptr && p.out_dtype == DMC_BF16 &&
                 (reinterpret_cast<uintptr_t>(p.stat_center) & 15) == 0;
@@ -1322,7 +1342,7 @@ extern "C" int dmc_gemm(const dmc_gemm_args* a, void* stream) {
   d.resident = pl.resident; d.tma_store = pl.tma_store; d.dual = pl.dual; d.banks = pl.banks;
   d.stat_sc2 = a->stat_scale * 1.4426950408889634f; d.stat_center = a->stat_center;
   d.stat_row_partials = reinterpret_cast<float2*>(a->stat_row_partials); d.stat_colsum_partials = a->stat_colsum_partials;
-  d.stat_bound = a->stat_bound;
+  d.stat_bound = a->stat_bound; d.stat_bound2 = a->stat_bound2;
   d.dbg = (debug_flags() >> 3) & 7;
   static const bool trace_on = (getenv("DMC_GEMM_TRACE") != nullptr);       // debug only: never set in production
   static long long* trace_dev = nullptr;
@@ -1359,7 +1379,7 @@ const bool plain = (a->col_scale == nullptr && a->bias == nullptr && (a->act == 
   (amn ? (bmn ? DMC_LAUNCH(ESZ_, true, true) : DMC_LAUNCH(ESZ_, true, false))                                 \
        : (bmn ? DMC_LAUNCH(ESZ_, false, true) : DMC_LAUNCH(ESZ_, false, false)))
   if (stats) {          // last-layer forward only: K-major operands
-    if (a->stat_center != nullptr && esz == 2)      // teacher: center + running maximum (+ column sums), lean path in EPI 3
+    if (a->stat_center != nullptr && esz == 2 && a->stat_bound == nullptr)   // teacher: center + running maximum (+ column sums), lean path in EPI 3
       rc = launch_tc<2, false, false, 3>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st, pl.cg2);
     else
       rc = (esz == 2) ? launch_tc<2, false, false, 2>(tA0, tA1, tB0, tB1, tD, d, pl.smem_bytes, grid, st, pl.cg2)

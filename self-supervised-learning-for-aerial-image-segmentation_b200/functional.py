@@ -347,8 +347,13 @@ class NormLastLayerFn(torch.autograd.Function):
                 loss_mod.sync_center()
                 cen = loss_mod.center
                 rp = torch.empty((rows, parts, 2), dtype=torch.float32, device=z.device)
+                # bounds for the fixed-shift statistics: |logit| <= the largest gain (unit rows x weight-normed rows), plus max |center|
+                bounds = torch.empty(2, dtype=torch.float32, device=z.device)
+                ops.absmax_into(g.detach(), bounds[0:1])
+                ops.absmax_into(cen.detach(), bounds[1:2])
                 stats = dict(kind="teacher", scale=loss_mod._last_inv_tt, center=cen.reshape(-1), row_partials=rp,
-                             colsum_partials=None, center_ptr=cen.data_ptr(), center_version=cen._version)
+                             colsum_partials=None, center_ptr=cen.data_ptr(), center_version=cen._version,
+                             bound=bounds[0:1], bound2=bounds[1:2])
                 side = _AuxRegion(z.device)
                 with side, ops.polite(polite_ctas):
                     zbar = ops.colsum(zhat_bf16)

@@ -248,6 +248,7 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, A_lo=None, B_lo=None, out=Non
         g.stat_row_partials = stats["row_partials"].data_ptr()
         g.stat_colsum_partials = _p(stats.get("colsum_partials"))
         g.stat_bound = _p(stats.get("bound"))
+        g.stat_bound2 = _p(stats.get("bound2"))
     if simt:
         with _timed(tag):
             L.check(lib.dmc_gemm_simt(C.byref(g), _stream()), "dmc_gemm_simt")

@@ -169,10 +169,10 @@ def test_xrank_allreduce_kernel_two_gpus(tmp_path):
         ref = (r[0][name][0].double() + r[1][name][0].double()) / 2
         for i in range(2):
             got = r[i][name][1].double()
-            tol = 5e-3 if name != "f32" else 1e-6
+            tol = 1e-2 if name != "f32" else 1e-6            # bf16: the switch rounds the sum, the scaling rounds again
             assert float((got - ref).abs().max()) <= tol * float(ref.abs().max()), name
         assert torch.equal(r[0][name][1], r[1][name][1])
     ref = (r[0]["widen"][0].double() + r[1]["widen"][0].double()) / 2
     for i in range(2):
-        assert float((r[i]["widen"][1].double() - ref[:4096]).abs().max()) <= 5e-3 * float(ref.abs().max())
-        assert float((r[i]["widen"][2].double() - ref[4096:4107]).abs().max()) <= 5e-3 * float(ref.abs().max())
+        assert float((r[i]["widen"][1].double() - ref[:4096]).abs().max()) <= 1e-2 * float(ref.abs().max())
+        assert float((r[i]["widen"][2].double() - ref[4096:4107]).abs().max()) <= 1e-2 * float(ref.abs().max())
