@@ -231,6 +231,7 @@ extern "C" int dmc_xrank_allreduce(void* multicast_ptr, void* const* peer_ptrs_h
                 out_offsets_host[t] + out_numels_host[t] <= numel, "dmc_xrank_allreduce: bad output slice %d", t);
     a.out[t] = out_ptrs_host[t]; a.out_off[t] = out_offsets_host[t]; a.out_n[t] = out_numels_host[t];
   }
+  prefer_max_smem_carveout(reinterpret_cast<const void*>(xrank_allreduce_kernel));    // stay co-resident with the tcgen05 GEMMs
   launch_kernel(xrank_allreduce_kernel, dim3(static_cast<unsigned>(ctas)), dim3(kXThreads), 0, static_cast<cudaStream_t>(stream), a);
   DMC_LAUNCH_CHECK("xrank_allreduce_kernel launch");
   return 0;

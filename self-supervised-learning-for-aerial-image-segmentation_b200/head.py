@@ -47,7 +47,9 @@ def set_operand_shadows(enabled: bool):
 
 
 _wn_after_first_gemm = os.environ.get("DMC_WN_AFTER_FIRST_GEMM", "1") != "0"       # env: timing experiments
-_bounded_teacher_stats = os.environ.get("DMC_BOUNDED_TEACHER_STATS", "1") != "0"      # env: timing experiments
+# fixed-shift teacher pass (dmc_teacher_stats_colsum_bounded): correct and tested, but MEASURED no faster than the general pass
+# (the pass is latency- not instruction-bound at 512 rows) and its two absmax launches add ~10 us: off by default
+_bounded_teacher_stats = os.environ.get("DMC_BOUNDED_TEACHER_STATS", "0") != "0"
 _early_teacher_stats = os.environ.get("DMC_EARLY_TEACHER_STATS", "1") != "0"
 
 
