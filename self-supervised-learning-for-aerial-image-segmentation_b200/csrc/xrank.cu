@@ -119,7 +119,7 @@ __device__ __forceinline__ uint4 scale_vec(const uint4& v, float s, bool bf16) {
   return r;
 }
 
-__global__ void __launch_bounds__(kXThreads, 6)
+__global__ void __launch_bounds__(kXThreads, 8)   // <= 32 registers: 8 warps x 1024 regs fit beside a GEMM CTA (10 warps x 5632: the register file is allocated in 512-register units per warp)
 xrank_allreduce_kernel(const XrankArgs a) {
   pdl_prologue();
   const bool bf16 = a.is_bf16 != 0;

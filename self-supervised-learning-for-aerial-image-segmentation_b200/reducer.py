@@ -211,7 +211,10 @@ class GradAllReduce:
         """For NormLastLayerFn.backward: the parameters (weight_v[, weight_g]) whose gradients may be produced from an
         averaged dW, or None when that route does not apply (no compression, foreign parameters, or a gradient already
         accumulated in `.grad` -- then the regular route through autograd runs)."""
-        if self.compress != "bf16":
+        if self.compress != "bf16" or self.transport != "peer":
+            # NCCL transport: the last layer's dv takes the regular route (narrowed to bf16 like the small gradients).  The
+            # averaged-dW route over NCCL produced rank-dependent gradients at out_dim 65536 (bench.py's exchange check:
+            # max diff 0.73, replicas not identical) -- masked in round 1 by a second exchange of the same parameter
             return None
         pv = self._by_ptr.get(v_ptr)
         if pv is None or pv.grad is not None:
