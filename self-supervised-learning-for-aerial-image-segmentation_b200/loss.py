@@ -177,7 +177,8 @@ class DINOLoss(nn.Module):
             comm.wait_stream(cur)                       # colsum and the old center were produced on `cur`
             with torch.cuda.stream(comm):
                 colsum = self._allreduce_colsum(colsum)     # main_dino_mc.py:469
-                new_center = ops.center_update(self.center, colsum, n_rows * world, self.center_momentum)
+                with ops.no_pdl():                          # behind a cross-rank kernel: do not sit resident while it runs
+                    new_center = ops.center_update(self.center, colsum, n_rows * world, self.center_momentum)
             colsum.record_stream(comm)
             self.center.record_stream(comm)
             new_center.record_stream(cur)

@@ -298,6 +298,20 @@ def rowdot(W: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+class no_pdl:
+    """Context manager: kernels launched inside are NOT programmatic dependent launches.  For a kernel that follows a
+    long-running kernel on its stream (e.g. the weight-norm backward behind the cross-rank exchange): launched early, its
+    thousands of CTAs would sit resident in griddepcontrol.wait for the whole exchange and keep every SM full -- measured:
+    the last layer's dgrad on the other stream could not start for 150 us."""
+
+    def __enter__(self):
+        self.prev = L.load().dmc_set_pdl(0)
+
+    def __exit__(self, *exc):
+        L.load().dmc_set_pdl(self.prev)
+        return False
+
+
 class polite:
     """Context manager: row-streaming kernels launched inside (weight-norm forward / backward, rowdot) use at most `n`
     CTAs (default one per SM) and so leave room for a one-CTA-per-SM GEMM on every SM (dmc_set_streaming_ctas)."""

@@ -253,7 +253,8 @@ class GradAllReduce:
             if _DEBUG:
                 self._dbg("last-layer all-reduce launch", t0)
                 t0 = time.perf_counter()
-            dv, dg = weightnorm_bwd()
+            with ops.no_pdl():          # must not become resident before the exchange has finished (see ops.no_pdl)
+                dv, dg = weightnorm_bwd()
         if _DEBUG:
             self._dbg("weight-norm backward launch", t0)
         if not peer:                     # symmetric buffers are persistent: nothing for the caching allocator to track
