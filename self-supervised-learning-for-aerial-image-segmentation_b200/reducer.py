@@ -62,8 +62,12 @@ class GradAllReduce:
         self._keep = []                 # tensors produced on the caller's stream and read on the communication stream: kept
                                         # alive until wait() (inside a graph capture record_stream() does not defer reuse)
         self._flush_bytes = _FLUSH
+        self._xrank_ctas = int(os.environ.get("DMC_XRANK_CTAS", "32"))
         if transport == "peer":
-            reserve_sms = 0             # the exchange kernel shares SMs with the GEMMs
+            # The exchange kernel gets its own SMs: the backward GEMM grids leave `reserve_sms` SMs free and the kernel runs
+            # `_xrank_ctas` CTAs there.  Sharing SMs with the GEMMs (148 CTAs, one per SM, co-resident) was measured slower:
+            # the co-resident warps slow the GEMMs' single MMA / TMA warps (dgrad 61 -> 108 us, MLP backward 120 -> 200 us).
+            reserve_sms = int(os.environ.get("DMC_XRANK_RESERVE_SMS", str(reserve_sms)))
             # flush the small gradients in two batches: the later MLP layers' (19 of 25 MB) leave while the first layer's
             # backward still runs, only the first layer's 3 MB are exchanged after the last wgrad
             self._flush_bytes = int(float(os.environ.get("DMC_PEER_FLUSH_MB", "8")) * (1 << 20))
@@ -162,7 +166,7 @@ class GradAllReduce:
             return None
         if self._dw_buf is None or self._dw_buf.numel != K * dim:
             from .xrank import SymmetricBuffer
-            self._dw_buf = SymmetricBuffer(K * dim, torch.bfloat16, group=self.group)
+            self._dw_buf = SymmetricBuffer(K * dim, torch.bfloat16, group=self.group, ctas=self._xrank_ctas)
         return self._dw_buf.tensor.view(K, dim)
 
     def _exchange_bf16_peer(self, grads):
@@ -176,7 +180,7 @@ class GradAllReduce:
         buf = self._small_bufs.get(key)
         if buf is None:
             from .xrank import SymmetricBuffer
-            buf = self._small_bufs[key] = SymmetricBuffer(total, torch.bfloat16, group=self.group)
+            buf = self._small_bufs[key] = SymmetricBuffer(total, torch.bfloat16, group=self.group, ctas=self._xrank_ctas)
         import time
         t0 = time.perf_counter()
         flat = buf.tensor
