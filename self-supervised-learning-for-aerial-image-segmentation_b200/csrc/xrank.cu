@@ -168,9 +168,34 @@ xrank_allreduce_kernel(const XrankArgs a) {
     }
   }
   __threadfence_system();                    // this CTA's remote stores are visible before it signals
-  block_barrier(a, 1);                       // every rank's slice has landed in every buffer
-  // epilogue: widen the complete bf16 buffer into fp32 tensors (gradients exchanged in bf16 -> fp32 .grad)
+  block_barrier(a, 1);                       // CTA b of every rank has finished its part of every slice
+  // epilogue: widen the bf16 buffer into fp32 tensors (gradients exchanged in bf16 -> fp32 .grad).  block_barrier only pairs
+  // CTA b with the CTAs b of the other ranks, but the epilogue reads what ALL remote CTAs wrote: first a rank-local grid
+  // barrier -- once every local CTA has passed barrier 1, every remote CTA has arrived at it, i.e. all slices are complete.
+  // (Measured without it: wrong gradients on one rank as soon as the kernel ran with 16 or 32 CTAs instead of 148.)
+  // Sense-reversing counter in the local signal pad: self-resetting, reusable launch after launch.
   if (a.n_out > 0) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t* ctr = a.pads[a.rank] + 2ll * gridDim.x * a.world;
+      uint32_t* gen = ctr + 1;
+      uint32_t g0, old;
+      asm volatile("ld.global.acquire.gpu.b32 %0, [%1];" : "=r"(g0) : "l"(gen) : "memory");
+      asm volatile("atom.global.acq_rel.gpu.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(ctr) : "memory");
+      if (old == gridDim.x - 1) {
+        asm volatile("st.global.relaxed.gpu.b32 [%0], %1;" :: "l"(ctr), "r"(0u) : "memory");
+        asm volatile("st.global.release.gpu.b32 [%0], %1;" :: "l"(gen), "r"(g0 + 1u) : "memory");
+      } else {
+        uint32_t g1;
+        long long spins = 0;
+        do {
+          __nanosleep(128);
+          asm volatile("ld.global.acquire.gpu.b32 %0, [%1];" : "=r"(g1) : "l"(gen) : "memory");
+          if (++spins > (1ll << 26)) __trap();
+        } while (g1 == g0);
+      }
+    }
+    __syncthreads();
     const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(a.peers[a.rank]);
     for (int t = 0; t < a.n_out; ++t) {
       const __nv_bfloat16* s = src + a.out_off[t];
@@ -200,7 +225,7 @@ using namespace dmc;
 
 extern "C" size_t dmc_xrank_signal_bytes(int32_t world, int32_t ctas) {
   if (world <= 0 || ctas <= 0) return 0;
-  return static_cast<size_t>(2) * ctas * world * sizeof(uint32_t);
+  return (static_cast<size_t>(2) * ctas * world + 2) * sizeof(uint32_t);      // + the local grid barrier's counter and generation
 }
 
 extern "C" int dmc_xrank_allreduce(void* multicast_ptr, void* const* peer_ptrs_host, void* const* signal_pads_host, int64_t numel,

@@ -62,12 +62,13 @@ class GradAllReduce:
         self._keep = []                 # tensors produced on the caller's stream and read on the communication stream: kept
                                         # alive until wait() (inside a graph capture record_stream() does not defer reuse)
         self._flush_bytes = _FLUSH
-        self._xrank_ctas = int(os.environ.get("DMC_XRANK_CTAS", "32"))
+        self._xrank_ctas = int(os.environ.get("DMC_XRANK_CTAS", "148"))
         if transport == "peer":
-            # The exchange kernel gets its own SMs: the backward GEMM grids leave `reserve_sms` SMs free and the kernel runs
-            # `_xrank_ctas` CTAs there.  Sharing SMs with the GEMMs (148 CTAs, one per SM, co-resident) was measured slower:
-            # the co-resident warps slow the GEMMs' single MMA / TMA warps (dgrad 61 -> 108 us, MLP backward 120 -> 200 us).
-            reserve_sms = int(os.environ.get("DMC_XRANK_RESERVE_SMS", str(reserve_sms)))
+            # One exchange CTA per SM (256 threads, 32 registers), co-resident with the backward GEMMs; no SMs reserved.
+            # MEASURED at 2 GPUs (profiles/r02_exchange_ab.md): 148 CTAs / 0 reserved 0.909 ms; 48 CTAs on 24 reserved SMs
+            # 0.939; 32 on 16 0.956; 16 on 8 1.018 -- NVLink wants the loads of many SMs in flight, and the GEMMs lose more
+            # from 16-24 missing SMs than from sharing.  DMC_XRANK_CTAS / DMC_XRANK_RESERVE_SMS override.
+            reserve_sms = int(os.environ.get("DMC_XRANK_RESERVE_SMS", "0"))
             # flush the small gradients in two batches: the later MLP layers' (19 of 25 MB) leave while the first layer's
             # backward still runs, only the first layer's 3 MB are exchanged after the last wgrad
             self._flush_bytes = int(float(os.environ.get("DMC_PEER_FLUSH_MB", "8")) * (1 << 20))
