@@ -75,6 +75,9 @@ class GradAllReduce:
         self.params = [p for p in params if p.requires_grad]
         self._by_ptr = {p.data_ptr(): p for p in self.params}
         self.comm = torch.cuda.Stream(priority=-1)
+        self.comm2 = torch.cuda.Stream(priority=-1)
+        self._late = None
+        self._late_wn = os.environ.get("DMC_LATE_WN_BWD", "1") != "0"
         self._pending = []
         self._pending_bytes = 0
         self._seen = 0
@@ -126,6 +129,8 @@ class GradAllReduce:
             self._flush()
 
     def _flush(self):
+        if self._seen >= len(self.params):
+            self._run_late()
         if self._pending:
             if all(ev is not None for _, ev in self._pending):
                 for _, ev in self._pending:              # start as soon as the producing kernels are done
@@ -181,7 +186,10 @@ class GradAllReduce:
         buf = self._small_bufs.get(key)
         if buf is None:
             from .xrank import SymmetricBuffer
-            buf = self._small_bufs[key] = SymmetricBuffer(total, torch.bfloat16, group=self.group, ctas=self._xrank_ctas)
+            # few CTAs for small buffers: each CTA costs 2 x world remote signals per barrier, and a 1.6 MB exchange on 148
+            # CTAs is all barrier (measured 50 us at 8 GPUs)
+            ctas = max(8, min(self._xrank_ctas, (2 * total) >> int(os.environ.get("DMC_XRANK_BYTES_PER_CTA_LOG2", "16"))))
+            buf = self._small_bufs[key] = SymmetricBuffer(total, torch.bfloat16, group=self.group, ctas=ctas)
         import time
         t0 = time.perf_counter()
         flat = buf.tensor
@@ -258,30 +266,64 @@ class GradAllReduce:
             if _DEBUG:
                 self._dbg("last-layer all-reduce launch", t0)
                 t0 = time.perf_counter()
-            with ops.no_pdl():          # must not become resident before the exchange has finished (see ops.no_pdl)
-                dv, dg = weightnorm_bwd()
+            if peer and self._late_wn:
+                # The weight-norm backward of the averaged dW (HBM-bound, ~30 us, thousands of CTAs) is NOT run here: behind
+                # the exchange it lands in the middle of the MLP backward and its CTAs keep the next GEMMs off the SMs
+                # (measured at 8 GPUs: MLP backward starts 20 us late).  It runs at the final flush instead, on a second
+                # stream, next to the last (latency-bound) small exchange -- both are needed only by wait().
+                done = torch.cuda.Event()
+                done.record(self.comm)
+                self._late = (weightnorm_bwd, pv, pg, done)
+                dv = dg = None
+            else:
+                with ops.no_pdl():      # must not become resident before the exchange has finished (see ops.no_pdl)
+                    dv, dg = weightnorm_bwd()
         if _DEBUG:
             self._dbg("weight-norm backward launch", t0)
         if not peer:                     # symmetric buffers are persistent: nothing for the caching allocator to track
             dw.record_stream(self.comm)
             self._keep.append(dw)        # ... and inside a graph capture only a live reference keeps the block from being reused
-        dv.record_stream(cur)
-        pv.grad = dv.view_as(pv)
+        if dv is not None:
+            dv.record_stream(cur)
+            pv.grad = dv.view_as(pv)
         self._claimed.add(id(pv))
         self._seen += 1
         if pg is not None:
-            dg.record_stream(cur)
-            pg.grad = dg.view_as(pg)
+            if dg is not None:
+                dg.record_stream(cur)
+                pg.grad = dg.view_as(pg)
             self._claimed.add(id(pg))
             self._seen += 1
         if self._seen == len(self.params):
             self._flush()
 
+    def _run_late(self):
+        """The deferred weight-norm backward (see exchange_last_layer), on the second stream, after everything the backward
+        pass has queued on the caller's stream so far (i.e. after its last GEMM)."""
+        if self._late is None:
+            return
+        fn, pv, pg, done = self._late
+        self._late = None
+        cur = torch.cuda.current_stream()
+        end = torch.cuda.Event()
+        end.record(cur)
+        self.comm2.wait_event(done)
+        self.comm2.wait_event(end)
+        with torch.cuda.stream(self.comm2), ops.no_pdl():
+            dv, dg = fn()
+        dv.record_stream(cur)
+        pv.grad = dv.view_as(pv)
+        if pg is not None and dg is not None:
+            dg.record_stream(cur)
+            pg.grad = dg.view_as(pg)
+
     def wait(self):
         """Join: later work on the current stream sees the averaged gradients."""
         self._flush()
+        self._run_late()
         self._seen = 0
         torch.cuda.current_stream().wait_stream(self.comm)
+        torch.cuda.current_stream().wait_stream(self.comm2)
         self._keep.clear()
 
     def remove(self):
