@@ -77,6 +77,8 @@ class GradAllReduce:
         self.comm = torch.cuda.Stream(priority=-1)
         self.comm2 = torch.cuda.Stream(priority=-1)
         self._late = None
+        self._late_used = False
+        self._narrow_done = None
         self._late_wn = os.environ.get("DMC_LATE_WN_BWD", "1") != "0"
         self._pending = []
         self._pending_bytes = 0
@@ -129,8 +131,7 @@ class GradAllReduce:
             self._flush()
 
     def _flush(self):
-        if self._seen >= len(self.params):
-            self._run_late()
+        final = self._seen >= len(self.params)
         if self._pending:
             if all(ev is not None for _, ev in self._pending):
                 for _, ev in self._pending:              # start as soon as the producing kernels are done
@@ -158,6 +159,9 @@ class GradAllReduce:
                 g.record_stream(self.comm)
             self._pending = []
             self._pending_bytes = 0
+        if final:
+            self._run_late()            # AFTER the last small exchange is queued: launched first, its CTAs would keep that
+                                        # exchange's tiny narrow kernel off the SMs for the whole pass (measured: +20 us)
         if self._seen >= len(self.params):
             self._seen = 0
 
@@ -195,6 +199,8 @@ class GradAllReduce:
         flat = buf.tensor
         views = [flat[o:o + g.numel()] for o, g in zip(offs, grads)]
         ops.narrow_bf16_into([g.view(-1) for g in grads], views)
+        self._narrow_done = torch.cuda.Event()
+        self._narrow_done.record()              # (current stream = the communication stream) see _run_late
         if _DEBUG:
             self._dbg("narrow launch", t0)
         world = dist.get_world_size(self.group)
@@ -304,11 +310,15 @@ class GradAllReduce:
             return
         fn, pv, pg, done = self._late
         self._late = None
+        self._late_used = True
         cur = torch.cuda.current_stream()
         end = torch.cuda.Event()
         end.record(cur)
         self.comm2.wait_event(done)
         self.comm2.wait_event(end)
+        if self._narrow_done is not None:       # let the last exchange's tiny narrow kernel onto the SMs first
+            self.comm2.wait_event(self._narrow_done)
+            self._narrow_done = None
         with torch.cuda.stream(self.comm2), ops.no_pdl():
             dv, dg = fn()
         dv.record_stream(cur)
@@ -323,7 +333,9 @@ class GradAllReduce:
         self._run_late()
         self._seen = 0
         torch.cuda.current_stream().wait_stream(self.comm)
-        torch.cuda.current_stream().wait_stream(self.comm2)
+        if self._late_used:
+            torch.cuda.current_stream().wait_stream(self.comm2)
+            self._late_used = False
         self._keep.clear()
 
     def remove(self):
