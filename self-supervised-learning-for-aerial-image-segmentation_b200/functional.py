@@ -246,13 +246,11 @@ class LinearFn(torch.autograd.Function):
         dW = db = d_in = None
         ctx.bias_grad_empty = ctx.bias_param is not None and ctx.bias_param.grad is None
         with ops.backward_cap():
-            d = Operand(d_full) if (mode == "bf16" and d_full.dtype == torch.bfloat16) else prep(d_full, mode)
-            if ctx.needs_input_grad[3]:
-                # wgrad: dW[fo,fi] = dz^T . h_in   (both operands MN-major straight from their row-major storage)
-                dW = mm(mode, d, ctx.h_op, fo, fi, rows, a_mn=True, b_mn=True, out_dtype=torch.float32, tag="gemm_mlp_wgrad")
-                ops.mark_ready(dW)
             region = None
             if ctx.has_bias and ctx.needs_input_grad[4]:
+                # bias gradient FIRST, forked before the wgrad is queued: it depends on dz only.  Forked after the wgrad it
+                # waited for that GEMM and then for SM space under the dgrad, so the LAST layer's bias gradient was the last
+                # gradient of the backward pass to become final -- and held back the final gradient exchange (8 GPUs: -30 us)
                 if aux_overlap:          # HBM-bound column sum next to the tensor-bound wgrad / dgrad of this layer
                     region = _AuxRegion(d_full.device)
                     with region:
@@ -261,6 +259,11 @@ class LinearFn(torch.autograd.Function):
                 else:
                     db = ops.colsum(d_full)
                     ops.mark_ready(db)
+            d = Operand(d_full) if (mode == "bf16" and d_full.dtype == torch.bfloat16) else prep(d_full, mode)
+            if ctx.needs_input_grad[3]:
+                # wgrad: dW[fo,fi] = dz^T . h_in   (both operands MN-major straight from their row-major storage)
+                dW = mm(mode, d, ctx.h_op, fo, fi, rows, a_mn=True, b_mn=True, out_dtype=torch.float32, tag="gemm_mlp_wgrad")
+                ops.mark_ready(dW)
             if ctx.z_in is not None:
                 # dgrad with gelu'(z_in) fused: what flows upstream is already dL/dz_in
                 d_in = mm(mode, d, ctx.w_op, rows, fi, fo, b_mn=True, out_dtype=sd, act=L.ACT_MUL_AUX if ctx.gelu_dg else L.ACT_GELU_BWD, aux=ctx.z_in,
