@@ -6,7 +6,8 @@
 // allocator maps every rank's buffer into every process and, on NVSwitch, also behind ONE multicast address).
 //
 // dmc_xrank_allreduce is a two-shot all-reduce written for that memory:
-//   barrier (all ranks' producers have finished)                                -- signal pads, CAS put / wait, per CTA
+//   barrier (all ranks' producers have finished)                                -- hierarchical: rank-local counter, then one
+//                                                                                  signal per rank pair on the signal pads
 //   shot 1: rank r reduces slice r of the buffer over all ranks
 //             multicast:  ONE multimem.ld_reduce per 16 bytes -- the NVSwitch adds the 8 ranks' values in flight
 //             peer-to-peer fallback: W-1 remote 16-byte loads + local adds
@@ -69,14 +70,46 @@ __device__ __forceinline__ void wait_signal(uint32_t* addr) {
   asm volatile("st.global.relaxed.sys.b32 [%0], %1;" :: "l"(addr), "r"(0u) : "memory");
 }
 
-// All CTAs with the same blockIdx on every rank meet.  Slot layout of a pad: [channel][block][sender rank].
-__device__ __forceinline__ void block_barrier(const XrankArgs& a, int channel) {
+// Barrier over ALL CTAs of ALL ranks, hierarchical: the CTAs of a rank meet at a rank-local counter (cheap local atomics);
+// the LAST one to arrive exchanges ONE signal with every peer (threads 0..world-1 in parallel: put at the peer's pad, wait at
+// the own pad) and then releases its rank's CTAs through a generation word.  Remote atomics per barrier and rank: `world`
+// instead of `ctas x world` -- with one signal per CTA pair the 1.6 MB exchange at the end of the step took 47-67 us at 8 GPUs
+// (1184 remote CAS into each GPU's signal pad per barrier), i.e. it was all barrier.  Needs every CTA of the kernel resident
+// (<= 148 CTAs of 256 threads / 32 registers: true next to a GEMM as well).  Self-resetting, reusable launch after launch.
+// Pad layout (32-bit words): [channel 0..1][sender rank 0..world-1] signals, then [channel 0..1]{counter, generation}.
+__device__ __forceinline__ void rank_barrier(const XrankArgs& a, int channel) {
+  __shared__ uint32_t s_last;
+  uint32_t* own = a.pads[a.rank];
+  uint32_t* ctr = own + 2 * a.world + 2 * channel;
+  uint32_t* gen = ctr + 1;
   __syncthreads();
-  if (threadIdx.x < static_cast<unsigned>(a.world)) {
-    const int peer = threadIdx.x;
-    const long long slot = (static_cast<long long>(channel) * gridDim.x + blockIdx.x) * a.world;
-    put_signal(a.pads[peer] + slot + a.rank);        // tell `peer` that this rank's CTA got here
-    wait_signal(a.pads[a.rank] + slot + peer);       // ... and wait for `peer`'s CTA
+  uint32_t g0 = 0;
+  if (threadIdx.x == 0) {
+    uint32_t old;
+    asm volatile("ld.global.acquire.gpu.b32 %0, [%1];" : "=r"(g0) : "l"(gen) : "memory");
+    asm volatile("atom.global.acq_rel.gpu.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(ctr) : "memory");
+    s_last = (old == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last) {                                   // uniform per CTA
+    if (threadIdx.x < static_cast<unsigned>(a.world)) {
+      const int peer = threadIdx.x;
+      put_signal(a.pads[peer] + channel * a.world + a.rank);     // this rank has arrived
+      wait_signal(own + channel * a.world + peer);               // ... and so has `peer`
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("st.global.relaxed.gpu.b32 [%0], %1;" :: "l"(ctr), "r"(0u) : "memory");
+      asm volatile("st.global.release.gpu.b32 [%0], %1;" :: "l"(gen), "r"(g0 + 1u) : "memory");
+    }
+  } else if (threadIdx.x == 0) {
+    uint32_t g1;
+    long long spins = 0;
+    do {
+      __nanosleep(64);
+      asm volatile("ld.global.acquire.gpu.b32 %0, [%1];" : "=r"(g1) : "l"(gen) : "memory");
+      if (++spins > (1ll << 27)) __trap();        // a rank never arrived: fail loudly instead of hanging the box
+    } while (g1 == g0);
   }
   __syncthreads();
 }
@@ -123,7 +156,7 @@ __global__ void __launch_bounds__(kXThreads, 8)   // <= 32 registers: 8 warps x 
 xrank_allreduce_kernel(const XrankArgs a) {
   pdl_prologue();
   const bool bf16 = a.is_bf16 != 0;
-  block_barrier(a, 0);                       // every rank's producer kernels precede this kernel in its stream: data is final
+  rank_barrier(a, 0);                        // every rank's producer kernels precede this kernel in its stream: data is final
   // slice of this rank, in 16-byte vectors
   const long long per = (a.n_vec + a.world - 1) / a.world;
   const long long v0 = min(per * a.rank, a.n_vec), v1 = min(v0 + per, a.n_vec);
@@ -168,34 +201,9 @@ xrank_allreduce_kernel(const XrankArgs a) {
     }
   }
   __threadfence_system();                    // this CTA's remote stores are visible before it signals
-  block_barrier(a, 1);                       // CTA b of every rank has finished its part of every slice
-  // epilogue: widen the bf16 buffer into fp32 tensors (gradients exchanged in bf16 -> fp32 .grad).  block_barrier only pairs
-  // CTA b with the CTAs b of the other ranks, but the epilogue reads what ALL remote CTAs wrote: first a rank-local grid
-  // barrier -- once every local CTA has passed barrier 1, every remote CTA has arrived at it, i.e. all slices are complete.
-  // (Measured without it: wrong gradients on one rank as soon as the kernel ran with 16 or 32 CTAs instead of 148.)
-  // Sense-reversing counter in the local signal pad: self-resetting, reusable launch after launch.
+  rank_barrier(a, 1);                        // every CTA of every rank has finished: all slices have landed in every buffer
+  // epilogue: widen the (now complete) bf16 buffer into fp32 tensors (gradients exchanged in bf16 -> fp32 .grad)
   if (a.n_out > 0) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t* ctr = a.pads[a.rank] + 2ll * gridDim.x * a.world;
-      uint32_t* gen = ctr + 1;
-      uint32_t g0, old;
-      asm volatile("ld.global.acquire.gpu.b32 %0, [%1];" : "=r"(g0) : "l"(gen) : "memory");
-      asm volatile("atom.global.acq_rel.gpu.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(ctr) : "memory");
-      if (old == gridDim.x - 1) {
-        asm volatile("st.global.relaxed.gpu.b32 [%0], %1;" :: "l"(ctr), "r"(0u) : "memory");
-        asm volatile("st.global.release.gpu.b32 [%0], %1;" :: "l"(gen), "r"(g0 + 1u) : "memory");
-      } else {
-        uint32_t g1;
-        long long spins = 0;
-        do {
-          __nanosleep(128);
-          asm volatile("ld.global.acquire.gpu.b32 %0, [%1];" : "=r"(g1) : "l"(gen) : "memory");
-          if (++spins > (1ll << 26)) __trap();
-        } while (g1 == g0);
-      }
-    }
-    __syncthreads();
     const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(a.peers[a.rank]);
     for (int t = 0; t < a.n_out; ++t) {
       const __nv_bfloat16* s = src + a.out_off[t];
@@ -225,7 +233,8 @@ using namespace dmc;
 
 extern "C" size_t dmc_xrank_signal_bytes(int32_t world, int32_t ctas) {
   if (world <= 0 || ctas <= 0) return 0;
-  return (static_cast<size_t>(2) * ctas * world + 2) * sizeof(uint32_t);      // + the local grid barrier's counter and generation
+  (void)ctas;
+  return (static_cast<size_t>(2) * world + 4) * sizeof(uint32_t);      // two channels of per-rank signals + {counter, generation} each
 }
 
 extern "C" int dmc_xrank_allreduce(void* multicast_ptr, void* const* peer_ptrs_host, void* const* signal_pads_host, int64_t numel,
