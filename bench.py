@@ -87,13 +87,15 @@ def op_models(w, P, e):
         "ce_fused": (e * K * (2 * Ns + Nt), 0), "ce_bwd": (e * K * (2 * Ns + Nt), 0), "ce_fwd": (e * K * (Ns + Nt), 0),
         "teacher_stats_colsum": (e * K * Nt, 0),
         # EMA (+ the teacher's operand shadows it emits)
-        "ema": (12 * P, 0),
+        "ema": (12 * P + (2 * (mlp_w + K * BN) + 8 * K if e == 2 else 0), 0),   # + the teacher's bf16 operand shadows (bf16 mode)
         # last layer
         "gemm_last_fwd_student": (e * K * Ns + 2 * BN * (K + Ns), f_last(Ns)),
         "gemm_last_fwd_teacher": (e * K * Nt + 2 * BN * (K + Nt), f_last(Nt)),
-        "gemm_last_wgrad": (e * K * Ns + 2 * BN * Ns + 4 * K * BN, f_last(Ns)),
+        "gemm_last_wgrad": (e * K * Ns + 2 * BN * Ns + (2 if e == 2 else 4) * K * BN, f_last(Ns)),     # dW stored bf16 in the bf16 mode
         "gemm_last_dgrad": (e * K * Ns + 2 * K * BN + 4 * BN * Ns, f_last(Ns)),
-        "weightnorm_fwd": ((4 + e) * K * BN, 0), "weightnorm_bwd": (12 * K * BN, 0),
+        "weightnorm_fwd": ((4 + e) * K * BN, 0),                 # student only: the teacher's operand comes out of the EMA pass
+        "weightnorm_bwd": ((8 + (2 if e == 2 else 4)) * K * BN, 0),
+        "xrank_allreduce": (2 * (K * BN + mlp_w), 0),           # N > 1: bf16 dW + the small gradients, once over NVLink each way
         # MLP (bf16 operands / activations, fp32 weight gradients)
         "gemm_mlp_fwd": (2 * (act(Ns) + act(Nt)) + 2 * 2 * mlp_w, f_mlp(Ns) + f_mlp(Nt)),
         "gemm_mlp_dgrad": (2 * 2 * act(Ns) + 2 * mlp_w, f_mlp(Ns)),
@@ -596,10 +598,23 @@ def main():
     peaks = load_peaks()
     prof_steps = min(args.steps, 10)
     prof_us, timing = {}, "cupti"
+    # Profiled with the auxiliary / side streams OFF: every kernel then runs alone on one stream, so its CUPTI duration is its
+    # own (with the overlaps on, co-running kernels inflate each other's durations and the split would be meaningless).
+    Fn = D.functional
+    saved = (Fn.aux_overlap, D.head._teacher_overlap, D.head._early_teacher_stats)
+    Fn.aux_overlap = False
+    D.set_teacher_overlap(False)
+    D.head.set_early_teacher_stats(False)
     try:
+        step.run()
+        torch.cuda.synchronize()
         prof_us = ops.profile_kernels(step.run, prof_steps)                      # {op: (us per step, kernels per step)}
     except Exception as e:              # noqa: BLE001
         print(f"[rank {rank}] profile_kernels failed ({type(e).__name__}: {e}); using CUDA events", file=sys.stderr)
+    finally:
+        Fn.aux_overlap = saved[0]
+        D.set_teacher_overlap(saved[1])
+        D.head.set_early_teacher_stats(saved[2])
     if not prof_us:
         timing = "cuda_events"
         ev = per_kernel_times(step, prof_steps)
@@ -632,7 +647,8 @@ def main():
     if dom is not None:
         roofline = {"bound": dom["bound"], "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": dom["peak"],
                     "unit": dom["unit"], "frac": dom["frac"], "traffic": dom["traffic"], "peak_source": peaks["source"],
-                    "timing": timing + " kernel durations over eager steps, all launches of the op per step",
+                    "timing": timing + " kernel durations (CUPTI activity records, kernels serialised on one stream: auxiliary-stream overlaps off "
+                                       "for this pass), all launches of the op per step; the timed `value` runs with the overlaps on",
                     "step": {"t_roof_ms": t_roof_ms, "alg_GB": nbytes / 1e9, "alg_GFLOP": flops / 1e9,
                              "frac_of_step_roofline": t_roof_ms / ms_step},
                     "kernels": kernels}

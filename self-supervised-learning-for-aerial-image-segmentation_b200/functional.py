@@ -218,7 +218,11 @@ class LinearFn(torch.autograd.Function):
         if w_op is None:
             w_op = prep(W.detach(), mode)
         bias = None if b is None else b.detach().float().contiguous()
-        if apply_gelu:
+        if apply_gelu and not any(ctx.needs_input_grad):
+            # no autograd graph (the teacher): nothing is saved for a backward pass -- plain GELU epilogue, no second output
+            z_out = h_in.new_empty(0)
+            h_out = mm(mode, h_op, w_op, rows, fo, fi, out_dtype=sd, bias=bias, act=L.ACT_GELU, tag="gemm_mlp_fwd")
+        elif apply_gelu:
             z_out = torch.empty((rows, fo), dtype=sd, device=h_in.device)
             # with `gelu_dg` the epilogue saves gelu'(z) instead of z (same bytes): the backward epilogue becomes a multiply
             h_out = mm(mode, h_op, w_op, rows, fo, fi, out_dtype=sd, bias=bias, act=L.ACT_GELU_DG if gelu_dg else L.ACT_GELU,
