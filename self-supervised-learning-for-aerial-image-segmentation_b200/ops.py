@@ -40,8 +40,15 @@ class backward_cap:
         return False
 
 
+track_ready = False      # set by an active GradAllReduce: without a consumer no events are recorded (nothing would pop them)
+
+
 def mark_ready(t: torch.Tensor):
-    """Record "this buffer is final" on the current stream (see ready_events)."""
+    """Record "this buffer is final" on the current stream (see ready_events).  No-op unless a gradient exchange is active;
+    the exchange pops an entry when it takes the gradient and clears the table at the end of its step (`GradAllReduce.wait`),
+    so an entry never outlives the step that recorded it."""
+    if not track_ready:
+        return
     ev = torch.cuda.Event()
     ev.record()
     if len(ready_events) > 64:

@@ -40,6 +40,10 @@ if os.environ.get("DMC_REDUCER_FLUSH_MB"):      # env: timing experiments only
 
 
 class GradAllReduce:
+    """One instance per model and process.  Not supported: gradient accumulation over several backward passes before `wait()`
+    (a gradient already sitting in `.grad` would be averaged again) -- call `wait()` and consume / clear the gradients after
+    every backward pass, as main_dino_mc.py does."""
+
     def __init__(self, params, group=None, reserve_sms: int = 16, compress=None, transport="nccl"):
         """transport = "nccl": torch.distributed all-reduces (fp32, or bf16 with compress="bf16").
         transport = "peer": the bf16 exchange runs on libdinomc's own NVLink / NVSwitch all-reduce kernel over symmetric
@@ -91,6 +95,7 @@ class GradAllReduce:
         from . import functional
         functional.grad_exchange_active = os.environ.get("DMC_REDUCER_AUXWN", "") != "1"      # env: timing experiments only
         functional.grad_exchange = self
+        ops.track_ready = True
         # early-launched (PDL) GEMM CTAs hold SMs while they wait for their predecessor, which delays the NCCL kernels
         # that share the machine: measured 0.992 -> 0.969 ms per step at 2 GPUs without it
         from . import _lib
@@ -337,6 +342,7 @@ class GradAllReduce:
             torch.cuda.current_stream().wait_stream(self.comm2)
             self._late_used = False
         self._keep.clear()
+        ops.ready_events.clear()         # every gradient of this step has been taken: nothing recorded so far is still needed
 
     def remove(self):
         for h in self._handles:
@@ -347,4 +353,6 @@ class GradAllReduce:
         functional.grad_exchange_active = False
         if functional.grad_exchange is self:
             functional.grad_exchange = None
+            ops.track_ready = False
+            ops.ready_events.clear()
         _lib.load().dmc_set_pdl(self._pdl_prev)
