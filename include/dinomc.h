@@ -326,11 +326,13 @@ int dmc_lars_multi_tensor(const void* plan_dev, int64_t n_chunks, double lr, dou
  * ._symmetric_memory provides all three, plus one zero-initialised signal pad per rank of at least
  * dmc_xrank_signal_bytes(world, ctas) bytes).  In place, on every rank: buffer <- scale * sum_ranks buffer (two-shot:
  * rank r reduces slice r -- one multimem.ld_reduce per 16 bytes with a multicast address, else world-1 peer loads --
- * and broadcasts it -- one multimem.st, else world-1 peer stores), framed by two cross-rank barriers on the signal pads.
+ * and broadcasts it -- one multimem.st, else world-1 peer stores), framed by two barriers over all CTAs of all ranks (rank-local
+ * counter, then one signal per rank pair on the signal pads).
  * BF16 buffers are summed in fp32 and rounded once.  Optional epilogue (n_out > 0, BF16 only): widen element ranges of
  * the finished buffer into fp32 tensors (out_ptrs_host[i][0..n) <- buffer[off..off+n), off % 8 == 0).
  * All ranks must call it with the same numel / dtype / ctas, in the same order per signal pad.  ctas x 256 threads,
- * <= 40 registers, no shared memory: with ctas = 148 one CTA per SM, co-resident with a tcgen05 GEMM CTA. */
+ * 32 registers, 4 bytes of shared memory: with ctas = 148 one CTA per SM, co-resident with a tcgen05 GEMM CTA.  Every CTA of a
+ * launch must be resident at the same time (the barrier is grid-wide per rank): keep ctas <= 148. */
 size_t dmc_xrank_signal_bytes(int32_t world, int32_t ctas);
 int dmc_xrank_allreduce(void* multicast_ptr, void* const* peer_ptrs_host, void* const* signal_pads_host, int64_t numel,
                         int32_t dtype, int32_t rank, int32_t world, float scale, int32_t ctas, int32_t n_out,

@@ -50,7 +50,7 @@ class GradAllReduce:
         memory (xrank.SymmetricBuffer; needs compress="bf16"): the last layer's wgrad GEMM writes dW straight into a
         symmetric buffer, ONE kernel averages it over the ranks (multimem.ld_reduce / multimem.st through the switch),
         the weight-norm backward runs on the average; the small gradients travel as one flat bf16 buffer whose all-reduce
-        kernel also widens the result back into the fp32 .grad tensors.  The kernel is one 256-thread, <= 40-register
+        kernel also widens the result back into the fp32 .grad tensors.  The kernel is one 256-thread, 32-register
         CTA per SM: it is co-resident with the backward GEMMs, so no SMs are reserved."""
         if compress not in (None, "bf16"):
             raise ValueError(f"GradAllReduce: compress must be None or 'bf16', got {compress!r}")
@@ -111,6 +111,10 @@ class GradAllReduce:
             return
         g = p.grad
         self._seen += 1
+        if g is None:                   # the hook also fires for a parameter that received no gradient in this pass
+            if self._seen == len(self.params):
+                self._flush()
+            return
         skip = os.environ.get("DMC_REDUCER_SKIP", "")       # timing experiments only: "big" / "small"
         big = g.numel() * g.element_size() >= _BIG
         if (skip == "big" and big) or (skip == "small" and not big) or skip == "all":
