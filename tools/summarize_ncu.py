@@ -34,7 +34,7 @@ def launches(src, dst):
         v = float(r[ival].replace(",", ""))
         v = v / 1000.0 if r[iunit] == "ns" else v
         seq.append((clean(r[iname]), v, r[ig]))
-    idx = [i for i, (n, _, _) in enumerate(seq) if n.startswith("ema_kernel")]
+    idx = [i for i, (n, _, _) in enumerate(seq) if n.startswith("ema_kernel") or n.startswith("ema2_kernel")]
     a, b = idx[-3] + 1, idx[-2] + 1
     step = seq[a:b]
     tot = sum(v for _, v, _ in step)
