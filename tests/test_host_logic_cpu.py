@@ -1,0 +1,84 @@
+"""CPU: host-side logic added in round 2 that needs no device -- which teacher tensors get operand shadows in the EMA plan,
+the stand-in metric logger of the drop-in training step, the reference arm's bookkeeping in bench.py."""
+import types
+
+import pytest
+import torch
+
+
+def _teacher():
+    import dinomc_b200 as D
+    t = D.DINOHead(24, 256, nlayers=3, hidden_dim=32, bottleneck_dim=16)
+    for p in t.parameters():
+        p.requires_grad = False
+    return t
+
+
+def _fake_shadow(t):
+    lins = t._linears()
+    K, dim = t.last_layer.weight_v.shape
+    t._shadow = dict(device=torch.device("cpu"), state=None, weights=[lin.weight for lin in lins],
+                     mlp=[torch.empty(lin.weight.shape, dtype=torch.bfloat16) for lin in lins],
+                     what=torch.empty((K, dim), dtype=torch.bfloat16), scale=torch.empty(K), inv_norm=torch.empty(K))
+
+
+def test_shadow_spec_maps_head_tensors_to_their_position_in_the_ema_list():
+    from dinomc_b200 import ema
+    t = _teacher()
+    _fake_shadow(t)
+    ema.register_shadow_head(t)
+    backbone = [torch.zeros(7), torch.zeros(3, 3)]                    # EMA list = backbone parameters first, then the head
+    tp = backbone + [p.data for p in t.parameters()]
+    shadows, wn, heads = ema._shadow_spec(tp)
+    assert heads == [t]
+    names = [n for n, _ in t.named_parameters()]
+    off = len(backbone)
+    assert sorted(shadows) == [off + names.index(n) for n in ("mlp.0.weight", "mlp.2.weight", "mlp.4.weight")]
+    assert wn[0] == off + names.index("last_layer.weight_v") and wn[1] == off + names.index("last_layer.weight_g")
+    assert wn[2] == 16 and wn[3] is t._shadow["what"]
+    # a list that lacks part of the head gets no shadows at all (the plan must never write a half-updated operand set)
+    shadows, wn, heads = ema._shadow_spec(tp[:-1])
+    assert shadows == {} and wn is None and heads == []
+
+
+def test_shadow_freshness_follows_parameter_versions():
+    t = _teacher()
+    _fake_shadow(t)
+    t._mark_shadow_fresh()
+    assert t._shadow["state"] == t._shadow_state()
+    with torch.no_grad():
+        t.last_layer.weight_v.mul_(2.0)                               # any foreign write bumps _version
+    assert t._shadow["state"] != t._shadow_state()
+    x = torch.zeros(2, 24)
+    assert t._is_inference(x)                                         # frozen parameters, input without gradient: no no_grad needed
+    assert not t._is_inference(x.requires_grad_(True))
+    with torch.no_grad():
+        assert t._is_inference(x)
+
+
+def test_plain_meters_and_train_loop_argument_checks():
+    from dinomc_b200 import dropin
+    m = dropin._PlainMeters()
+    m.update(loss=1.0, lr=0.1)
+    m.update(loss=3.0)
+    assert m.meters["loss"].global_avg == 2.0 and m.meters["lr"].global_avg == pytest.approx(0.1)
+    assert list(m.log_every([1, 2, 3], 10, "x")) == [1, 2, 3]
+    assert "loss" in str(m)
+    with pytest.raises(ValueError, match="host_sync"):
+        dropin.train_one_epoch(None, None, None, None, [], None, None, None, None, 0, None, types.SimpleNamespace(epochs=1),
+                               host_sync="sometimes")
+
+
+def test_bench_op_models_cover_the_profiled_ops_and_the_step_model():
+    import bench
+    w = bench.WORKLOADS["cfg2"]
+    models = bench.op_models(w, 44_020_000, 2)
+    for tag in ("ce_fused", "ema", "gemm_last_fwd_student", "gemm_last_wgrad", "gemm_last_dgrad", "gemm_mlp_fwd", "gemm_mlp_dgrad",
+                "gemm_mlp_wgrad", "weightnorm_fwd", "weightnorm_bwd", "teacher_stats_colsum", "cast_bf16", "colsum", "xrank_allreduce"):
+        b, f = models[tag]
+        assert b > 0 and f >= 0, tag
+    flops, nbytes = bench.roofline_model(w, 44_020_000, 2)
+    assert abs(flops / 1e9 - 296.6) < 0.5 and abs(nbytes / 2 ** 30 - 2.88) < 0.01         # SURVEY 8d worked numbers for cfg2
+    # the GEMM ops of the step add up to the step model's flops
+    gemm = sum(models[t][1] for t in models if t.startswith("gemm_"))
+    assert abs(gemm - flops) / flops < 1e-9
