@@ -82,7 +82,7 @@ def op_models(w, P, e):
     f_mlp = lambda n: 2 * n * mlp_w
     f_last = lambda n: 2 * n * BN * K
     act = lambda n: n * (D + 2 * H + BN)                # activation elements of one head forward
-    return {
+    m = {
         # loss
         "ce_fused": (e * K * (2 * Ns + Nt), 0), "ce_bwd": (e * K * (2 * Ns + Nt), 0), "ce_fwd": (e * K * (Ns + Nt), 0),
         "teacher_stats_colsum": (e * K * Nt, 0),
@@ -96,14 +96,24 @@ def op_models(w, P, e):
         "weightnorm_fwd": ((4 + e) * K * BN, 0),                 # student only: the teacher's operand comes out of the EMA pass
         "weightnorm_bwd": ((8 + (2 if e == 2 else 4)) * K * BN, 0),
         "xrank_allreduce": (2 * (K * BN + mlp_w), 0),           # N > 1: bf16 dW + the small gradients, once over NVLink each way
-        # MLP (bf16 operands / activations, fp32 weight gradients)
-        "gemm_mlp_fwd": (2 * (act(Ns) + act(Nt)) + 2 * 2 * mlp_w, f_mlp(Ns) + f_mlp(Nt)),
-        "gemm_mlp_dgrad": (2 * 2 * act(Ns) + 2 * mlp_w, f_mlp(Ns)),
-        "gemm_mlp_wgrad": (2 * 2 * act(Ns) + 4 * mlp_w, f_mlp(Ns)),
         "cast_bf16": (6 * (Ns * D + Nt * D + mlp_w), 0),
         "colsum": (2 * Ns * (2 * H + BN), 0),
         "normalize_fwd": (10 * BN * (Ns + Nt), 0), "normalize_bwd": (12 * BN * Ns, 0),
     }
+
+    def add(tag, nbytes, flops):            # D == H (ResNet-50 features): the first two Linears share a tag -- their models add up
+        b0, f0 = m.get(tag, (0, 0))
+        m[tag] = (b0 + nbytes, f0 + flops)
+
+    # MLP, one op per Linear (in x out) -- bf16 operands / activations, fp32 weight gradients; student + teacher forward; the
+    # hidden layers' forward also writes gelu'(z) for the backward (student rows), their dgrad reads it
+    for li, (fi, fo) in enumerate(((D, H), (H, H), (H, BN))):
+        out_b = 2 if li < 2 else 4                     # the bottleneck output (input of F.normalize) is stored fp32
+        add(f"gemm_mlp_fwd_{fi}x{fo}", (Ns + Nt) * (2 * fi + out_b * fo) + (2 * Ns * fo if li < 2 else 0) + 2 * 2 * fi * fo, 2 * (Ns + Nt) * fi * fo)
+        din_b = 2 if li > 0 else 4                     # the gradient of the features leaves in fp32
+        add(f"gemm_mlp_dgrad_{fi}x{fo}", Ns * (2 * fo + din_b * fi) + (2 * Ns * fi if li > 0 else 0) + 2 * fi * fo, 2 * Ns * fi * fo)
+        add(f"gemm_mlp_wgrad_{fi}x{fo}", 2 * Ns * (fi + fo) + 4 * fi * fo, 2 * Ns * fi * fo)
+    return m
 
 
 def load_peaks():

@@ -221,14 +221,14 @@ class LinearFn(torch.autograd.Function):
         if apply_gelu and not any(ctx.needs_input_grad):
             # no autograd graph (the teacher): nothing is saved for a backward pass -- plain GELU epilogue, no second output
             z_out = h_in.new_empty(0)
-            h_out = mm(mode, h_op, w_op, rows, fo, fi, out_dtype=sd, bias=bias, act=L.ACT_GELU, tag="gemm_mlp_fwd")
+            h_out = mm(mode, h_op, w_op, rows, fo, fi, out_dtype=sd, bias=bias, act=L.ACT_GELU, tag=f"gemm_mlp_fwd_{fi}x{fo}")
         elif apply_gelu:
             z_out = torch.empty((rows, fo), dtype=sd, device=h_in.device)
             # with `gelu_dg` the epilogue saves gelu'(z) instead of z (same bytes): the backward epilogue becomes a multiply
             h_out = mm(mode, h_op, w_op, rows, fo, fi, out_dtype=sd, bias=bias, act=L.ACT_GELU_DG if gelu_dg else L.ACT_GELU,
-                       aux=z_out, tag="gemm_mlp_fwd")
+                       aux=z_out, tag=f"gemm_mlp_fwd_{fi}x{fo}")
         else:
-            h_out = mm(mode, h_op, w_op, rows, fo, fi, out_dtype=torch.float32, bias=bias, tag="gemm_mlp_fwd")
+            h_out = mm(mode, h_op, w_op, rows, fo, fi, out_dtype=torch.float32, bias=bias, tag=f"gemm_mlp_fwd_{fi}x{fo}")
             z_out = h_out.new_empty(0)
         ctx.mode, ctx.dims = mode, (rows, fo, fi)
         ctx.gelu_dg = gelu_dg               # what THIS layer's z_out holds; the consumer layer reads it from its own ctx.z_in_is_dg
@@ -266,14 +266,14 @@ class LinearFn(torch.autograd.Function):
             d = Operand(d_full) if (mode == "bf16" and d_full.dtype == torch.bfloat16) else prep(d_full, mode)
             if ctx.needs_input_grad[3]:
                 # wgrad: dW[fo,fi] = dz^T . h_in   (both operands MN-major straight from their row-major storage)
-                dW = mm(mode, d, ctx.h_op, fo, fi, rows, a_mn=True, b_mn=True, out_dtype=torch.float32, tag="gemm_mlp_wgrad")
+                dW = mm(mode, d, ctx.h_op, fo, fi, rows, a_mn=True, b_mn=True, out_dtype=torch.float32, tag=f"gemm_mlp_wgrad_{fi}x{fo}")
                 ops.mark_ready(dW)
             if ctx.z_in is not None:
                 # dgrad with gelu'(z_in) fused: what flows upstream is already dL/dz_in
                 d_in = mm(mode, d, ctx.w_op, rows, fi, fo, b_mn=True, out_dtype=sd, act=L.ACT_MUL_AUX if ctx.gelu_dg else L.ACT_GELU_BWD, aux=ctx.z_in,
-                          tag="gemm_mlp_dgrad")
+                          tag=f"gemm_mlp_dgrad_{fi}x{fo}")
             elif ctx.needs_input_grad[1]:
-                d_in = mm(mode, d, ctx.w_op, rows, fi, fo, b_mn=True, out_dtype=torch.float32, tag="gemm_mlp_dgrad")
+                d_in = mm(mode, d, ctx.w_op, rows, fi, fo, b_mn=True, out_dtype=torch.float32, tag=f"gemm_mlp_dgrad_{fi}x{fo}")
             if region is not None:
                 if ctx.bias_grad_empty:              # only AccumulateGrad consumes db, and only to store it
                     with torch.cuda.stream(region.aux):

@@ -73,8 +73,9 @@ def test_bench_op_models_cover_the_profiled_ops_and_the_step_model():
     import bench
     w = bench.WORKLOADS["cfg2"]
     models = bench.op_models(w, 44_020_000, 2)
-    for tag in ("ce_fused", "ema", "gemm_last_fwd_student", "gemm_last_wgrad", "gemm_last_dgrad", "gemm_mlp_fwd", "gemm_mlp_dgrad",
-                "gemm_mlp_wgrad", "weightnorm_fwd", "weightnorm_bwd", "teacher_stats_colsum", "cast_bf16", "colsum", "xrank_allreduce"):
+    for tag in ("ce_fused", "ema", "gemm_last_fwd_student", "gemm_last_wgrad", "gemm_last_dgrad", "gemm_mlp_fwd_384x2048",
+                "gemm_mlp_fwd_2048x2048", "gemm_mlp_dgrad_2048x256", "gemm_mlp_wgrad_2048x2048", "weightnorm_fwd", "weightnorm_bwd",
+                "teacher_stats_colsum", "cast_bf16", "colsum", "xrank_allreduce"):
         b, f = models[tag]
         assert b > 0 and f >= 0, tag
     flops, nbytes = bench.roofline_model(w, 44_020_000, 2)
