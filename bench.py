@@ -615,6 +615,10 @@ def main():
     Fn.aux_overlap = False
     D.set_teacher_overlap(False)
     D.head.set_early_teacher_stats(False)
+    # ... and WITHOUT programmatic dependent launch: a PDL kernel becomes resident while its predecessor still runs and sits in
+    # griddepcontrol.wait, and CUPTI counts that wait as part of its duration (profiles/r02_timeline_1gpu.txt: the 3 us
+    # center_update shows as 17 us, the last layer's dgrad as 91 us for 62 us of work)
+    pdl_prev = D._lib.load().dmc_set_pdl(0)
     try:
         step.run()
         torch.cuda.synchronize()
@@ -622,6 +626,7 @@ def main():
     except Exception as e:              # noqa: BLE001
         print(f"[rank {rank}] profile_kernels failed ({type(e).__name__}: {e}); using CUDA events", file=sys.stderr)
     finally:
+        D._lib.load().dmc_set_pdl(pdl_prev)
         Fn.aux_overlap = saved[0]
         D.set_teacher_overlap(saved[1])
         D.head.set_early_teacher_stats(saved[2])
@@ -651,14 +656,18 @@ def main():
                 k["achieved"], k["peak"], k["unit"] = f / 1e12 / (us * 1e-6), peaks["bf16_tflops"], "TFLOP/s"
             k["frac"] = k["achieved"] / k["peak"]
             k["traffic"] = traffic_db.get(name)
+            if name == "xrank_allreduce":
+                # its duration contains two cross-rank barriers, i.e. the wait for the slowest rank's gradients (in this eager,
+                # profiler-instrumented pass: milliseconds of host skew) -- not a bandwidth figure, never the roofline kernel
+                k["note"] = "duration includes waiting for the other ranks at its barriers; not a bandwidth measurement"
         kernels.append(k)
-    dom = next((k for k in kernels if "frac" in k), None)           # largest time share
+    dom = next((k for k in kernels if "frac" in k and "note" not in k), None)           # largest time share
     roofline = None
     if dom is not None:
         roofline = {"bound": dom["bound"], "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": dom["peak"],
                     "unit": dom["unit"], "frac": dom["frac"], "traffic": dom["traffic"], "peak_source": peaks["source"],
                     "timing": timing + " kernel durations (CUPTI activity records, kernels serialised on one stream: auxiliary-stream overlaps off "
-                                       "for this pass), all launches of the op per step; the timed `value` runs with the overlaps on",
+                                       "and programmatic dependent launch off for this pass), all launches of the op per step; the timed `value` runs with both on",
                     "step": {"t_roof_ms": t_roof_ms, "alg_GB": nbytes / 1e9, "alg_GFLOP": flops / 1e9,
                              "frac_of_step_roofline": t_roof_ms / ms_step},
                     "kernels": kernels}
