@@ -123,10 +123,14 @@ class DINOLoss(nn.Module):
                                       and t_pre["center_version"] == self.center._version
                                       and (t_pre["row_partials"].shape[0] if t_pre["kind"] == "teacher" else t_pre["rows"]) == t.shape[0]):
             t_pre = None
-        if t_pre is not None and t_pre["kind"] == "teacher_final":
+        if t_pre is not None:
+            # the statistics may have been allocated on another stream (side-stream statistics pass, or a teacher head that
+            # ran on the overlap stream): tell the caching allocator that this stream reads them too
             cur = torch.cuda.current_stream()
-            t_pre["t_stats"].record_stream(cur)
-            t_pre["colsum"].record_stream(cur)
+            for key in ("t_stats", "colsum", "row_partials", "colsum_partials"):
+                buf = t_pre.get(key)
+                if buf is not None:
+                    buf.record_stream(cur)
         self._last_inv_tt = inv_tt
         Fn.register_loss(self)
         loss, colsum = Fn.DinoLossFn.apply(s, t, self.center, inv_ts, inv_tt, B, C, G, s_pre, t_pre)
