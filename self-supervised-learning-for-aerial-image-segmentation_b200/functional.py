@@ -20,8 +20,13 @@ MODES = ("bf16", "fp32", "fp32_simt")
 # Fused logit statistics.  The last-layer GEMM can emit, from its epilogue, the softmax statistics DINOLoss
 # needs (student log-sum-exp partials; teacher softmax partials + column sums), which removes the loss's own
 # statistics passes over the logits.  The head does not know the temperatures or the center -- they belong to
-# DINOLoss -- so the most recently used DINOLoss registers itself here (weak reference) and the head asks it.
-# Everything is validated again inside DINOLoss.forward; on any mismatch the separate passes run instead.
+# DINOLoss.  A head learns which DINOLoss its logits go to either explicitly (`DINOHead.bind_loss(loss)`) or, for code
+# that constructs heads and loss independently and never connects them (main_dino_mc.py:236-270 -- the drop-in case),
+# from the default below: the most recently constructed / used DINOLoss registers itself here (weak reference).  The
+# head passes the module it resolved to NormLastLayerFn as an argument and gets the statistics record back through the
+# same argument: the autograd Functions themselves read no module-level state for this.  Everything is validated again
+# inside DINOLoss.forward (temperature, center identity and version, row count, tensor identity); on any mismatch the
+# separate passes run instead, so a wrong guess costs time, never correctness.
 # ---------------------------------------------------------------------------------------------------------
 import os as _os0
 import weakref
@@ -34,8 +39,7 @@ fused_teacher_stats = False   # teacher row statistics + column sums from the GE
                               # (step 0.810 ms against 0.796 ms: the center subtraction, the running maximum and the column
                               # sums weigh on an epilogue with two warps per scheduler), so off by default; the student's
                               # log-sum-exp partials are always fused
-_loss_ref = None          # weakref to the DINOLoss whose temperatures / center the heads should use
-last_stats = None         # stats record of the most recent NormLastLayerFn.forward (picked up by DINOHead)
+_loss_ref = None          # weakref: the DEFAULT DINOLoss of heads without an explicit bind_loss()
 
 
 def register_loss(loss_module):
@@ -319,10 +323,14 @@ def mlp_forward(mode, x, wb, w_ops=None, after_first_gemm=None):
 
 class NormLastLayerFn(torch.autograd.Function):
     """F.normalize -> weight_norm(Linear(bottleneck, out_dim, bias=False))
-    (utils/vision_transformer.py:292-293, :279).  forward(mode, z, weight_g, weight_v) -> logits."""
+    (utils/vision_transformer.py:292-293, :279).  forward(mode, z, weight_g, weight_v[, prepared[, link]]) -> logits.
+
+    `link`: optional dict, the channel between the calling head and the GEMM epilogue's fused statistics: on entry
+    link["loss"] is the DINOLoss the logits will go to (or None: no fused statistics), on return link["stats"] holds the
+    statistics record for `DINOLoss.forward` (or None)."""
 
     @staticmethod
-    def forward(ctx, mode, z, g, v, prepared=None):
+    def forward(ctx, mode, z, g, v, prepared=None, link=None):
         rows, dim = z.shape
         K = v.shape[0]
         mode = resolve_mode(mode, dim, K)
@@ -340,10 +348,8 @@ class NormLastLayerFn(torch.autograd.Function):
             prepared["region"].join(wop.main, wop.lo, scale, inv_vnorm, gmax)
             prepared["region"] = None
         who = "student" if any(ctx.needs_input_grad) else "teacher"
-        global last_stats
-        last_stats = None
         stats = None
-        loss_mod = _current_loss() if (fused_stats_enabled and mode != "fp32_simt" and K > 128) else None
+        loss_mod = link.get("loss") if (link is not None and fused_stats_enabled and mode != "fp32_simt" and K > 128) else None
         if loss_mod is not None:
             parts = ops.gemm_stats_parts(K)
             rp = torch.empty((rows, parts, 2), dtype=torch.float32, device=z.device) if (who == "student" or fused_teacher_stats) else None
@@ -383,7 +389,8 @@ class NormLastLayerFn(torch.autograd.Function):
             t_stats, _ = ops.teacher_finalize(stats["row_partials"], None, rows, K)
             stats = dict(kind="teacher_final", scale=stats["scale"], t_stats=t_stats, colsum=side_colsum, event=side.event,
                          center_ptr=stats["center_ptr"], center_version=stats["center_version"], rows=rows)
-        last_stats = stats
+        if link is not None:
+            link["stats"] = stats
         ctx.mode = mode
         ctx.zop, ctx.wop = zop, wop
         ctx.save_for_backward(zhat, inv_den, v.detach(), scale, inv_vnorm)
@@ -447,7 +454,7 @@ class NormLastLayerFn(torch.autograd.Function):
                     region.join(dv, dg)
             if not ctx.needs_input_grad[3]:
                 dv = None
-        return None, dz, dg, dv, None
+        return None, dz, dg, dv, None, None
 
 
 class DinoLossFn(torch.autograd.Function):

@@ -168,6 +168,29 @@ class DINOHead(nn.Module):
         self.use_bn = use_bn
         self.precision = None                   # None -> module default (set_default_precision / autocast)
         self._shadow = None                     # operand shadows of a frozen (teacher) head, see set_operand_shadows
+        self._loss_ref = None                   # weakref to the DINOLoss bound with bind_loss(); None -> functional's default
+
+    def bind_loss(self, loss_module):
+        """Tell this head which `dinomc_b200.DINOLoss` consumes its logits (temperatures and center for the statistics its
+        last GEMM / its teacher pass produce on the loss's behalf).  Optional: an unbound head uses the most recently
+        constructed or used DINOLoss of the process, which is what the reference's single-loss training script needs; bind
+        explicitly when several DINOLoss modules are alive.  `None` removes the binding.  The binding is a weak reference and
+        not part of the state_dict.  Whatever the head assumes is re-validated by `DINOLoss.forward`."""
+        import weakref
+        self._loss_ref = None if loss_module is None else weakref.ref(loss_module)
+        return self
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_loss_ref"] = None               # a weak reference cannot be pickled, and a copy is not bound to anything
+        return state
+
+    def _loss_module(self):
+        if self._loss_ref is not None:
+            bound = self._loss_ref()
+            if bound is not None:
+                return bound
+        return Fn._current_loss()
 
     def _init_weights(self, m):
         if isinstance(m, nn.Linear):
@@ -280,10 +303,10 @@ class DINOHead(nn.Module):
                     prepared = Fn.last_layer_weights(mode, self.last_layer.weight_g, self.last_layer.weight_v,
                                                      self.last_layer.in_features)
                     z = Fn.mlp_forward(mode, x, wb)
-            out = Fn.NormLastLayerFn.apply(mode, z, self.last_layer.weight_g, self.last_layer.weight_v, prepared)
-            if Fn.last_stats is not None:       # statistics the GEMM epilogue produced for dinomc_b200.DINOLoss
-                out._dmc_stats = Fn.last_stats
-                Fn.last_stats = None
+            link = {"loss": self._loss_module(), "stats": None}
+            out = Fn.NormLastLayerFn.apply(mode, z, self.last_layer.weight_g, self.last_layer.weight_v, prepared, link)
+            if link["stats"] is not None:       # statistics the GEMM epilogue produced for dinomc_b200.DINOLoss
+                out._dmc_stats = link["stats"]
             elif _early_teacher_stats and out.dtype in (torch.bfloat16, torch.float32) and self._is_inference(x):
                 self._launch_teacher_stats(out)
             return out
@@ -291,7 +314,7 @@ class DINOHead(nn.Module):
     def _launch_teacher_stats(self, out):
         """The registered DINOLoss's teacher pass over `out`, on a side stream (see set_early_teacher_stats)."""
         from . import ops
-        loss_mod = Fn._current_loss()
+        loss_mod = self._loss_module()
         if loss_mod is None or loss_mod.center.shape[-1] != out.shape[1] or loss_mod.center.device != out.device:
             return
         if out.shape[0] % loss_mod.teacher_crops_number:

@@ -83,3 +83,42 @@ def test_bench_op_models_cover_the_profiled_ops_and_the_step_model():
     # the GEMM ops of the step add up to the step model's flops
     gemm = sum(models[t][1] for t in models if t.startswith("gemm_"))
     assert abs(gemm - flops) / flops < 1e-9
+
+
+def test_bench_op_models_add_up_when_two_linears_share_a_shape():
+    """D == H (ResNet-50 features, cfg3): the first two Linears carry the same tag; their models must add, and the GEMM ops
+    must still account for every flop of the step model."""
+    import bench
+    w = bench.WORKLOADS["cfg3"]
+    assert w["D"] == bench.H
+    models = bench.op_models(w, 25_000_000, 2)
+    Ns, Nt = w["C"] * w["B"], w["G"] * w["B"]
+    assert models["gemm_mlp_fwd_2048x2048"][1] == 2 * (2 * (Ns + Nt) * bench.H * bench.H)
+    assert models["gemm_mlp_wgrad_2048x2048"][1] == 2 * (2 * Ns * bench.H * bench.H)
+    flops, _ = bench.roofline_model(w, 25_000_000, 2)
+    assert abs(sum(models[t][1] for t in models if t.startswith("gemm_")) - flops) / flops < 1e-9
+
+
+def test_head_loss_binding_is_explicit_weak_and_not_state():
+    """DINOHead.bind_loss: an explicit binding wins over the process default (the most recently constructed / used DINOLoss), is
+    a weak reference, is not part of the state_dict, and does not travel with copies or pickles of the head."""
+    import copy
+    import gc
+    import pickle
+    import dinomc_b200 as D
+    from dinomc_b200 import functional as Fn
+    head = D.DINOHead(16, 64, hidden_dim=32, bottleneck_dim=16)
+    keys = set(head.state_dict())
+    first = D.DINOLoss(64, 4, 0.04, 0.04, 0, 10)
+    second = D.DINOLoss(64, 4, 0.04, 0.04, 0, 10)
+    assert Fn._current_loss() is second and head._loss_module() is second          # unbound: the default
+    assert head.bind_loss(first) is head and head._loss_module() is first          # bound: explicit wins
+    assert set(head.state_dict()) == keys
+    assert copy.deepcopy(head)._loss_module() is second                             # a copy is unbound
+    assert pickle.loads(pickle.dumps(head))._loss_module() is second
+    assert head._loss_module() is first                                             # ... and the original still is
+    del first
+    gc.collect()
+    assert head._loss_module() is second                                            # weak: a dead binding falls back
+    head.bind_loss(None)
+    assert head._loss_ref is None

@@ -1,0 +1,139 @@
+"""Host logic above the C ABI, on CPU: the real DINOHead / DINOLoss / autograd Functions run with the kernels replaced by the
+torch restatements of tests/_ops_double.py, and the whole step is compared with the fp64 numpy oracle.  Catches wiring
+mistakes (operand layouts, epilogue requests, saved tensors, gradient arity, the head -> loss statistics hand-over) in the
+container that has no GPU; the kernels themselves are covered by the `-m gpu` suite."""
+import numpy as np
+import pytest
+import torch
+
+import dinomc_b200 as D
+from oracle import np_oracle as O
+
+import _ops_double as dbl  # noqa: E402  (tests/ is on sys.path: rootdir conftest)
+
+
+def _rel(a, b):
+    b = np.asarray(b, np.float64)
+    return float(np.abs(np.asarray(a, np.float64) - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def _build(mode, K=1024, in_dim=64, B=4, C=8, G=2, norm_last_layer=True, seed=0, **kw):
+    torch.manual_seed(seed)
+    kw = dict(dict(hidden_dim=128, bottleneck_dim=64), **kw)
+    student = D.DINOHead(in_dim, K, norm_last_layer=norm_last_layer, **kw)
+    teacher = D.DINOHead(in_dim, K, norm_last_layer=norm_last_layer, **kw)
+    for p in teacher.parameters():
+        p.requires_grad = False
+    student.precision = teacher.precision = mode
+    with torch.no_grad():
+        for p in list(student.parameters()) + list(teacher.parameters()):
+            if p.dim() == 1:
+                p.add_(0.05 * torch.randn_like(p))
+        if not norm_last_layer:
+            student.last_layer.weight_g.mul_(1.0 + 0.1 * torch.randn_like(student.last_layer.weight_g))
+    loss_mod = D.DINOLoss(K, C, 0.04, 0.04, 0, 10, teacher_crops_number=G)
+    with torch.no_grad():
+        loss_mod.center.normal_(0, 0.3)
+    xs = torch.randn(C * B, in_dim, requires_grad=True)
+    xt = torch.randn(G * B, in_dim)
+    return student, teacher, loss_mod, xs, xt
+
+
+def _oracle(student, teacher, center0, xs, xt, C, G):
+    ssd = {k: v.detach().numpy() for k, v in student.state_dict().items()}
+    tsd = {k: v.detach().numpy() for k, v in teacher.state_dict().items()}
+    return O.full_step(xs.detach().numpy(), xt.numpy(), ssd, tsd, center0.numpy(), 0.04, C, G, ema_m=0.996)
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-5), ("bf16", 2e-2)])
+@pytest.mark.parametrize("norm_last_layer", [True, False])
+def test_step_wiring_against_the_oracle(monkeypatch, mode, tol, norm_last_layer):
+    dbl.install(monkeypatch)
+    C, G = 8, 2
+    student, teacher, loss_mod, xs, xt = _build(mode, norm_last_layer=norm_last_layer)
+    center0 = loss_mod.center.clone()
+    ref = _oracle(student, teacher, center0, xs, xt, C, G)
+    with torch.no_grad():
+        t_out = teacher(xt)
+    s_out = student(xs)
+    assert getattr(s_out, "_dmc_stats", None) is not None and s_out._dmc_stats["kind"] == "student"      # fused statistics attached
+    assert getattr(t_out, "_dmc_stats", None) is None
+    loss = loss_mod(s_out, t_out, 0)
+    assert "ce_fused" in dbl.calls and "ce_fwd" not in dbl.calls            # the fused route ran ...
+    loss.backward()
+    assert "ce_bwd" not in dbl.calls                                        # ... and its gradient was reused, not recomputed
+    errs = {"loss": abs(float(loss.detach()) - ref["loss"]) / abs(ref["loss"]), "x": _rel(xs.grad.numpy(), ref["grads"]["x"])}
+    for name, p in student.named_parameters():
+        if p.requires_grad:
+            assert p.grad is not None, name
+            errs[name] = _rel(p.grad.numpy(), ref["grads"][name])
+        else:
+            assert p.grad is None, name
+    assert all(e < tol for e in errs.values()), errs
+    assert _rel(loss_mod.center.numpy(), ref["center"]) < (1e-6 if mode == "fp32" else 2e-3)
+    assert loss_mod.center.data_ptr() != center0.data_ptr()                 # rebound like the reference (main_dino_mc.py:473)
+    # the teacher built no autograd graph and saved nothing: its MLP GEMMs were launched without the second (gelu') output
+    assert not t_out.requires_grad
+
+
+def test_plain_route_when_the_statistics_do_not_match(monkeypatch):
+    """Logits that did not come from a head bound to this loss (here: a clone) take the separate-pass route and give the same
+    numbers; a second DINOLoss with another student temperature invalidates the head's statistics instead of using them."""
+    dbl.install(monkeypatch)
+    C, G = 8, 2
+    student, teacher, loss_mod, xs, xt = _build("fp32")
+    center0 = loss_mod.center.clone()
+    ref = _oracle(student, teacher, center0, xs, xt, C, G)
+    with torch.no_grad():
+        t_out = teacher(xt)
+    s_out = student(xs)
+    plain = s_out.clone()                                                    # no _dmc_stats attribute
+    loss = loss_mod(plain, t_out, 0)
+    assert "ce_fwd" in dbl.calls and "ce_fused" not in dbl.calls
+    loss.backward()
+    assert "ce_bwd" in dbl.calls
+    assert abs(float(loss.detach()) - ref["loss"]) / abs(ref["loss"]) < 2e-5
+    assert _rel(xs.grad.numpy(), ref["grads"]["x"]) < 2e-5
+    # another loss module, other temperature: the statistics the head attached (computed for `loss_mod`) must be rejected
+    dbl.calls.clear()
+    other = D.DINOLoss(1024, C, 0.04, 0.04, 0, 10, teacher_crops_number=G, student_temp=0.2)
+    student.bind_loss(loss_mod)
+    s2 = student(xs)
+    assert s2._dmc_stats["scale"] == pytest.approx(1.0 / loss_mod.student_temp)
+    other(s2, t_out, 0)
+    assert "ce_fwd" in dbl.calls and "ce_fused" not in dbl.calls
+
+
+def test_explicit_binding_survives_a_later_loss_module(monkeypatch):
+    """Two DINOLoss modules alive: an unbound head follows the most recent one, a bound head keeps its own."""
+    dbl.install(monkeypatch)
+    C, G = 8, 2
+    student, teacher, loss_a, xs, xt = _build("fp32")
+    loss_b = D.DINOLoss(1024, C, 0.04, 0.04, 0, 10, teacher_crops_number=G, student_temp=0.25)     # constructed later: the default
+    assert student(xs)._dmc_stats["scale"] == pytest.approx(4.0)
+    student.bind_loss(loss_a)
+    s_out = student(xs)
+    assert s_out._dmc_stats["scale"] == pytest.approx(10.0)
+    with torch.no_grad():
+        t_out = teacher(xt)
+    dbl.calls.clear()
+    loss_a(s_out, t_out, 0)
+    assert "ce_fused" in dbl.calls
+    assert loss_b is not None
+
+
+def test_nlayers_one_and_upstream_gradient_scale(monkeypatch):
+    """nlayers = 1 (a bare Linear as `mlp`) and a non-unit upstream gradient (what a GradScaler delivers): the fused route
+    rescales its stored gradient."""
+    dbl.install(monkeypatch)
+    C, G = 8, 2
+    student, teacher, loss_mod, xs, xt = _build("fp32", nlayers=1)
+    center0 = loss_mod.center.clone()
+    ref = _oracle(student, teacher, center0, xs, xt, C, G)
+    with torch.no_grad():
+        t_out = teacher(xt)
+    loss = loss_mod(student(xs), t_out, 0)
+    (loss * 8.0).backward()
+    assert "scale_if" in dbl.calls
+    assert _rel(xs.grad.numpy() / 8.0, ref["grads"]["x"]) < 2e-5
+    assert _rel(student.mlp.weight.grad.numpy() / 8.0, ref["grads"]["mlp.weight"]) < 2e-5
