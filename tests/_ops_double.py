@@ -217,7 +217,41 @@ def center_update(center, colsum_, count, momentum):
     return center * momentum + batch_center * (1 - momentum)
 
 
-_REPLACED = ("gemm", "lse_finalize", "cast_bf16", "cast_bf16_batch", "split_tf32", "colsum", "normalize_rows_fwd", "normalize_rows_bwd",
+class ClipPlan:
+    """utils/utils.py:145-154 per parameter: g *= clip / (||g|| + 1e-6) when that is below 1; returns the pre-clip norms."""
+
+    def __init__(self, grads):
+        self.grads = list(grads)
+
+    def run(self, clip):
+        calls.append("clip_grads")
+        norms = torch.stack([g.double().norm() for g in self.grads])
+        for g, n in zip(self.grads, norms):
+            coef = float(clip) / (float(n) + 1e-6)
+            if coef < 1:
+                g.mul_(coef)
+        return norms.float()
+
+
+class EmaPlan:
+    """main_dino_mc.py:403-406 with its three fp32 roundings (the shadow outputs of the real plan are not modelled)."""
+
+    def __init__(self, teacher_params, student_params, shadows=None, wn=None):
+        self.pairs = list(zip(teacher_params, student_params))
+
+    def run(self, m):
+        calls.append("ema")
+        m = 1.0 if ops_preserve_state() else float(m)
+        for pk, pq in self.pairs:
+            pk.mul_(m).add_((1 - m) * pq)
+
+
+def ops_preserve_state():
+    import dinomc_b200 as D
+    return D.ops.preserve_state
+
+
+_REPLACED = ("ClipPlan", "EmaPlan", "gemm", "lse_finalize", "cast_bf16", "cast_bf16_batch", "split_tf32", "colsum", "normalize_rows_fwd", "normalize_rows_bwd",
              "weightnorm_fwd", "weightnorm_bwd", "teacher_stats_colsum", "ce_fused", "ce_fwd", "ce_bwd", "scale_inplace_if",
              "center_update", "last_gmax")
 
@@ -236,4 +270,9 @@ def install(monkeypatch):
     monkeypatch.setattr(H, "_operand_shadows", False)
     monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
     monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True), raising=False)   # the modules refuse CPU tensors
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self, raising=False)        # the drop-in loop moves its crops
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    from dinomc_b200 import ema, optim
+    monkeypatch.setattr(ema, "_plans", {})                # plans are cached by data_ptr: never reuse one across tests
+    monkeypatch.setattr(optim, "_plans", {})
     calls.clear()

@@ -46,10 +46,9 @@ def _schedules():
     return lr, wd, mom
 
 
-def _reference_loop(student_sd, teacher_sd, batches, clip):
+def _reference_loop(student_sd, teacher_sd, batches, clip, dev="cuda"):
     """float64 on the device, oracle functions, the reference's order of operations."""
     from oracle import torch_port as T
-    dev = "cuda"
     sp = {k: v.detach().double().to(dev).clone().requires_grad_(True) for k, v in student_sd.items()}
     tp = {k: v.detach().double().to(dev).clone() for k, v in teacher_sd.items()}
     head_s = {k[len("head."):]: v for k, v in sp.items() if k.startswith("head.")}

@@ -137,3 +137,39 @@ def test_nlayers_one_and_upstream_gradient_scale(monkeypatch):
     assert "scale_if" in dbl.calls
     assert _rel(xs.grad.numpy() / 8.0, ref["grads"]["x"]) < 2e-5
     assert _rel(student.mlp.weight.grad.numpy() / 8.0, ref["grads"]["mlp.weight"]) < 2e-5
+
+
+def test_dropin_train_one_epoch_host_logic(monkeypatch):
+    """`dropin.train_one_epoch` (the seam for main_dino_mc.py:356-416) executed on CPU over the kernel double: schedules written into
+    the optimizer, MultiCropWrapper over a list of crops of two resolutions, loss, backward, per-parameter clip, optimizer step,
+    EMA with the scheduled momentum -- against the same loop written with oracle/torch_port.py in float64."""
+    import types
+    import test_gpu_dropin as G
+    from dinomc_b200 import dropin
+    dbl.install(monkeypatch)
+    torch.manual_seed(0)
+    student = D.MultiCropWrapper(G.ToyBackbone(), D.DINOHead(G.D_FEAT, G.K, hidden_dim=G.HID, bottleneck_dim=G.BOT))
+    teacher = D.MultiCropWrapper(G.ToyBackbone(), D.DINOHead(G.D_FEAT, G.K, hidden_dim=G.HID, bottleneck_dim=G.BOT))
+    teacher.load_state_dict(student.state_dict())
+    for p in teacher.parameters():
+        p.requires_grad = False
+    student.head.precision = teacher.head.precision = "fp32"
+    student_sd = {k: v.detach().clone() for k, v in student.named_parameters()}
+    teacher_sd = {k: v.detach().clone() for k, v in teacher.named_parameters()}
+    loss_mod = D.DINOLoss(G.K, G.C, 0.04, 0.04, 0, 10, teacher_crops_number=G.G)
+    opt = torch.optim.SGD([p for p in student.parameters() if p.requires_grad], lr=0.0)
+    lr, wd, mom = G._schedules()
+    args = types.SimpleNamespace(epochs=1, global_crops_number=G.G, clip_grad=0.3, freeze_last_layer=0)
+    batches = G._loader(5)
+    stats = dropin.train_one_epoch(student, teacher, teacher, loss_mod, batches, opt, lr, wd, mom, 0, None, args,
+                                   meters=dropin._PlainMeters(), host_sync="reference")
+    assert dbl.calls.count("ema") == G.STEPS and dbl.calls.count("clip_grads") == G.STEPS
+    ref_losses, sp, tp, center = G._reference_loop(student_sd, teacher_sd, batches, 0.3, dev="cpu")
+    tol = 2e-5
+    assert abs(stats["loss"] - float(np.mean(ref_losses))) / abs(float(np.mean(ref_losses))) < tol
+    assert stats["lr"] == pytest.approx(float(np.mean(lr)))
+    for k, v in student.named_parameters():
+        assert _rel(v.detach().numpy(), sp[k].detach().numpy()) < tol, k
+    for k, v in teacher.named_parameters():
+        assert _rel(v.detach().numpy(), tp[k].detach().numpy()) < tol, k
+    assert _rel(loss_mod.center.numpy(), center.numpy()) < 1e-5
