@@ -276,3 +276,139 @@ def install(monkeypatch):
     monkeypatch.setattr(ema, "_plans", {})                # plans are cached by data_ptr: never reuse one across tests
     monkeypatch.setattr(optim, "_plans", {})
     calls.clear()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Data-parallel host logic (GradAllReduce) on CPU / gloo: stand-ins for CUDA streams and events (program order is the only
+# order there is on the host), the bf16 narrow / widen launches, and the symmetric-memory exchange buffer.
+# ----------------------------------------------------------------------------------------------------------------
+class Patcher:
+    """monkeypatch.setattr for processes that pytest did not start (spawned ranks): no undo needed, the process exits."""
+
+    def setattr(self, obj, name, value, raising=True):
+        setattr(obj, name, value)
+
+
+class _Stream:
+    cuda_stream = 0
+
+    def __init__(self, *a, **k):
+        pass
+
+    def wait_event(self, ev):
+        pass
+
+    def wait_stream(self, st):
+        pass
+
+    def synchronize(self):
+        pass
+
+
+class _Event:
+    def __init__(self, *a, **k):
+        pass
+
+    def record(self, stream=None):
+        pass
+
+    def synchronize(self):
+        pass
+
+    def wait(self, stream=None):
+        pass
+
+
+class _NullCtx:
+    def __init__(self, *a, **k):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def narrow_bf16_into(srcs, dsts):
+    calls.append("narrow_bf16")
+    for a, b in zip(srcs, dsts):
+        assert a.dtype == torch.float32 and b.dtype == torch.bfloat16 and a.numel() == b.numel()
+        b.copy_(a.to(torch.bfloat16))
+
+
+def widen_bf16_batch(srcs, dsts):
+    calls.append("widen_bf16")
+    for a, b in zip(srcs, dsts):
+        assert a.dtype == torch.bfloat16 and b.dtype == torch.float32 and a.numel() == b.numel()
+        b.copy_(a.float())
+
+
+class SymmetricBuffer:
+    """xrank.SymmetricBuffer's contract over gloo: a flat buffer per rank; allreduce_ leaves scale * (sum over ranks) in it on
+    every rank (bf16 buffers: summed in fp32, rounded once) and optionally widens element ranges into fp32 tensors."""
+    instances = 0
+
+    def __init__(self, numel, dtype, group=None, ctas=148):
+        import torch.distributed as dist
+        SymmetricBuffer.instances += 1
+        per16 = 16 // (2 if dtype == torch.bfloat16 else 4)
+        self.numel = (int(numel) + per16 - 1) // per16 * per16
+        self.tensor = torch.zeros(self.numel, dtype=dtype)
+        self.group, self.ctas, self.multicast = group, int(ctas), False
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def allreduce_(self, scale=1.0, widen_to=None, widen_offsets=None):
+        import torch.distributed as dist
+        calls.append("xrank_allreduce")
+        acc = self.tensor.float()
+        _real_all_reduce(acc, group=self.group)
+        self.tensor.copy_((acc * float(scale)).to(self.tensor.dtype))
+        for t, off in zip(widen_to or [], widen_offsets or []):
+            assert t.dtype == torch.float32 and t.is_contiguous() and off % 8 == 0
+            t.copy_(self.tensor[off:off + t.numel()].float())
+        return self.tensor
+
+
+_real_all_reduce = None
+
+
+def install_data_parallel(patch):
+    """On top of install(): what GradAllReduce touches.  gloo has no AVG: the stand-in all_reduce sums and divides."""
+    global _real_all_reduce
+    import contextlib
+    import sys
+    import torch.distributed as dist
+    import dinomc_b200 as D
+    from dinomc_b200 import xrank
+    me = sys.modules[__name__]
+    patch.setattr(torch.cuda, "Stream", _Stream)
+    patch.setattr(torch.cuda, "Event", _Event)
+    patch.setattr(torch.cuda, "stream", _NullCtx)
+    patch.setattr(torch.cuda, "current_stream", lambda *a, **k: _Stream())
+    patch.setattr(torch.Tensor, "record_stream", lambda self, s: None, raising=False)
+    patch.setattr(D.ops, "narrow_bf16_into", me.narrow_bf16_into)
+    patch.setattr(D.ops, "widen_bf16_batch", me.widen_bf16_batch)
+    patch.setattr(xrank, "SymmetricBuffer", me.SymmetricBuffer)
+    if _real_all_reduce is None:
+        _real_all_reduce = dist.all_reduce
+
+    def all_reduce(t, op=dist.ReduceOp.SUM, group=None, async_op=False):
+        if op == dist.ReduceOp.AVG:
+            if t.dtype == torch.bfloat16:           # NCCL averages bf16 buffers natively; gloo: widen, sum, divide, round once
+                acc = t.float()
+                _real_all_reduce(acc, group=group)
+                t.copy_((acc / dist.get_world_size(group)).to(torch.bfloat16))
+            else:
+                _real_all_reduce(t, group=group)
+                t.div_(dist.get_world_size(group))
+            return None
+        return _real_all_reduce(t, op=op, group=group, async_op=async_op)
+
+    patch.setattr(dist, "all_reduce", all_reduce)
+
+    @contextlib.contextmanager
+    def no_coalescing(*a, **k):                     # gloo cannot coalesce; one all-reduce per tensor is the same exchange
+        yield
+
+    patch.setattr(dist, "_coalescing_manager", no_coalescing)
