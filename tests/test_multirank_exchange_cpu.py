@@ -118,3 +118,72 @@ def test_gradient_exchange_host_logic_two_ranks(tmp_path, compress, transport, t
     for i in range(2):
         assert np.abs(r[i]["center"].double().numpy() - ref).max() / np.abs(ref).max() < 1e-6
     assert torch.equal(r[0]["center"], r[1]["center"])
+
+
+def _ddp_worker(rank, world, port, out_dir):
+    """The reference's own data-parallel wrapper (main_dino_mc.py:260: DistributedDataParallel around the student) over the drop-in
+    head: DDP must see ordinary leaf parameters, receive every gradient through the custom autograd Functions, and average them."""
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    for p in (HERE, os.path.dirname(HERE)):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import _ops_double as dbl
+        import dinomc_b200 as D
+        patch = dbl.Patcher()
+        dbl.install(patch)
+        torch.manual_seed(0)
+        Din, K, B, C, G = 64, 1024, 4, 8, 2
+        head = D.DINOHead(Din, K, hidden_dim=128, bottleneck_dim=64)
+        teacher = D.DINOHead(Din, K, hidden_dim=128, bottleneck_dim=64)
+        for p in teacher.parameters():
+            p.requires_grad = False
+        head.precision = teacher.precision = "fp32"
+        loss_mod = D.DINOLoss(K, C, 0.04, 0.04, 0, 10, teacher_crops_number=G)
+        g = torch.Generator().manual_seed(100 + rank)
+        xs = torch.randn(C * B, Din, generator=g)
+        xt = torch.randn(G * B, Din, generator=g)
+
+        def step(model):
+            with torch.no_grad():
+                loss_mod.center.zero_()
+                t_out = teacher(xt)
+            loss = loss_mod(model(xs), t_out, 0)
+            loss.backward()
+            return loss
+
+        step(head)
+        local = {n: p.grad.clone() for n, p in head.named_parameters() if p.grad is not None}
+        for p in head.parameters():
+            p.grad = None
+        ddp = DDP(head)
+        dbl.calls.clear()
+        step(ddp)
+        fused = "ce_fused" in dbl.calls                        # did the statistics attached by the head survive the DDP wrapper?
+        reduced = {n: p.grad.clone() for n, p in head.named_parameters() if p.grad is not None}
+        torch.save({"local": local, "reduced": reduced, "fused": fused}, os.path.join(out_dir, f"rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_reference_ddp_wrapper_over_dropin_head_two_ranks(tmp_path):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_ddp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r = [torch.load(os.path.join(tmp_path, f"rank{i}.pt")) for i in range(2)]
+    assert set(r[0]["reduced"]) == set(r[0]["local"]) and len(r[0]["local"]) == 7
+    for name in r[0]["local"]:
+        mean = (r[0]["local"][name].double() + r[1]["local"][name].double()) / 2
+        for i in range(2):
+            err = (r[i]["reduced"][name].double() - mean).abs().max() / mean.abs().max()
+            assert err < 1e-6, (name, float(err))
+        assert torch.equal(r[0]["reduced"][name], r[1]["reduced"][name])
+    # DDP hands the module's output tensor through unchanged (no find_unused_parameters): the statistics record the head attached
+    # to its logits reaches DINOLoss and the single-pass loss route runs.  (Were a wrapper to re-wrap the tensor, DINOLoss would
+    # find no record and take the separate-pass route -- slower, same numbers: test_host_wiring_cpu.)
+    assert r[0]["fused"] is True and r[1]["fused"] is True
