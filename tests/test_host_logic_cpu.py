@@ -122,3 +122,44 @@ def test_head_loss_binding_is_explicit_weak_and_not_state():
     assert head._loss_module() is second                                            # weak: a dead binding falls back
     head.bind_loss(None)
     assert head._loss_ref is None
+
+
+def _run_bench(args, env_extra=None):
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, **(env_extra or {}))
+    return subprocess.run([sys.executable, os.path.join(root, "bench.py")] + args, capture_output=True, text=True, env=env, timeout=600)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference`: ONE JSON line on stdout with the contract's keys, describing what it ran (one host process,
+    n_gpus 1, its own batch), whatever --gpus says; ranks other than 0 of a torchrun launch print nothing and exit 0."""
+    import json
+    r = _run_bench(["--impl", "reference", "--workload", "cfg1", "--steps", "1", "--warmup", "1", "--cpu-sample-batch", "2", "--gpus", "8"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["n_gpus"] == 1 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["gpu_launches"] == 0 and d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["config"]["global_batch"] == 2 and "reduced batch of 2" in d["config"]["workload"] and d["config"]["launched_with_gpus"] == 8
+    assert abs(d["value"] - 2 / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+    other = _run_bench(["--impl", "reference", "--workload", "cfg1", "--steps", "1", "--gpus", "8"], {"RANK": "3", "LOCAL_RANK": "3", "WORLD_SIZE": "8"})
+    assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def test_bench_own_arm_refuses_to_run_without_a_gpu():
+    """No CPU fallback: without a CUDA device the product arm stops with an error instead of timing something else."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a CUDA device is visible")
+    r = _run_bench(["--steps", "1", "--no-cpu-baseline"])
+    assert r.returncode != 0 and r.stdout.strip() == ""
+    assert "no CPU fallback" in r.stderr
