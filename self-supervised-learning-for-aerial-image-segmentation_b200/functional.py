@@ -9,6 +9,9 @@ Precision modes (how the GEMMs run; everything around them is fp32):
 """
 from __future__ import annotations
 
+import os
+import weakref
+
 import torch
 
 from . import _lib as L
@@ -28,10 +31,7 @@ MODES = ("bf16", "fp32", "fp32_simt")
 # inside DINOLoss.forward (temperature, center identity and version, row count, tensor identity); on any mismatch the
 # separate passes run instead, so a wrong guess costs time, never correctness.
 # ---------------------------------------------------------------------------------------------------------
-import os as _os0
-import weakref
-
-_os_environ_get = _os0.environ.get
+_os_environ_get = os.environ.get
 
 fused_stats_enabled = True
 fused_teacher_stats = False   # teacher row statistics + column sums from the GEMM epilogue (EPI 3, lean path for bf16 logits):
@@ -73,8 +73,7 @@ gelu_dg = _os_environ_get("DMC_GELU_DG", "1") != "0"      # MLP forward saves ge
 grad_exchange_active = False     # set by GradAllReduce: the last layer's dv (64 MiB, the largest all-reduce of the step) must
                                  # then be final as early as possible, so its weight-norm backward stays in front of the dgrad
 grad_exchange = None             # the active GradAllReduce (or None); with compress="bf16" the last layer hands it a bf16 dW
-import os as _os
-wgrad_bf16 = _os.environ.get("DMC_WGRAD_BF16", "1") == "1"   # (measured: step 0.797 -> 0.785 ms) in the bf16-GEMM mode the last layer's
+wgrad_bf16 = _os_environ_get("DMC_WGRAD_BF16", "1") == "1"   # (measured: step 0.797 -> 0.785 ms) in the bf16-GEMM mode the last layer's
                                  # wgrad stores dW in bf16 and the weight-norm backward reads it (-64 MB of traffic per step at
                                  # K = 65536; same kernels as the bf16 gradient exchange, gradients stay within the 2e-2 tolerance)
 _aux_streams = {}

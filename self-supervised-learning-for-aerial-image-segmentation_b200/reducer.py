@@ -25,6 +25,8 @@ NVSwitch) does the transport.
 from __future__ import annotations
 
 import os
+import sys
+import time
 
 import torch
 import torch.distributed as dist
@@ -203,7 +205,6 @@ class GradAllReduce:
             # CTAs is all barrier (measured 50 us at 8 GPUs)
             ctas = max(8, min(self._xrank_ctas, (2 * total) >> int(os.environ.get("DMC_XRANK_BYTES_PER_CTA_LOG2", "16"))))
             buf = self._small_bufs[key] = SymmetricBuffer(total, torch.bfloat16, group=self.group, ctas=ctas)
-        import time
         t0 = time.perf_counter()
         flat = buf.tensor
         views = [flat[o:o + g.numel()] for o, g in zip(offs, grads)]
@@ -255,8 +256,6 @@ class GradAllReduce:
         return pv, pg
 
     def _dbg(self, what, t0):
-        import sys
-        import time
         dt = time.perf_counter() - t0
         if dt > 2e-3:
             print(f"[reducer] {what} took {dt * 1e3:.1f} ms on the host", file=sys.stderr, flush=True)
@@ -270,7 +269,6 @@ class GradAllReduce:
             self.comm.wait_event(ev)
         else:
             self.comm.wait_stream(cur)
-        import time
         t0 = time.perf_counter()
         peer = self.transport == "peer" and self._dw_buf is not None and dw.data_ptr() == self._dw_buf.tensor.data_ptr()
         with torch.cuda.stream(self.comm):
