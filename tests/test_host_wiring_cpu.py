@@ -173,3 +173,34 @@ def test_dropin_train_one_epoch_host_logic(monkeypatch):
     for k, v in teacher.named_parameters():
         assert _rel(v.detach().numpy(), tp[k].detach().numpy()) < tol, k
     assert _rel(loss_mod.center.numpy(), center.numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_shapes_tma_cannot_express_take_the_ffma_route(monkeypatch, mode):
+    """Row strides that are not multiples of 16 bytes (in_dim 63, out_dim 1001) cannot be described by a TMA tensor map: every GEMM of
+    the head must then be requested from the FFMA kernel (`simt=True`), the normalize backward runs as its own launch, no statistics
+    are fused -- and the numbers are the oracle's."""
+    dbl.install(monkeypatch)
+    seen = []
+    real_gemm = dbl.gemm
+
+    def spy(*a, **k):
+        seen.append((k.get("tag"), bool(k.get("simt"))))
+        return real_gemm(*a, **k)
+
+    monkeypatch.setattr(D.ops, "gemm", spy)
+    C, G = 8, 2
+    student, teacher, loss_mod, xs, xt = _build(mode, K=1001, in_dim=63)
+    center0 = loss_mod.center.clone()
+    ref = _oracle(student, teacher, center0, xs, xt, C, G)
+    with torch.no_grad():
+        t_out = teacher(xt)
+    s_out = student(xs)
+    assert getattr(s_out, "_dmc_stats", None) is None and s_out.dtype == torch.float32
+    loss = loss_mod(s_out, t_out, 0)
+    loss.backward()
+    assert seen and all(simt for _, simt in seen), seen
+    assert "normalize_bwd" in dbl.calls and "ce_fwd" in dbl.calls and "ce_bwd" in dbl.calls
+    assert abs(float(loss.detach()) - ref["loss"]) / abs(ref["loss"]) < 2e-5
+    assert _rel(xs.grad.numpy(), ref["grads"]["x"]) < 2e-5
+    assert _rel(student.last_layer.weight_v.grad.numpy(), ref["grads"]["last_layer.weight_v"]) < 2e-5
