@@ -204,3 +204,39 @@ def test_shapes_tma_cannot_express_take_the_ffma_route(monkeypatch, mode):
     assert abs(float(loss.detach()) - ref["loss"]) / abs(ref["loss"]) < 2e-5
     assert _rel(xs.grad.numpy(), ref["grads"]["x"]) < 2e-5
     assert _rel(student.last_layer.weight_v.grad.numpy(), ref["grads"]["last_layer.weight_v"]) < 2e-5
+
+
+def test_use_bn_head_wiring(monkeypatch):
+    """`use_bn_in_head` (utils/vision_transformer.py:268-274): every Linear goes through `LinearFn` (own GEMM), BatchNorm1d and GELU
+    stay torch modules between them; forward, every gradient and the running statistics against the same head in float64 torch."""
+    import copy
+    import torch.nn.functional as F
+    dbl.install(monkeypatch)
+    torch.manual_seed(11)
+    head = D.DINOHead(64, 1024, use_bn=True, norm_last_layer=False, hidden_dim=128, bottleneck_dim=64)
+    assert [type(m).__name__ for m in head.mlp] == ["Linear", "BatchNorm1d", "GELU", "Linear", "BatchNorm1d", "GELU", "Linear"]
+    head.precision = "fp32"
+    with torch.no_grad():
+        head.last_layer.weight_g.uniform_(0.5, 1.5)
+    ref_mlp = copy.deepcopy(head.mlp).double()
+    g64 = head.last_layer.weight_g.detach().double().requires_grad_(True)
+    v64 = head.last_layer.weight_v.detach().double().requires_grad_(True)
+    x = torch.randn(48, 64, generator=torch.Generator().manual_seed(12))
+    up = torch.randn(48, 1024, generator=torch.Generator().manual_seed(13))
+    xg = x.clone().requires_grad_(True)
+    out = head(xg)
+    assert [c for c in dbl.calls if c.startswith("gemm_mlp_fwd")] == ["gemm_mlp_fwd_64x128", "gemm_mlp_fwd_128x128", "gemm_mlp_fwd_128x64"]
+    (out.float() * up).sum().backward()
+    x64 = x.double().requires_grad_(True)
+    z = F.normalize(ref_mlp(x64), dim=-1, p=2)
+    ref = z @ (v64 * (g64 / v64.norm(dim=1, keepdim=True))).t()
+    (ref * up.double()).sum().backward()
+    tol = 2e-5
+    assert _rel(out.detach().numpy(), ref.detach().numpy()) < tol
+    assert _rel(xg.grad.numpy(), x64.grad.numpy()) < tol
+    assert _rel(head.last_layer.weight_v.grad.numpy(), v64.grad.numpy()) < tol
+    assert _rel(head.last_layer.weight_g.grad.numpy(), g64.grad.numpy()) < tol
+    for (n, p), q in zip(head.mlp.named_parameters(), ref_mlp.parameters()):
+        if n not in ("0.bias", "3.bias"):      # a bias in front of a BatchNorm has an exactly-zero gradient
+            assert _rel(p.grad.numpy(), q.grad.numpy()) < tol, n
+    assert _rel(head.mlp[1].running_var.numpy(), ref_mlp[1].running_var.numpy()) < 1e-5
