@@ -82,6 +82,7 @@ def _worker(rank, world, port, out_dir, compress, transport, norm_last_layer):
         dist.destroy_process_group()
 
 
+@pytest.mark.timeout(300)
 @pytest.mark.parametrize("compress,transport,tol", [(None, "nccl", 1e-6), ("bf16", "nccl", 2e-2), ("bf16", "peer", 2e-2)])
 @pytest.mark.parametrize("norm_last_layer", [True, False])
 def test_gradient_exchange_host_logic_two_ranks(tmp_path, compress, transport, tol, norm_last_layer):
@@ -171,6 +172,7 @@ def _ddp_worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
+@pytest.mark.timeout(300)
 def test_reference_ddp_wrapper_over_dropin_head_two_ranks(tmp_path):
     import torch.multiprocessing as mp
     port = _free_port()
