@@ -283,3 +283,73 @@ def test_xrank_argument_validation_without_a_device():
     assert lib.dmc_xrank_allreduce(None, peers, pads, 1024, L.DMC_F32, 0, 2, 1.0, 8, 1, outs, offs, ns, None) < 0
     offs_bad = (L.i64 * 1)(4)                                                    # offsets must be multiples of 8 elements
     assert lib.dmc_xrank_allreduce(None, peers, pads, 1024, L.DMC_BF16, 0, 2, 1.0, 8, 1, outs, offs_bad, ns, None) < 0
+
+
+def test_gemm_argument_validation_messages_without_a_device():
+    """Every structural mistake in a dmc_gemm_args is refused on the host, before any CUDA call, with a negative code and a message
+    naming it (the Python layer turns that into a RuntimeError)."""
+    import dinomc_b200
+    L = dinomc_b200._lib
+    lib = L.load()
+    buf = (C.c_char * 4096)()                      # any non-null, 16-byte aligned host address: validation never dereferences it
+    base = (C.addressof(buf) + 15) & ~15
+
+    def args(**kw):
+        g = L.GemmArgs()
+        g.M, g.N, g.K = 128, 128, 64
+        g.A, g.B, g.D = base, base, base
+        g.lda, g.ldb, g.ldd = 64, 64, 128
+        g.in_dtype, g.out_dtype = L.DMC_BF16, L.DMC_F32
+        for k, v in kw.items():
+            setattr(g, k, v)
+        return g
+
+    def refused(g, text):
+        rc = lib.dmc_gemm(C.byref(g), None)
+        msg = lib.dmc_last_error_string().decode()
+        assert rc < 0 and text in msg, (rc, msg)
+
+    refused(args(K=0), "empty problem")
+    refused(args(M=1 << 31), "dimension too large")
+    refused(args(A=None), "null operand")
+    refused(args(in_dtype=7), "bad in_dtype")
+    refused(args(out_dtype=-1), "bad out_dtype")
+    refused(args(act=99), "bad act")
+    refused(args(act=L.ACT_GELU_DG), "need aux")
+    refused(args(act=L.ACT_MUL_AUX), "need aux")
+    refused(args(act=L.ACT_GELU_BWD), "needs aux")
+    refused(args(act=L.ACT_NORMALIZE_BWD), "needs aux (fp32 rows) and row_scale")
+    refused(args(act=L.ACT_NORMALIZE_BWD, aux=base, aux_dtype=L.DMC_F32, ldaux=128, row_scale=base, N=2048, ldd=2048), "N <= 1024")
+    refused(args(act=L.ACT_NORMALIZE_BWD, aux=base, aux_dtype=L.DMC_F32, ldaux=128, row_scale=base, K=64), "at least two k-blocks")
+    refused(args(A_lo=base), "A_lo and B_lo must be given together")
+    refused(args(A_lo=base, B_lo=base), "require in_dtype F32")
+    refused(args(split_k=2, K=256), "split-K needs a workspace")
+    refused(args(split_k=2, K=256, workspace=base + 4, workspace_bytes=1 << 30), "workspace must be 16-byte aligned")
+    refused(args(split_k=2, K=256, workspace=base, workspace_bytes=16), "split-K needs a workspace")
+    assert lib.dmc_gemm(None, None) < 0 and b"null args" in lib.dmc_last_error_string()
+
+
+def test_gemm_planner_workspace_invariants_on_host():
+    """dmc_gemm_workspace_bytes exposes the planner's split-K decision: 0 (no split) or splits * M * N * 4 bytes with
+    2 <= splits <= number of 128-byte k-blocks; wide outputs of short contractions are never split; the step's own shapes get
+    the plans DESIGN.md section 4.1 describes."""
+    import dinomc_b200
+    L = dinomc_b200._lib
+    lib = L.load()
+    for dt, per_kb in ((L.DMC_BF16, 64), (L.DMC_F32, 32)):
+        for M in (8, 128, 512, 2048, 4096):
+            for N in (64, 256, 384, 2048, 65536):
+                for K in (64, 256, 384, 2048, 65536):
+                    nbytes = lib.dmc_gemm_workspace_bytes(M, N, K, dt)
+                    assert nbytes % (M * N * 4) == 0, (M, N, K, dt)
+                    splits = nbytes // (M * N * 4)
+                    kb = -(-K // per_kb)
+                    assert splits == 0 or 2 <= splits <= 3 * kb, (M, N, K, dt, splits)      # fp32 operands: up to 3 virtual passes
+                    if dt == L.DMC_BF16 and (M // 128 or 1) * -(-N // 256) >= 148:
+                        assert splits == 0, (M, N, K)                                       # a full wave of tiles: never split
+    # the step's shapes at cfg2 (bf16): last-layer forward and the square MLP layers unsplit, last-layer dgrad split over CTA pairs
+    assert lib.dmc_gemm_workspace_bytes(2048, 65536, 256, L.DMC_BF16) == 0
+    assert lib.dmc_gemm_workspace_bytes(2048, 2048, 2048, L.DMC_BF16) == 0
+    dgrad = lib.dmc_gemm_workspace_bytes(2048, 256, 65536, L.DMC_BF16) // (2048 * 256 * 4)
+    assert 2 <= dgrad <= 18
+    assert lib.dmc_gemm_workspace_bytes(0, 256, 256, L.DMC_BF16) == 0
