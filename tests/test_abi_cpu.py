@@ -353,3 +353,30 @@ def test_gemm_planner_workspace_invariants_on_host():
     dgrad = lib.dmc_gemm_workspace_bytes(2048, 256, 65536, L.DMC_BF16) // (2048 * 256 * 4)
     assert 2 <= dgrad <= 18
     assert lib.dmc_gemm_workspace_bytes(0, 256, 256, L.DMC_BF16) == 0
+
+
+def test_every_compute_entry_refuses_an_empty_call_on_the_host():
+    """All-zero / all-null arguments: every int-returning entry point of the ABI validates before it touches CUDA and answers with a
+    negative code and a message (no crash, no launch) -- the contract that lets the Python layer fail loudly."""
+    import dinomc_b200
+    L = dinomc_b200._lib
+    lib = L.load()
+    not_compute = {"dmc_version", "dmc_set_pdl", "dmc_set_streaming_ctas", "dmc_device_check"}
+    checked = 0
+    for name, (res, argtypes) in L.SIGNATURES.items():
+        if res is not C.c_int or name in not_compute:
+            continue
+        args = []
+        for t in argtypes:
+            if t in (L.vp, C.c_char_p) or hasattr(t, "contents") or (isinstance(t, type) and issubclass(t, C._Pointer)):
+                args.append(None)
+            elif t in (C.c_float, C.c_double, L.f32):
+                args.append(0.0)
+            else:
+                args.append(0)
+        rc = getattr(lib, name)(*args)
+        msg = lib.dmc_last_error_string().decode()
+        assert rc < 0, (name, rc, msg)
+        assert msg, name
+        checked += 1
+    assert checked == 34          # 50 entries - 12 size / count queries and string getters - 4 switches
