@@ -240,3 +240,37 @@ def test_use_bn_head_wiring(monkeypatch):
         if n not in ("0.bias", "3.bias"):      # a bias in front of a BatchNorm has an exactly-zero gradient
             assert _rel(p.grad.numpy(), q.grad.numpy()) < tol, n
     assert _rel(head.mlp[1].running_var.numpy(), ref_mlp[1].running_var.numpy()) < 1e-5
+
+
+def test_dino_tp_layout_and_warmup_temperature(monkeypatch):
+    """DINO-TP (main_dino_tp.py layout: 3 teacher crops, 9 crops in all, trainable gain) at an epoch inside the teacher-temperature
+    warm-up: DINOLoss must take schedule[epoch] (main_dino_mc.py:445) and pass the crop layout through unchanged."""
+    dbl.install(monkeypatch)
+    C, G, K, B = 9, 3, 1024, 3
+    torch.manual_seed(5)
+    student = D.DINOHead(64, K, norm_last_layer=False, hidden_dim=128, bottleneck_dim=64)
+    teacher = D.DINOHead(64, K, norm_last_layer=False, hidden_dim=128, bottleneck_dim=64)
+    for p in teacher.parameters():
+        p.requires_grad = False
+    student.precision = teacher.precision = "fp32"
+    loss_mod = D.DINOLoss(K, C, 0.04, 0.07, 3, 10, teacher_crops_number=G)
+    temps = [float(t) for t in loss_mod.teacher_temp_schedule[:4]]
+    assert temps == pytest.approx([0.04, 0.055, 0.07, 0.07])
+    with torch.no_grad():
+        loss_mod.center.normal_(0, 0.3)
+    center0 = loss_mod.center.clone()
+    xs = torch.randn(C * B, 64, requires_grad=True)
+    xt = torch.randn(G * B, 64)
+    ssd = {k: v.detach().numpy() for k, v in student.state_dict().items()}
+    tsd = {k: v.detach().numpy() for k, v in teacher.state_dict().items()}
+    ref = O.full_step(xs.detach().numpy(), xt.numpy(), ssd, tsd, center0.numpy(), temps[1], C, G)
+    with torch.no_grad():
+        t_out = teacher(xt)
+    loss = loss_mod(student(xs), t_out, 1)
+    loss.backward()
+    assert abs(float(loss.detach()) - ref["loss"]) / abs(ref["loss"]) < 2e-5
+    assert _rel(xs.grad.numpy(), ref["grads"]["x"]) < 2e-5
+    assert _rel(student.last_layer.weight_g.grad.numpy(), ref["grads"]["last_layer.weight_g"]) < 2e-5
+    assert _rel(loss_mod.center.numpy(), ref["center"]) < 1e-6
+    with pytest.raises(ValueError):
+        loss_mod(student(xs)[:-1], t_out, 1)                 # rows must be ncrops * B
